@@ -1,0 +1,176 @@
+"""ctypes binding of libhsbp.so (the C-ABI declared in include/hsbp.h).
+
+This is the Python twin of the `ccall` layer a Julia host would use
+(INTEGRATION.md): same symbols, same argument order, no array abstraction in
+between.  There is deliberately no fallback: if the shared library is missing
+or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsbp.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hsbp.h")
+
+
+class HsbpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libhsbp error %d: %s" % (code, msg))
+        self.code = code
+
+
+def declared_symbols(header=HEADER_PATH):
+    """Names of all functions include/hsbp.h declares."""
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hsbp_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib():
+    """Load libhsbp.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HsbpError(-100, "libhsbp.so not built (run python -c 'import __graft_entry__ as g; g.build()'); "
+                              "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i64p, dp, cint, i64, dbl = C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int, C.c_int64, C.c_double
+    sig = {
+        "hsbp_version": (cint, []),
+        "hsbp_ctx_create": (cint, [cint, C.POINTER(vp)]),
+        "hsbp_ctx_destroy": (cint, [vp]),
+        "hsbp_last_error": (C.c_char_p, [vp]),
+        "hsbp_malloc": (cint, [vp, C.c_size_t, C.POINTER(vp)]),
+        "hsbp_free": (cint, [vp, vp]),
+        "hsbp_h2d": (cint, [vp, vp, vp, C.c_size_t]),
+        "hsbp_d2h": (cint, [vp, vp, vp, C.c_size_t]),
+        "hsbp_memset0": (cint, [vp, vp, C.c_size_t]),
+        "hsbp_sync": (cint, [vp]),
+        "hsbp_host_register": (cint, [vp, vp, C.c_size_t]),
+        "hsbp_host_unregister": (cint, [vp, vp]),
+        "hsbp_stream": (vp, [vp]),
+        "hsbp_timer_start": (cint, [vp]),
+        "hsbp_timer_stop": (cint, [vp, C.POINTER(dbl)]),
+        "hsbp_blocks_create": (cint, [vp, cint, i64, i64p, i64p, C.POINTER(vp)]),
+        "hsbp_blocks_destroy": (cint, [vp]),
+        "hsbp_blocks_num_volume_points": (i64, [vp]),
+        "hsbp_blocks_num_face_points": (i64, [vp]),
+        "hsbp_blocks_set_metrics": (cint, [vp, dp, dp, dp]),
+        "hsbp_blocks_set_metrics_dev": (cint, [vp, dp, dp, dp]),
+        "hsbp_blocks_set_bc": (cint, [vp, i64p]),
+        "hsbp_blocks_compute_tau": (cint, [vp, dbl]),
+        "hsbp_blocks_set_tau": (cint, [vp, dp]),
+        "hsbp_blocks_get_tau": (cint, [vp, dp]),
+        "hsbp_apply": (cint, [vp, dp, dp]),
+        "hsbp_apply_host": (cint, [vp, dp, dp]),
+        "hsbp_apply_variant": (cint, [vp]),
+        "hsbp_blocks_force_generic": (cint, [vp, cint]),
+        "hsbp_face_FT": (cint, [vp, dp, dp]),
+        "hsbp_face_F_add": (cint, [vp, dp, dbl, dp]),
+        "hsbp_face_traction": (cint, [vp, dp, dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._signatures = sig
+    _lib = L
+    return L
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, C.c_void_p(a.ctypes.data)
+
+
+class DeviceArray:
+    """A device buffer of float64 owned through hsbp_malloc / hsbp_free."""
+
+    def __init__(self, ctx, n):
+        self.ctx = ctx
+        self.n = int(n)
+        p = C.c_void_p()
+        ctx._check(lib().hsbp_malloc(ctx.h, self.n * 8, C.byref(p)))
+        self.ptr = p
+
+    @classmethod
+    def from_host(cls, ctx, a):
+        a, pa = _f64(a)
+        d = cls(ctx, a.size)
+        ctx._check(lib().hsbp_h2d(ctx.h, d.ptr, pa, a.size * 8))
+        return d
+
+    def set(self, a):
+        a, pa = _f64(a)
+        assert a.size == self.n
+        self.ctx._check(lib().hsbp_h2d(self.ctx.h, self.ptr, pa, a.size * 8))
+
+    def zero(self):
+        self.ctx._check(lib().hsbp_memset0(self.ctx.h, self.ptr, self.n * 8))
+
+    def get(self):
+        out = np.empty(self.n, dtype=np.float64)
+        self.ctx._check(lib().hsbp_d2h(self.ctx.h, C.c_void_p(out.ctypes.data), self.ptr, self.n * 8))
+        return out
+
+    def free(self):
+        if self.ptr is not None and self.ctx.h is not None:
+            lib().hsbp_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = lib().hsbp_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise HsbpError(rc, "hsbp_ctx_create failed (a B200 / sm_100 GPU is required; no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HsbpError(rc, lib().hsbp_last_error(self.h).decode())
+
+    def sync(self):
+        self._check(lib().hsbp_sync(self.h))
+
+    def array(self, a):
+        return DeviceArray.from_host(self, a)
+
+    def empty(self, n):
+        return DeviceArray(self, n)
+
+    def timer_start(self):
+        self._check(lib().hsbp_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(lib().hsbp_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def stream(self):
+        return lib().hsbp_stream(self.h)
+
+    def close(self):
+        if self.h is not None:
+            lib().hsbp_ctx_destroy(self.h)
+            self.h = None

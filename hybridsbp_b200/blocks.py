@@ -1,0 +1,114 @@
+"""Device-resident block-local operators (thin object wrapper over the hsbp_blocks_* C-ABI).
+
+Replaces what the reference's `locoperator` assembles per block -- the sparse
+M-tilde, F_k, HfI_FT_k (global_curved.jl:211-506) -- by matrix-free CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Context, DeviceArray, _f64, _i64, lib
+
+
+class Blocks:
+    """A set of blocks on one GPU.
+
+    p: SBP interior order (2, 4, 6); Nr, Ns: per-block grid sizes (length nblocks).
+    Volume vectors are the blocks' (Nr+1)x(Ns+1) fields, r fastest, concatenated
+    (the reference's `vstarts` layout); face vectors hold faces 1..4 of each block.
+    """
+
+    def __init__(self, ctx: Context, p, Nr, Ns):
+        self.ctx = ctx
+        self.p = int(p)
+        self.Nr = np.ascontiguousarray(Nr, dtype=np.int64).ravel()
+        self.Ns = np.ascontiguousarray(Ns, dtype=np.int64).ravel()
+        assert self.Nr.shape == self.Ns.shape
+        self.nblocks = self.Nr.size
+        h = C.c_void_p()
+        _, pNr = _i64(self.Nr)
+        _, pNs = _i64(self.Ns)
+        ctx._check(lib().hsbp_blocks_create(ctx.h, self.p, self.nblocks, pNr, pNs, C.byref(h)))
+        self.h = h
+        self.VNp = lib().hsbp_blocks_num_volume_points(h)
+        self.FNp = lib().hsbp_blocks_num_face_points(h)
+        npts = (self.Nr + 1) * (self.Ns + 1)
+        self.vstarts = np.concatenate([[1], 1 + np.cumsum(npts)]).astype(np.int64)     # 1-based, as the reference
+        nface = 2 * (self.Nr + 1) + 2 * (self.Ns + 1)
+        self.fstarts = np.concatenate([[0], np.cumsum(nface)]).astype(np.int64)         # 0-based block face offsets
+
+    # -- setup -------------------------------------------------------------------------------
+    def set_metrics(self, crr, css, crs):
+        a, pa = _f64(crr); b, pb = _f64(css); c, pc = _f64(crs)
+        assert a.size == b.size == c.size == self.VNp
+        self.ctx._check(lib().hsbp_blocks_set_metrics(self.h, pa, pb, pc))
+
+    def set_metrics_dev(self, crr: DeviceArray, css: DeviceArray, crs: DeviceArray):
+        self.ctx._check(lib().hsbp_blocks_set_metrics_dev(self.h, crr.ptr, css.ptr, crs.ptr))
+
+    def set_bc(self, bctype):
+        a, pa = _i64(np.asarray(bctype).reshape(-1))
+        assert a.size == 4 * self.nblocks
+        self.ctx._check(lib().hsbp_blocks_set_bc(self.h, pa))
+
+    def compute_tau(self, tauscale=2.0):
+        self.ctx._check(lib().hsbp_blocks_compute_tau(self.h, float(tauscale)))
+
+    def set_tau(self, tau):
+        a, pa = _f64(tau)
+        assert a.size == self.FNp
+        self.ctx._check(lib().hsbp_blocks_set_tau(self.h, pa))
+
+    def get_tau(self):
+        out = np.empty(self.FNp)
+        self.ctx._check(lib().hsbp_blocks_get_tau(self.h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def face_slice(self, e, lf):
+        """Slice of block e's local face lf (1-based) inside a face vector."""
+        nsp, nrp = self.Ns[e] + 1, self.Nr[e] + 1
+        start = self.fstarts[e] + (0, nsp, 2 * nsp, 2 * nsp + nrp)[lf - 1]
+        return slice(int(start), int(start + (nsp if lf <= 2 else nrp)))
+
+    def vol_slice(self, e):
+        return slice(int(self.vstarts[e] - 1), int(self.vstarts[e + 1] - 1))
+
+    # -- operators ---------------------------------------------------------------------------
+    def apply(self, u: DeviceArray, y: DeviceArray):
+        """y = M-tilde u   (device vectors)."""
+        self.ctx._check(lib().hsbp_apply(self.h, u.ptr, y.ptr))
+
+    def apply_host(self, u, y=None):
+        """y = M-tilde u through host buffers (H2D + kernels + D2H inside the call)."""
+        u, pu = _f64(u)
+        assert u.size == self.VNp
+        if y is None:
+            y = np.empty(self.VNp)
+        self.ctx._check(lib().hsbp_apply_host(self.h, pu, C.c_void_p(y.ctypes.data)))
+        return y
+
+    def apply_variant(self):
+        return lib().hsbp_apply_variant(self.h)
+
+    def force_generic(self, on=True):
+        self.ctx._check(lib().hsbp_blocks_force_generic(self.h, 1 if on else 0))
+
+    def face_FT(self, u: DeviceArray, ft: DeviceArray):
+        self.ctx._check(lib().hsbp_face_FT(self.h, u.ptr, ft.ptr))
+
+    def face_F_add(self, v: DeviceArray, alpha, y: DeviceArray):
+        self.ctx._check(lib().hsbp_face_F_add(self.h, v.ptr, float(alpha), y.ptr))
+
+    def face_traction(self, u: DeviceArray, tr: DeviceArray):
+        self.ctx._check(lib().hsbp_face_traction(self.h, u.ptr, tr.ptr))
+
+    def close(self):
+        if self.h is not None:
+            lib().hsbp_blocks_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

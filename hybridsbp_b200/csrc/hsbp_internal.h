@@ -1,0 +1,67 @@
+// Internal data structures of libhsbp (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hsbp.h"
+
+struct hsbp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  std::string err;
+};
+
+// Per-block descriptor on the device (one per block, 64 bytes).
+struct BlockDesc {
+  int32_t Nr, Ns;        // grid sizes (points are Nr+1, Ns+1)
+  int64_t voff;          // 0-based offset of the block in volume vectors
+  int64_t foff;          // 0-based offset of the block's face 1 in face vectors
+  int32_t bc[4];         // boundary-condition code of local faces 1..4
+  int32_t pad[2];
+  // face k of this block starts at foff + fstart(k):
+  //   k=0: 0, k=1: Ns+1, k=2: 2(Ns+1), k=3: 2(Ns+1)+(Nr+1)
+};
+
+struct hsbp_blocks {
+  hsbp_ctx *ctx = nullptr;
+  int p = 0;
+  int64_t nblocks = 0;
+  int64_t VNp = 0;       // volume points
+  int64_t FNp = 0;       // face points (all blocks, all four faces)
+  std::vector<BlockDesc> h_desc;
+  BlockDesc *d_desc = nullptr;
+  double *d_crr = nullptr, *d_css = nullptr, *d_crs = nullptr;
+  double *d_tau = nullptr;          // FNp
+  double *d_fa = nullptr;           // FNp scratch: alpha (or F^T u)
+  double *d_fb = nullptr;           // FNp scratch: beta
+  double *d_t = nullptr, *d_w = nullptr;   // VNp scratch of the generic kernels (lazy)
+  bool have_metrics = false, have_bc = false, have_tau = false;
+  bool uniform = false;             // all blocks share (Nr, Ns)
+  int max_Nr = 0, max_Ns = 0;
+  int force_generic = 0;
+  int last_variant = -1;
+  // pinned staging for hsbp_apply_host (lazy)
+  double *d_stage_u = nullptr, *d_stage_y = nullptr;
+};
+
+#define HSBP_CUDA(ctx, call)                                                     \
+  do {                                                                           \
+    cudaError_t _e = (call);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);           \
+      return HSBP_ERR_CUDA;                                                      \
+    }                                                                            \
+  } while (0)
+
+#define HSBP_FAIL(ctx, code, msg) \
+  do {                            \
+    (ctx)->err = (msg);           \
+    return (code);                \
+  } while (0)

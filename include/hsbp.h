@@ -1,0 +1,119 @@
+/*
+ * libhsbp -- C-ABI of the B200-native (sm_100a) hybridized-SBP solve path.
+ *
+ * This is the drop-in boundary for ONE path of brittany-erickson/HybridSBP: the
+ * block-local curvilinear SBP operator, the per-block local solves, the trace
+ * (lambda) operators and solve, and the BP1 rate-and-state stage.  The reference
+ * is pure Julia with no FFI of its own; every entry point below names the
+ * reference interface (file:line under the reference tree) whose *work* it
+ * replaces, and INTEGRATION.md shows the `ccall` stubs a maintainer would add.
+ *
+ * Conventions (same as the reference):
+ *   - values are fp64, ids / sizes / offsets are int64;
+ *   - a block field is (Nr+1) x (Ns+1), column-major, r fastest; blocks are
+ *     concatenated in block order (the reference's `vstarts` layout);
+ *   - ids held in arrays (FToE, FToLF, EToS ...) are 1-based exactly as the
+ *     reference produces them; the library converts internally;
+ *   - boundary-condition codes: 0 locked interface, 1 Dirichlet, 2 Neumann,
+ *     >= 7 jump interface (global_curved.jl:13-16);
+ *   - face data of one block is laid out face 1..4, face k having Ns+1 points
+ *     (k = 1, 2) or Nr+1 points (k = 3, 4).
+ *
+ * Every function returns 0 on success, < 0 for an argument error, > 0 for a
+ * CUDA / NCCL failure; nothing throws or exits.  `hsbp_last_error` gives the
+ * text.  Pointers named *_dev are device pointers (from hsbp_malloc or any CUDA
+ * allocation of the same device); all others are host pointers which the
+ * library only reads/writes during the call.
+ *
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef HSBP_H
+#define HSBP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSBP_BC_LOCKED    0
+#define HSBP_BC_DIRICHLET 1
+#define HSBP_BC_NEUMANN   2
+#define HSBP_BC_JUMP      7
+
+#define HSBP_OK            0
+#define HSBP_ERR_ARG      -1
+#define HSBP_ERR_STATE    -2
+#define HSBP_ERR_UNSUPP   -3
+#define HSBP_ERR_CUDA      1
+#define HSBP_ERR_NCCL      2
+
+typedef struct hsbp_ctx    hsbp_ctx;     /* one device + its streams                         */
+typedef struct hsbp_blocks hsbp_blocks;  /* block-local operators of a set of blocks          */
+typedef struct hsbp_trace  hsbp_trace;   /* trace (lambda) operators + Schur-complement solve */
+
+/* ---- context / memory --------------------------------------------------- */
+int  hsbp_version(void);
+int  hsbp_ctx_create(int device, hsbp_ctx **ctx);
+int  hsbp_ctx_destroy(hsbp_ctx *ctx);
+const char *hsbp_last_error(hsbp_ctx *ctx);      /* valid until the next call on ctx */
+int  hsbp_malloc(hsbp_ctx *ctx, size_t bytes, void **dptr);
+int  hsbp_free(hsbp_ctx *ctx, void *dptr);
+int  hsbp_h2d(hsbp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int  hsbp_d2h(hsbp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int  hsbp_memset0(hsbp_ctx *ctx, void *dst_dev, size_t bytes);
+int  hsbp_sync(hsbp_ctx *ctx);
+int  hsbp_host_register(hsbp_ctx *ctx, void *host, size_t bytes);    /* pin a caller buffer */
+int  hsbp_host_unregister(hsbp_ctx *ctx, void *host);
+/* the CUDA stream all work of ctx is issued on (a cudaStream_t), for callers that time with events */
+void *hsbp_stream(hsbp_ctx *ctx);
+/* elapsed-time helpers on that stream (CUDA events owned by the library) */
+int  hsbp_timer_start(hsbp_ctx *ctx);
+int  hsbp_timer_stop(hsbp_ctx *ctx, double *milliseconds);  /* synchronises */
+
+/* ---- block-local operator: replaces locoperator's assembled M-tilde ------
+ * reference: locoperator, global_curved.jl:211-506 (sparse M-tilde :470-486,
+ * F_k :455-458, tau :418-442); variable_diagonal_sbp_D2, diagonal_sbp.jl:474-764.
+ * Nothing is assembled: the library keeps crr/css/crs, tau and bc codes and
+ * applies M-tilde matrix-free.  p in {2, 4, 6} (global_curved.jl:402-416).      */
+int  hsbp_blocks_create(hsbp_ctx *ctx, int p, int64_t nblocks,
+                        const int64_t *Nr, const int64_t *Ns, hsbp_blocks **blocks);
+int  hsbp_blocks_destroy(hsbp_blocks *blocks);
+int64_t hsbp_blocks_num_volume_points(const hsbp_blocks *blocks);   /* VNp  */
+int64_t hsbp_blocks_num_face_points(const hsbp_blocks *blocks);     /* sum over blocks and faces */
+/* coefficient fields from create_metrics (global_curved.jl:160-162), concatenated by block */
+int  hsbp_blocks_set_metrics(hsbp_blocks *blocks, const double *crr, const double *css,
+                             const double *crs);
+/* same, from device memory (e.g. synthetic meshes generated on the device) */
+int  hsbp_blocks_set_metrics_dev(hsbp_blocks *blocks, const double *crr_dev,
+                                 const double *css_dev, const double *crs_dev);
+/* LFToB of every block: 4 * nblocks codes (argument LFToB of locoperator, :212) */
+int  hsbp_blocks_set_bc(hsbp_blocks *blocks, const int64_t *bctype);
+/* penalty tau_1..4 on the device as global_curved.jl:418-437 (psi_min, l nearest lines) */
+int  hsbp_blocks_compute_tau(hsbp_blocks *blocks, double tauscale);
+/* or supply / read back tau (face layout, see top) */
+int  hsbp_blocks_set_tau(hsbp_blocks *blocks, const double *tau);
+int  hsbp_blocks_get_tau(hsbp_blocks *blocks, double *tau);
+
+/* y = M-tilde u for all blocks (the SpMV `lop[e].M̃ * u`, global_curved.jl:470-492)      */
+int  hsbp_apply(hsbp_blocks *blocks, const double *u_dev, double *y_dev);
+/* same through host buffers: H2D of u, apply, D2H of y inside the call                 */
+int  hsbp_apply_host(hsbp_blocks *blocks, const double *u, double *y);
+/* which kernel variant hsbp_apply last used: 0 generic, 1 line-marching TMA kernel     */
+int  hsbp_apply_variant(const hsbp_blocks *blocks);
+/* force the generic kernels (testing) */
+int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
+
+/* face operators of the blocks, block-face layout (no inter-block coupling):
+ *   ft = F_k^T u                 (rows of Fbar^T before orientation, global_curved.jl:455-458)
+ *   y += F_k v                   (columns; used by locbcarray!, global_curved.jl:596-623)
+ *   tr = HfI_FT_k u              (traction operator, global_curved.jl:460-463)               */
+int  hsbp_face_FT(hsbp_blocks *blocks, const double *u_dev, double *ft_dev);
+int  hsbp_face_F_add(hsbp_blocks *blocks, const double *v_dev, double alpha, double *y_dev);
+int  hsbp_face_traction(hsbp_blocks *blocks, const double *u_dev, double *tr_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSBP_H */

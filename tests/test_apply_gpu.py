@@ -1,0 +1,97 @@
+"""GPU parity: matrix-free M-tilde u (CUDA, through the C-ABI) against the oracle's assembled
+sparse M-tilde (reference locoperator, global_curved.jl:211-506).  Tolerance from the north
+star: 1e-12 relative, normwise (||dy||_inf / || |M| |u| ||_inf)."""
+import numpy as np
+import pytest
+
+from oracle import hybrid as orc
+from tests.util import flat, random_spd_metrics, rel_err_apply, upload_blocks, warped_metrics
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+BCS = [(1, 1, 1, 1), (0, 0, 0, 0), (1, 2, 2, 2), (2, 1, 0, 7), (2, 2, 2, 1), (7, 0, 2, 1)]
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+@pytest.mark.parametrize("generic", [True, False])
+def test_apply_random_spd_small(ctx, p, generic):
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(777 + p)
+    N = 3 * p - 1 if p > 2 else 5
+    shapes = [(N, N), (N + 3, N + 1), (N + 8, N + 13), (2 * N + 1, N + 2)] * 2
+    mets, bcs, lops = [], [], []
+    for i, (Nr, Ns) in enumerate(shapes):
+        m = random_spd_metrics(p, Nr, Ns, rng)
+        bc = BCS[i % len(BCS)]
+        mets.append(m); bcs.append(bc)
+        lops.append(orc.locoperator(p, Nr, Ns, m, bc, tauscale=1.0))
+    blk = upload_blocks(hs, ctx, p, mets, bcs, tauscale=1.0)
+    blk.force_generic(generic)
+    u = rng.uniform(-1, 1, blk.VNp)
+    du, dy = ctx.array(u), ctx.empty(blk.VNp)
+    blk.apply(du, dy)
+    y = dy.get()
+    # tau parity first (global_curved.jl:418-437)
+    tau = blk.get_tau()
+    for e, lop in enumerate(lops):
+        for lf in range(1, 5):
+            tref = lop.tau[lf - 1].diagonal()
+            assert np.allclose(tau[blk.face_slice(e, lf)], tref, rtol=1e-13, atol=0)
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        yref = lop.Mt @ u[sl]
+        err = rel_err_apply(y[sl], yref, lop.Mt, u[sl])
+        assert err < TOL, (p, e, shapes[e], bcs[e], err)
+
+
+@pytest.mark.parametrize("p,N", [(2, 40), (4, 31), (4, 63), (6, 47)])
+def test_apply_warped_mesh(ctx, p, N):
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(p * 100 + N)
+    nbx = nby = 2
+    mets, bcs, lops = [], [], []
+    for by in range(nby):
+        for bx in range(nbx):
+            m = warped_metrics(p, N, N, bx, by, nbx, nby, amp=0.15)
+            bc = (1 if bx == 0 else 0, 1 if bx == nbx - 1 else 0, 2 if by == 0 else 0, 2 if by == nby - 1 else 0)
+            mets.append(m); bcs.append(bc)
+            lops.append(orc.locoperator(p, N, N, m, bc))
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    u = rng.uniform(-1, 1, blk.VNp)
+    y = blk.apply_host(u)
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        err = rel_err_apply(y[sl], lop.Mt @ u[sl], lop.Mt, u[sl])
+        assert err < TOL, (p, e, err)
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_face_operators(ctx, p):
+    """F_k^T u, F_k v and the traction operator against the oracle's sparse F_k / HfI_FT_k."""
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(5 + p)
+    N = 3 * p + 2
+    shapes = [(N, N + 4), (N + 5, N)]
+    mets = [random_spd_metrics(p, a, b, rng) for a, b in shapes]
+    bcs = [(0, 7, 1, 2), (2, 0, 0, 1)]
+    lops = [orc.locoperator(p, a, b, m, bc, tauscale=1.5) for (a, b), m, bc in zip(shapes, mets, bcs)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs, tauscale=1.5)
+    u = rng.uniform(-1, 1, blk.VNp)
+    v = rng.uniform(-1, 1, blk.FNp)
+    du, dv = ctx.array(u), ctx.array(v)
+    dft, dtr, dy = ctx.empty(blk.FNp), ctx.empty(blk.FNp), ctx.array(np.zeros(blk.VNp))
+    blk.face_FT(du, dft); blk.face_traction(du, dtr); blk.face_F_add(dv, -0.5, dy)
+    ft, tr, y = dft.get(), dtr.get(), dy.get()
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        yref = np.zeros(sl.stop - sl.start)
+        for lf in range(1, 5):
+            fs = blk.face_slice(e, lf)
+            F = lop.F[lf - 1]
+            ref = F.T @ u[sl]
+            assert np.max(np.abs(ft[fs] - ref)) <= 1e-12 * np.max(abs(F.T) @ np.abs(u[sl]))
+            T = lop.HfI_FT[lf - 1]
+            assert np.max(np.abs(tr[fs] - T @ u[sl])) <= 1e-12 * np.max(abs(T) @ np.abs(u[sl]))
+            yref += -0.5 * (F @ v[fs])
+        assert np.max(np.abs(y[sl] - yref)) <= 1e-12 * np.max(np.abs(yref))

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Extract the published SBP coefficient tables into oracle/sbp_tables.json.
+"""Extract the published SBP coefficient tables into oracle/sbp_tables.json and
+hybridsbp_b200/csrc/sbp_tables_gen.h (two independent encodings of the same numbers).
 
 TEST INFRASTRUCTURE (oracle side).  Run once in the build container, where
 /root/reference is mounted; the JSON it writes is committed, this script is the
@@ -28,6 +29,7 @@ import sys
 
 REF = os.environ.get("HSBP_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 
 
 def _func_body(lines, header_prefix):
@@ -141,9 +143,63 @@ def main():
             "closure": [[i, j, m0[(i, j)]] for i in range(1, size + 1) for j in range(1, size + 1)],
         }
     tables["D2var"] = d2
-    dst = os.path.join(HERE, "sbp_tables.json")
+    dst = os.path.join(ROOT, "oracle", "sbp_tables.json")
     with open(dst, "w") as f:
         json.dump(tables, f, indent=0, separators=(",", ":"))
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+    write_cuda_header(tables, os.path.join(ROOT, "hybridsbp_b200", "csrc", "sbp_tables_gen.h"))
+
+
+def _f(c):
+    if isinstance(c, list):
+        v = float(int(c[0])) / float(int(c[1]))
+    else:
+        v = float(c)
+    return v
+
+
+def _lit(v):
+    return float(v).hex() if v != 0 else "0.0"
+
+
+def write_cuda_header(tables, dst):
+    """Dense device tables: first-derivative closures and, for the variable-coefficient
+    second derivative, T[i][j][k] with M0[i][j] = sum_k T[i][j][k] * b[k]."""
+    out = ["// GENERATED by tools/gen_sbp_tables.py -- do not edit.",
+           "// Published SBP coefficient data (Strand 1994; Mattsson & Nordstrom 2004; Mattsson 2012)",
+           "// as used by reference diagonal_sbp.jl:69-92 (D1) and :507-690 (variable D2 closures).",
+           "// Literals are C99 hex floats so that the device sees exactly the doubles the host computed.",
+           "#pragma once", ""]
+    for p in (2, 4, 6):
+        t = tables["D1"][str(p)]
+        bm, bn = len(t["bd"]), len(t["bd"][0])
+        out.append("// ---- p = %d first derivative: interior d[%d], closure bd[%d][%d], norm weights hw = 1/bhinv" % (p, p + 1, bm, bn))
+        out.append("#define HSBP_D1_BM_%d %d" % (p, bm))
+        out.append("#define HSBP_D1_BN_%d %d" % (p, bn))
+        out.append("#define HSBP_D1_D_%d {%s}" % (p, ", ".join(_lit(v) for v in t["d"])))
+        out.append("#define HSBP_D1_BD_%d {%s}" % (p, ", ".join(_lit(v) for row in t["bd"] for v in row)))
+        out.append("#define HSBP_D1_HW_%d {%s}" % (p, ", ".join(_lit(1.0 / v) for v in t["bhinv"])))
+        out.append("")
+    for p, nk in ((4, 8), (6, 12)):
+        t = tables["D2var"][str(p)]
+        m = t["size"]
+        T = [[[0.0] * nk for _ in range(m)] for _ in range(m)]
+        for i, j, terms in t["closure"]:
+            for k, c in terms:
+                assert T[i - 1][j - 1][k - 1] == 0.0
+                T[i - 1][j - 1][k - 1] = _f(c)
+        out.append("// ---- p = %d variable-coefficient second derivative closure tensor [%d][%d][%d]" % (p, m, m, nk))
+        out.append("#define HSBP_D2_M_%d %d" % (p, m))
+        out.append("#define HSBP_D2_NK_%d %d" % (p, nk))
+        out.append("#define HSBP_D2_BS_%d {%s}" % (p, ", ".join(_lit(v) for v in t["BS"])))
+        out.append("#define HSBP_D2_T_%d {\\" % p)
+        for i in range(m):
+            for j in range(m):
+                out.append("  %s,\\" % ", ".join(_lit(v) for v in T[i][j]))
+        out.append("}")
+        out.append("")
+    with open(dst, "w") as f:
+        f.write("\n".join(out) + "\n")
     print("wrote", dst, os.path.getsize(dst), "bytes")
 
 
