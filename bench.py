@@ -1,0 +1,301 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: fp64 matrix-free SBP operator apply (y = M-tilde u) on the synthetic
+warped multiblock mesh of BASELINE.json config 4 (1024 blocks x 256x256 points, p = 4) per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one operator apply over all blocks of this rank.  Prints ONE JSON line (rank 0).
+Under torchrun every rank holds its own 1024 blocks (a 32-block-wide strip of a 32G x 32 mesh):
+weak scaling; the operator apply has no exchange step, so there is no collective in the timed
+region besides the barriers.
+
+The reference arm (--impl reference) times the reference's CPU algorithm for this path -- the
+sparse product of the assembled M-tilde (global_curved.jl:470-492) -- through the oracle port
+(oracle/, C + OpenMP SpMV over the matrices the restated locoperator assembles) on a bounded
+sample of the same workload, on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_DOF = 40.0      # u 8 + crr, css, crs 24 + y 8  
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_baseline(p, N, nblk_sample, seconds, threads):
+    """Oracle port of the reference's CPU operator apply on `nblk_sample` blocks of the workload."""
+    from oracle import hybrid as orc                      # CPU baseline leg only
+    from oracle.cbuild import BlockSpMV
+    from hybridsbp_b200 import host, synthetic
+    t0 = time.time()
+    mats = []
+    for b in range(nblk_sample):
+        xf, yf = synthetic.warp_maps(b, 5, 32.0, 32.0 / 40.0)
+        m = orc.create_metrics(p, N, N, xf, yf)
+        mats.append(orc.locoperator(p, N, N, m, (1 if b == 0 else 0, 0, 0, 0)).Mt)
+    S = BlockSpMV(mats)
+    t_asm = time.time() - t0
+    nthreads = S.max_threads if threads <= 0 else threads
+    u = np.random.default_rng(778).uniform(-1, 1, S.n)
+    y = np.empty(S.n)
+    S(u, y, nthreads)
+    reps, t0 = 0, time.time()
+    while True:
+        S(u, y, nthreads)
+        reps += 1
+        if time.time() - t0 > seconds:
+            break
+    dt = (time.time() - t0) / reps
+    return S, {"value": S.n / dt / 1e9, "unit": "GDOF/s", "cores": int(nthreads), "kind": "port",
+               "sample": "%d of 1024 blocks (256x256 points, p=%d): assembled sparse M-tilde (%.1f nnz/row, %.1f s to "
+                         "assemble with the oracle), CSR SpMV in C/OpenMP, %d repetitions" %
+                         (nblk_sample, p, S.nnz / S.n, t_asm, reps)}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    p, N = args.p, args.n
+    t0 = time.time()
+    S, base = cpu_baseline(p, N, args.cpu_blocks, 0.5, 0)
+    u = np.random.default_rng(778).uniform(-1, 1, S.n)
+    y = np.empty(S.n)
+    for _ in range(args.warmup):
+        S(u, y, 0)
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        S(u, y, 0)
+    dt = (time.perf_counter() - t1) / args.steps
+    val = S.n / dt / 1e9
+    base["value"] = val
+    line = {"impl": "reference", "metric": "fp64 SBP operator-apply GDOF/s", "value": val, "unit": "GDOF/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference CPU path = sparse M-tilde * u (global_curved.jl:470-492) via the oracle port; "
+                    "each step is one SpMV over a bounded sample of the workload's blocks"}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "synthetic warped multiblock mesh, %d blocks x %dx%d points per GPU, p=%d (BASELINE config 4%s)"
+                        % (args.blocks, args.n + 1, args.n + 1, args.p, "" if world == 1 else "/5"),
+            "blocks_per_gpu": args.blocks, "points_per_block": (args.n + 1) ** 2, "sbp_order": args.p,
+            "dof_per_gpu": args.blocks * (args.n + 1) ** 2,
+            "cache": "inputs (%.2f GB per apply) exceed the 126 MB L2; no flush needed" %
+                     (args.blocks * (args.n + 1) ** 2 * 32 / 1e9),
+            "parallelism": "blocks partitioned across GPUs, no exchange in operator apply"}
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    from hybridsbp_b200 import build as _build
+    if rank == 0 or world == 1:
+        _build.build()
+    import hybridsbp_b200 as hs
+    from hybridsbp_b200 import synthetic
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = hs.Context(local)
+    p, N = args.p, args.n
+    nbx = nby = int(round(args.blocks ** 0.5))
+    assert nbx * nby == args.blocks, "--blocks must be a square number"
+    Lglob = float(max(nbx * world, nby))
+    # this rank's strip of the (nbx*world) x nby mesh
+    verts, EToV, EToF, FToB = synthetic.block_grid_connectivity(nbx, nby)
+    if world > 1:                         # the strip's left/right outer faces are interfaces unless at the mesh edge
+        for by in range(nby):
+            if rank > 0:
+                FToB[EToF[0, 0 + nbx * by] - 1] = 0
+            if rank < world - 1:
+                FToB[EToF[1, nbx - 1 + nbx * by] - 1] = 0
+    crr, css, crs = synthetic.warped_coefficients(nbx, nby, N, L=Lglob, A=Lglob / 40.0, bx0=rank * nbx)
+    blk = hs.Blocks(ctx, p, [N] * args.blocks, [N] * args.blocks)
+    blk.set_metrics(crr, css, crs)
+    del crr, css, crs
+    blk.set_bc(synthetic.block_bcs(EToF, FToB))
+    blk.compute_tau(2.0)
+    rng = np.random.default_rng(778 + rank)
+    u_host = rng.uniform(-1, 1, blk.VNp)
+    u = ctx.array(u_host)
+    y = ctx.empty(blk.VNp)
+    dof = blk.VNp
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        blk.apply(u, y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        blk.apply(u, y)
+    ms_total = ctx.timer_stop()
+    barrier()
+    # dominant-kernel time, live, with events between the stages of the same call
+    stage = np.zeros(3)
+    nrep = max(3, min(args.steps, 10))
+    for _ in range(nrep):
+        stage += blk.apply_timed(u, y)
+    stage /= nrep
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+
+    # end to end through the C-ABI with host buffers (pinned): H2D u, apply, D2H y every step
+    y_host = np.empty(blk.VNp)
+    ctx.host_register(u_host); ctx.host_register(y_host)
+    blk.apply_host_pinned(u_host, y_host)
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        blk.apply_host_pinned(u_host, y_host)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(np.abs(y_host).sum())
+    ctx.host_unregister(u_host); ctx.host_unregister(y_host)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        variant = blk.apply_variant()
+        achieved = BYTES_PER_DOF * dof / (stage[0] * 1e-3) / 1e9
+        line = {"metric": "fp64 SBP operator-apply GDOF/s", "value": world * dof / (ms_step * 1e-3) / 1e9,
+                "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None,
+                             "kernel": ("k_march (volume stage, single kernel)" if variant == 1 else
+                                        "k_cross_pre + k_vol_apply (two-pass generic volume stage)"),
+                             "algorithmic_bytes_per_launch": BYTES_PER_DOF * dof,
+                             "kernel_ms": float(stage[0]), "face_gather_ms": float(stage[1]),
+                             "face_scatter_ms": float(stage[2]), "peak_source": peak_src},
+                "e2e": {"value": world * dof / e2e_s / 1e9, "unit": "GDOF/s",
+                        "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
+                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                        "note": "hsbp_apply_host on pinned host buffers: H2D of u, apply, D2H of y inside each call"},
+                "gpu_launches": args.steps * (3 if variant == 1 else 4),
+                "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum}
+        if world == 1 and not args.no_cpu:
+            _, base = cpu_baseline(p, N, args.cpu_blocks, args.cpu_seconds, 1)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks", type=int, default=1024)
+    ap.add_argument("--n", type=int, default=255, help="N per block (points = N+1)")
+    ap.add_argument("--p", type=int, default=4)
+    ap.add_argument("--cpu-blocks", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=5.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

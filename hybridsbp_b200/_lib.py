@@ -70,6 +70,7 @@ def lib():
         "hsbp_blocks_get_tau": (cint, [vp, dp]),
         "hsbp_apply": (cint, [vp, dp, dp]),
         "hsbp_apply_host": (cint, [vp, dp, dp]),
+        "hsbp_apply_timed": (cint, [vp, dp, dp, dp]),
         "hsbp_apply_variant": (cint, [vp]),
         "hsbp_blocks_force_generic": (cint, [vp, cint]),
         "hsbp_face_FT": (cint, [vp, dp, dp]),
@@ -158,6 +159,12 @@ class Context:
 
     def empty(self, n):
         return DeviceArray(self, n)
+
+    def host_register(self, a):
+        self._check(lib().hsbp_host_register(self.h, C.c_void_p(a.ctypes.data), a.nbytes))
+
+    def host_unregister(self, a):
+        self._check(lib().hsbp_host_unregister(self.h, C.c_void_p(a.ctypes.data)))
 
     def timer_start(self):
         self._check(lib().hsbp_timer_start(self.h))

@@ -87,6 +87,16 @@ class Blocks:
         self.ctx._check(lib().hsbp_apply_host(self.h, pu, C.c_void_p(y.ctypes.data)))
         return y
 
+    def apply_timed(self, u: DeviceArray, y: DeviceArray):
+        """apply with per-stage CUDA-event times: (volume ms, face gather ms, face scatter ms)."""
+        ms = np.zeros(3)
+        self.ctx._check(lib().hsbp_apply_timed(self.h, u.ptr, y.ptr, C.c_void_p(ms.ctypes.data)))
+        return ms
+
+    def apply_host_pinned(self, u, y):
+        """apply_host on caller buffers that were registered with ctx.host_register."""
+        self.ctx._check(lib().hsbp_apply_host(self.h, C.c_void_p(u.ctypes.data), C.c_void_p(y.ctypes.data)))
+
     def apply_variant(self):
         return lib().hsbp_apply_variant(self.h)
 

@@ -327,7 +327,7 @@ template <int P> static int vol_generic(hsbp_blocks *b, const double *u, double 
   return check_launch(ctx, "k_vol_apply");
 }
 
-static int apply_async(hsbp_blocks *b, const double *u, double *y) {
+static int apply_async(hsbp_blocks *b, const double *u, double *y, cudaEvent_t *evs = nullptr) {
   hsbp_ctx *ctx = b->ctx;
   if (!b->have_metrics || !b->have_tau) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_apply: metrics / tau not set");
   if (!u || !y || u == y) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_apply: bad pointers");
@@ -335,6 +335,7 @@ static int apply_async(hsbp_blocks *b, const double *u, double *y) {
   return dispatch_p(b->p, [&](auto Pc) {
     constexpr int P = decltype(Pc)::value;
     int rc;
+    if (evs) cudaEventRecord(evs[0], ctx->stream);
     if (!b->force_generic && march_eligible<P>(b)) {
       rc = vol_march<P>(b, u, y);
       b->last_variant = 1;
@@ -343,11 +344,14 @@ static int apply_async(hsbp_blocks *b, const double *u, double *y) {
       b->last_variant = 0;
     }
     if (rc) return rc;
+    if (evs) cudaEventRecord(evs[1], ctx->stream);
     k_face_gather<P><<<(unsigned)(4 * b->nblocks), 128, 0, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, FACE_APPLY);
     if ((rc = check_launch(ctx, "k_face_gather"))) return rc;
+    if (evs) cudaEventRecord(evs[2], ctx->stream);
     k_face_scatter<P><<<(unsigned)b->nblocks, 256, 0, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_fa, b->d_fb, y);
+    if (evs) cudaEventRecord(evs[3], ctx->stream);
     return check_launch(ctx, "k_face_scatter");
   });
 }
@@ -357,6 +361,27 @@ extern "C" {
 int hsbp_apply(hsbp_blocks *b, const double *u_dev, double *y_dev) {
   if (!b) return HSBP_ERR_ARG;
   return apply_async(b, u_dev, y_dev);
+}
+
+int hsbp_apply_timed(hsbp_blocks *b, const double *u_dev, double *y_dev, double *ms) {
+  if (!b) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = b->ctx;
+  if (!ms) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_apply_timed: null pointer");
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaEvent_t evs[4];
+  for (int i = 0; i < 4; ++i) HSBP_CUDA(ctx, cudaEventCreate(&evs[i]));
+  int rc = apply_async(b, u_dev, y_dev, evs);
+  if (rc == HSBP_OK) {
+    cudaError_t e = cudaEventSynchronize(evs[3]);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+      float f = 0.f;
+      e = cudaEventElapsedTime(&f, evs[i], evs[i + 1]);
+      ms[i] = f;
+    }
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = HSBP_ERR_CUDA; }
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(evs[i]);
+  return rc;
 }
 
 int hsbp_apply_host(hsbp_blocks *b, const double *u, double *y) {

@@ -204,17 +204,23 @@ k_compute_tau(const BlockDesc *__restrict__ desc, const double *__restrict__ crr
   penalty_consts(P, beta, alpha);
   const double *rr = crr + d.voff, *ss = css + d.voff, *rs = crs + d.voff;
   for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) {
+    // Evaluated with explicitly rounded operations (no FMA contraction) in the reference's
+    // operation order: psi_min is a difference of nearly equal numbers for strongly anisotropic
+    // tensors, so a contracted multiply-add would change tau in the 10th digit.
     double psi = 1e300;
     for (int m = 0; m < S::LPSI; ++m) {
       const int64_t v = face_vol(d, k, n, m);
       const double a = rr[v], b = ss[v], c = rs[v];
-      const double pm = 0.5 * (a + b - sqrt((a - b) * (a - b) + 4.0 * c * c));   // :418
+      const double dab = __dsub_rn(a, b);
+      const double disc = __dadd_rn(__dmul_rn(dab, dab), __dmul_rn(4.0, __dmul_rn(c, c)));
+      const double pm = __dmul_rn(__dsub_rn(__dadd_rn(a, b), __dsqrt_rn(disc)), 0.5);   // :418
       psi = fmin(psi, pm);
     }
     if (!(psi > 0.0)) atomicExch(bad, 1);                                        // :419
     const int64_t f0 = face_vol(d, k, n, 0);
     const double cn = (k < 2 ? rr : ss)[f0], cx = rs[f0];
-    tau[d.foff + fg.fstart + n] = (2.0 * tauscale / fg.hn) * (cn * cn / beta + cx * cx / alpha) / psi;
+    const double num = __dadd_rn(__ddiv_rn(__dmul_rn(cn, cn), beta), __ddiv_rn(__dmul_rn(cx, cx), alpha));
+    tau[d.foff + fg.fstart + n] = __ddiv_rn(__dmul_rn(__ddiv_rn(__dmul_rn(2.0, tauscale), fg.hn), num), psi);
   }
 }
 

@@ -1,0 +1,200 @@
+// Solver-side kernels: vector primitives, the batched per-block PCG update (K2b), the trace-space
+// gather / scatter between block faces and lambda (K3), and the Schur-complement pieces (K4).
+//
+// Reference being replaced:
+//   local solves   factorization(M-tilde) and F \ g      global_curved.jl:698, 734; square_circle.jl:383
+//   Fbar^T, D      glolambdaoperator                     global_curved.jl:510-565
+//   B lambda       assemblelambdamatrix + cholesky(B)    global_curved.jl:743-797; square_circle.jl:313-377
+#pragma once
+#include "hsbp_internal.h"
+#include "k_generic.cuh"
+
+namespace hsbp {
+
+// ---- small vector kernels (lambda space and volume space) ----------------------------------
+constexpr int VEC_THREADS = 256;
+constexpr int DOT_BLOCKS = 296;     // 2 per SM; partial sums are combined in a fixed order
+
+__global__ void k_fill(double *x, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+// z = a*x + b*y   (z may alias x or y)
+__global__ void k_axpby(int64_t n, double a, const double *x, double b, const double *y, double *z) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = a * x[i] + b * y[i];
+}
+// z = x * y (elementwise), or z = x / y
+__global__ void k_ewise(int64_t n, const double *x, const double *y, double *z, int divide) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = divide ? x[i] / y[i] : x[i] * y[i];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the CTA; result valid in every thread; scratch >= 32 doubles
+__device__ __forceinline__ double cta_sum(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();                 // protect scratch from the previous use
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double t = (lane < nw) ? scratch[lane] : 0.0;
+  t = warp_sum(t);
+  return t;
+}
+
+// partial[b] = sum over this CTA's slice of x*y ; up to 3 dot products at once
+__global__ void __launch_bounds__(VEC_THREADS)
+k_dot3_partial(int64_t n, const double *x0, const double *y0, const double *x1, const double *y1,
+               const double *x2, const double *y2, double *partial) {
+  __shared__ double scratch[32];
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    s0 += x0[i] * y0[i];
+    if (x1) s1 += x1[i] * y1[i];
+    if (x2) s2 += x2[i] * y2[i];
+  }
+  s0 = cta_sum(s0, scratch); s1 = cta_sum(s1, scratch); s2 = cta_sum(s2, scratch);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s0; partial[gridDim.x + blockIdx.x] = s1; partial[2 * gridDim.x + blockIdx.x] = s2;
+  }
+}
+__global__ void k_dot3_final(int nb, const double *partial, double *out) {
+  __shared__ double scratch[32];
+  for (int q = 0; q < 3; ++q) {
+    double s = 0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[q * nb + i];
+    s = cta_sum(s, scratch);
+    if (threadIdx.x == 0) out[q] = s;
+  }
+}
+
+// ---- probing the diagonal of M-tilde (setup of the Jacobi preconditioner) -------------------
+template <int P>
+__global__ void k_color_vector(const BlockDesc *__restrict__ desc, int c, int ci, int cj, double *__restrict__ u) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int Nrp = d.Nr + 1;
+  const int64_t np = (int64_t)Nrp * (d.Ns + 1);
+  for (int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; idx < np; idx += (int64_t)gridDim.y * blockDim.x) {
+    const int j = (int)(idx / Nrp), i = (int)(idx - (int64_t)j * Nrp);
+    u[d.voff + idx] = (i % c == ci && j % c == cj) ? 1.0 : 0.0;
+  }
+}
+template <int P>
+__global__ void k_color_pick(const BlockDesc *__restrict__ desc, int c, int ci, int cj,
+                             const double *__restrict__ y, double *__restrict__ dinv) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int Nrp = d.Nr + 1;
+  const int64_t np = (int64_t)Nrp * (d.Ns + 1);
+  for (int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; idx < np; idx += (int64_t)gridDim.y * blockDim.x) {
+    const int j = (int)(idx / Nrp), i = (int)(idx - (int64_t)j * Nrp);
+    if (i % c == ci && j % c == cj) dinv[d.voff + idx] = 1.0 / y[d.voff + idx];
+  }
+}
+
+// ---- batched PCG, one CTA per block ---------------------------------------------------------
+struct PcgState {      // per block
+  double rz, g2, rr;
+  int32_t active, iters;
+};
+
+// x = 0, r = g, z = Dinv r, p = z, rz = r.z, g2 = g.g
+__global__ void __launch_bounds__(1024)
+k_pcg_init(const BlockDesc *__restrict__ desc, const double *__restrict__ g, const double *__restrict__ dinv,
+           double *__restrict__ x, double *__restrict__ r, double *__restrict__ p, PcgState *__restrict__ st,
+           double tol2) {
+  __shared__ double scratch[32];
+  const BlockDesc d = desc[blockIdx.x];
+  const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1);
+  double s_rz = 0, s_gg = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+    const double gi = g[d.voff + i], zi = dinv[d.voff + i] * gi;
+    x[d.voff + i] = 0.0; r[d.voff + i] = gi; p[d.voff + i] = zi;
+    s_rz += gi * zi; s_gg += gi * gi;
+  }
+  s_rz = cta_sum(s_rz, scratch); s_gg = cta_sum(s_gg, scratch);
+  if (threadIdx.x == 0) {
+    PcgState s; s.rz = s_rz; s.g2 = s_gg; s.rr = s_gg; s.iters = 0;
+    s.active = (s_gg > 0.0 && s_gg > tol2 * s_gg) ? 1 : 0;     // g == 0 -> x = 0 (global_curved.jl:733)
+    st[blockIdx.x] = s;
+  }
+}
+
+// one PCG iteration's vector work for every still-active block (Ap = M-tilde p was just computed)
+__global__ void __launch_bounds__(1024)
+k_pcg_update(const BlockDesc *__restrict__ desc, const double *__restrict__ dinv, const double *__restrict__ Ap,
+             double *__restrict__ x, double *__restrict__ r, double *__restrict__ p, PcgState *__restrict__ st,
+             double tol2, int *__restrict__ nactive) {
+  __shared__ double scratch[32];
+  const BlockDesc d = desc[blockIdx.x];
+  PcgState s = st[blockIdx.x];
+  if (!s.active) return;
+  const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1);
+  const int64_t o = d.voff;
+  double pAp = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) pAp += p[o + i] * Ap[o + i];
+  pAp = cta_sum(pAp, scratch);
+  const double alpha = s.rz / pAp;
+  double rr = 0, rz = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+    x[o + i] += alpha * p[o + i];
+    const double ri = r[o + i] - alpha * Ap[o + i];
+    r[o + i] = ri;
+    rr += ri * ri; rz += ri * ri * dinv[o + i];
+  }
+  rr = cta_sum(rr, scratch); rz = cta_sum(rz, scratch);
+  const double beta = rz / s.rz;
+  const bool done = !(rr > tol2 * s.g2);
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x)
+    p[o + i] = done ? 0.0 : dinv[o + i] * r[o + i] + beta * p[o + i];
+  if (threadIdx.x == 0) {
+    s.rz = rz; s.rr = rr; s.iters += 1; s.active = done ? 0 : 1;
+    st[blockIdx.x] = s;
+    if (!done) atomicAdd(nactive, 1);
+  }
+}
+
+// ---- trace space <-> block faces -------------------------------------------------------------
+struct LamFace {       // one face that carries lambda
+  int32_t em, km, ep, kp;   // 0-based block and local face of the minus / plus side (ep = -1: remote / none)
+  int32_t flip, nl;
+  int64_t loff;             // 0-based offset in lambda vectors
+  int64_t fm, fp;           // offsets of the two block faces in block-face vectors
+};
+
+// lam = (F^T u)_minus + orient((F^T u)_plus)        rows of Fbar^T (global_curved.jl:533-553)
+__global__ void k_lam_gather(const LamFace *__restrict__ lf, const double *__restrict__ ft, double *__restrict__ lam) {
+  const LamFace f = lf[blockIdx.x];
+  for (int n = threadIdx.x; n < f.nl; n += blockDim.x) {
+    double v = ft[f.fm + n];
+    if (f.ep >= 0) v += ft[f.fp + (f.flip ? f.nl - 1 - n : n)];
+    lam[f.loff + n] = v;
+  }
+}
+// block-face vector v = lambda seen from each block face (0 on faces without lambda)
+__global__ void k_lam_scatter(const LamFace *__restrict__ lf, const double *__restrict__ lam, double *__restrict__ v) {
+  const LamFace f = lf[blockIdx.x];
+  for (int n = threadIdx.x; n < f.nl; n += blockDim.x) {
+    const double l = lam[f.loff + n];
+    v[f.fm + n] = l;
+    if (f.ep >= 0) v[f.fp + (f.flip ? f.nl - 1 - n : n)] = l;
+  }
+}
+// D = Hf o (tau_minus + orient(tau_plus))            global_curved.jl:556-557
+template <int P>
+__global__ void k_lam_D(const LamFace *__restrict__ lf, const BlockDesc *__restrict__ desc,
+                        const double *__restrict__ tau, double *__restrict__ D) {
+  const LamFace f = lf[blockIdx.x];
+  const BlockDesc d = desc[f.em];
+  const FaceGeom fg = face_geom(d, f.km);
+  for (int n = threadIdx.x; n < f.nl; n += blockDim.x) {
+    double t = tau[f.fm + n];
+    if (f.ep >= 0) t += tau[f.fp + (f.flip ? f.nl - 1 - n : n)];
+    D[f.loff + n] = fg.ht * hweight<P>(n, fg.Nt) * t;
+  }
+}
+
+}  // namespace hsbp

@@ -100,6 +100,9 @@ int  hsbp_blocks_get_tau(hsbp_blocks *blocks, double *tau);
 int  hsbp_apply(hsbp_blocks *blocks, const double *u_dev, double *y_dev);
 /* same through host buffers: H2D of u, apply, D2H of y inside the call                 */
 int  hsbp_apply_host(hsbp_blocks *blocks, const double *u, double *y);
+/* hsbp_apply with CUDA events between its stages: ms[0] volume stage (the dominant kernel),
+ * ms[1] face gather, ms[2] face scatter.  Synchronises; for benchmarking.                        */
+int  hsbp_apply_timed(hsbp_blocks *blocks, const double *u_dev, double *y_dev, double *ms);
 /* which kernel variant hsbp_apply last used: 0 generic, 1 line-marching TMA kernel     */
 int  hsbp_apply_variant(const hsbp_blocks *blocks);
 /* force the generic kernels (testing) */
