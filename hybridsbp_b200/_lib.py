@@ -76,6 +76,18 @@ def lib():
         "hsbp_face_FT": (cint, [vp, dp, dp]),
         "hsbp_face_F_add": (cint, [vp, dp, dbl, dp]),
         "hsbp_face_traction": (cint, [vp, dp, dp]),
+        "hsbp_local_setup": (cint, [vp, cint, dbl, i64]),
+        "hsbp_local_solve": (cint, [vp, dp, dp, vp]),
+        "hsbp_trace_create": (cint, [vp, i64, i64p, i64p, i64p, vp, i64p, C.POINTER(vp)]),
+        "hsbp_trace_destroy": (cint, [vp]),
+        "hsbp_trace_num_lambda": (i64, [vp]),
+        "hsbp_trace_get_starts": (cint, [vp, i64p]),
+        "hsbp_trace_get_D": (cint, [vp, dp]),
+        "hsbp_trace_FbarT": (cint, [vp, dp, dp]),
+        "hsbp_trace_Fbar_add": (cint, [vp, dp, dbl, dp]),
+        "hsbp_trace_schur_apply": (cint, [vp, dp, dp]),
+        "hsbp_trace_rhs": (cint, [vp, dp, dp, dp]),
+        "hsbp_trace_solve": (cint, [vp, dp, dp, dp, dp, dbl, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -84,6 +96,23 @@ def lib():
     L._signatures = sig
     _lib = L
     return L
+
+
+class LocalStats(C.Structure):
+    _fields_ = [("iterations_max", C.c_int64), ("iterations_sum", C.c_int64),
+                ("failed_blocks", C.c_int64), ("max_rel_residual", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("outer_iterations", C.c_int64), ("converged", C.c_int64), ("rel_residual", C.c_double),
+                ("inner_iterations_sum", C.c_int64), ("inner_iterations_max", C.c_int64),
+                ("local_solves", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def _i64(a):

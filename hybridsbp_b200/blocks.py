@@ -7,7 +7,10 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import Context, DeviceArray, _f64, _i64, lib
+from ._lib import Context, DeviceArray, LocalStats, TraceStats, _f64, _i64, lib
+
+LOCAL_PCG = 1
+LOCAL_CHOLESKY = 2
 
 
 class Blocks:
@@ -112,9 +115,79 @@ class Blocks:
     def face_traction(self, u: DeviceArray, tr: DeviceArray):
         self.ctx._check(lib().hsbp_face_traction(self.h, u.ptr, tr.ptr))
 
+    # -- local solves (the reference's `factorization` plugin) --------------------------------
+    def local_setup(self, mode=LOCAL_PCG, tol=1e-13, maxit=100000):
+        self.ctx._check(lib().hsbp_local_setup(self.h, int(mode), float(tol), int(maxit)))
+
+    def local_solve(self, g: DeviceArray, u: DeviceArray):
+        """u = M-tilde^-1 g for every block; returns the solver statistics."""
+        st = LocalStats()
+        self.ctx._check(lib().hsbp_local_solve(self.h, g.ptr, u.ptr, C.byref(st)))
+        return st.as_dict()
+
     def close(self):
         if self.h is not None:
             lib().hsbp_blocks_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Trace:
+    """Trace (lambda) operators of a multiblock mesh on top of a Blocks object.
+
+    Replaces glo-lambda-operator's sparse Fbar^T / D (global_curved.jl:510-565) and the explicit Schur
+    complement of assemble-lambda-matrix (:743-797) by matrix-free kernels and a device CG."""
+
+    def __init__(self, blocks: Blocks, FToB, FToE, FToLF, EToO, EToS):
+        self.blocks = blocks
+        self.ctx = blocks.ctx
+        FToB = np.ascontiguousarray(FToB, dtype=np.int64)
+        nf = FToB.size
+        col = lambda a, dt: np.ascontiguousarray(np.asarray(a).T, dtype=dt).reshape(-1)     # column-major flattening
+        fe, fl = col(FToE, np.int64), col(FToLF, np.int64)
+        eo, es = col(EToO, np.uint8), col(EToS, np.int64)
+        assert fe.size == 2 * nf and eo.size == 4 * blocks.nblocks
+        h = C.c_void_p()
+        P = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        self.ctx._check(lib().hsbp_trace_create(blocks.h, nf, P(FToB), P(fe), P(fl), C.c_void_p(eo.ctypes.data),
+                                                P(es), C.byref(h)))
+        self.h = h
+        self.nfaces = nf
+        self.lNp = lib().hsbp_trace_num_lambda(h)
+        self.FTolambdastarts = np.zeros(nf + 1, dtype=np.int64)
+        self.ctx._check(lib().hsbp_trace_get_starts(h, P(self.FTolambdastarts)))
+
+    def D(self):
+        out = np.empty(self.lNp)
+        self.ctx._check(lib().hsbp_trace_get_D(self.h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def FbarT(self, u: DeviceArray, lam: DeviceArray):
+        self.ctx._check(lib().hsbp_trace_FbarT(self.h, u.ptr, lam.ptr))
+
+    def Fbar_add(self, lam: DeviceArray, alpha, y: DeviceArray):
+        self.ctx._check(lib().hsbp_trace_Fbar_add(self.h, lam.ptr, float(alpha), y.ptr))
+
+    def schur_apply(self, lam: DeviceArray, out: DeviceArray):
+        self.ctx._check(lib().hsbp_trace_schur_apply(self.h, lam.ptr, out.ptr))
+
+    def rhs(self, g: DeviceArray, gdelta: DeviceArray, b: DeviceArray):
+        self.ctx._check(lib().hsbp_trace_rhs(self.h, g.ptr, gdelta.ptr, b.ptr))
+
+    def solve(self, g: DeviceArray, gdelta: DeviceArray, lam: DeviceArray, u: DeviceArray, tol=1e-10, maxit=10000):
+        st = TraceStats()
+        self.ctx._check(lib().hsbp_trace_solve(self.h, g.ptr, gdelta.ptr, lam.ptr, u.ptr, float(tol), int(maxit),
+                                               C.byref(st)))
+        return st.as_dict()
+
+    def close(self):
+        if self.h is not None:
+            lib().hsbp_trace_destroy(self.h)
             self.h = None
 
     def __del__(self):

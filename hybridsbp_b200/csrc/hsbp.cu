@@ -204,6 +204,8 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
+  cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
+  cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off);
   delete b;
   return HSBP_OK;
 }
@@ -445,3 +447,6 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 }
 
 }  // extern "C"
+
+#include "api_chol.cuh"
+#include "api_solve.cuh"

@@ -47,6 +47,16 @@ struct hsbp_blocks {
   int max_Nr = 0, max_Ns = 0;
   int force_generic = 0;
   int last_variant = -1;
+  // local solves
+  int local_mode = 0;
+  double local_tol = 1e-13;
+  int64_t local_maxit = 100000;
+  double *d_dinv = nullptr, *d_pr = nullptr, *d_pp = nullptr, *d_pAp = nullptr;
+  void *d_pcg = nullptr;
+  int *d_nactive = nullptr;
+  double *d_chol = nullptr;                 // dense factors, block e at chol_off[e], leading dimension Np_e
+  std::vector<int64_t> chol_off;
+  int64_t *d_chol_off = nullptr;
   // pinned staging for hsbp_apply_host (lazy)
   double *d_stage_u = nullptr, *d_stage_y = nullptr;
 };

@@ -116,6 +116,54 @@ int  hsbp_face_FT(hsbp_blocks *blocks, const double *u_dev, double *ft_dev);
 int  hsbp_face_F_add(hsbp_blocks *blocks, const double *v_dev, double alpha, double *y_dev);
 int  hsbp_face_traction(hsbp_blocks *blocks, const double *u_dev, double *tr_dev);
 
+/* ---- per-block local solves: replaces the `factorization` plugin ---------------------------
+ * reference: SBPLocalOperator1 stores factors[e] = factorization(lop[e].M̃) (global_curved.jl:672-703,
+ * plugin supplied as x -> cholesky(Symmetric(x)) at square_circle.jl:299, BP1.jl:78) and every use is
+ * `F \ g` (global_curved.jl:734, square_circle.jl:383, odefun.jl:43).
+ *   HSBP_LOCAL_PCG       batched matrix-free Jacobi-PCG on the block operator (any block size)
+ *   HSBP_LOCAL_CHOLESKY  batched dense fp64 Cholesky of M-tilde_e (small blocks)
+ * tol is the relative residual ||g - M u|| / ||g|| per block (PCG only).                         */
+#define HSBP_LOCAL_PCG      1
+#define HSBP_LOCAL_CHOLESKY 2
+typedef struct {
+  int64_t iterations_max;     /* PCG: largest iteration count over blocks (0 for Cholesky) */
+  int64_t iterations_sum;     /* PCG: sum over blocks                                      */
+  int64_t failed_blocks;      /* blocks that did not reach tol within maxit                */
+  double  max_rel_residual;   /* PCG: max over blocks of ||r|| / ||g||                     */
+} hsbp_local_stats;
+int  hsbp_local_setup(hsbp_blocks *blocks, int mode, double tol, int64_t maxit);
+int  hsbp_local_solve(hsbp_blocks *blocks, const double *g_dev, double *u_dev, hsbp_local_stats *stats);
+
+/* ---- trace (lambda) operators and Schur-complement solve ------------------------------------
+ * reference: gloλoperator (global_curved.jl:510-565) builds FToλstarts, the sparse Fbar^T and the
+ * diagonal D; assembleλmatrix (:743-797) forms B = D - Fbar^T M̃^-1 Fbar explicitly and
+ * square_circle.jl:314,377 factorises and solves it.  Here Fbar / Fbar^T / B are applied matrix-free
+ * and B lambda = b is solved by a GPU-resident preconditioned CG.
+ * Connectivity arrays are exactly connectivityarrays' outputs (global_curved.jl:82-132), 1-based:
+ * FToE, FToLF are 2 x nfaces (column-major), EToO (uint8 / Bool) and EToS are 4 x nblocks.       */
+int  hsbp_trace_create(hsbp_blocks *blocks, int64_t nfaces, const int64_t *FToB, const int64_t *FToE,
+                       const int64_t *FToLF, const uint8_t *EToO, const int64_t *EToS, hsbp_trace **trace);
+int  hsbp_trace_destroy(hsbp_trace *trace);
+int64_t hsbp_trace_num_lambda(const hsbp_trace *trace);                       /* lambda-Np */
+int  hsbp_trace_get_starts(const hsbp_trace *trace, int64_t *FTolambdastarts);   /* nfaces+1, 1-based */
+int  hsbp_trace_get_D(hsbp_trace *trace, double *D);                          /* host, lambda-Np */
+int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u   */
+int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
+int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam      */
+/* b = gdelta - Fbar^T M̃^-1 g   (LocalToGLobalRHS!, global_curved.jl:730-740)                    */
+int  hsbp_trace_rhs(hsbp_trace *trace, const double *g_dev, const double *gdelta_dev, double *b_dev);
+typedef struct {
+  int64_t outer_iterations;
+  int64_t converged;              /* 1 if ||b - B lambda|| / ||b|| <= tol was reached */
+  double  rel_residual;
+  int64_t inner_iterations_sum;   /* over all local solves of the call (PCG)          */
+  int64_t inner_iterations_max;
+  int64_t local_solves;
+} hsbp_trace_stats;
+/* lambda = B^-1 (gdelta - Fbar^T M̃^-1 g), u = M̃^-1 (g - Fbar lambda)   (square_circle.jl:376-388) */
+int  hsbp_trace_solve(hsbp_trace *trace, const double *g_dev, const double *gdelta_dev,
+                      double *lambda_dev, double *u_dev, double tol, int64_t maxit, hsbp_trace_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

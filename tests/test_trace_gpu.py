@@ -1,0 +1,124 @@
+"""GPU parity of the local solves, the trace operators and the Schur-complement solve against the
+oracle's assembled sparse path (global_curved.jl:510-565, 730-797; square_circle.jl:376-388).
+Tolerance from the north star: lambda and u within 1e-10 relative (2-norm) at equal CG tolerance."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import hybrid as orc
+from tests.util import flat, random_spd_metrics, upload_blocks, warped_metrics
+
+pytestmark = pytest.mark.gpu
+
+
+def two_block_mesh():
+    """the hand-made connectivity of global_op_eigenvalues.jl:12-19"""
+    EToV = np.array([[1, 2, 4, 5], [2, 3, 5, 6]]).T
+    EToF = np.array([[1, 2, 3, 4], [2, 5, 6, 7]]).T
+    FToB = np.full(7, orc.BC_DIRICHLET)
+    FToB[1] = orc.BC_LOCKED_INTERFACE
+    return EToV, EToF, FToB
+
+
+def flipped_four_block_mesh():
+    """2 x 2 blocks around a centre vertex; blocks 2 and 3 are rotated so that some interface
+    faces meet with opposite orientation (EToO == false, global_curved.jl:544-552)."""
+    # vertices 1..9 on a 3x3 grid, row-major from bottom-left
+    v = lambda ix, iy: 1 + ix + 3 * iy
+    blocks = [
+        (v(0, 0), v(1, 0), v(0, 1), v(1, 1)),            # standard
+        (v(2, 1), v(2, 0), v(1, 1), v(1, 0)),            # rotated: r runs downwards
+        (v(1, 2), v(0, 2), v(1, 1), v(0, 1)),            # mirrored twice
+        (v(1, 1), v(2, 1), v(1, 2), v(2, 2)),            # standard
+    ]
+    EToV = np.array(blocks).T
+    from hybridsbp_b200.host import _FACE_VERTS
+    EToF = np.zeros((4, 4), dtype=np.int64)
+    known = {}
+    for e in range(4):
+        for lf in range(4):
+            a, b = EToV[_FACE_VERTS[lf], e]
+            EToF[lf, e] = known.setdefault((min(a, b), max(a, b)), len(known) + 1)
+    FToB = np.zeros(len(known), dtype=np.int64)
+    count = np.zeros(len(known), dtype=int)
+    for e in range(4):
+        for lf in range(4):
+            count[EToF[lf, e] - 1] += 1
+    k = 0
+    for f in range(len(known)):
+        if count[f] == 1:
+            FToB[f] = orc.BC_DIRICHLET if k % 2 == 0 else orc.BC_NEUMANN
+            k += 1
+    FToB[np.where(count == 2)[0][0]] = orc.BC_JUMP_INTERFACE
+    return EToV, EToF, FToB
+
+
+def build_case(hs, ctx, p, N, mesh, rng, tauscale=1.0):
+    EToV, EToF, FToB = mesh
+    ne = EToV.shape[1]
+    FToE, FToLF, EToO, EToS = orc.connectivityarrays(EToV, EToF)
+    mets = [random_spd_metrics(p, N, N, rng, scale2=0.2) for _ in range(ne)]
+    bcs = [[FToB[f - 1] for f in EToF[:, e]] for e in range(ne)]
+    lops = [orc.locoperator(p, N, N, m, bc, tauscale=tauscale) for m, bc in zip(mets, bcs)]
+    Nr = [N] * ne
+    M, FbarT, D, vstarts, Fl = orc.LocalGlobalOperators(lops, Nr, Nr, FToB, FToE, FToLF, EToO, EToS)
+    blk = upload_blocks(hs, ctx, p, mets, bcs, tauscale=tauscale)
+    tr = hs.Trace(blk, FToB, FToE, FToLF, EToO, EToS)
+    return dict(lops=lops, M=M, FbarT=FbarT, D=D, vstarts=vstarts, Fl=Fl, blk=blk, tr=tr, EToF=EToF, FToB=FToB)
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+@pytest.mark.parametrize("meshname", ["two", "flipped"])
+def test_trace_operators_and_solve(ctx, p, meshname):
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(31 * p + len(meshname))
+    N = 3 * p - 1 if p > 2 else 6
+    mesh = two_block_mesh() if meshname == "two" else flipped_four_block_mesh()
+    c = build_case(hs, ctx, p, N, mesh, rng)
+    blk, tr, FbarT = c["blk"], c["tr"], c["FbarT"]
+    if meshname == "flipped":
+        _, _, EToO, _ = orc.connectivityarrays(mesh[0], mesh[1])
+        assert (~EToO).any(), "this mesh must exercise reversed faces"
+    assert np.array_equal(tr.FTolambdastarts, c["Fl"])
+    assert np.allclose(tr.D(), c["D"], rtol=1e-13)
+    u = rng.uniform(-1, 1, blk.VNp)
+    lam = rng.uniform(-1, 1, tr.lNp)
+    du, dl = ctx.array(u), ctx.array(lam)
+    dlo, dy = ctx.empty(tr.lNp), ctx.array(np.zeros(blk.VNp))
+    tr.FbarT(du, dlo)
+    ref = FbarT @ u
+    assert np.max(np.abs(dlo.get() - ref)) <= 1e-12 * np.max(abs(FbarT) @ np.abs(u))
+    tr.Fbar_add(dl, 1.0, dy)
+    ref = FbarT.T @ lam
+    assert np.max(np.abs(dy.get() - ref)) <= 1e-12 * np.max(abs(FbarT.T) @ np.abs(lam))
+
+    # local solves
+    blk.local_setup(hs.LOCAL_PCG, tol=1e-14, maxit=20000)
+    g = rng.uniform(-1, 1, blk.VNp)
+    dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    st = blk.local_solve(dg, dx)
+    assert st["failed_blocks"] == 0, st
+    x = dx.get()
+    for e, lop in enumerate(c["lops"]):
+        sl = blk.vol_slice(e)
+        xr = c["M"].F[e].solve(g[sl])
+        assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, st)
+
+    # Schur complement apply against the oracle's explicit B
+    B = orc.assemblelambdamatrix(c["Fl"], c["vstarts"], c["EToF"], c["FToB"], c["M"].F, c["D"], FbarT)
+    tr.schur_apply(dl, dlo)
+    ref = B @ lam
+    assert np.linalg.norm(dlo.get() - ref) <= 1e-10 * np.linalg.norm(ref)
+
+    # full trace solve: lambda = B^-1 (gd - Fbar^T M^-1 g), u = M^-1 (g - Fbar lambda)
+    gd = rng.uniform(-1, 1, tr.lNp)
+    bl = np.zeros(tr.lNp); uu = np.zeros(blk.VNp)
+    orc.LocalToGLobalRHS(bl, g, gd, uu, c["M"].F, FbarT, c["vstarts"])
+    lam_ref = np.linalg.solve(B.toarray(), bl)
+    rhs = g - FbarT.T @ lam_ref
+    u_ref = np.concatenate([c["M"].F[e].solve(rhs[blk.vol_slice(e)]) for e in range(blk.nblocks)])
+    dgd, dlam, dsol = ctx.array(gd), ctx.empty(tr.lNp), ctx.empty(blk.VNp)
+    st = tr.solve(dg, dgd, dlam, dsol, tol=1e-13, maxit=2000)
+    assert st["converged"] == 1, st
+    assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
+    assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
