@@ -138,7 +138,10 @@ template <int P, class Tt> __device__ __forceinline__ double qt_apply(int j, int
     return acc;
   }
   const int k0 = max(0, j - S::W), k1 = min(N, j + S::W);
-  for (int k = k0; k <= k1; ++k) acc += q_entry<P>(k, j, N) * t(k);
+  for (int k = k0; k <= k1; ++k) {
+    const double c = q_entry<P>(k, j, N);
+    if (c != 0.0) acc += c * t(k);       // never touch t outside the sparsity pattern
+  }
   return acc;
 }
 

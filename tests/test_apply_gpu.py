@@ -95,3 +95,49 @@ def test_face_operators(ctx, p):
             assert np.max(np.abs(tr[fs] - T @ u[sl])) <= 1e-12 * np.max(abs(T) @ np.abs(u[sl]))
             yref += -0.5 * (F @ v[fs])
         assert np.max(np.abs(y[sl] - yref)) <= 1e-12 * np.max(np.abs(yref))
+
+
+@pytest.mark.parametrize("p,Nr,Ns", [(2, 31, 20), (4, 31, 31), (4, 63, 40), (4, 255, 37), (6, 47, 47), (6, 63, 80), (2, 255, 255)])
+def test_apply_marching_kernel_vs_oracle(ctx, p, Nr, Ns):
+    """uniform blocks with an even number of r-points take the TMA line-marching kernel"""
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(1000 * p + Nr + Ns)
+    nb = 3
+    mets = [random_spd_metrics(p, Nr, Ns, rng, scale2=0.05) for _ in range(nb)]
+    bcs = [BCS[(i + p) % len(BCS)] for i in range(nb)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    u = rng.uniform(-1, 1, blk.VNp)
+    du, dy = ctx.array(u), ctx.empty(blk.VNp)
+    blk.apply(du, dy)
+    assert blk.apply_variant() == 1
+    y = dy.get()
+    for e in range(nb):
+        lop = orc.locoperator(p, Nr, Ns, mets[e], bcs[e])
+        sl = blk.vol_slice(e)
+        err = rel_err_apply(y[sl], lop.Mt @ u[sl], lop.Mt, u[sl])
+        assert err < TOL, (p, e, err)
+
+
+@pytest.mark.parametrize("p", [4, 6])
+def test_apply_marching_equals_generic_at_full_block_size(ctx, p):
+    """256 x 256-point blocks (BASELINE config 4 shape): the two independent CUDA paths must agree
+    to rounding; the generic one is checked against the oracle at sizes the oracle can assemble."""
+    import hybridsbp_b200 as hs
+    from hybridsbp_b200 import synthetic
+    nbx, nby, N = 4, 2, 255
+    crr, css, crs = synthetic.warped_coefficients(nbx, nby, N)
+    _, EToV, EToF, FToB = synthetic.block_grid_connectivity(nbx, nby)
+    blk = hs.Blocks(ctx, p, [N] * (nbx * nby), [N] * (nbx * nby))
+    blk.set_metrics(crr, css, crs)
+    blk.set_bc(synthetic.block_bcs(EToF, FToB))
+    blk.compute_tau(2.0)
+    u = np.random.default_rng(3).uniform(-1, 1, blk.VNp)
+    du, dy = ctx.array(u), ctx.empty(blk.VNp)
+    blk.apply(du, dy)
+    assert blk.apply_variant() == 1
+    y1 = dy.get()
+    blk.force_generic(True)
+    blk.apply(du, dy)
+    assert blk.apply_variant() == 0
+    y0 = dy.get()
+    assert np.max(np.abs(y1 - y0)) <= 1e-12 * np.max(np.abs(y0))
