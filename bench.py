@@ -192,6 +192,9 @@ def run_ours(args):
     del crr, css, crs
     blk.set_bc(synthetic.block_bcs(EToF, FToB))
     blk.compute_tau(2.0)
+    blk.set_option("sweep_points_per_thread", args.sweep_r)
+    blk.set_option("sweep_chunks_per_side", args.sweep_ncs)
+    blk.set_option("force_generic", 1 if args.generic else 0)
     rng = np.random.default_rng(778 + rank)
     u_host = rng.uniform(-1, 1, blk.VNp)
     u = ctx.array(u_host)
@@ -258,7 +261,7 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None,
-                             "kernel": ("k_march (volume stage, single kernel)" if variant == 1 else
+                             "kernel": ("k_sweep (line-marching volume kernel, all closures, one launch)" if variant == 1 else
                                         "k_cross_pre + k_vol_apply (two-pass generic volume stage)"),
                              "algorithmic_bytes_per_launch": BYTES_PER_DOF * dof,
                              "kernel_ms": float(stage[0]), "face_gather_ms": float(stage[1]),
@@ -267,7 +270,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                         "note": "hsbp_apply_host on pinned host buffers: H2D of u, apply, D2H of y inside each call"},
-                "gpu_launches": args.steps * (3 if variant == 1 else 4),
+                "gpu_launches": (args.steps + nrep + e2e_steps + 1) * (3 if variant == 1 else 4),
                 "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum}
         if world == 1 and not args.no_cpu:
             _, base = cpu_baseline(p, N, args.cpu_blocks, args.cpu_seconds, 1)
@@ -291,6 +294,9 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=5.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")
+    ap.add_argument("--sweep-ncs", type=int, default=0, help="chunks per side of k_sweep (0 = heuristic)")
+    ap.add_argument("--generic", action="store_true", help="force the generic two-pass kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

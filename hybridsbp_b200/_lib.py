@@ -73,6 +73,7 @@ def lib():
         "hsbp_apply_timed": (cint, [vp, dp, dp, dp]),
         "hsbp_apply_variant": (cint, [vp]),
         "hsbp_blocks_force_generic": (cint, [vp, cint]),
+        "hsbp_blocks_set_option": (cint, [vp, C.c_char_p, i64]),
         "hsbp_face_FT": (cint, [vp, dp, dp]),
         "hsbp_face_F_add": (cint, [vp, dp, dbl, dp]),
         "hsbp_face_traction": (cint, [vp, dp, dp]),

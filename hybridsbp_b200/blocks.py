@@ -106,6 +106,10 @@ class Blocks:
     def force_generic(self, on=True):
         self.ctx._check(lib().hsbp_blocks_force_generic(self.h, 1 if on else 0))
 
+    def set_option(self, name, value):
+        """tuning / testing knobs of the kernels, see hsbp_blocks_set_option in include/hsbp.h"""
+        self.ctx._check(lib().hsbp_blocks_set_option(self.h, name.encode(), int(value)))
+
     def face_FT(self, u: DeviceArray, ft: DeviceArray):
         self.ctx._check(lib().hsbp_face_FT(self.h, u.ptr, ft.ptr))
 

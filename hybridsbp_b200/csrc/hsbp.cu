@@ -6,7 +6,7 @@
 
 #include "hsbp_internal.h"
 #include "k_generic.cuh"
-#include "k_march.cuh"
+#include "k_sweep.cuh"
 
 using namespace hsbp;
 
@@ -299,6 +299,17 @@ int hsbp_blocks_force_generic(hsbp_blocks *b, int on) {
   return HSBP_OK;
 }
 int hsbp_apply_variant(const hsbp_blocks *b) { return b ? b->last_variant : -1; }
+int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
+  if (!b) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = b->ctx;
+  if (!name) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: null name");
+  const std::string n(name);
+  if (n == "force_generic") b->force_generic = (int)value;
+  else if (n == "sweep_chunks_per_side") b->sweep_ncs_override = (int)value;
+  else if (n == "sweep_points_per_thread") b->sweep_r_override = (int)value;
+  else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);
+  return HSBP_OK;
+}
 
 }  // extern "C"
 
@@ -338,8 +349,8 @@ static int apply_async(hsbp_blocks *b, const double *u, double *y, cudaEvent_t *
     constexpr int P = decltype(Pc)::value;
     int rc;
     if (evs) cudaEventRecord(evs[0], ctx->stream);
-    if (!b->force_generic && march_eligible<P>(b)) {
-      rc = vol_march<P>(b, u, y);
+    if (!b->force_generic && sweep_eligible<P>(b)) {
+      rc = vol_sweep<P>(b, u, y);
       b->last_variant = 1;
     } else {
       rc = vol_generic<P>(b, u, y);

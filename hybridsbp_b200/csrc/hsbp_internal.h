@@ -46,6 +46,8 @@ struct hsbp_blocks {
   bool uniform = false;             // all blocks share (Nr, Ns)
   int max_Nr = 0, max_Ns = 0;
   int force_generic = 0;
+  int sweep_r_override = 0;         // points per thread of the line-marching kernel (0 = heuristic, 2 or 4)
+  int sweep_ncs_override = 0;       // chunks per side of the line-marching kernel (0 = heuristic)
   int last_variant = -1;
   // local solves
   int local_mode = 0;

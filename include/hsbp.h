@@ -103,10 +103,13 @@ int  hsbp_apply_host(hsbp_blocks *blocks, const double *u, double *y);
 /* hsbp_apply with CUDA events between its stages: ms[0] volume stage (the dominant kernel),
  * ms[1] face gather, ms[2] face scatter.  Synchronises; for benchmarking.                        */
 int  hsbp_apply_timed(hsbp_blocks *blocks, const double *u_dev, double *y_dev, double *ms);
-/* which kernel variant hsbp_apply last used: 0 generic, 1 line-marching TMA kernel     */
+/* which kernel variant hsbp_apply last used: 0 generic two-pass kernels, 1 line-marching TMA kernel (k_sweep)     */
 int  hsbp_apply_variant(const hsbp_blocks *blocks);
 /* force the generic kernels (testing) */
 int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
+/* tuning / testing knobs: "force_generic" (0/1), "sweep_chunks_per_side" (0 = heuristic),
+ * "sweep_points_per_thread" (0 = heuristic, 2, 4)                                       */
+int  hsbp_blocks_set_option(hsbp_blocks *blocks, const char *name, int64_t value);
 
 /* face operators of the blocks, block-face layout (no inter-block coupling):
  *   ft = F_k^T u                 (rows of Fbar^T before orientation, global_curved.jl:455-458)

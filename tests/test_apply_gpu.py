@@ -97,17 +97,30 @@ def test_face_operators(ctx, p):
         assert np.max(np.abs(y[sl] - yref)) <= 1e-12 * np.max(np.abs(yref))
 
 
-@pytest.mark.parametrize("p,Nr,Ns", [(2, 31, 20), (4, 31, 31), (4, 63, 40), (4, 255, 37), (6, 47, 47), (6, 63, 80), (2, 255, 255)])
-def test_apply_marching_kernel_vs_oracle(ctx, p, Nr, Ns):
-    """uniform blocks with an even number of r-points take the TMA line-marching kernel"""
+SWEEP_CASES = [
+    # p, Nr, Ns, points per thread, chunks per side
+    (2, 31, 31, 0, 0), (2, 63, 40, 2, 2), (2, 127, 95, 4, 0),
+    (4, 31, 40, 0, 1), (4, 63, 33, 2, 0), (4, 127, 64, 4, 2), (4, 127, 64, 2, 1), (4, 255, 37, 0, 0),
+    (4, 259, 50, 4, 0), (4, 255, 255, 0, 0),
+    (6, 47, 47, 0, 0), (6, 63, 80, 2, 2), (6, 127, 40, 4, 1), (6, 131, 64, 4, 2),
+]
+
+
+@pytest.mark.parametrize("p,Nr,Ns,R,ncs", SWEEP_CASES)
+def test_apply_marching_kernel_vs_oracle(ctx, p, Nr, Ns, R, ncs):
+    """uniform blocks with an even number (>= 32) of r-points take the TMA line-marching kernel
+    (k_sweep): every closure, both marching directions, chunk seams, 2 and 4 points per thread"""
     import hybridsbp_b200 as hs
     rng = np.random.default_rng(1000 * p + Nr + Ns)
-    nb = 3
+    nb = 3 if Nr * Ns < 40000 else 2
     mets = [random_spd_metrics(p, Nr, Ns, rng, scale2=0.05) for _ in range(nb)]
     bcs = [BCS[(i + p) % len(BCS)] for i in range(nb)]
     blk = upload_blocks(hs, ctx, p, mets, bcs)
+    blk.set_option("sweep_points_per_thread", R)
+    blk.set_option("sweep_chunks_per_side", ncs)
     u = rng.uniform(-1, 1, blk.VNp)
     du, dy = ctx.array(u), ctx.empty(blk.VNp)
+    dy.set(np.full(blk.VNp, np.nan))
     blk.apply(du, dy)
     assert blk.apply_variant() == 1
     y = dy.get()
@@ -118,7 +131,7 @@ def test_apply_marching_kernel_vs_oracle(ctx, p, Nr, Ns):
         assert err < TOL, (p, e, err)
 
 
-@pytest.mark.parametrize("p", [4, 6])
+@pytest.mark.parametrize("p", [2, 4, 6])
 def test_apply_marching_equals_generic_at_full_block_size(ctx, p):
     """256 x 256-point blocks (BASELINE config 4 shape): the two independent CUDA paths must agree
     to rounding; the generic one is checked against the oracle at sizes the oracle can assemble."""
@@ -133,11 +146,16 @@ def test_apply_marching_equals_generic_at_full_block_size(ctx, p):
     blk.compute_tau(2.0)
     u = np.random.default_rng(3).uniform(-1, 1, blk.VNp)
     du, dy = ctx.array(u), ctx.empty(blk.VNp)
-    blk.apply(du, dy)
-    assert blk.apply_variant() == 1
-    y1 = dy.get()
     blk.force_generic(True)
     blk.apply(du, dy)
     assert blk.apply_variant() == 0
     y0 = dy.get()
-    assert np.max(np.abs(y1 - y0)) <= 1e-12 * np.max(np.abs(y0))
+    blk.force_generic(False)
+    for R, ncs in ((0, 0), (2, 3), (4, 1), (4, 5)):
+        blk.set_option("sweep_points_per_thread", R)
+        blk.set_option("sweep_chunks_per_side", ncs)
+        dy.set(np.full(blk.VNp, np.nan))
+        blk.apply(du, dy)
+        assert blk.apply_variant() == 1
+        y1 = dy.get()
+        assert np.max(np.abs(y1 - y0)) <= 1e-12 * np.max(np.abs(y0)), (R, ncs)
