@@ -12,7 +12,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsbp.so")
+LIB_PATH = os.environ.get("HSBP_LIB", os.path.join(_HERE, "libhsbp.so"))   # HSBP_LIB: kernel-variant experiments
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hsbp.h")
 
 

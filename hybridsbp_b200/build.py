@@ -24,7 +24,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++20", "-lineinfo",
            "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC,-O2",
            "-shared", "-cudart", "shared", "-o", LIB, os.path.join(CSRC, "hsbp.cu"), "-ldl"]
     if verbose:

@@ -15,9 +15,11 @@ thread_local std::string g_noctx_err;
 
 template <class F> int dispatch_p(int p, F &&f) {
   switch (p) {
+#ifndef HSBP_ONLY_P4          // experiment builds: one order only, to cut the compile time
     case 2: return f(std::integral_constant<int, 2>{});
-    case 4: return f(std::integral_constant<int, 4>{});
     case 6: return f(std::integral_constant<int, 6>{});
+#endif
+    case 4: return f(std::integral_constant<int, 4>{});
   }
   return HSBP_ERR_UNSUPP;
 }
@@ -202,6 +204,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
+  cudaFree(b->d_crr_s); cudaFree(b->d_css_s);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
@@ -224,6 +227,7 @@ static int set_metrics(hsbp_blocks *b, const double *crr, const double *css, con
   HSBP_CUDA(ctx, cudaMemcpyAsync(b->d_crs, crs, vb, kind, ctx->stream));
   HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   b->have_metrics = true;
+  b->sweep_scaled_valid = false;
   return HSBP_OK;
 }
 int hsbp_blocks_set_metrics(hsbp_blocks *b, const double *crr, const double *css, const double *crs) {

@@ -38,6 +38,8 @@ struct hsbp_blocks {
   std::vector<BlockDesc> h_desc;
   BlockDesc *d_desc = nullptr;
   double *d_crr = nullptr, *d_css = nullptr, *d_crs = nullptr;
+  double *d_crr_s = nullptr, *d_css_s = nullptr;   // norm-weighted copies for the line-marching kernel (lazy)
+  bool sweep_scaled_valid = false;
   double *d_tau = nullptr;          // FNp
   double *d_fa = nullptr;           // FNp scratch: alpha (or F^T u)
   double *d_fb = nullptr;           // FNp scratch: beta

@@ -64,6 +64,9 @@ constexpr int SW_NST = 3;              // ring stages: one being consumed, two i
 constexpr int SW_MAX_THREADS = 256;
 
 struct SweepParams {
+  // crr, css: the coefficient fields pre-multiplied by the norm weights of the *other* direction,
+  //   crr'(i,j) = crr(i,j) * Hs[j] / hr,  css'(i,j) = css(i,j) * Hr[i] / hs   (global_curved.jl:261-268, 313-322);
+  // every stiffness coupling is linear in its coefficient, so the kernel needs no scaling at all.
   const double *crr, *css, *crs, *u;
   double *y;
   int Nr, Ns;         // uniform block size
@@ -137,8 +140,18 @@ __device__ __noinline__ double sweep_sclosure_row(int row, const double *__restr
   return d2_closure_row<P>(row, b, uu);
 }
 
-template <int P, int R>
-__global__ void __launch_bounds__(SW_MAX_THREADS)
+// compile-time loop over lane numbers T0 .. T1-1
+template <int T0, int T1, class F> __device__ __forceinline__ void for_lanes(F &&f) {
+  if constexpr (T0 < T1) {
+    f(std::integral_constant<int, T0>{});
+    for_lanes<T0 + 1, T1>(f);
+  }
+}
+
+// NT: upper bound of the CTA size; MINB: CTAs per SM the register allocation is sized for
+// (R = 2: 128 registers per thread, R = 4: 255).
+template <int P, int R, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_sweep(const SweepParams prm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -202,41 +215,36 @@ k_sweep(const SweepParams prm) {
 
   const int i0 = tid * R;
   const bool own = i0 < Nrp;
-  const double hr = 2.0 / Nr, hs = 2.0 / Ns;
-  const double *hwt = C::hw();
+  const int nown = Nrp / R;                               // threads that own points (Nrp % R == 0)
   const double *qc = C::Qc();
-  double sc_ss[R];                                        // Hr[i] / hs  (global_curved.jl:313-322)
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    const int i = i0 + q;
-    const double hwi = i < BM ? hwt[i] : (i > Nr - BM && i <= Nr ? hwt[Nr - i] : 1.0);
-    sc_ss[q] = hr * hwi / hs;
-  }
   const double *gu = prm.u + base + i0;                   // + j*lstride: this thread's points on marching line j
   const double *gss = prm.css + base + i0;
   double *gy = prm.y + base + i0;
 
-  double uw[W][R], bw[LB][R], cw[H + 1][R], acc[W][R];
+  // s-direction windows.  Logical index k <-> marching line j-(W-1)+k (u, scaled css, crs) or j-H+k
+  // (accumulators); the physical slot of logical k in a step with rotation PH is (PH+1+k) % W, so the
+  // W-fold unrolled steady-state loop never moves a register.  bw uses k >= 1, cw uses k >= H.
+  double uw[W][R], bw[W][R], cw[W][R], acc[W][R];
 #pragma unroll
-  for (int q = 0; q < R; ++q) {
+  for (int q = 0; q < R; ++q)
 #pragma unroll
-    for (int k = 0; k < W; ++k) { uw[k][q] = 0.0; acc[k][q] = 0.0; }
-#pragma unroll
-    for (int k = 0; k < LB; ++k) bw[k][q] = 0.0;
-#pragma unroll
-    for (int k = 0; k <= H; ++k) cw[k][q] = 0.0;
-  }
+    for (int k = 0; k < W; ++k) { uw[k][q] = 0.0; bw[k][q] = 0.0; cw[k][q] = 0.0; acc[k][q] = 0.0; }
   if (prologue && own) {                                  // lines that collect read-modify-write contributions
     for (int l = 0; l < BM; ++l)
 #pragma unroll
       for (int q = 0; q < R; ++q) gy[l * lstride + q] = 0.0;
   }
 
-#pragma unroll 1
-  for (int n = 0; n < nlines; ++n) {
-    const int j = jstart + n;
-    const int st = n % NST;
-    const int ng = n % G;
+  int j = jstart, n = 0, st = 0, ng = 0;
+  uint32_t parity = 0;
+
+  // one marching step: line j arrives, line j-H is completed.  PH: rotation of the register windows
+  // (compile time); FAST: steady state, no s-end closure logic.
+  auto step = [&](auto PHc, auto FASTc) {
+    constexpr int PH = decltype(PHc)::value;
+    constexpr bool FAST = decltype(FASTc)::value;
+    constexpr auto SL = [](int k) constexpr { return (PH + 1 + k) % W; };
+    const bool pro = FAST ? false : prologue;
 
     // ---- r-closure table for lines j .. j+G-1: thread -> (line, end) ---------------------------
     if (ng == 0) {
@@ -248,14 +256,24 @@ k_sweep(const SweepParams prm) {
       __syncthreads();
     }
 
-    mbar_wait(&full[st], (uint32_t)((n / NST) & 1));
+    mbar_wait(&full[st], parity);
     const double *sb = ring + (size_t)st * 4 * LW;
     const int jo = j - H;
     const bool outp = (jo >= o0) && (jo < o1);
     double *wb = wbuf + (size_t)(n & 1) * LW;
 
     if (own) {
-      // ---- shift the windows, take in line j ------------------------------------------------
+      if constexpr (!FAST) {                              // canonical slot order: shift by one line
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+#pragma unroll
+          for (int k = 0; k < W - 1; ++k) {               // only the slots that are read later (bw: k >= 1, cw: k >= H)
+            uw[k][q] = uw[k + 1][q]; acc[k][q] = acc[k + 1][q];
+            if (k >= 1) bw[k][q] = bw[k + 1][q];
+            if (k >= H) cw[k][q] = cw[k + 1][q];
+          }
+      }
+      // ---- take in line j -------------------------------------------------------------------
       double U[NV], Bq[NV];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
@@ -264,28 +282,18 @@ k_sweep(const SweepParams prm) {
         U[2 * k] = a.x; U[2 * k + 1] = a.y; Bq[2 * k] = b2.x; Bq[2 * k + 1] = b2.y;
       }
 #pragma unroll
-      for (int q = 0; q < R; ++q) {
-#pragma unroll
-        for (int k = 0; k < W - 1; ++k) { uw[k][q] = uw[k + 1][q]; acc[k][q] = acc[k + 1][q]; }
-#pragma unroll
-        for (int k = 0; k < LB - 1; ++k) bw[k][q] = bw[k + 1][q];
-#pragma unroll
-        for (int k = 0; k < H; ++k) cw[k][q] = cw[k + 1][q];
-        uw[W - 1][q] = U[PAD + q];
-        acc[W - 1][q] = 0.0;
-      }
+      for (int q = 0; q < R; ++q) { uw[SL(W - 1)][q] = U[PAD + q]; acc[SL(W - 1)][q] = 0.0; }
 #pragma unroll
       for (int k = 0; k < R / 2; ++k) {
         const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + PAD + i0 + 2 * k);
         const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + PAD + i0 + 2 * k);
-        bw[LB - 1][2 * k] = a.x * sc_ss[2 * k]; bw[LB - 1][2 * k + 1] = a.y * sc_ss[2 * k + 1];
-        cw[H][2 * k] = b2.x; cw[H][2 * k + 1] = b2.y;
+        bw[SL(W - 1)][2 * k] = a.x; bw[SL(W - 1)][2 * k + 1] = a.y;
+        cw[SL(W - 1)][2 * k] = b2.x; cw[SL(W - 1)][2 * k + 1] = b2.y;
       }
 
-      // ---- r-direction on line j: rr = M(crr) u (pair form), qr = Qr u -------------------------
+      // ---- r-direction on line j: rr = M(crr') u (pair form) goes straight into the accumulator of
+      //      line j, qr = Qr u ----------------------------------------------------------------------
       double rr[R], qr[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) { rr[q] = 0.0; qr[q] = 0.0; }
       for_offsets<1, H>([&](auto Oc) {
         constexpr int O = decltype(Oc)::value;
         double f[R + O];
@@ -297,43 +305,50 @@ k_sweep(const SweepParams prm) {
         }
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-          rr[q] += f[q + O] - f[q];
-          qr[q] += C::template D<O>() * (U[PAD + q + O] - U[PAD + q - O]);
+          if constexpr (O == 1) {
+            rr[q] = f[q + O] - f[q];
+            qr[q] = C::template D<O>() * (U[PAD + q + O] - U[PAD + q - O]);
+          } else {
+            rr[q] += f[q + O] - f[q];
+            qr[q] = fma(C::template D<O>(), U[PAD + q + O] - U[PAD + q - O], qr[q]);
+          }
         }
       });
-      if (i0 < MC) {                                      // near r-end: closure rows from the table
-        const double *cl = clbuf + (size_t)(2 * ng) * CLW;
+      // closure rows at the r-ends come from the table; the owning lanes are known at compile time
+      for_lanes<0, (MC + R - 1) / R>([&](auto Tc) {
+        constexpr int TL = decltype(Tc)::value;
+        if (tid == TL) {                                  // near end: rows TL*R + q
+          const double *cl = clbuf + (size_t)(2 * ng) * CLW;
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          if (i0 + q < MC) rr[q] = cl[i0 + q];
-          if (i0 + q < BM) qr[q] = cl[MC + i0 + q];
+          for (int q = 0; q < R; ++q) {
+            if (TL * R + q < MC) rr[q] = cl[TL * R + q];
+            if (TL * R + q < BM) qr[q] = cl[MC + TL * R + q];
+          }
         }
-      }
-      if (i0 + R > Nrp - MC) {                            // far r-end
-        const double *cl = clbuf + (size_t)(2 * ng + 1) * CLW;
+        if (tid == nown - 1 - TL) {                       // far end: rows m = TL*R + (R-1-q) counted from Nr
+          const double *cl = clbuf + (size_t)(2 * ng + 1) * CLW;
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          const int m = Nr - (i0 + q);
-          if (m < MC) rr[q] = cl[m];
-          if (m < BM) qr[q] = cl[MC + m];
+          for (int q = 0; q < R; ++q) {
+            if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
+            if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MC + TL * R + (R - 1 - q)];
+          }
         }
-      }
-      const double scrr = (hs / hr) * (j < BM ? hwt[j] : 1.0);       // Hs[j] / hr  (global_curved.jl:261-268)
+      });
       double t[R];
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        acc[H][q] = fma(scrr, rr[q], acc[H][q]);
-        t[q] = cw[H][q] * qr[q];                          // t = crs o (Qr u) on line j
+        acc[SL(H)][q] += rr[q];
+        t[q] = cw[SL(W - 1)][q] * qr[q];                  // t = crs o (Qr u) on line j
       }
       // ---- Qs^T t, pushed from row j: (Qs^T t)(l) += Qs[j][l] t(j) ------------------------------
-      if (j >= BM) {
+      if (FAST || j >= BM) {
         for_offsets<1, H>([&](auto Oc) {
           constexpr int O = decltype(Oc)::value;
           const double d = sig * C::template D<O>();
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            acc[H + O][q] = fma(d, t[q], acc[H + O][q]);
-            acc[H - O][q] = fma(-d, t[q], acc[H - O][q]);
+            acc[SL(H + O)][q] = fma(d, t[q], acc[SL(H + O)][q]);
+            acc[SL(H - O)][q] = fma(-d, t[q], acc[SL(H - O)][q]);
           }
         });
       } else {
@@ -351,23 +366,23 @@ k_sweep(const SweepParams prm) {
           if (l >= BM && l < BN) {
             const double d = sig * qc[j * BN + l];
 #pragma unroll
-            for (int q = 0; q < R; ++q) acc[H + O][q] = fma(d, t[q], acc[H + O][q]);
+            for (int q = 0; q < R; ++q) acc[SL(H + O)][q] = fma(d, t[q], acc[SL(H + O)][q]);
           }
         });
       }
       // ---- s-direction stiffness: pairs (a, a+O), a = j-H; rows a <-> acc[0], a+O <-> acc[O] ------
       {
         const int a = j - H;
-        const bool row_a_closure = prologue && (a < MC);
+        const bool row_a_closure = pro && (a < MC);
         for_offsets<1, H>([&](auto Oc) {
           constexpr int O = decltype(Oc)::value;
-          if (!(prologue && (a + O < MC))) {
+          if (!(pro && (a + O < MC))) {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-              const double cf = pair_coef<P, O>([&](int s) { return bw[H - 1 + s][q]; });
-              const double f = cf * (uw[H + O][q] - uw[H][q]);
-              if (!row_a_closure) acc[0][q] += f;
-              acc[O][q] -= f;
+              const double cf = pair_coef<P, O>([&](int s) { return bw[SL(H + s)][q]; });    // line a+s = j-H+s
+              const double f = cf * (uw[SL(H + O)][q] - uw[SL(H)][q]);
+              if (!row_a_closure) acc[SL(0)][q] += f;
+              acc[SL(O)][q] -= f;
             }
           }
         });
@@ -375,16 +390,19 @@ k_sweep(const SweepParams prm) {
       // ---- w = crs o (Qs u) on the output line, shared with the r-neighbours ------------------
       if (outp) {
         double qs[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) qs[q] = 0.0;
-        if (jo >= BM) {
+        if (FAST || jo >= BM) {
           for_offsets<1, H>([&](auto Oc) {
             constexpr int O = decltype(Oc)::value;
             const double d = sig * C::template D<O>();
 #pragma unroll
-            for (int q = 0; q < R; ++q) qs[q] = fma(d, uw[H + O][q] - uw[H - O][q], qs[q]);
+            for (int q = 0; q < R; ++q) {
+              if constexpr (O == 1) qs[q] = d * (uw[SL(H + O)][q] - uw[SL(H - O)][q]);
+              else qs[q] = fma(d, uw[SL(H + O)][q] - uw[SL(H - O)][q], qs[q]);
+            }
           });
         } else {
+#pragma unroll
+          for (int q = 0; q < R; ++q) qs[q] = 0.0;
           for (int l = 0; l < BN; ++l) {
             const double d = sig * qc[jo * BN + l];
             if (d != 0.0) {
@@ -397,7 +415,7 @@ k_sweep(const SweepParams prm) {
 #pragma unroll
         for (int k = 0; k < R / 2; ++k)
           *reinterpret_cast<double2 *>(wb + PAD + i0 + 2 * k) =
-              make_double2(cw[0][2 * k] * qs[2 * k], cw[0][2 * k + 1] * qs[2 * k + 1]);
+              make_double2(cw[SL(H)][2 * k] * qs[2 * k], cw[SL(H)][2 * k + 1] * qs[2 * k + 1]);
       }
     }
     __syncthreads();
@@ -411,37 +429,38 @@ k_sweep(const SweepParams prm) {
         Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
       }
 #pragma unroll
-      for (int q = 0; q < R; ++q) val[q] = 0.0;
+      for (int q = 0; q < R; ++q) val[q] = acc[SL(0)][q];
       for_offsets<1, H>([&](auto Oc) {
         constexpr int O = decltype(Oc)::value;
 #pragma unroll
         for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
       });
-      if (i0 < BM) {                                      // near r-end rows of Qr^T
-        const double *w0 = wb + PAD;
+      for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
+        constexpr int TL = decltype(Tc)::value;
+        if (tid == TL) {
+          const double *w0 = wb + PAD;
 #pragma unroll
-        for (int q = 0; q < R; ++q)
-          if (i0 + q < BM) val[q] = qt_closure_row<P>(i0 + q, w0);
-      }
-      if (i0 + R > Nrp - BM) {                            // far r-end: mirrored, sign flipped
-        double wr[BN];
+          for (int q = 0; q < R; ++q)
+            if (TL * R + q < BM) val[q] = acc[SL(0)][q] + qt_closure_row<P>(TL * R + q, w0);
+        }
+        if (tid == nown - 1 - TL) {                       // mirrored, sign flipped
+          double wr[BN];
 #pragma unroll
-        for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
+          for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          const int m = Nr - (i0 + q);
-          if (m < BM) val[q] = -qt_closure_row<P>(m, wr);
+          for (int q = 0; q < R; ++q)
+            if (TL * R + (R - 1 - q) < BM) val[q] = acc[SL(0)][q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
+        }
+      });
+      double *yl = gy + jo * lstride;
+      if constexpr (!FAST) {
+        if (pro && jo < MC) {                             // closure row jo of M(css) u, straight from memory
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            val[q] += sweep_sclosure_row<P>(jo, gss + q, gu + q, lstride);
         }
       }
-#pragma unroll
-      for (int q = 0; q < R; ++q) val[q] += acc[0][q];
-      if (prologue && jo < MC) {                          // closure row jo of M(css) u, straight from memory
-#pragma unroll
-        for (int q = 0; q < R; ++q)
-          val[q] = fma(sc_ss[q], sweep_sclosure_row<P>(jo, gss + q, gu + q, lstride), val[q]);
-      }
-      double *yl = gy + jo * lstride;
-      if (prologue && jo < BM) {
+      if (!FAST && pro && jo < BM) {
 #pragma unroll
         for (int q = 0; q < R; ++q) yl[q] += val[q];
       } else {
@@ -450,7 +469,187 @@ k_sweep(const SweepParams prm) {
           *reinterpret_cast<double2 *>(yl + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
       }
     }
-  }
+    ++j; ++n;
+    if (++st == NST) { st = 0; parity ^= 1u; }
+    if (++ng == G) ng = 0;
+  };
+
+  // ---- steady state --------------------------------------------------------------------------
+  // Same step without any s-end closure logic, arranged so that the instruction footprint stays
+  // inside the instruction cache: everything that does not touch the register windows (waiting for
+  // the line, the r-direction work, the w exchange and the output) exists once; only the short
+  // window section is specialised for the W rotations and selected by a uniform branch.
+  int ph = 0;                                             // rotation of the next steady-state step
+  auto fast_step = [&]() {
+    if (ng == 0) {                                        // r-closure table for lines j .. j+G-1
+      const int jj = j + (tid >> 1), side = tid & 1;
+      if (jj <= jend) {
+        const int64_t g = base + (int64_t)jj * lstride + (side ? Nr : 0);
+        sweep_rclosure<P>(prm.crr + g, prm.u + g, side ? -1 : 1, clbuf + (size_t)tid * CLW);
+      }
+      __syncthreads();
+    }
+    mbar_wait(&full[st], parity);
+    const double *sb = ring + (size_t)st * 4 * LW;
+    const int jo = j - H;
+    const bool outp = (jo >= o0) && (jo < o1);
+    double *wb = wbuf + (size_t)(n & 1) * LW;
+    double accout[R];
+    if (own) {
+      // ---- A: line j from shared memory, r-direction work (rotation independent) ---------------
+      double U[NV], Bq[NV], bn[R], cn[R], rr[R], qr[R], wout[R];
+#pragma unroll
+      for (int k = 0; k < NV / 2; ++k) {
+        const double2 a = *reinterpret_cast<const double2 *>(sb + i0 + 2 * k);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + i0 + 2 * k);
+        U[2 * k] = a.x; U[2 * k + 1] = a.y; Bq[2 * k] = b2.x; Bq[2 * k + 1] = b2.y;
+      }
+#pragma unroll
+      for (int k = 0; k < R / 2; ++k) {
+        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + PAD + i0 + 2 * k);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + PAD + i0 + 2 * k);
+        bn[2 * k] = a.x; bn[2 * k + 1] = a.y; cn[2 * k] = b2.x; cn[2 * k + 1] = b2.y;
+      }
+      for_offsets<1, H>([&](auto Oc) {
+        constexpr int O = decltype(Oc)::value;
+        double f[R + O];
+#pragma unroll
+        for (int k = 0; k < R + O; ++k) {                 // pair (a, a+O), a = i0 - O + k
+          const int ia = PAD - O + k;
+          const double cf = pair_coef<P, O>([&](int s2) { return Bq[ia + s2]; });
+          f[k] = cf * (U[ia + O] - U[ia]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          if constexpr (O == 1) {
+            rr[q] = f[q + O] - f[q];
+            qr[q] = C::template D<O>() * (U[PAD + q + O] - U[PAD + q - O]);
+          } else {
+            rr[q] += f[q + O] - f[q];
+            qr[q] = fma(C::template D<O>(), U[PAD + q + O] - U[PAD + q - O], qr[q]);
+          }
+        }
+      });
+      for_lanes<0, (MC + R - 1) / R>([&](auto Tc) {
+        constexpr int TL = decltype(Tc)::value;
+        if (tid == TL) {
+          const double *cl = clbuf + (size_t)(2 * ng) * CLW;
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            if (TL * R + q < MC) rr[q] = cl[TL * R + q];
+            if (TL * R + q < BM) qr[q] = cl[MC + TL * R + q];
+          }
+        }
+        if (tid == nown - 1 - TL) {
+          const double *cl = clbuf + (size_t)(2 * ng + 1) * CLW;
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
+            if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MC + TL * R + (R - 1 - q)];
+          }
+        }
+      });
+      // ---- S: the register windows, one specialisation per rotation -----------------------------
+      auto windows = [&](auto PHc) {
+        constexpr int PH = decltype(PHc)::value;
+        constexpr auto SL = [](int k) constexpr { return (PH + 1 + k) % W; };
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          uw[SL(W - 1)][q] = U[PAD + q]; bw[SL(W - 1)][q] = bn[q]; cw[SL(W - 1)][q] = cn[q];
+          acc[SL(W - 1)][q] = 0.0;
+          acc[SL(H)][q] += rr[q];
+        }
+        for_offsets<1, H>([&](auto Oc) {                  // Qs^T t pushed from row j
+          constexpr int O = decltype(Oc)::value;
+          const double d = sig * C::template D<O>();
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const double t = cn[q] * qr[q];
+            acc[SL(H + O)][q] = fma(d, t, acc[SL(H + O)][q]);
+            acc[SL(H - O)][q] = fma(-d, t, acc[SL(H - O)][q]);
+          }
+        });
+        for_offsets<1, H>([&](auto Oc) {                  // s-direction stiffness pairs (a, a+O), a = j-H
+          constexpr int O = decltype(Oc)::value;
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const double cf = pair_coef<P, O>([&](int s2) { return bw[SL(H + s2)][q]; });
+            const double f = cf * (uw[SL(H + O)][q] - uw[SL(H)][q]);
+            acc[SL(0)][q] += f;
+            acc[SL(O)][q] -= f;
+          }
+        });
+        for_offsets<1, H>([&](auto Oc) {                  // w = crs o (Qs u) on line jo
+          constexpr int O = decltype(Oc)::value;
+          const double d = sig * C::template D<O>();
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            if constexpr (O == 1) wout[q] = d * (uw[SL(H + O)][q] - uw[SL(H - O)][q]);
+            else wout[q] = fma(d, uw[SL(H + O)][q] - uw[SL(H - O)][q], wout[q]);
+          }
+        });
+#pragma unroll
+        for (int q = 0; q < R; ++q) { wout[q] *= cw[SL(H)][q]; accout[q] = acc[SL(0)][q]; }
+      };
+      [&]<int... PHs>(std::integer_sequence<int, PHs...>) {
+        ((ph == PHs ? (windows(std::integral_constant<int, PHs>{}), 0) : 0), ...);
+      }(std::make_integer_sequence<int, W>{});
+      if (outp) {
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k)
+          *reinterpret_cast<double2 *>(wb + PAD + i0 + 2 * k) = make_double2(wout[2 * k], wout[2 * k + 1]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && n + NST < nlines) { fence_proxy_async(); issue(n + NST); }
+    if (own && outp) {
+      // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
+      double Wv[NV], val[R];
+#pragma unroll
+      for (int k = 0; k < NV / 2; ++k) {
+        const double2 a = *reinterpret_cast<const double2 *>(wb + i0 + 2 * k);
+        Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) val[q] = accout[q];
+      for_offsets<1, H>([&](auto Oc) {
+        constexpr int O = decltype(Oc)::value;
+#pragma unroll
+        for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
+      });
+      for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
+        constexpr int TL = decltype(Tc)::value;
+        if (tid == TL) {
+          const double *w0 = wb + PAD;
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            if (TL * R + q < BM) val[q] = accout[q] + qt_closure_row<P>(TL * R + q, w0);
+        }
+        if (tid == nown - 1 - TL) {
+          double wr[BN];
+#pragma unroll
+          for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            if (TL * R + (R - 1 - q) < BM) val[q] = accout[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
+        }
+      });
+      double *yl = gy + jo * lstride;
+#pragma unroll
+      for (int k = 0; k < R / 2; ++k)
+        *reinterpret_cast<double2 *>(yl + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+    }
+    ++j; ++n;
+    if (++st == NST) { st = 0; parity ^= 1u; }
+    if (++ng == G) ng = 0;
+    if (++ph == W) ph = 0;
+  };
+
+  using GenericPH = std::integral_constant<int, W - 1>;    // rotation W-1: slot(k) == k (canonical order)
+  const int jfast = prologue ? MC + H : jstart;            // first step without s-end closure logic
+  while (j < jfast && j <= jend) step(GenericPH{}, std::false_type{});
+#pragma unroll 1
+  while (j <= jend) fast_step();
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -478,21 +677,65 @@ template <int P> static bool sweep_eligible(const hsbp_blocks *b) {
   return sweep_smem<P>(Nrp, nthreads) <= b->ctx->smem_optin;
 }
 
-template <int P, int R> static int sweep_launch(hsbp_blocks *b, const double *u, double *y) {
+// crr' = crr * Hs[j] / hr, css' = css * Hr[i] / hs for uniform blocks (see SweepParams)
+template <int P>
+__global__ void __launch_bounds__(256)
+k_sweep_scale(const double *__restrict__ crr, const double *__restrict__ css, double *__restrict__ crr_s,
+              double *__restrict__ css_s, int Nr, int Ns, int64_t total) {
+  using C = SweepCfg<P>;
+  constexpr int BM = SweepTab<P>::BM;
+  const int Nrp = Nr + 1;
+  const int64_t np = (int64_t)Nrp * (Ns + 1);
+  const double hr = 2.0 / Nr, hs = 2.0 / Ns;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t loc = idx % np;
+    const int jj = (int)(loc / Nrp), i = (int)(loc - (int64_t)jj * Nrp);
+    const double hwi = i < BM ? C::hw()[i] : (i > Nr - BM ? C::hw()[Nr - i] : 1.0);
+    const double hwj = jj < BM ? C::hw()[jj] : (jj > Ns - BM ? C::hw()[Ns - jj] : 1.0);
+    crr_s[idx] = crr[idx] * (hs * hwj / hr);
+    css_s[idx] = css[idx] * (hr * hwi / hs);
+  }
+}
+
+template <int P> static int sweep_prepare(hsbp_blocks *b) {
   hsbp_ctx *ctx = b->ctx;
+  if (b->sweep_scaled_valid) return HSBP_OK;
+  const size_t vb = (size_t)b->VNp * sizeof(double);
+  if (!b->d_crr_s) {
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crr_s, vb));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_css_s, vb));
+  }
+  k_sweep_scale<P><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->d_crr, b->d_css, b->d_crr_s, b->d_css_s, b->max_Nr,
+                                                              b->max_Ns, b->VNp);
+  cudaError_t e1 = cudaGetLastError();
+  if (e1 != cudaSuccess) {
+    ctx->err = std::string("k_sweep_scale: ") + cudaGetErrorString(e1);
+    return HSBP_ERR_CUDA;
+  }
+  b->sweep_scaled_valid = true;
+  return HSBP_OK;
+}
+
+template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y) {
+  hsbp_ctx *ctx = b->ctx;
+#ifndef SW_REGS2
+#define SW_REGS2 128
+#endif
+  constexpr int MINB = (R == 2 ? 65536 / SW_REGS2 : 256) / NT;   // SW_REGS2 / 255 registers per thread
+  auto kern = k_sweep<P, R, NT, MINB>;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
   const size_t sm = sweep_smem<P>(Nrp, nthreads);
   static bool attr_set = false;
   static int ctas_per_sm = 1;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_sweep<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
       ctx->err = "cudaFuncSetAttribute(max dynamic shared memory) failed";
       return HSBP_ERR_CUDA;
     }
     attr_set = true;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_sweep<P, R>, nthreads, sm) != cudaSuccess || ctas_per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, nthreads, sm) != cudaSuccess || ctas_per_sm < 1)
     ctas_per_sm = 1;
   // chunks per side: enough CTAs to fill the machine in an almost whole number of waves, chunks of
   // at least 16 output lines (each chunk re-reads 2H halo lines)
@@ -508,13 +751,13 @@ template <int P, int R> static int sweep_launch(hsbp_blocks *b, const double *u,
     const double eff = waves / std::ceil(waves) * ((double)per / (per + 2 * SweepCfg<P>::H));
     if (eff > best_eff + 1e-9) { best_eff = eff; best = ncs; }
   }
-  if (b->sweep_ncs_override > 0) best = b->sweep_ncs_override;
+  if (b->sweep_ncs_override > 0) best = std::min(b->sweep_ncs_override, std::max(1, K / 16));
   SweepParams prm;
-  prm.crr = b->d_crr; prm.css = b->d_css; prm.crs = b->d_crs; prm.u = u; prm.y = y;
+  prm.crr = b->d_crr_s; prm.css = b->d_css_s; prm.crs = b->d_crs; prm.u = u; prm.y = y;
   prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
-  k_sweep<P, R><<<(unsigned)(b->nblocks * 2 * best), nthreads, sm, ctx->stream>>>(prm);
+  kern<<<(unsigned)(b->nblocks * 2 * best), nthreads, sm, ctx->stream>>>(prm);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_sweep: ") + cudaGetErrorString(e1);
@@ -523,13 +766,22 @@ template <int P, int R> static int sweep_launch(hsbp_blocks *b, const double *u,
   return HSBP_OK;
 }
 
+template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double *u, double *y) {
+  const int nthreads = (((b->max_Nr + 1) / R) + 31) & ~31;
+  if (nthreads <= 64) return sweep_launch<P, R, 64>(b, u, y);
+  if (nthreads <= 128) return sweep_launch<P, R, 128>(b, u, y);
+  return sweep_launch<P, R, 256>(b, u, y);
+}
+
 template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y) {
   hsbp_ctx *ctx = b->ctx;
   if (((uintptr_t)u & 15) || ((uintptr_t)y & 15)) {
     ctx->err = "hsbp_apply: u / y must be 16-byte aligned for the line-marching kernel";
     return HSBP_ERR_ARG;
   }
-  return sweep_points_per_thread(b) == 4 ? sweep_launch<P, 4>(b, u, y) : sweep_launch<P, 2>(b, u, y);
+  int rc = sweep_prepare<P>(b);
+  if (rc) return rc;
+  return sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y) : sweep_launch_nt<P, 2>(b, u, y);
 }
 
 }  // namespace hsbp
