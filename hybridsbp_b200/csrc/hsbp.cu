@@ -204,7 +204,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
-  cudaFree(b->d_crr_s); cudaFree(b->d_css_s);
+  cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
@@ -311,6 +311,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   if (n == "force_generic") b->force_generic = (int)value;
   else if (n == "sweep_chunks_per_side") b->sweep_ncs_override = (int)value;
   else if (n == "sweep_points_per_thread") b->sweep_r_override = (int)value;
+  else if (n == "sweep_fold_faces") b->sweep_fold_faces = (int)value;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);
   return HSBP_OK;
 }
@@ -354,8 +355,15 @@ static int apply_async(hsbp_blocks *b, const double *u, double *y, cudaEvent_t *
     int rc;
     if (evs) cudaEventRecord(evs[0], ctx->stream);
     if (!b->force_generic && sweep_eligible<P>(b)) {
-      rc = vol_sweep<P>(b, u, y);
       b->last_variant = 1;
+      if (b->sweep_fold_faces) {
+        // k_edge_prep (rim of every block: face terms + r-end closure rows; only reads u), then one pass
+        // that produces y = M-tilde u
+        rc = vol_sweep<P>(b, u, y, true, evs ? evs[1] : nullptr);
+        if (evs) { cudaEventRecord(evs[2], ctx->stream); cudaEventRecord(evs[3], ctx->stream); }
+        return rc;
+      }
+      rc = vol_sweep<P>(b, u, y, false);                   // volume part only; face terms by the two generic kernels
     } else {
       rc = vol_generic<P>(b, u, y);
       b->last_variant = 0;
@@ -396,6 +404,7 @@ int hsbp_apply_timed(hsbp_blocks *b, const double *u_dev, double *y_dev, double 
       ms[i] = f;
     }
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = HSBP_ERR_CUDA; }
+    if (b->last_variant == 1 && b->sweep_fold_faces) std::swap(ms[0], ms[1]);     // launch order there: face preparation, then k_sweep
   }
   for (int i = 0; i < 4; ++i) cudaEventDestroy(evs[i]);
   return rc;

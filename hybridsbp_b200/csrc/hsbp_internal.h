@@ -38,6 +38,7 @@ struct hsbp_blocks {
   std::vector<BlockDesc> h_desc;
   BlockDesc *d_desc = nullptr;
   double *d_crr = nullptr, *d_css = nullptr, *d_crs = nullptr;
+  double *d_rtab = nullptr;                        // r-end table of the line-marching kernel (k_edge_prep)
   double *d_crr_s = nullptr, *d_css_s = nullptr;   // norm-weighted copies for the line-marching kernel (lazy)
   bool sweep_scaled_valid = false;
   double *d_tau = nullptr;          // FNp
@@ -49,6 +50,7 @@ struct hsbp_blocks {
   int max_Nr = 0, max_Ns = 0;
   int force_generic = 0;
   int sweep_r_override = 0;         // points per thread of the line-marching kernel (0 = heuristic, 2 or 4)
+  int sweep_fold_faces = 1;         // fold the face terms into k_sweep (0: separate gather / scatter kernels)
   int sweep_ncs_override = 0;       // chunks per side of the line-marching kernel (0 = heuristic)
   int last_variant = -1;
   // local solves

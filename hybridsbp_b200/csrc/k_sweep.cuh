@@ -17,9 +17,9 @@
 // Arithmetic.  The variable-coefficient stiffness matrix M(b) (diagonal_sbp.jl:474-746) is symmetric
 // with zero row sums, so (M u)_i = sum_j M_ij (u_j - u_i); only the couplings M_ij are formed and each
 // is used for both rows ("pair form", tools/sbp_coeffs.py).  Closure rows:
-//   r-ends   every G lines the CTA evaluates the MC closure rows of M(crr) u and the BM closure rows of
-//            Qr u for the next G lines, one (line, end) per thread, from global memory (L2) into a small
-//            shared table; the edge lanes pick their values up when the line arrives.
+//   r-ends   the MCX closure rows of M(crr) u (with the face terms of faces 1, 2 already added) and the BM
+//            closure rows of Qr u are prepared per (line, end) by k_edge_prep into a small table; the row of
+//            each staged line rides along in the TMA ring and the edge lanes pick their values from it.
 //   s-ends   closure rows of M(css) u and Qs u are evaluated directly from global memory at output
 //            time; contributions of the dense BM x BM closure block of Qs^T, which reach further than
 //            the H-line lag, are added to y by read-modify-write from the thread that owns the points.
@@ -30,6 +30,7 @@
 #pragma once
 #include "hsbp_internal.h"
 #include "sbp1d.cuh"
+#include "k_generic.cuh"
 #include "sweep_tables_gen.h"
 
 namespace hsbp {
@@ -68,6 +69,11 @@ struct SweepParams {
   //   crr'(i,j) = crr(i,j) * Hs[j] / hr,  css'(i,j) = css(i,j) * Hr[i] / hs   (global_curved.jl:261-268, 313-322);
   // every stiffness coupling is linear in its coefficient, so the kernel needs no scaling at all.
   const double *crr, *css, *crs, *u;
+  // face terms of M-tilde, prepared per face point by k_face_prep (k_generic.cuh), block-face layout:
+  //   y(point at normal offset m from face point n) += BS[m] * fcn[n] + (m == 0) * fgm[n];   null: volume part only
+  const double *fcn, *fgm;
+  // r-end table made by k_edge_prep: [block][line][end (near, far)][CLW], see SweepCfg::CLW
+  const double *rtab;
   double *y;
   int Nr, Ns;         // uniform block size
   int ncs;            // chunks per side (a block is 2*ncs CTAs)
@@ -79,7 +85,12 @@ template <int P> struct SweepCfg {
   using T = SweepTab<P>;
   static constexpr int H = T::H, W = 2 * T::H + 1, LB = 2 * T::H;
   static constexpr int PAD = (T::H + 1) & ~1;               // halo of a shared line, even (16-byte vectors)
-  static constexpr int CLW = T::MC + T::BM;                 // r-closure table: MC rows of M u, BM rows of Q u
+  static constexpr int NB = (P == 2 ? 3 : (P == 4 ? 4 : 5)); // points of the boundary derivative BS (diagonal_sbp.jl:507,511,591)
+  static constexpr int MCX = T::MC > NB ? T::MC : NB;       // rows of an r-end that take table values
+  // r-closure table of one (line, end): MCX rows (closure rows of M u, replaced; rows MC..NB-1 only carry the
+  // face terms and are added) followed by the BM closure rows of Q u
+  static constexpr int CLW = MCX + T::BM;
+  __device__ static const double *bs() { return Sbp<P>::bs(); }
   __device__ static const double *hw() { return P == 2 ? c_sw_hw2 : (P == 4 ? c_sw_hw4 : c_sw_hw6); }
   __device__ static const double *Qc() { return P == 2 ? c_sw_Qc2 : (P == 4 ? c_sw_Qc4 : c_sw_Qc6); }
   template <int O> __device__ static constexpr double D() {
@@ -114,20 +125,6 @@ template <int O, int H, class F> __device__ __forceinline__ void for_offsets(F &
 
 // ---- rarely executed closure evaluations, kept out of line so that their temporaries do not add to
 // the register footprint of the marching loop ----------------------------------------------------
-// r-end closure rows of one line: cl[0..MC) = rows of M(crr) u, cl[MC..MC+BM) = rows of Qr u.
-// pb / pu point at the end point of the line, sg = +1 (near end) or -1 (far end, mirrored: Q flips sign).
-template <int P>
-__device__ __noinline__ void sweep_rclosure(const double *__restrict__ pb, const double *__restrict__ pu, int sg,
-                                            double *cl) {
-  using T = SweepTab<P>;
-  double b[T::NK], uu[T::NK], qq[T::BM];
-#pragma unroll
-  for (int k = 0; k < T::NK; ++k) { b[k] = __ldg(pb + sg * k); uu[k] = __ldg(pu + sg * k); }
-  d2_closure_rows<P>(b, uu, cl);
-  q_closure_rows<P>(uu, qq);
-#pragma unroll
-  for (int k = 0; k < T::BM; ++k) cl[T::MC + k] = sg < 0 ? -qq[k] : qq[k];
-}
 // s-end closure row `row` of M(css) u for one column, straight from memory (pb / pu: the column's point on
 // marching line 0, lstride: distance between marching lines)
 template <int P>
@@ -156,19 +153,19 @@ k_sweep(const SweepParams prm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
   constexpr int H = C::H, W = C::W, LB = C::LB, PAD = C::PAD, CLW = C::CLW, NST = SW_NST;
-  constexpr int MC = T::MC, NK = T::NK, BM = T::BM, BN = T::BN;
+  constexpr int MC = T::MC, NK = T::NK, BM = T::BM, BN = T::BN, MCX = C::MCX, NB = C::NB;
   constexpr int NV = R + 2 * PAD;                         // values of a line a thread looks at
+  constexpr int CLR = 2 * CLW;                            // r-end table entries per line (both ends); 2*CLW*8 B is a multiple of 16
   static_assert(R % 2 == 0 && PAD >= H, "layout");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int Nr = prm.Nr, Ns = prm.Ns, Nrp = Nr + 1, Nsp = Ns + 1;
   const int LW = Nrp + 2 * PAD;
-  const int G = nthreads >> 1;                            // lines per r-closure table refill
   double *ring = reinterpret_cast<double *>(smem_raw);    // [NST][4][LW]
   double *wbuf = ring + (size_t)NST * 4 * LW;             // [2][LW]
-  double *clbuf = wbuf + 2 * LW;                          // [G][2][CLW]
-  uint64_t *full = reinterpret_cast<uint64_t *>(clbuf + (size_t)G * 2 * CLW);
+  double *clring = wbuf + 2 * LW;                         // [NST][CLR]: r-end table rows of the staged lines
+  uint64_t *full = reinterpret_cast<uint64_t *>(clring + (size_t)NST * CLR);
 
   // ---- which chunk --------------------------------------------------------------------------
   const int nch = 2 * prm.ncs;
@@ -187,6 +184,7 @@ k_sweep(const SweepParams prm) {
   const int64_t lstride = up ? (int64_t)Nrp : -(int64_t)Nrp;
   const int64_t base = e * (int64_t)Nrp * Nsp + (up ? 0 : (int64_t)Ns * Nrp);   // marching line j starts at base + j*lstride
   const uint32_t line_bytes = (uint32_t)Nrp * 8u;
+  const int64_t foff = e * (2 * (int64_t)Nrp + 2 * (int64_t)Nsp);    // block e in the block-face layout
 
   // ---- one-time setup: zero the halos of the shared lines, barriers --------------------------
   for (int idx = tid; idx < (NST * 4 + 2) * 2 * PAD; idx += nthreads) {
@@ -202,11 +200,13 @@ k_sweep(const SweepParams prm) {
     const int st = n % NST;
     double *dst = ring + (size_t)st * 4 * LW + PAD;
     const int64_t g = base + (int64_t)(jstart + n) * lstride;
-    mbar_expect_tx(&full[st], 4u * line_bytes);
+    mbar_expect_tx(&full[st], 4u * line_bytes + (uint32_t)(CLR * 8));
     bulk_g2s(dst, prm.u + g, line_bytes, &full[st]);
     bulk_g2s(dst + LW, prm.crr + g, line_bytes, &full[st]);
     bulk_g2s(dst + 2 * LW, prm.css + g, line_bytes, &full[st]);
     bulk_g2s(dst + 3 * LW, prm.crs + g, line_bytes, &full[st]);
+    const int64_t jl = up ? (int64_t)(jstart + n) : (int64_t)Ns - (jstart + n);       // actual line index
+    bulk_g2s(clring + (size_t)st * CLR, prm.rtab + ((e * Nsp + jl) * CLR), (uint32_t)(CLR * 8), &full[st]);
   };
   if (tid == 0) {
     fence_proxy_async();
@@ -235,7 +235,7 @@ k_sweep(const SweepParams prm) {
       for (int q = 0; q < R; ++q) gy[l * lstride + q] = 0.0;
   }
 
-  int j = jstart, n = 0, st = 0, ng = 0;
+  int j = jstart, n = 0, st = 0;
   uint32_t parity = 0;
 
   // one marching step: line j arrives, line j-H is completed.  PH: rotation of the register windows
@@ -245,16 +245,6 @@ k_sweep(const SweepParams prm) {
     constexpr bool FAST = decltype(FASTc)::value;
     constexpr auto SL = [](int k) constexpr { return (PH + 1 + k) % W; };
     const bool pro = FAST ? false : prologue;
-
-    // ---- r-closure table for lines j .. j+G-1: thread -> (line, end) ---------------------------
-    if (ng == 0) {
-      const int jj = j + (tid >> 1), side = tid & 1;
-      if (jj <= jend) {
-        const int64_t g = base + (int64_t)jj * lstride + (side ? Nr : 0);
-        sweep_rclosure<P>(prm.crr + g, prm.u + g, side ? -1 : 1, clbuf + (size_t)tid * CLW);   // (tid>>1)*2 + side == tid
-      }
-      __syncthreads();
-    }
 
     mbar_wait(&full[st], parity);
     const double *sb = ring + (size_t)st * 4 * LW;
@@ -315,22 +305,24 @@ k_sweep(const SweepParams prm) {
         }
       });
       // closure rows at the r-ends come from the table; the owning lanes are known at compile time
-      for_lanes<0, (MC + R - 1) / R>([&](auto Tc) {
+      for_lanes<0, (MCX + R - 1) / R>([&](auto Tc) {
         constexpr int TL = decltype(Tc)::value;
         if (tid == TL) {                                  // near end: rows TL*R + q
-          const double *cl = clbuf + (size_t)(2 * ng) * CLW;
+          const double *cl = clring + (size_t)st * CLR;
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             if (TL * R + q < MC) rr[q] = cl[TL * R + q];
-            if (TL * R + q < BM) qr[q] = cl[MC + TL * R + q];
+              else if (TL * R + q < MCX) rr[q] += cl[TL * R + q];
+            if (TL * R + q < BM) qr[q] = cl[MCX + TL * R + q];
           }
         }
         if (tid == nown - 1 - TL) {                       // far end: rows m = TL*R + (R-1-q) counted from Nr
-          const double *cl = clbuf + (size_t)(2 * ng + 1) * CLW;
+          const double *cl = clring + (size_t)st * CLR + CLW;
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
-            if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MC + TL * R + (R - 1 - q)];
+              else if (TL * R + (R - 1 - q) < MCX) rr[q] += cl[TL * R + (R - 1 - q)];
+            if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MCX + TL * R + (R - 1 - q)];
           }
         }
       });
@@ -460,6 +452,17 @@ k_sweep(const SweepParams prm) {
             val[q] += sweep_sclosure_row<P>(jo, gss + q, gu + q, lstride);
         }
       }
+      if constexpr (!FAST) {
+        if (pro && jo < NB && prm.fcn != nullptr) {       // s-face terms: face 3 (line 0 side) / 4 (line Ns side)
+          const int64_t fi = foff + 2 * Nsp + (up ? 0 : Nrp) + i0;
+          const double bsm = C::bs()[jo];
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            val[q] = fma(bsm, prm.fcn[fi + q], val[q]);
+            if (jo == 0) val[q] += prm.fgm[fi + q];
+          }
+        }
+      }
       if (!FAST && pro && jo < BM) {
 #pragma unroll
         for (int q = 0; q < R; ++q) yl[q] += val[q];
@@ -471,7 +474,6 @@ k_sweep(const SweepParams prm) {
     }
     ++j; ++n;
     if (++st == NST) { st = 0; parity ^= 1u; }
-    if (++ng == G) ng = 0;
   };
 
   // ---- steady state --------------------------------------------------------------------------
@@ -480,19 +482,13 @@ k_sweep(const SweepParams prm) {
   // the line, the r-direction work, the w exchange and the output) exists once; only the short
   // window section is specialised for the W rotations and selected by a uniform branch.
   int ph = 0;                                             // rotation of the next steady-state step
+  const int nout0 = o0 + H - jstart;                      // first step whose line j-H belongs to the chunk
+  const int nrefill = nlines - NST;                       // steps after which no line is left to fetch
+  double *yout = nullptr;                                 // output line of the next steady-state step
   auto fast_step = [&]() {
-    if (ng == 0) {                                        // r-closure table for lines j .. j+G-1
-      const int jj = j + (tid >> 1), side = tid & 1;
-      if (jj <= jend) {
-        const int64_t g = base + (int64_t)jj * lstride + (side ? Nr : 0);
-        sweep_rclosure<P>(prm.crr + g, prm.u + g, side ? -1 : 1, clbuf + (size_t)tid * CLW);
-      }
-      __syncthreads();
-    }
     mbar_wait(&full[st], parity);
     const double *sb = ring + (size_t)st * 4 * LW;
-    const int jo = j - H;
-    const bool outp = (jo >= o0) && (jo < o1);
+    const bool outp = n >= nout0;                         // line j-H is an output line of this chunk
     double *wb = wbuf + (size_t)(n & 1) * LW;
     double accout[R];
     if (own) {
@@ -530,25 +526,35 @@ k_sweep(const SweepParams prm) {
           }
         }
       });
-      for_lanes<0, (MC + R - 1) / R>([&](auto Tc) {
-        constexpr int TL = decltype(Tc)::value;
-        if (tid == TL) {
-          const double *cl = clbuf + (size_t)(2 * ng) * CLW;
+      // closure rows at the r-ends come from the table (lanes known at compile time, predicated)
+      {
+        for_lanes<0, (MCX + R - 1) / R>([&](auto Tc) {
+          constexpr int TL = decltype(Tc)::value;
+          if (tid == TL) {
+            const double *cl = clring + (size_t)st * CLR;
 #pragma unroll
-          for (int q = 0; q < R; ++q) {
-            if (TL * R + q < MC) rr[q] = cl[TL * R + q];
-            if (TL * R + q < BM) qr[q] = cl[MC + TL * R + q];
+            for (int q = 0; q < R; ++q) {
+              if (TL * R + q < MC) rr[q] = cl[TL * R + q];
+              else if (TL * R + q < MCX) rr[q] += cl[TL * R + q];
+              if (TL * R + q < BM) qr[q] = cl[MCX + TL * R + q];
+            }
           }
-        }
-        if (tid == nown - 1 - TL) {
-          const double *cl = clbuf + (size_t)(2 * ng + 1) * CLW;
+        });
+      }
+      {
+        for_lanes<0, (MCX + R - 1) / R>([&](auto Tc) {
+          constexpr int TL = decltype(Tc)::value;
+          if (tid == nown - 1 - TL) {
+            const double *cl = clring + (size_t)st * CLR + CLW;
 #pragma unroll
-          for (int q = 0; q < R; ++q) {
-            if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
-            if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MC + TL * R + (R - 1 - q)];
+            for (int q = 0; q < R; ++q) {
+              if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
+              else if (TL * R + (R - 1 - q) < MCX) rr[q] += cl[TL * R + (R - 1 - q)];
+              if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MCX + TL * R + (R - 1 - q)];
+            }
           }
-        }
-      });
+        });
+      }
       // ---- S: the register windows, one specialisation per rotation -----------------------------
       auto windows = [&](auto PHc) {
         constexpr int PH = decltype(PHc)::value;
@@ -601,7 +607,7 @@ k_sweep(const SweepParams prm) {
       }
     }
     __syncthreads();
-    if (tid == 0 && n + NST < nlines) { fence_proxy_async(); issue(n + NST); }
+    if (tid == 0 && n < nrefill) { fence_proxy_async(); issue(n + NST); }
     if (own && outp) {
       // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
       double Wv[NV], val[R];
@@ -617,46 +623,137 @@ k_sweep(const SweepParams prm) {
 #pragma unroll
         for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
       });
-      for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
-        constexpr int TL = decltype(Tc)::value;
-        if (tid == TL) {
-          const double *w0 = wb + PAD;
+      {
+        for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
+          constexpr int TL = decltype(Tc)::value;
+          if (tid == TL) {
+            const double *w0 = wb + PAD;
 #pragma unroll
-          for (int q = 0; q < R; ++q)
-            if (TL * R + q < BM) val[q] = accout[q] + qt_closure_row<P>(TL * R + q, w0);
-        }
-        if (tid == nown - 1 - TL) {
-          double wr[BN];
+            for (int q = 0; q < R; ++q)
+              if (TL * R + q < BM) val[q] = accout[q] + qt_closure_row<P>(TL * R + q, w0);
+          }
+        });
+      }
+      {
+        for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
+          constexpr int TL = decltype(Tc)::value;
+          if (tid == nown - 1 - TL) {
+            double wr[BN];
 #pragma unroll
-          for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
+            for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
 #pragma unroll
-          for (int q = 0; q < R; ++q)
-            if (TL * R + (R - 1 - q) < BM) val[q] = accout[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
-        }
-      });
-      double *yl = gy + jo * lstride;
+            for (int q = 0; q < R; ++q)
+              if (TL * R + (R - 1 - q) < BM) val[q] = accout[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
+          }
+        });
+      }
 #pragma unroll
       for (int k = 0; k < R / 2; ++k)
-        *reinterpret_cast<double2 *>(yl + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+        *reinterpret_cast<double2 *>(yout + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
     }
+    yout += lstride;
     ++j; ++n;
     if (++st == NST) { st = 0; parity ^= 1u; }
-    if (++ng == G) ng = 0;
     if (++ph == W) ph = 0;
   };
 
   using GenericPH = std::integral_constant<int, W - 1>;    // rotation W-1: slot(k) == k (canonical order)
-  const int jfast = prologue ? MC + H : jstart;            // first step without s-end closure logic
+  const int jfast = prologue ? MCX + H : jstart;           // first step without s-end closure / face logic
   while (j < jfast && j <= jend) step(GenericPH{}, std::false_type{});
+  yout = gy + (int64_t)(j - H) * lstride;
 #pragma unroll 1
   while (j <= jend) fast_step();
+}
+
+// ---- edge preparation ---------------------------------------------------------------------------
+// One CTA per (block, face), launched before k_sweep.  Everything that lives on the rim of a block and
+// would otherwise need a second pass over y:
+//   * the face terms of M-tilde (reference locoperator, global_curved.jl:444-458, 478-486): from a = L u,
+//     g = G u and the face's boundary condition (k_generic.cuh header) the per-face-point quantities
+//       fcn[n] = (Hf/hn) c_nn alpha,   fgm[n] = sgn (Q_t^T (c_x o alpha))_n + beta
+//     with  y(point m deep behind face point n) += BS[m] fcn[n] + (m == 0) fgm[n];
+//   * for the r-faces (k = 1, 2) the table row of every line n: the MCX closure rows of Hs[n]/hr M(crr) u at that
+//     end with the face terms added, and the BM closure rows of Qr u (mirrored and sign-flipped at the far end).
+// with_faces = 0 leaves the face terms out (volume operator A-tilde only).
+// dynamic shared memory: 2 * (max face points) doubles
+template <int P>
+__global__ void __launch_bounds__(256)
+k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
+            const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
+            double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces) {
+  using S = Sbp<P>;
+  using T = SweepTab<P>;
+  using C = SweepCfg<P>;
+  extern __shared__ double sm_face[];
+  const int e = blockIdx.x >> 2, k = blockIdx.x & 3;
+  const BlockDesc d = desc[e];
+  const FaceGeom fg = face_geom(d, k);
+  double *sa = sm_face, *sx = sm_face + fg.nf;
+  const double *ub = u + d.voff;
+  const double *cnn = (k < 2 ? crr : css) + d.voff;
+  const double *cx = crs + d.voff;
+  if (with_faces) {
+    for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) sa[n] = ub[face_vol(d, k, n, 0)];
+    __syncthreads();
+    for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) {
+      const int64_t f0 = face_vol(d, k, n, 0);
+      double bsu = S::bs()[0] * sa[n];
+#pragma unroll
+      for (int m = 1; m < S::NB; ++m) bsu += S::bs()[m] * ub[face_vol(d, k, n, m)];
+      const double Hf = fg.ht * hweight<P>(n, fg.Nt);
+      const double qt = q_apply<P>(n, fg.Nt, [&](int l) { return sa[l]; });
+      const double cn = (Hf / fg.hn) * cnn[f0], cxf = cx[f0];
+      const double g = cn * bsu + fg.sgn * cxf * qt;
+      const int64_t fi = d.foff + fg.fstart + n;
+      const double tH = tau[fi] * Hf;
+      double alpha, beta;
+      if (d.bc[k] == HSBP_BC_NEUMANN) { alpha = -g / tH; beta = 0.0; }
+      else                            { alpha = -sa[n];  beta = tH * sa[n] - g; }
+      fcn[fi] = cn * alpha;
+      fgm[fi] = beta;
+      sx[n] = cxf * alpha;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) {
+      const int64_t fi = d.foff + fg.fstart + n;
+      fgm[fi] += fg.sgn * qt_apply<P>(n, fg.Nt, [&](int l) { return sx[l]; });
+    }
+  }
+  if (k >= 2) return;
+  // r-end table rows (face k = 0: near end i = 0, k = 1: far end i = Nr, mirrored)
+  const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
+  const int sg = k == 0 ? 1 : -1;
+  for (int n = threadIdx.x; n < Nsp; n += blockDim.x) {
+    const int64_t g0 = d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : d.Nr);
+    double b[T::NK], uu[T::NK], rows[C::MCX], qq[T::BM];
+    const double sc = fg.ht * hweight<P>(n, fg.Nt) / fg.hn;          // Hs[n] / hr  (global_curved.jl:261-268)
+#pragma unroll
+    for (int m = 0; m < T::NK; ++m) { b[m] = sc * crr[g0 + sg * m]; uu[m] = u[g0 + sg * m]; }
+#pragma unroll
+    for (int m = 0; m < C::MCX; ++m) rows[m] = 0.0;
+    d2_closure_rows<P>(b, uu, rows);
+    if (with_faces) {
+      const int64_t fi = d.foff + fg.fstart + n;
+      const double cn = fcn[fi], gm = fgm[fi];                        // written by this thread above
+#pragma unroll
+      for (int m = 0; m < C::NB; ++m) rows[m] = fma(S::bs()[m], cn, rows[m]);
+      rows[0] += gm;
+    }
+    q_closure_rows<P>(uu, qq);
+    double *out = rtab + (((int64_t)e * Nsp + n) * 2 + k) * C::CLW;
+#pragma unroll
+    for (int m = 0; m < C::MCX; ++m) out[m] = rows[m];
+#pragma unroll
+    for (int m = 0; m < T::BM; ++m) out[C::MCX + m] = sg < 0 ? -qq[m] : qq[m];
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------
 template <int P> static size_t sweep_smem(int Nrp, int nthreads) {
   using C = SweepCfg<P>;
+  (void)nthreads;
   const int LW = Nrp + 2 * C::PAD;
-  return (size_t)(SW_NST * 4 + 2) * LW * sizeof(double) + (size_t)(nthreads / 2) * 2 * C::CLW * sizeof(double) +
+  return (size_t)(SW_NST * 4 + 2) * LW * sizeof(double) + (size_t)SW_NST * 2 * C::CLW * sizeof(double) +
          SW_NST * sizeof(uint64_t);
 }
 
@@ -704,6 +801,7 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   if (!b->d_crr_s) {
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crr_s, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_css_s, vb));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * 2 * SweepCfg<P>::CLW * sizeof(double)));
   }
   k_sweep_scale<P><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->d_crr, b->d_css, b->d_crr_s, b->d_css_s, b->max_Nr,
                                                               b->max_Ns, b->VNp);
@@ -716,7 +814,7 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   return HSBP_OK;
 }
 
-template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y) {
+template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces) {
   hsbp_ctx *ctx = b->ctx;
 #ifndef SW_REGS2
 #define SW_REGS2 128
@@ -754,6 +852,8 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   if (b->sweep_ncs_override > 0) best = std::min(b->sweep_ncs_override, std::max(1, K / 16));
   SweepParams prm;
   prm.crr = b->d_crr_s; prm.css = b->d_css_s; prm.crs = b->d_crs; prm.u = u; prm.y = y;
+  prm.fcn = with_faces ? b->d_fa : nullptr; prm.fgm = with_faces ? b->d_fb : nullptr;
+  prm.rtab = b->d_rtab;
   prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
@@ -766,14 +866,16 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   return HSBP_OK;
 }
 
-template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double *u, double *y) {
+template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double *u, double *y, bool with_faces) {
   const int nthreads = (((b->max_Nr + 1) / R) + 31) & ~31;
-  if (nthreads <= 64) return sweep_launch<P, R, 64>(b, u, y);
-  if (nthreads <= 128) return sweep_launch<P, R, 128>(b, u, y);
-  return sweep_launch<P, R, 256>(b, u, y);
+  if (nthreads <= 64) return sweep_launch<P, R, 64>(b, u, y, with_faces);
+  if (nthreads <= 128) return sweep_launch<P, R, 128>(b, u, y, with_faces);
+  return sweep_launch<P, R, 256>(b, u, y, with_faces);
 }
 
-template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y) {
+// y = A-tilde u (with_faces = false) or y = M-tilde u with the face terms prepared in d_fa / d_fb by k_face_prep
+template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y, bool with_faces,
+                                     cudaEvent_t ev_between = nullptr) {
   hsbp_ctx *ctx = b->ctx;
   if (((uintptr_t)u & 15) || ((uintptr_t)y & 15)) {
     ctx->err = "hsbp_apply: u / y must be 16-byte aligned for the line-marching kernel";
@@ -781,7 +883,16 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
   }
   int rc = sweep_prepare<P>(b);
   if (rc) return rc;
-  return sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y) : sweep_launch_nt<P, 2>(b, u, y);
+  const size_t fsm = 2 * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
+  k_edge_prep<P><<<(unsigned)(4 * b->nblocks), 256, fsm, ctx->stream>>>(
+      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0);
+  cudaError_t e1 = cudaGetLastError();
+  if (e1 != cudaSuccess) {
+    ctx->err = std::string("k_edge_prep: ") + cudaGetErrorString(e1);
+    return HSBP_ERR_CUDA;
+  }
+  if (ev_between) cudaEventRecord(ev_between, ctx->stream);
+  return sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces) : sweep_launch_nt<P, 2>(b, u, y, with_faces);
 }
 
 }  // namespace hsbp

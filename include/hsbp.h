@@ -100,8 +100,10 @@ int  hsbp_blocks_get_tau(hsbp_blocks *blocks, double *tau);
 int  hsbp_apply(hsbp_blocks *blocks, const double *u_dev, double *y_dev);
 /* same through host buffers: H2D of u, apply, D2H of y inside the call                 */
 int  hsbp_apply_host(hsbp_blocks *blocks, const double *u, double *y);
-/* hsbp_apply with CUDA events between its stages: ms[0] volume stage (the dominant kernel),
- * ms[1] face gather, ms[2] face scatter.  Synchronises; for benchmarking.                        */
+/* hsbp_apply with CUDA events between its stages.  ms[0] is always the dominant volume kernel:
+ *   line-marching variant: ms[0] k_sweep (volume + folded face terms), ms[1] k_face_prep, ms[2] 0
+ *   generic variant:       ms[0] two-pass volume kernels, ms[1] face gather, ms[2] face scatter
+ * Synchronises; for benchmarking.                                                                   */
 int  hsbp_apply_timed(hsbp_blocks *blocks, const double *u_dev, double *y_dev, double *ms);
 /* which kernel variant hsbp_apply last used: 0 generic two-pass kernels, 1 line-marching TMA kernel (k_sweep)     */
 int  hsbp_apply_variant(const hsbp_blocks *blocks);
