@@ -684,67 +684,105 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
+  // points normal to the face that are looked at: the closure rows need T::NK, the boundary derivative NB
+  constexpr int NK = T::NK >= S::NB ? T::NK : ((S::NB + 1) & ~1);
+  static_assert(NK % 2 == 0 && NK >= S::NB && NK >= T::NK, "normal extent");
   extern __shared__ double sm_face[];
   const int e = blockIdx.x >> 2, k = blockIdx.x & 3;
   const BlockDesc d = desc[e];
   const FaceGeom fg = face_geom(d, k);
   double *sa = sm_face, *sx = sm_face + fg.nf;
-  const double *ub = u + d.voff;
-  const double *cnn = (k < 2 ? crr : css) + d.voff;
-  const double *cx = crs + d.voff;
-  if (with_faces) {
-    for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) sa[n] = ub[face_vol(d, k, n, 0)];
-    __syncthreads();
-    for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) {
-      const int64_t f0 = face_vol(d, k, n, 0);
-      double bsu = S::bs()[0] * sa[n];
-#pragma unroll
-      for (int m = 1; m < S::NB; ++m) bsu += S::bs()[m] * ub[face_vol(d, k, n, m)];
-      const double Hf = fg.ht * hweight<P>(n, fg.Nt);
-      const double qt = q_apply<P>(n, fg.Nt, [&](int l) { return sa[l]; });
-      const double cn = (Hf / fg.hn) * cnn[f0], cxf = cx[f0];
-      const double g = cn * bsu + fg.sgn * cxf * qt;
-      const int64_t fi = d.foff + fg.fstart + n;
-      const double tH = tau[fi] * Hf;
-      double alpha, beta;
-      if (d.bc[k] == HSBP_BC_NEUMANN) { alpha = -g / tH; beta = 0.0; }
-      else                            { alpha = -sa[n];  beta = tH * sa[n] - g; }
-      fcn[fi] = cn * alpha;
-      fgm[fi] = beta;
-      sx[n] = cxf * alpha;
-    }
-    __syncthreads();
-    for (int n = threadIdx.x; n < fg.nf; n += blockDim.x) {
-      const int64_t fi = d.foff + fg.fstart + n;
-      fgm[fi] += fg.sgn * qt_apply<P>(n, fg.Nt, [&](int l) { return sx[l]; });
-    }
-  }
-  if (k >= 2) return;
-  // r-end table rows (face k = 0: near end i = 0, k = 1: far end i = Nr, mirrored)
   const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
-  const int sg = k == 0 ? 1 : -1;
-  for (int n = threadIdx.x; n < Nsp; n += blockDim.x) {
-    const int64_t g0 = d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : d.Nr);
-    double b[T::NK], uu[T::NK], rows[C::MCX], qq[T::BM];
-    const double sc = fg.ht * hweight<P>(n, fg.Nt) / fg.hn;          // Hs[n] / hr  (global_curved.jl:261-268)
-#pragma unroll
-    for (int m = 0; m < T::NK; ++m) { b[m] = sc * crr[g0 + sg * m]; uu[m] = u[g0 + sg * m]; }
-#pragma unroll
-    for (int m = 0; m < C::MCX; ++m) rows[m] = 0.0;
-    d2_closure_rows<P>(b, uu, rows);
-    if (with_faces) {
+  // One face point per thread and trip; every global load of a trip is issued before its first use.
+  // Faces longer than the CTA take several trips: the tangential operators need the whole face in shared
+  // memory, so alpha-dependent data is parked in fcn / fgm between the passes (STAGE 0, 1, 2); a face that
+  // fits does everything in one go (STAGE -1).
+  const bool single = fg.nf <= (int)blockDim.x;
+  for (int stage = single ? -1 : 0; stage < (single ? 0 : 3); ++stage) {
+    for (int n0 = 0; n0 < fg.nf; n0 += blockDim.x) {
+      const int n = n0 + threadIdx.x;
+      const bool act = n < fg.nf;
+      double b[NK], uu[NK];                    // c_nn and u at normal offsets 0 .. NK-1 behind face point n
+      double cxf = 0.0, tauf = 0.0;
       const int64_t fi = d.foff + fg.fstart + n;
-      const double cn = fcn[fi], gm = fgm[fi];                        // written by this thread above
+      if (act) {
+        if (k < 2) {                           // r-faces: the NK points are contiguous in memory (16-byte aligned)
+          const int64_t g0 = d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : Nrp - NK);
+          const double2 *pb = reinterpret_cast<const double2 *>(crr + g0), *pu = reinterpret_cast<const double2 *>(u + g0);
 #pragma unroll
-      for (int m = 0; m < C::NB; ++m) rows[m] = fma(S::bs()[m], cn, rows[m]);
-      rows[0] += gm;
+          for (int m = 0; m < NK / 2; ++m) {
+            const double2 vb = pb[m], vu = pu[m];
+            if (k == 0) { b[2 * m] = vb.x; b[2 * m + 1] = vb.y; uu[2 * m] = vu.x; uu[2 * m + 1] = vu.y; }
+            else { b[NK - 1 - 2 * m] = vb.x; b[NK - 2 - 2 * m] = vb.y; uu[NK - 1 - 2 * m] = vu.x; uu[NK - 2 - 2 * m] = vu.y; }
+          }
+          cxf = crs[d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : d.Nr)];
+        } else {                               // s-faces: lines 0 .. NB-1 (or Ns .. Ns-NB+1), coalesced along the face
+          const int64_t g0 = d.voff + n + (k == 2 ? 0 : (int64_t)Nrp * d.Ns);
+          const int64_t ls = k == 2 ? Nrp : -Nrp;
+#pragma unroll
+          for (int m = 0; m < S::NB; ++m) uu[m] = u[g0 + ls * m];
+          b[0] = css[g0];
+          cxf = crs[g0];
+        }
+        if (with_faces) tauf = tau[fi];
+      }
+      double cn = 0.0, beta = 0.0, alpha = 0.0;
+      const double Hf = fg.ht * hweight<P>(act ? n : 0, fg.Nt);
+      if (with_faces) {
+        if (stage <= 0) {                      // restriction a = L u of the whole face
+          if (act) sa[n] = uu[0];
+          if (stage == 0) continue;
+          __syncthreads();
+        }
+        if (stage < 0 || stage == 1) {         // g = G u, then alpha / beta of the boundary condition
+          if (act) {
+            double bsu = S::bs()[0] * uu[0];
+#pragma unroll
+            for (int m = 1; m < S::NB; ++m) bsu += S::bs()[m] * uu[m];
+            const double qt = q_apply<P>(n, fg.Nt, [&](int l) { return sa[l]; });
+            cn = (Hf / fg.hn) * b[0];
+            const double g = cn * bsu + fg.sgn * cxf * qt;
+            const double tH = tauf * Hf;
+            if (d.bc[k] == HSBP_BC_NEUMANN) { alpha = -g / tH; beta = 0.0; }
+            else                            { alpha = -uu[0];  beta = tH * uu[0] - g; }
+            sx[n] = cxf * alpha;
+            cn *= alpha;
+            if (stage == 1) { fcn[fi] = cn; fgm[fi] = beta; }
+          }
+          if (stage == 1) continue;
+          __syncthreads();
+        }
+        if (act) {                             // tangential part of G^T alpha lands on the face point itself
+          if (stage == 2) { cn = fcn[fi]; beta = fgm[fi]; }
+          beta += fg.sgn * qt_apply<P>(n, fg.Nt, [&](int l) { return sx[l]; });
+          if (k >= 2 || stage == 2) { fcn[fi] = cn; fgm[fi] = beta; }   // (r-faces: only needed by the table below)
+        }
+      } else if (stage >= 0 && stage < 2) {
+        continue;
+      }
+      if (k < 2 && act) {
+        // r-end table row of line n: closure rows of Hs[n]/hr M(crr) u with the face terms, closure rows of Qr u
+        double rows[C::MCX], qq[T::BM];
+        const double sc = Hf / fg.hn;          // Hs[n] / hr  (global_curved.jl:261-268)
+#pragma unroll
+        for (int m = 0; m < NK; ++m) b[m] *= sc;
+#pragma unroll
+        for (int m = 0; m < C::MCX; ++m) rows[m] = 0.0;
+        d2_closure_rows<P>(b, uu, rows);
+        if (with_faces) {
+#pragma unroll
+          for (int m = 0; m < C::NB; ++m) rows[m] = fma(S::bs()[m], cn, rows[m]);
+          rows[0] += beta;
+        }
+        q_closure_rows<P>(uu, qq);
+        double *out = rtab + (((int64_t)e * Nsp + n) * 2 + k) * C::CLW;
+#pragma unroll
+        for (int m = 0; m < C::MCX; ++m) out[m] = rows[m];
+#pragma unroll
+        for (int m = 0; m < T::BM; ++m) out[C::MCX + m] = k == 1 ? -qq[m] : qq[m];
+      }
     }
-    q_closure_rows<P>(uu, qq);
-    double *out = rtab + (((int64_t)e * Nsp + n) * 2 + k) * C::CLW;
-#pragma unroll
-    for (int m = 0; m < C::MCX; ++m) out[m] = rows[m];
-#pragma unroll
-    for (int m = 0; m < T::BM; ++m) out[C::MCX + m] = sg < 0 ? -qq[m] : qq[m];
+    __syncthreads();                           // stage boundary: sa / sx of the whole face are complete
   }
 }
 
