@@ -1,0 +1,181 @@
+# HybridSBPB200.jl -- thin `ccall` layer over libhsbp.so (include/hsbp.h) plus the drop-in type for the
+# reference's `factorization` plugin.
+#
+# NOT EXECUTED IN THE BUILD CONTAINER: Julia is not installed there.  This file mirrors, call for call,
+# hybridsbp_b200/_lib.py + blocks.py (the ctypes twin that the tests run); keep the two in sync.
+#
+# Usage inside the reference (square_circle.jl:297-299, seas/BP1/BP1.jl:78):
+#
+#     include("global_curved.jl"); include("HybridSBPB200.jl"); using .HybridSBPB200
+#     ctx = HybridSBPB200.Context(0)
+#     # metrics as create_metrics (global_curved.jl:136-209) returns them, LFToB as locoperator takes it
+#     blk = HybridSBPB200.Blocks(ctx, SBPp, Nr, Ns)                    # Nr, Ns :: Vector{Int}
+#     HybridSBPB200.set_metrics!(blk, crr, css, crs)                   # concatenated in vstarts layout
+#     HybridSBPB200.set_bc!(blk, LFToB)                                # 4 x nelems Int matrix
+#     HybridSBPB200.compute_tau!(blk, 2.0)                             # global_curved.jl:418-437
+#     tr  = HybridSBPB200.Trace(blk, FToB, FToE, FToLF, EToO, EToS)    # connectivityarrays' outputs, 1-based
+#     λ, u, stats = HybridSBPB200.trace_solve(tr, g, gδ; tol = 1e-10)  # square_circle.jl:376-388
+#
+module HybridSBPB200
+
+using LinearAlgebra
+import LinearAlgebra: Factorization
+import Base: \, size
+
+const libhsbp = get(ENV, "HSBP_LIB", joinpath(@__DIR__, "..", "hybridsbp_b200", "libhsbp.so"))
+
+struct HsbpError <: Exception
+  code::Cint
+  msg::String
+end
+
+mutable struct Context
+  h::Ptr{Cvoid}
+  function Context(device::Integer = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:hsbp_ctx_create, libhsbp), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h)
+    rc == 0 || throw(HsbpError(rc, "hsbp_ctx_create failed (a B200 / sm_100 GPU is required; no CPU fallback)"))
+    ctx = new(h[])
+    finalizer(c -> ccall((:hsbp_ctx_destroy, libhsbp), Cint, (Ptr{Cvoid},), c.h), ctx)
+  end
+end
+
+lasterror(ctx::Context) = unsafe_string(ccall((:hsbp_last_error, libhsbp), Cstring, (Ptr{Cvoid},), ctx.h))
+check(ctx::Context, rc) = rc == 0 ? nothing : throw(HsbpError(rc, lasterror(ctx)))
+
+# ---- device vectors -------------------------------------------------------------------------------
+mutable struct DeviceVector
+  ctx::Context
+  ptr::Ptr{Cvoid}
+  n::Int
+  function DeviceVector(ctx::Context, n::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:hsbp_malloc, libhsbp), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.h, 8n, p))
+    v = new(ctx, p[], n)
+    finalizer(x -> ccall((:hsbp_free, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, x.ptr), v)
+  end
+end
+function DeviceVector(ctx::Context, a::AbstractVector{Float64})
+  v = DeviceVector(ctx, length(a)); upload!(v, a); v
+end
+upload!(v::DeviceVector, a::AbstractVector{Float64}) =
+  check(v.ctx, ccall((:hsbp_h2d, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Csize_t),
+                     v.ctx.h, v.ptr, a, 8 * v.n))
+function download(v::DeviceVector)
+  a = Vector{Float64}(undef, v.n)
+  check(v.ctx, ccall((:hsbp_d2h, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Csize_t),
+                     v.ctx.h, a, v.ptr, 8 * v.n))
+  a
+end
+
+# ---- block-local operators: replaces locoperator's assembled M̃ (global_curved.jl:211-506) ------------
+mutable struct Blocks
+  ctx::Context
+  h::Ptr{Cvoid}
+  p::Int
+  Nr::Vector{Int64}
+  Ns::Vector{Int64}
+  vstarts::Vector{Int64}     # 1-based, as SBPLocalOperator1 builds it (global_curved.jl:685-686)
+  function Blocks(ctx::Context, p::Integer, Nr::Vector{<:Integer}, Ns::Vector{<:Integer})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    nr, ns = Int64.(Nr), Int64.(Ns)
+    check(ctx, ccall((:hsbp_blocks_create, libhsbp), Cint,
+                     (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                     ctx.h, p, length(nr), nr, ns, h))
+    b = new(ctx, h[], p, nr, ns, cumsum([1; (nr .+ 1) .* (ns .+ 1)]))
+    finalizer(x -> ccall((:hsbp_blocks_destroy, libhsbp), Cint, (Ptr{Cvoid},), x.h), b)
+  end
+end
+num_volume_points(b::Blocks) = ccall((:hsbp_blocks_num_volume_points, libhsbp), Int64, (Ptr{Cvoid},), b.h)
+num_face_points(b::Blocks) = ccall((:hsbp_blocks_num_face_points, libhsbp), Int64, (Ptr{Cvoid},), b.h)
+
+set_metrics!(b::Blocks, crr::Vector{Float64}, css::Vector{Float64}, crs::Vector{Float64}) =
+  check(b.ctx, ccall((:hsbp_blocks_set_metrics, libhsbp), Cint,
+                     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), b.h, crr, css, crs))
+set_bc!(b::Blocks, LFToB::AbstractMatrix{<:Integer}) =       # 4 x nelems, column-major = block by block
+  check(b.ctx, ccall((:hsbp_blocks_set_bc, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Int64}), b.h, Int64.(vec(LFToB))))
+compute_tau!(b::Blocks, tauscale::Real = 2.0) =
+  check(b.ctx, ccall((:hsbp_blocks_compute_tau, libhsbp), Cint, (Ptr{Cvoid}, Cdouble), b.h, tauscale))
+
+"y = M̃ u for every block (the SpMV lop[e].M̃ * u, global_curved.jl:470-492), device vectors"
+apply!(y::DeviceVector, b::Blocks, u::DeviceVector) =
+  check(b.ctx, ccall((:hsbp_apply, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), b.h, u.ptr, y.ptr))
+"same through host arrays (H2D, kernels, D2H inside the call)"
+function apply(b::Blocks, u::Vector{Float64})
+  y = similar(u)
+  check(b.ctx, ccall((:hsbp_apply_host, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), b.h, u, y))
+  y
+end
+
+# ---- the `factorization` plugin (global_curved.jl:659, 672, 698, 734) ------------------------------------
+# SBPLocalOperator1 requires `factors[e] <: Factorization` and uses `F \ g`.  All blocks are solved in one
+# batched call, so the per-block object is a view into a shared batch solver.
+const LOCAL_PCG = 1
+const LOCAL_CHOLESKY = 2
+struct LocalStats
+  iterations_max::Int64
+  iterations_sum::Int64
+  failed_blocks::Int64
+  max_rel_residual::Float64
+end
+local_setup!(b::Blocks; mode = LOCAL_PCG, tol = 1e-13, maxit = 100_000) =
+  check(b.ctx, ccall((:hsbp_local_setup, libhsbp), Cint, (Ptr{Cvoid}, Cint, Cdouble, Int64), b.h, mode, tol, maxit))
+function local_solve!(u::DeviceVector, b::Blocks, g::DeviceVector)
+  st = Ref(LocalStats(0, 0, 0, 0.0))
+  check(b.ctx, ccall((:hsbp_local_solve, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{LocalStats}),
+                     b.h, g.ptr, u.ptr, st))
+  st[]
+end
+"All-blocks solve as one Factorization: `F \\ g` with g the concatenated volume vector."
+struct B200LocalSolve <: Factorization{Float64}
+  blocks::Blocks
+end
+size(F::B200LocalSolve) = (n = num_volume_points(F.blocks); (n, n))
+function \(F::B200LocalSolve, g::AbstractVector{Float64})
+  dg = DeviceVector(F.blocks.ctx, collect(g)); du = DeviceVector(F.blocks.ctx, length(g))
+  st = local_solve!(du, F.blocks, dg)
+  st.failed_blocks == 0 || @warn "local PCG did not converge on $(st.failed_blocks) blocks" st
+  download(du)
+end
+
+# ---- trace (λ) operators and the Schur-complement solve (global_curved.jl:510-565, 730-797) --------------
+mutable struct Trace
+  blocks::Blocks
+  h::Ptr{Cvoid}
+  function Trace(b::Blocks, FToB::Vector{<:Integer}, FToE::AbstractMatrix{<:Integer}, FToLF::AbstractMatrix{<:Integer},
+                 EToO::AbstractMatrix{Bool}, EToS::AbstractMatrix{<:Integer})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(b.ctx, ccall((:hsbp_trace_create, libhsbp), Cint,
+                       (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                       b.h, length(FToB), Int64.(FToB), Int64.(vec(FToE)), Int64.(vec(FToLF)),
+                       UInt8.(vec(EToO)), Int64.(vec(EToS)), h))
+    t = new(b, h[])
+    finalizer(x -> ccall((:hsbp_trace_destroy, libhsbp), Cint, (Ptr{Cvoid},), x.h), t)
+  end
+end
+num_lambda(t::Trace) = ccall((:hsbp_trace_num_lambda, libhsbp), Int64, (Ptr{Cvoid},), t.h)
+function FToλstarts(t::Trace, nfaces::Integer)
+  s = Vector{Int64}(undef, nfaces + 1)
+  check(t.blocks.ctx, ccall((:hsbp_trace_get_starts, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Int64}), t.h, s)); s
+end
+struct TraceStats
+  outer_iterations::Int64
+  converged::Int64
+  rel_residual::Float64
+  inner_iterations_sum::Int64
+  inner_iterations_max::Int64
+  local_solves::Int64
+end
+"λ = B⁻¹(gδ − F̄ᵀM̃⁻¹g), u = M̃⁻¹(g − F̄λ)   (square_circle.jl:376-388); returns (λ, u, stats)"
+function trace_solve(t::Trace, g::Vector{Float64}, gδ::Vector{Float64}; tol = 1e-10, maxit = 10_000)
+  ctx = t.blocks.ctx
+  dg, dgd = DeviceVector(ctx, g), DeviceVector(ctx, gδ)
+  dl, du = DeviceVector(ctx, length(gδ)), DeviceVector(ctx, length(g))
+  st = Ref(TraceStats(0, 0, 0.0, 0, 0, 0))
+  check(ctx, ccall((:hsbp_trace_solve, libhsbp), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ref{TraceStats}),
+                   t.h, dg.ptr, dgd.ptr, dl.ptr, du.ptr, tol, maxit, st))
+  download(dl), download(du), st[]
+end
+
+end # module
