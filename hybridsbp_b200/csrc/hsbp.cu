@@ -207,6 +207,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
+  for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
   cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off);
   delete b;
@@ -414,18 +415,56 @@ int hsbp_apply_host(hsbp_blocks *b, const double *u, double *y) {
   if (!b) return HSBP_ERR_ARG;
   hsbp_ctx *ctx = b->ctx;
   if (!u || !y) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_apply_host: null pointer");
+  if (!b->have_metrics || !b->have_tau) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_apply_host: metrics / tau not set");
   HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t vb = (size_t)b->VNp * sizeof(double);
   if (!b->d_stage_u) {
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_stage_u, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_stage_y, vb));
   }
-  HSBP_CUDA(ctx, cudaMemcpyAsync(b->d_stage_u, u, vb, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = apply_async(b, b->d_stage_u, b->d_stage_y);
-  if (rc) return rc;
-  HSBP_CUDA(ctx, cudaMemcpyAsync(y, b->d_stage_y, vb, cudaMemcpyDeviceToHost, ctx->stream));
+  // Blocks are independent in M-tilde u, so the call is pipelined over groups of blocks: the H2D copy of
+  // group g+1, the kernels of group g and the D2H copy of group g-1 overlap (three streams, PCIe is full duplex).
+  const bool pipelined = !b->force_generic && b->sweep_fold_faces && b->nblocks >= 16 &&
+                         dispatch_p(b->p, [&](auto Pc) { return sweep_eligible<decltype(Pc)::value>(b) ? 1 : 0; }) == 1;
+  if (!pipelined) {
+    HSBP_CUDA(ctx, cudaMemcpyAsync(b->d_stage_u, u, vb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = apply_async(b, b->d_stage_u, b->d_stage_y);
+    if (rc) return rc;
+    HSBP_CUDA(ctx, cudaMemcpyAsync(y, b->d_stage_y, vb, cudaMemcpyDeviceToHost, ctx->stream));
+    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HSBP_OK;
+  }
+  const int ngroups = (int)std::min<int64_t>(16, b->nblocks / 8);
+  const int64_t per = (b->nblocks + ngroups - 1) / ngroups;
+  const int64_t np = (int64_t)(b->max_Nr + 1) * (b->max_Ns + 1);
+  if ((int)b->pipe_ev.size() < 2 * ngroups) {
+    const size_t old = b->pipe_ev.size();
+    b->pipe_ev.resize(2 * ngroups, nullptr);
+    for (size_t i = old; i < b->pipe_ev.size(); ++i)
+      HSBP_CUDA(ctx, cudaEventCreateWithFlags(&b->pipe_ev[i], cudaEventDisableTiming));
+  }
+  b->last_variant = 1;
+  HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // earlier work on the compute stream (setup) is done
+  int rc = HSBP_OK;
+  for (int g = 0; g < ngroups && rc == HSBP_OK; ++g) {
+    const int64_t e0 = g * per, ne = std::min<int64_t>(per, b->nblocks - e0);
+    if (ne <= 0) break;
+    const size_t off = (size_t)(e0 * np), nbytes = (size_t)(ne * np) * sizeof(double);
+    HSBP_CUDA(ctx, cudaMemcpyAsync(b->d_stage_u + off, u + off, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+    HSBP_CUDA(ctx, cudaEventRecord(b->pipe_ev[2 * g], ctx->copy_stream[0]));
+    HSBP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, b->pipe_ev[2 * g], 0));
+    rc = dispatch_p(b->p, [&](auto Pc) {
+      return vol_sweep<decltype(Pc)::value>(b, b->d_stage_u, b->d_stage_y, true, nullptr, e0, ne);
+    });
+    if (rc) break;
+    HSBP_CUDA(ctx, cudaEventRecord(b->pipe_ev[2 * g + 1], ctx->stream));
+    HSBP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream[1], b->pipe_ev[2 * g + 1], 0));
+    HSBP_CUDA(ctx, cudaMemcpyAsync(y + off, b->d_stage_y + off, nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream[1]));
+  }
+  HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[0]));
   HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return HSBP_OK;
+  HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[1]));
+  return rc;
 }
 
 int hsbp_face_FT(hsbp_blocks *b, const double *u_dev, double *ft_dev) {

@@ -65,6 +65,7 @@ struct hsbp_blocks {
   int64_t *d_chol_off = nullptr;
   // pinned staging for hsbp_apply_host (lazy)
   double *d_stage_u = nullptr, *d_stage_y = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;          // per block group: H2D done, kernels done
 };
 
 #define HSBP_CUDA(ctx, call)                                                     \

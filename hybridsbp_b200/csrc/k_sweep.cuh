@@ -76,6 +76,7 @@ struct SweepParams {
   const double *rtab;
   double *y;
   int Nr, Ns;         // uniform block size
+  int e0;             // first block of this launch (a launch may cover a range of the blocks)
   int ncs;            // chunks per side (a block is 2*ncs CTAs)
   int K;              // lines [0, K) are marched upwards, lines [K, Ns] downwards
   int per_up, per_dn; // output lines per chunk on either side
@@ -169,8 +170,9 @@ k_sweep(const SweepParams prm) {
 
   // ---- which chunk --------------------------------------------------------------------------
   const int nch = 2 * prm.ncs;
-  const int64_t e = blockIdx.x / nch;
-  const int c = (int)(blockIdx.x - e * nch);
+  const int64_t el = blockIdx.x / nch;
+  const int c = (int)(blockIdx.x - el * nch);
+  const int64_t e = prm.e0 + el;
   const bool up = c < prm.ncs;
   const int cc = up ? c : c - prm.ncs;
   const int nside = up ? prm.K : Nsp - prm.K;
@@ -680,7 +682,7 @@ template <int P>
 __global__ void __launch_bounds__(256)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
-            double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces) {
+            double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0) {
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -688,7 +690,7 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   constexpr int NK = T::NK >= S::NB ? T::NK : ((S::NB + 1) & ~1);
   static_assert(NK % 2 == 0 && NK >= S::NB && NK >= T::NK, "normal extent");
   extern __shared__ double sm_face[];
-  const int e = blockIdx.x >> 2, k = blockIdx.x & 3;
+  const int e = e0 + (blockIdx.x >> 2), k = blockIdx.x & 3;
   const BlockDesc d = desc[e];
   const FaceGeom fg = face_geom(d, k);
   double *sa = sm_face, *sx = sm_face + fg.nf;
@@ -852,7 +854,8 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   return HSBP_OK;
 }
 
-template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces) {
+template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
+                                                        int64_t e0, int64_t ne) {
   hsbp_ctx *ctx = b->ctx;
 #ifndef SW_REGS2
 #define SW_REGS2 128
@@ -882,7 +885,7 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   for (int ncs = 1; ncs <= 16; ++ncs) {
     const int per = (K + ncs - 1) / ncs;
     if (ncs > 1 && per < 16) break;
-    const int64_t ctas = b->nblocks * 2 * ncs;
+    const int64_t ctas = ne * 2 * ncs;
     const double waves = (double)ctas / (double)slots;
     const double eff = waves / std::ceil(waves) * ((double)per / (per + 2 * SweepCfg<P>::H));
     if (eff > best_eff + 1e-9) { best_eff = eff; best = ncs; }
@@ -892,10 +895,10 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   prm.crr = b->d_crr_s; prm.css = b->d_css_s; prm.crs = b->d_crs; prm.u = u; prm.y = y;
   prm.fcn = with_faces ? b->d_fa : nullptr; prm.fgm = with_faces ? b->d_fb : nullptr;
   prm.rtab = b->d_rtab;
-  prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K;
+  prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K; prm.e0 = (int)e0;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
-  kern<<<(unsigned)(b->nblocks * 2 * best), nthreads, sm, ctx->stream>>>(prm);
+  kern<<<(unsigned)(ne * 2 * best), nthreads, sm, ctx->stream>>>(prm);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_sweep: ") + cudaGetErrorString(e1);
@@ -904,33 +907,37 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   return HSBP_OK;
 }
 
-template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double *u, double *y, bool with_faces) {
+template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double *u, double *y, bool with_faces,
+                                                   int64_t e0, int64_t ne) {
   const int nthreads = (((b->max_Nr + 1) / R) + 31) & ~31;
-  if (nthreads <= 64) return sweep_launch<P, R, 64>(b, u, y, with_faces);
-  if (nthreads <= 128) return sweep_launch<P, R, 128>(b, u, y, with_faces);
-  return sweep_launch<P, R, 256>(b, u, y, with_faces);
+  if (nthreads <= 64) return sweep_launch<P, R, 64>(b, u, y, with_faces, e0, ne);
+  if (nthreads <= 128) return sweep_launch<P, R, 128>(b, u, y, with_faces, e0, ne);
+  return sweep_launch<P, R, 256>(b, u, y, with_faces, e0, ne);
 }
 
 // y = A-tilde u (with_faces = false) or y = M-tilde u with the face terms prepared in d_fa / d_fb by k_face_prep
+// for the blocks [e0, e0 + ne); u and y are the full concatenated vectors
 template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y, bool with_faces,
-                                     cudaEvent_t ev_between = nullptr) {
+                                     cudaEvent_t ev_between = nullptr, int64_t e0 = 0, int64_t ne = -1) {
   hsbp_ctx *ctx = b->ctx;
   if (((uintptr_t)u & 15) || ((uintptr_t)y & 15)) {
     ctx->err = "hsbp_apply: u / y must be 16-byte aligned for the line-marching kernel";
     return HSBP_ERR_ARG;
   }
+  if (ne < 0) ne = b->nblocks - e0;
   int rc = sweep_prepare<P>(b);
   if (rc) return rc;
   const size_t fsm = 2 * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
-  k_edge_prep<P><<<(unsigned)(4 * b->nblocks), 256, fsm, ctx->stream>>>(
-      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0);
+  k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
+      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_edge_prep: ") + cudaGetErrorString(e1);
     return HSBP_ERR_CUDA;
   }
   if (ev_between) cudaEventRecord(ev_between, ctx->stream);
-  return sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces) : sweep_launch_nt<P, 2>(b, u, y, with_faces);
+  return sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces, e0, ne)
+                                         : sweep_launch_nt<P, 2>(b, u, y, with_faces, e0, ne);
 }
 
 }  // namespace hsbp
