@@ -89,6 +89,10 @@ def lib():
         "hsbp_trace_schur_apply": (cint, [vp, dp, dp]),
         "hsbp_trace_rhs": (cint, [vp, dp, dp, dp]),
         "hsbp_trace_solve": (cint, [vp, dp, dp, dp, dp, dbl, i64, vp]),
+        "hsbp_bp1_create": (cint, [vp, i64, i64, i64, dp, dp, vp, C.POINTER(vp)]),
+        "hsbp_bp1_destroy": (cint, [vp]),
+        "hsbp_bp1_rhs": (cint, [vp, dbl, dp, dp, vp]),
+        "hsbp_bp1_get_u": (cint, [vp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -111,6 +115,20 @@ class TraceStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_int64), ("converged", C.c_int64), ("rel_residual", C.c_double),
                 ("inner_iterations_sum", C.c_int64), ("inner_iterations_max", C.c_int64),
                 ("local_solves", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Bp1Params(C.Structure):
+    _fields_ = [("Vp", C.c_double), ("mu_shear", C.c_double), ("sigma_n", C.c_double), ("eta", C.c_double),
+                ("V0", C.c_double), ("tau_z0", C.c_double), ("Dc", C.c_double), ("f0", C.c_double), ("b", C.c_double),
+                ("ftol", C.c_double), ("atolx", C.c_double), ("rtolx", C.c_double), ("maxiter", C.c_int64)]
+
+
+class Bp1Stats(C.Structure):
+    _fields_ = [("rejected", C.c_int64), ("failure_bits", C.c_int64), ("failed_nodes", C.c_int64),
+                ("newton_iterations_max", C.c_int64), ("local_iterations", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

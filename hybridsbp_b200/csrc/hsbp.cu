@@ -513,3 +513,4 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 
 #include "api_chol.cuh"
 #include "api_solve.cuh"
+#include "api_bp1.cuh"

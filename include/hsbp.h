@@ -169,6 +169,34 @@ typedef struct {
 int  hsbp_trace_solve(hsbp_trace *trace, const double *g_dev, const double *gdelta_dev,
                       double *lambda_dev, double *u_dev, double tol, int64_t maxit, hsbp_trace_stats *stats);
 
+/* ---- SEAS BP1: ODE right-hand side with rate-and-state friction ---------------------------------
+ * reference: odefun (seas/BP1/odefun.jl:8-121) = boundary data (:36-42, locbcarray_mod! global_curved.jl:569-592)
+ * -> local solve (:43) -> shear traction on the fault (computetraction_mod, global_curved.jl:627-634) -> per fault
+ * node bracketed Newton on rateandstate (newtbndv, global_curved.jl:1031-1075, odefun.jl:69-96) -> d(psi)/dt (:101).
+ * The state vector is [psi; delta], the output [dpsi/dt; V], each 2 * (points of the fault face).
+ * Failures are not errors: stats.rejected != 0 is the reference's reject_step flag (BP1.jl:149-159).            */
+typedef struct hsbp_bp1 hsbp_bp1;
+typedef struct {
+  double Vp;                      /* plate rate; loading face carries t * Vp / 2            (odefun.jl:36)   */
+  double mu_shear;                /* shear modulus                                            (BP1.jl:24)      */
+  double sigma_n, eta, V0, tau_z0, Dc, f0, b;   /* rate-and-state parameters                 (BP1.jl:8-23,104) */
+  double ftol, atolx, rtolx;      /* newtbndv tolerances, 1e-9 in odefun.jl:83-85                              */
+  int64_t maxiter;                /* 500                                                      (global_curved.jl:1041) */
+} hsbp_bp1_params;
+typedef struct {
+  int64_t rejected;               /* any failure below, or a local solve that did not converge                  */
+  int64_t failure_bits;           /* 1: tau NaN (odefun.jl:73), 2: root find failed (:91), 4: dpsi not finite (:102) */
+  int64_t failed_nodes;
+  int64_t newton_iterations_max;
+  int64_t local_iterations;       /* PCG iterations of the local solve                                           */
+} hsbp_bp1_stats;
+/* block, fault_face, loading_face are 1-based; a and sJ live on the fault face (RSa of BP1.jl:96-102, lop.sJ) */
+int  hsbp_bp1_create(hsbp_blocks *blocks, int64_t block, int64_t fault_face, int64_t loading_face,
+                     const double *a, const double *sJ, const hsbp_bp1_params *params, hsbp_bp1 **bp1);
+int  hsbp_bp1_destroy(hsbp_bp1 *bp1);
+int  hsbp_bp1_rhs(hsbp_bp1 *bp1, double t, const double *psi_delta, double *dpsi_V, hsbp_bp1_stats *stats);
+int  hsbp_bp1_get_u(hsbp_bp1 *bp1, double *u);      /* displacement of the last rhs call, host array of VNp */
+
 #ifdef __cplusplus
 }
 #endif
