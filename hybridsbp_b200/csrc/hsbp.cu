@@ -209,7 +209,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
-  cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off);
+  cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off); cudaFree(b->d_chol_work);
   delete b;
   return HSBP_OK;
 }

@@ -62,7 +62,8 @@ struct hsbp_blocks {
   int *d_nactive = nullptr;
   double *d_chol = nullptr;                 // dense factors, block e at chol_off[e], leading dimension Np_e
   std::vector<int64_t> chol_off;
-  int64_t *d_chol_off = nullptr;
+  void *d_chol_off = nullptr;               // CholBlock descriptors
+  double *d_chol_work = nullptr;
   // pinned staging for hsbp_apply_host (lazy)
   double *d_stage_u = nullptr, *d_stage_y = nullptr;
   std::vector<cudaEvent_t> pipe_ev;          // per block group: H2D done, kernels done

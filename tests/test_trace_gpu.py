@@ -122,3 +122,48 @@ def test_trace_operators_and_solve(ctx, p, meshname):
     assert st["converged"] == 1, st
     assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
     assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_dense_cholesky_local_solver(ctx, p):
+    """K2a: the `factorization` plugin as a batched dense Cholesky (global_curved.jl:698, 734) on small,
+    differently shaped blocks; and the trace solve on top of it."""
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(400 + p)
+    N = 3 * p - 1 if p > 2 else 6
+    shapes = [(N, N), (N + 2, N + 5), (2 * N, N + 1), (N + 7, N)]
+    mets = [random_spd_metrics(p, a, b, rng, scale2=0.2) for a, b in shapes]
+    bcs = [(1, 1, 1, 1), (1, 2, 2, 2), (0, 1, 2, 7), (2, 0, 1, 1)]
+    lops = [orc.locoperator(p, a, b, m, bc) for (a, b), m, bc in zip(shapes, mets, bcs)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    blk.local_setup(hs.LOCAL_CHOLESKY)
+    g = rng.uniform(-1, 1, blk.VNp)
+    dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    st = blk.local_solve(dg, dx)
+    assert st["failed_blocks"] == 0 and st["iterations_max"] == 0
+    x = dx.get()
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        xr = orc.default_factorization(lop.Mt).solve(g[sl])
+        assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), e
+
+
+def test_trace_solve_with_cholesky_local_solver(ctx):
+    import hybridsbp_b200 as hs
+    p = 4
+    rng = np.random.default_rng(77)
+    c = build_case(hs, ctx, p, 3 * p - 1, flipped_four_block_mesh(), rng)
+    blk, tr, FbarT = c["blk"], c["tr"], c["FbarT"]
+    blk.local_setup(hs.LOCAL_CHOLESKY)
+    g = rng.uniform(-1, 1, blk.VNp); gd = rng.uniform(-1, 1, tr.lNp)
+    B = orc.assemblelambdamatrix(c["Fl"], c["vstarts"], c["EToF"], c["FToB"], c["M"].F, c["D"], FbarT)
+    bl = np.zeros(tr.lNp); uu = np.zeros(blk.VNp)
+    orc.LocalToGLobalRHS(bl, g, gd, uu, c["M"].F, FbarT, c["vstarts"])
+    lam_ref = np.linalg.solve(B.toarray(), bl)
+    rhs = g - FbarT.T @ lam_ref
+    u_ref = np.concatenate([c["M"].F[e].solve(rhs[blk.vol_slice(e)]) for e in range(blk.nblocks)])
+    dg, dgd, dlam, dsol = ctx.array(g), ctx.array(gd), ctx.empty(tr.lNp), ctx.empty(blk.VNp)
+    st = tr.solve(dg, dgd, dlam, dsol, tol=1e-13, maxit=2000)
+    assert st["converged"] == 1 and st["inner_iterations_sum"] == 0, st
+    assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
+    assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
