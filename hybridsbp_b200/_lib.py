@@ -84,6 +84,7 @@ def lib():
         "hsbp_trace_num_lambda": (i64, [vp]),
         "hsbp_trace_get_starts": (cint, [vp, i64p]),
         "hsbp_trace_get_D": (cint, [vp, dp]),
+        "hsbp_trace_set_D": (cint, [vp, dp]),
         "hsbp_trace_FbarT": (cint, [vp, dp, dp]),
         "hsbp_trace_Fbar_add": (cint, [vp, dp, dbl, dp]),
         "hsbp_trace_schur_apply": (cint, [vp, dp, dp]),

@@ -171,6 +171,11 @@ class Trace:
         self.ctx._check(lib().hsbp_trace_get_D(self.h, C.c_void_p(out.ctypes.data)))
         return out
 
+    def set_D(self, D):
+        a, pa = _f64(D)
+        assert a.size == self.lNp
+        self.ctx._check(lib().hsbp_trace_set_D(self.h, pa))
+
     def FbarT(self, u: DeviceArray, lam: DeviceArray):
         self.ctx._check(lib().hsbp_trace_FbarT(self.h, u.ptr, lam.ptr))
 

@@ -227,19 +227,26 @@ int hsbp_trace_create(hsbp_blocks *b, int64_t nfaces, const int64_t *FToB, const
     const int64_t bc = FToB[f];
     if (bc == HSBP_BC_DIRICHLET || bc == HSBP_BC_NEUMANN) { t->starts[f + 1] = t->starts[f]; continue; }   // :521-524
     if (!(bc == HSBP_BC_LOCKED || bc >= HSBP_BC_JUMP)) return fail("invalid bc");
+    // a side whose FToE entry is 0 lives on another device (partitioned mesh): the face still carries lambda here
     const int64_t em = FToE[2 * f] - 1, ep = FToE[2 * f + 1] - 1;
     const int km = (int)FToLF[2 * f] - 1, kp = (int)FToLF[2 * f + 1] - 1;
-    if (em < 0 || em >= b->nblocks || km < 0 || km > 3) return fail("hsbp_trace_create: bad FToE / FToLF");
-    if (ep < 0 || ep >= b->nblocks || kp < 0 || kp > 3) return fail("hsbp_trace_create: interface face with a single block");
-    const BlockDesc &dm = b->h_desc[em], &dp = b->h_desc[ep];
-    const int nl = (km <= 1 ? dm.Ns : dm.Nr) + 1;
-    if (nl != (kp <= 1 ? dp.Ns : dp.Nr) + 1) return fail("non-conforming interface (global_curved.jl:528)");
-    if (!EToO[km + 4 * em] || EToS[km + 4 * em] != 1) return fail("minus side must be oriented with the face (global_curved.jl:531)");
-    if (EToS[kp + 4 * ep] != 2) return fail("plus side must have EToS == 2 (global_curved.jl:539)");
+    if (em < 0 && ep < 0) return fail("hsbp_trace_create: interface face without a local block");
+    if (em >= b->nblocks || (em >= 0 && (km < 0 || km > 3))) return fail("hsbp_trace_create: bad FToE / FToLF");
+    if (ep >= b->nblocks || (ep >= 0 && (kp < 0 || kp > 3))) return fail("hsbp_trace_create: bad FToE / FToLF");
+    int nl = -1;
+    if (em >= 0) { const BlockDesc &dm = b->h_desc[em]; nl = (km <= 1 ? dm.Ns : dm.Nr) + 1; }
+    if (ep >= 0) {
+      const BlockDesc &dp = b->h_desc[ep];
+      const int nlp = (kp <= 1 ? dp.Ns : dp.Nr) + 1;
+      if (nl >= 0 && nl != nlp) return fail("non-conforming interface (global_curved.jl:528)");
+      nl = nlp;
+    }
+    if (em >= 0 && (!EToO[km + 4 * em] || EToS[km + 4 * em] != 1)) return fail("minus side must be oriented with the face (global_curved.jl:531)");
+    if (ep >= 0 && EToS[kp + 4 * ep] != 2) return fail("plus side must have EToS == 2 (global_curved.jl:539)");
     LamFace lf;
     lf.em = (int32_t)em; lf.km = km; lf.ep = (int32_t)ep; lf.kp = kp;
-    lf.flip = EToO[kp + 4 * ep] ? 0 : 1; lf.nl = nl;
-    lf.loff = t->starts[f] - 1; lf.fm = fstart(em, km); lf.fp = fstart(ep, kp);
+    lf.flip = (ep >= 0 && !EToO[kp + 4 * ep]) ? 1 : 0; lf.nl = nl;
+    lf.loff = t->starts[f] - 1; lf.fm = em >= 0 ? fstart(em, km) : 0; lf.fp = ep >= 0 ? fstart(ep, kp) : 0;
     t->h_faces.push_back(lf);
     t->starts[f + 1] = t->starts[f] + nl;
   }
@@ -294,6 +301,11 @@ int hsbp_trace_get_starts(const hsbp_trace *t, int64_t *s) {
 int hsbp_trace_get_D(hsbp_trace *t, double *D) {
   if (!t || !D) return HSBP_ERR_ARG;
   return hsbp_d2h(t->blocks->ctx, D, t->d_D, (size_t)t->lNp * sizeof(double));
+}
+
+int hsbp_trace_set_D(hsbp_trace *t, const double *D) {
+  if (!t || !D) return HSBP_ERR_ARG;
+  return hsbp_h2d(t->blocks->ctx, t->d_D, D, (size_t)t->lNp * sizeof(double));
 }
 
 int hsbp_trace_FbarT(hsbp_trace *t, const double *u_dev, double *lam_dev) {

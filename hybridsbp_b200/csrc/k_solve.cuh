@@ -159,7 +159,8 @@ k_pcg_update(const BlockDesc *__restrict__ desc, const double *__restrict__ dinv
 
 // ---- trace space <-> block faces -------------------------------------------------------------
 struct LamFace {       // one face that carries lambda
-  int32_t em, km, ep, kp;   // 0-based block and local face of the minus / plus side (ep = -1: remote / none)
+  int32_t em, km, ep, kp;   // 0-based block and local face of the minus / plus side; -1: that side lives on another
+                            // device (cut face of a partitioned mesh) -- its contribution is exchanged by the host layer
   int32_t flip, nl;
   int64_t loff;             // 0-based offset in lambda vectors
   int64_t fm, fp;           // offsets of the two block faces in block-face vectors
@@ -169,7 +170,8 @@ struct LamFace {       // one face that carries lambda
 __global__ void k_lam_gather(const LamFace *__restrict__ lf, const double *__restrict__ ft, double *__restrict__ lam) {
   const LamFace f = lf[blockIdx.x];
   for (int n = threadIdx.x; n < f.nl; n += blockDim.x) {
-    double v = ft[f.fm + n];
+    double v = 0.0;
+    if (f.em >= 0) v = ft[f.fm + n];
     if (f.ep >= 0) v += ft[f.fp + (f.flip ? f.nl - 1 - n : n)];
     lam[f.loff + n] = v;
   }
@@ -179,7 +181,7 @@ __global__ void k_lam_scatter(const LamFace *__restrict__ lf, const double *__re
   const LamFace f = lf[blockIdx.x];
   for (int n = threadIdx.x; n < f.nl; n += blockDim.x) {
     const double l = lam[f.loff + n];
-    v[f.fm + n] = l;
+    if (f.em >= 0) v[f.fm + n] = l;
     if (f.ep >= 0) v[f.fp + (f.flip ? f.nl - 1 - n : n)] = l;
   }
 }
@@ -188,12 +190,13 @@ template <int P>
 __global__ void k_lam_D(const LamFace *__restrict__ lf, const BlockDesc *__restrict__ desc,
                         const double *__restrict__ tau, double *__restrict__ D) {
   const LamFace f = lf[blockIdx.x];
-  const BlockDesc d = desc[f.em];
-  const FaceGeom fg = face_geom(d, f.km);
+  const BlockDesc d = desc[f.em >= 0 ? f.em : f.ep];
+  const FaceGeom fg = face_geom(d, f.em >= 0 ? f.km : f.kp);     // same points, same norm on both sides
   for (int n = threadIdx.x; n < f.nl; n += blockDim.x) {
-    double t = tau[f.fm + n];
+    double t = 0.0;
+    if (f.em >= 0) t = tau[f.fm + n];
     if (f.ep >= 0) t += tau[f.fp + (f.flip ? f.nl - 1 - n : n)];
-    D[f.loff + n] = fg.ht * hweight<P>(n, fg.Nt) * t;
+    D[f.loff + n] = fg.ht * hweight<P>(n, fg.Nt) * t;            // the norm weights are mirror symmetric
   }
 }
 

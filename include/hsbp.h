@@ -152,6 +152,12 @@ int  hsbp_trace_destroy(hsbp_trace *trace);
 int64_t hsbp_trace_num_lambda(const hsbp_trace *trace);                       /* lambda-Np */
 int  hsbp_trace_get_starts(const hsbp_trace *trace, int64_t *FTolambdastarts);   /* nfaces+1, 1-based */
 int  hsbp_trace_get_D(hsbp_trace *trace, double *D);                          /* host, lambda-Np */
+/* Partitioned meshes (blocks of one mesh spread over several devices, one hsbp_trace per device): pass the local
+ * connectivity with FToE = 0 for the side of an interface face that lives on another device.  Such a cut face
+ * still carries lambda on both devices; every operator below then returns this device's contribution and the host
+ * layer (hybridsbp_b200/parallel.py) exchanges and adds the partner's.  D is the sum of both sides' penalties:
+ * read the partial D, complete it with the partner's, write it back.                                           */
+int  hsbp_trace_set_D(hsbp_trace *trace, const double *D);
 int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u   */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
 int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam      */

@@ -1,0 +1,145 @@
+"""World-size-2 test (gloo, CPU) of the multi-GPU host logic in hybridsbp_b200/parallel.py: block partition,
+cut-face bookkeeping, point-to-point exchange of the partial Fbar^T contributions, masked inner products.
+The local operator is backed by the oracle's sparse matrices here (the GPU one wraps the C-ABI); the distributed
+solution must equal the single-process oracle solve of the whole mesh."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from hybridsbp_b200 import parallel
+from oracle import hybrid as orc
+from tests.util import random_spd_metrics
+
+
+def mesh_four_blocks_with_flips():
+    """2 x 2 blocks, two of them rotated so that interface faces meet with opposite orientation"""
+    v = lambda ix, iy: 1 + ix + 3 * iy
+    blocks = [(v(0, 0), v(1, 0), v(0, 1), v(1, 1)), (v(2, 1), v(2, 0), v(1, 1), v(1, 0)),
+              (v(1, 2), v(0, 2), v(1, 1), v(0, 1)), (v(1, 1), v(2, 1), v(1, 2), v(2, 2))]
+    EToV = np.array(blocks).T
+    fv = np.array([[0, 2], [1, 3], [0, 1], [2, 3]])
+    EToF = np.zeros((4, 4), dtype=np.int64)
+    known = {}
+    for e in range(4):
+        for lf in range(4):
+            a, b = EToV[fv[lf], e]
+            EToF[lf, e] = known.setdefault((min(a, b), max(a, b)), len(known) + 1)
+    count = np.bincount(EToF.reshape(-1) - 1, minlength=len(known))
+    FToB = np.where(count == 2, orc.BC_LOCKED_INTERFACE, orc.BC_DIRICHLET).astype(np.int64)
+    FToB[np.where(count == 1)[0][::2]] = orc.BC_NEUMANN
+    FToB[np.where(count == 2)[0][0]] = orc.BC_JUMP_INTERFACE
+    return EToV, EToF, FToB
+
+
+class OracleLocalOperator:
+    """rank-local pieces of the oracle's global sparse operators (restriction of Fbar^T to the local blocks'
+    columns = this rank's side of every face)"""
+
+    def __init__(self, lm, lops_all, FbarT_all, vstarts_all, starts_all, Dpart):
+        import torch
+        self.torch = torch
+        cols = np.concatenate([np.arange(vstarts_all[e] - 1, vstarts_all[e + 1] - 1) for e in lm.blocks])
+        rows = np.concatenate([np.arange(starts_all[f] - 1, starts_all[f + 1] - 1) for f in lm.faces])
+        self.FT = FbarT_all.tocsr()[rows][:, cols].tocsc()
+        self.M = spla.splu(sp.block_diag([lops_all[e].Mt for e in lm.blocks]).tocsc())
+        self.rows, self.cols = rows, cols
+        self.lNp = len(rows)
+        self._D = Dpart[rows].copy()
+
+    def get_D(self):
+        return self._D.copy()
+
+    def set_D(self, D):
+        self._D = np.asarray(D).copy()
+
+    def schur_apply(self, lam):
+        l = lam.numpy()
+        return self.torch.from_numpy(self._D * l - self.FT @ self.M.solve(self.FT.T @ l))
+
+    def rhs(self, g, gd):
+        return self.torch.from_numpy(gd.numpy() - self.FT @ self.M.solve(g.numpy()))
+
+    def back_substitute(self, g, lam):
+        return self.torch.from_numpy(self.M.solve(g.numpy() - self.FT.T @ lam.numpy()))
+
+
+def build_global(p=4, seed=3):
+    EToV, EToF, FToB = mesh_four_blocks_with_flips()
+    conn = orc.connectivityarrays(EToV, EToF)
+    FToE, FToLF, EToO, EToS = conn
+    assert (~EToO).any()
+    rng = np.random.default_rng(seed)
+    N = 3 * p - 1
+    ne = EToV.shape[1]
+    lops = [orc.locoperator(p, N, N, random_spd_metrics(p, N, N, rng, scale2=0.2), FToB[EToF[:, e] - 1]) for e in range(ne)]
+    Ns = [N] * ne
+    M, FbarT, D, vstarts, starts = orc.LocalGlobalOperators(lops, Ns, Ns, FToB, FToE, FToLF, EToO, EToS)
+    g = rng.uniform(-1, 1, vstarts[-1] - 1)
+    gd = rng.uniform(-1, 1, starts[-1] - 1)
+    return dict(EToF=EToF, FToB=FToB, conn=conn, lops=lops, M=M, FbarT=FbarT, D=D, vstarts=vstarts, starts=starts,
+                g=g, gd=gd, N=N, ne=ne)
+
+
+def partial_D(G, owner, rank):
+    """Hf * tau of the sides that live on `rank`, in the global lambda layout and minus-side orientation"""
+    FToE, FToLF, EToO, EToS = G["conn"]
+    Dp = np.zeros(G["starts"][-1] - 1)
+    for f in range(len(G["FToB"])):
+        if G["starts"][f + 1] == G["starts"][f]:
+            continue
+        sl = slice(G["starts"][f] - 1, G["starts"][f + 1] - 1)
+        for side in range(2):
+            e, k = FToE[side, f] - 1, FToLF[side, f] - 1
+            if owner[e] != rank:
+                continue
+            t = G["lops"][e].Hf[k].diagonal() * G["lops"][e].tau[k].diagonal()
+            Dp[sl] += t if EToO[k, e] else t[::-1]
+    return Dp
+
+
+def _worker(rank, world, port, owner, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        G = build_global()
+        FToE, FToLF, EToO, EToS = G["conn"]
+        lm = parallel.localize(rank, owner, G["EToF"], G["FToB"], FToE, FToLF, EToO, EToS)
+        op = OracleLocalOperator(lm, G["lops"], G["FbarT"], G["vstarts"], G["starts"], partial_D(G, owner, rank))
+        lstarts = np.concatenate([[1], 1 + np.cumsum([G["starts"][f + 1] - G["starts"][f] for f in lm.faces])])
+        dt = parallel.DistributedTrace(op, lstarts, lm, dist=dist)
+        lam, u, st = dt.solve(torch.from_numpy(G["g"][op.cols]), torch.from_numpy(G["gd"][op.rows]), tol=1e-13, maxit=500)
+        np.savez(out % rank, lam=lam.numpy(), u=u.numpy(), rows=op.rows, cols=op.cols, D=dt.D.numpy(),
+                 it=st["outer_iterations"], conv=st["converged"], ncut=sum(len(v) for v in lm.cut.values()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("owner", [[0, 0, 1, 1], [0, 1, 1, 0]])
+def test_two_rank_trace_solve_equals_single_process(tmp_path, owner):
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "rank%d.npz")
+    mp.spawn(_worker, args=(2, port, np.array(owner), out), nprocs=2, join=True)
+    G = build_global()
+    B = orc.assemblelambdamatrix(G["starts"], G["vstarts"], G["EToF"], G["FToB"], G["M"].F, G["D"], G["FbarT"])
+    bl = np.zeros(G["starts"][-1] - 1); uu = np.zeros(G["vstarts"][-1] - 1)
+    orc.LocalToGLobalRHS(bl, G["g"], G["gd"], uu, G["M"].F, G["FbarT"], G["vstarts"])
+    lam_ref = np.linalg.solve(B.toarray(), bl)
+    rhs = G["g"] - G["FbarT"].T @ lam_ref
+    u_ref = np.concatenate([G["M"].F[e].solve(rhs[G["vstarts"][e] - 1:G["vstarts"][e + 1] - 1]) for e in range(G["ne"])])
+    cuts = 0
+    for rank in range(2):
+        r = np.load(out % rank)
+        assert r["conv"] == 1
+        assert np.allclose(r["D"], G["D"][r["rows"]], rtol=1e-13)             # completed with the partner's half
+        assert np.linalg.norm(r["lam"] - lam_ref[r["rows"]]) <= 1e-10 * np.linalg.norm(lam_ref)
+        assert np.linalg.norm(r["u"] - u_ref[r["cols"]]) <= 1e-10 * np.linalg.norm(u_ref)
+        cuts += int(r["ncut"])
+    assert cuts > 0 and cuts % 2 == 0          # both ranks see the same cut faces
