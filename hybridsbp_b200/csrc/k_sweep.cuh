@@ -58,10 +58,43 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same with shared-window addresses that were converted once
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one lane of a fully active warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-constexpr int SW_NST = 3;              // ring stages: one being consumed, two in flight
+#ifndef SW_NST_OVERRIDE
+#define SW_NST_OVERRIDE 3
+#endif
+constexpr int SW_NST = SW_NST_OVERRIDE;   // ring stages: one being consumed, the others in flight
 constexpr int SW_MAX_THREADS = 256;
 
 struct SweepParams {
@@ -487,8 +520,13 @@ k_sweep(const SweepParams prm) {
   const int nout0 = o0 + H - jstart;                      // first step whose line j-H belongs to the chunk
   const int nrefill = nlines - NST;                       // steps after which no line is left to fetch
   double *yout = nullptr;                                 // output line of the next steady-state step
+  int64_t gofs = 0, tofs = 0;                             // offsets of marching line j (volume fields, r-end table)
+  const int64_t tstride = up ? CLR : -CLR;
+  const uint32_t full_s = smem_u32(full), ring_s = smem_u32(ring), clring_s = smem_u32(clring);
+  const int nwarps = nthreads >> 5;
+  int rw = 0;                                             // warp that issues the next refill
   auto fast_step = [&]() {
-    mbar_wait(&full[st], parity);
+    mbar_wait_s(full_s + 8u * st, parity);
     const double *sb = ring + (size_t)st * 4 * LW;
     const bool outp = n >= nout0;                         // line j-H is an output line of this chunk
     double *wb = wbuf + (size_t)(n & 1) * LW;
@@ -609,7 +647,19 @@ k_sweep(const SweepParams prm) {
       }
     }
     __syncthreads();
-    if (tid == 0 && n < nrefill) { fence_proxy_async(); issue(n + NST); }
+    if ((tid >> 5) == rw && n < nrefill) {                // stage st is free again: line j + NST goes into it
+                                                          // (the warps take turns, so no warp is the slow one)
+      if (elect_one()) {
+        const uint32_t bar = full_s + 8u * st, dst = ring_s + (uint32_t)(st * 4 * LW + PAD) * 8u;
+        const int64_t g = gofs + NST * lstride;
+        mbar_expect_tx_s(bar, 4u * line_bytes + (uint32_t)(CLR * 8));
+        bulk_g2s_s(dst, prm.u + g, line_bytes, bar);
+        bulk_g2s_s(dst + (uint32_t)LW * 8u, prm.crr + g, line_bytes, bar);
+        bulk_g2s_s(dst + (uint32_t)LW * 16u, prm.css + g, line_bytes, bar);
+        bulk_g2s_s(dst + (uint32_t)LW * 24u, prm.crs + g, line_bytes, bar);
+        bulk_g2s_s(clring_s + (uint32_t)(st * CLR) * 8u, prm.rtab + tofs + NST * tstride, (uint32_t)(CLR * 8), bar);
+      }
+    }
     if (own && outp) {
       // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
       double Wv[NV], val[R];
@@ -654,6 +704,8 @@ k_sweep(const SweepParams prm) {
         *reinterpret_cast<double2 *>(yout + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
     }
     yout += lstride;
+    gofs += lstride; tofs += tstride;
+    if (++rw == nwarps) rw = 0;
     ++j; ++n;
     if (++st == NST) { st = 0; parity ^= 1u; }
     if (++ph == W) ph = 0;
@@ -663,6 +715,8 @@ k_sweep(const SweepParams prm) {
   const int jfast = prologue ? MCX + H : jstart;           // first step without s-end closure / face logic
   while (j < jfast && j <= jend) step(GenericPH{}, std::false_type{});
   yout = gy + (int64_t)(j - H) * lstride;
+  gofs = base + (int64_t)j * lstride;                      // marching line j in the volume fields
+  tofs = (e * Nsp + (up ? (int64_t)j : (int64_t)Ns - j)) * CLR;   // ... and in the r-end table
 #pragma unroll 1
   while (j <= jend) fast_step();
 }
