@@ -204,7 +204,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
-  cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab);
+  cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab); cudaFree(b->d_rim);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);
@@ -229,6 +229,7 @@ static int set_metrics(hsbp_blocks *b, const double *crr, const double *css, con
   HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   b->have_metrics = true;
   b->sweep_scaled_valid = false;
+  b->rim_valid = false;
   return HSBP_OK;
 }
 int hsbp_blocks_set_metrics(hsbp_blocks *b, const double *crr, const double *css, const double *crs) {
@@ -279,6 +280,7 @@ int hsbp_blocks_compute_tau(hsbp_blocks *b, double tauscale) {
   if (rc != HSBP_OK) return rc;
   if (bad) HSBP_FAIL(ctx, HSBP_ERR_ARG, "coefficient tensor is not positive definite (psi_min <= 0)");
   b->have_tau = true;
+  b->rim_valid = false;
   return HSBP_OK;
 }
 
@@ -287,7 +289,7 @@ int hsbp_blocks_set_tau(hsbp_blocks *b, const double *tau) {
   hsbp_ctx *ctx = b->ctx;
   if (!tau) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_tau: null pointer");
   int rc = hsbp_h2d(ctx, b->d_tau, tau, (size_t)b->FNp * sizeof(double));
-  if (rc == HSBP_OK) b->have_tau = true;
+  if (rc == HSBP_OK) { b->have_tau = true; b->rim_valid = false; }
   return rc;
 }
 int hsbp_blocks_get_tau(hsbp_blocks *b, double *tau) {

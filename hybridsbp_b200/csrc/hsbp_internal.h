@@ -38,6 +38,8 @@ struct hsbp_blocks {
   std::vector<BlockDesc> h_desc;
   BlockDesc *d_desc = nullptr;
   double *d_crr = nullptr, *d_css = nullptr, *d_crs = nullptr;
+  double *d_rim = nullptr;                         // static r-face data for k_edge_prep (k_rim_build)
+  bool rim_valid = false;
   double *d_rtab = nullptr;                        // r-end table of the line-marching kernel (k_edge_prep)
   double *d_crr_s = nullptr, *d_css_s = nullptr;   // norm-weighted copies for the line-marching kernel (lazy)
   bool sweep_scaled_valid = false;

@@ -736,7 +736,8 @@ template <int P>
 __global__ void __launch_bounds__(256)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
-            double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0) {
+            double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
+            const double *__restrict__ rim) {
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -762,16 +763,21 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
       double cxf = 0.0, tauf = 0.0;
       const int64_t fi = d.foff + fg.fstart + n;
       if (act) {
-        if (k < 2) {                           // r-faces: the NK points are contiguous in memory (16-byte aligned)
+        if (k < 2) {                           // r-faces: u is strided in memory (NK contiguous points per line, 16-byte
+                                               // aligned); the static data comes from the rim table, coalesced in n
           const int64_t g0 = d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : Nrp - NK);
-          const double2 *pb = reinterpret_cast<const double2 *>(crr + g0), *pu = reinterpret_cast<const double2 *>(u + g0);
+          const double2 *pu = reinterpret_cast<const double2 *>(u + g0);
+          const double *pr = rim + (((int64_t)e * 2 + k) * (NK + 2)) * Nsp + n;
 #pragma unroll
           for (int m = 0; m < NK / 2; ++m) {
-            const double2 vb = pb[m], vu = pu[m];
-            if (k == 0) { b[2 * m] = vb.x; b[2 * m + 1] = vb.y; uu[2 * m] = vu.x; uu[2 * m + 1] = vu.y; }
-            else { b[NK - 1 - 2 * m] = vb.x; b[NK - 2 - 2 * m] = vb.y; uu[NK - 1 - 2 * m] = vu.x; uu[NK - 2 - 2 * m] = vu.y; }
+            const double2 vu = pu[m];
+            if (k == 0) { uu[2 * m] = vu.x; uu[2 * m + 1] = vu.y; }
+            else { uu[NK - 1 - 2 * m] = vu.x; uu[NK - 2 - 2 * m] = vu.y; }
           }
-          cxf = crs[d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : d.Nr)];
+#pragma unroll
+          for (int m = 0; m < NK; ++m) b[m] = pr[(int64_t)m * Nsp];       // already scaled by Hs[n] / hr
+          cxf = pr[(int64_t)NK * Nsp];
+          tauf = pr[(int64_t)(NK + 1) * Nsp];                              // tau * Hf
         } else {                               // s-faces: lines 0 .. NB-1 (or Ns .. Ns-NB+1), coalesced along the face
           const int64_t g0 = d.voff + n + (k == 2 ? 0 : (int64_t)Nrp * d.Ns);
           const int64_t ls = k == 2 ? Nrp : -Nrp;
@@ -780,7 +786,7 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
           b[0] = css[g0];
           cxf = crs[g0];
         }
-        if (with_faces) tauf = tau[fi];
+        if (with_faces && k >= 2) tauf = tau[fi] * (fg.ht * hweight<P>(n, fg.Nt));
       }
       double cn = 0.0, beta = 0.0, alpha = 0.0;
       const double Hf = fg.ht * hweight<P>(act ? n : 0, fg.Nt);
@@ -796,9 +802,9 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
 #pragma unroll
             for (int m = 1; m < S::NB; ++m) bsu += S::bs()[m] * uu[m];
             const double qt = q_apply<P>(n, fg.Nt, [&](int l) { return sa[l]; });
-            cn = (Hf / fg.hn) * b[0];
+            cn = k < 2 ? b[0] : (Hf / fg.hn) * b[0];
             const double g = cn * bsu + fg.sgn * cxf * qt;
-            const double tH = tauf * Hf;
+            const double tH = tauf;
             if (d.bc[k] == HSBP_BC_NEUMANN) { alpha = -g / tH; beta = 0.0; }
             else                            { alpha = -uu[0];  beta = tH * uu[0] - g; }
             sx[n] = cxf * alpha;
@@ -819,9 +825,6 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
       if (k < 2 && act) {
         // r-end table row of line n: closure rows of Hs[n]/hr M(crr) u with the face terms, closure rows of Qr u
         double rows[C::MCX], qq[T::BM];
-        const double sc = Hf / fg.hn;          // Hs[n] / hr  (global_curved.jl:261-268)
-#pragma unroll
-        for (int m = 0; m < NK; ++m) b[m] *= sc;
 #pragma unroll
         for (int m = 0; m < C::MCX; ++m) rows[m] = 0.0;
         d2_closure_rows<P>(b, uu, rows);
@@ -854,7 +857,9 @@ template <int P> static size_t sweep_smem(int Nrp, int nthreads) {
 static int sweep_points_per_thread(const hsbp_blocks *b) {
   const int Nrp = b->max_Nr + 1;
   if (b->sweep_r_override == 2 || (b->sweep_r_override == 4 && Nrp % 4 == 0)) return b->sweep_r_override;
-  return 2;      // measured on B200 at 256-point lines: R = 2 (128 registers, 16 warps/SM) 0.68 ms, R = 4 0.69 ms
+  // measured on B200 at 256-point lines: R = 4 (252 registers, 8 warps/SM) 0.675 ms, R = 2 (128 registers,
+  // 16 warps/SM, on the edge of spilling) 0.68 - 0.71 ms
+  return (Nrp % 4 == 0 && Nrp >= 128) ? 4 : 2;
 }
 
 template <int P> static bool sweep_eligible(const hsbp_blocks *b) {
@@ -888,14 +893,40 @@ k_sweep_scale(const double *__restrict__ crr, const double *__restrict__ css, do
   }
 }
 
+// static data of the r-faces for k_edge_prep, laid out [block][end][entry][line] so that threads (= lines) read it
+// coalesced: entries 0..NK-1 = Hs[n]/hr * crr at the NK points behind the face point, NK = crs at the face point,
+// NK+1 = tau * Hf
+template <int P>
+__global__ void __launch_bounds__(256)
+k_rim_build(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ crs,
+            const double *__restrict__ tau, double *__restrict__ rim) {
+  using S = Sbp<P>;
+  using T = SweepTab<P>;
+  constexpr int NK = T::NK >= S::NB ? T::NK : ((S::NB + 1) & ~1);
+  const int e = blockIdx.x >> 1, k = blockIdx.x & 1;
+  const BlockDesc d = desc[e];
+  const FaceGeom fg = face_geom(d, k);
+  const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
+  for (int n = threadIdx.x; n < Nsp; n += blockDim.x) {
+    const double Hf = fg.ht * hweight<P>(n, fg.Nt);
+    const int64_t g0 = d.voff + (int64_t)Nrp * n;
+    double *pr = rim + (((int64_t)e * 2 + k) * (NK + 2)) * Nsp + n;
+    for (int m = 0; m < NK; ++m) pr[(int64_t)m * Nsp] = (Hf / fg.hn) * crr[g0 + (k == 0 ? m : d.Nr - m)];
+    pr[(int64_t)NK * Nsp] = crs[g0 + (k == 0 ? 0 : d.Nr)];
+    pr[(int64_t)(NK + 1) * Nsp] = tau[d.foff + fg.fstart + n] * Hf;
+  }
+}
+
 template <int P> static int sweep_prepare(hsbp_blocks *b) {
   hsbp_ctx *ctx = b->ctx;
-  if (b->sweep_scaled_valid) return HSBP_OK;
+  if (b->sweep_scaled_valid && b->rim_valid) return HSBP_OK;
   const size_t vb = (size_t)b->VNp * sizeof(double);
+  constexpr int NKX = SweepTab<P>::NK >= Sbp<P>::NB ? SweepTab<P>::NK : ((Sbp<P>::NB + 1) & ~1);
   if (!b->d_crr_s) {
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crr_s, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_css_s, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * 2 * SweepCfg<P>::CLW * sizeof(double)));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rim, (size_t)b->nblocks * 2 * (NKX + 2) * (b->max_Ns + 1) * sizeof(double)));
   }
   k_sweep_scale<P><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->d_crr, b->d_css, b->d_crr_s, b->d_css_s, b->max_Nr,
                                                               b->max_Ns, b->VNp);
@@ -904,7 +935,13 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
     ctx->err = std::string("k_sweep_scale: ") + cudaGetErrorString(e1);
     return HSBP_ERR_CUDA;
   }
+  k_rim_build<P><<<(unsigned)(2 * b->nblocks), 256, 0, ctx->stream>>>(b->d_desc, b->d_crr, b->d_crs, b->d_tau, b->d_rim);
+  if ((e1 = cudaGetLastError()) != cudaSuccess) {
+    ctx->err = std::string("k_rim_build: ") + cudaGetErrorString(e1);
+    return HSBP_ERR_CUDA;
+  }
   b->sweep_scaled_valid = true;
+  b->rim_valid = true;
   return HSBP_OK;
 }
 
@@ -983,7 +1020,7 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
   if (rc) return rc;
   const size_t fsm = 2 * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
   k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
-      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0);
+      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_edge_prep: ") + cudaGetErrorString(e1);
