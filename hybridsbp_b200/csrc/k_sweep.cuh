@@ -859,6 +859,7 @@ static int sweep_points_per_thread(const hsbp_blocks *b) {
   if (b->sweep_r_override == 2 || (b->sweep_r_override == 4 && Nrp % 4 == 0)) return b->sweep_r_override;
   // measured on B200 at 256-point lines: R = 4 (252 registers, 8 warps/SM) 0.675 ms, R = 2 (128 registers,
   // 16 warps/SM, on the edge of spilling) 0.68 - 0.71 ms
+  if (b->p == 6) return 2;                                    // R = 4 spills heavily with the 7-line windows of p = 6
   return (Nrp % 4 == 0 && Nrp >= 128) ? 4 : 2;
 }
 
@@ -948,10 +949,12 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
 template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
                                                         int64_t e0, int64_t ne) {
   hsbp_ctx *ctx = b->ctx;
-#ifndef SW_REGS2
-#define SW_REGS2 128
+#ifndef SW_REGS2_P6
+#define SW_REGS2_P6 168
 #endif
-  constexpr int MINB = (R == 2 ? 65536 / SW_REGS2 : 256) / NT;   // SW_REGS2 / 255 registers per thread
+  // register budget per thread: R = 4 takes all 255; R = 2 fits 128 (p = 2, 4) -- p = 6 has 7-line windows and needs more
+  constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
+  constexpr int MINB = (R == 2 ? 65536 / REGS2 : 256) / NT;
   auto kern = k_sweep<P, R, NT, MINB>;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
