@@ -108,36 +108,39 @@ class ExactSolution:
                 (1 / r ** 2) * (-(r - 1) ** 2 * np.cos(th) - (r - 1) * np.sin(th)))
 
 
-def geometry(mesh, p, N):
+def geometry(mesh, p, N, maps=None):
     """metrics of every block at level size N (:285)."""
     verts, EToV, EToF, FToB, _ = mesh
+    maps = maps or block_maps
     out = []
     for e in range(EToV.shape[1]):
-        xt, yt = block_maps(verts, EToV, EToF, FToB, e)
+        xt, yt = maps(verts, EToV, EToF, FToB, e)
         out.append(host.create_metrics(p, N, N, xt, yt))
     return out
 
 
-def jump_data(mesh, conn, mets, FTods, N):
+def jump_data(mesh, conn, mets, FTods, N, exact=None):
     """delta on the jump faces: exact value on the plus side minus the minus side (:321-330)."""
     verts, EToV, EToF, FToB, dom = mesh
     FToE, FToLF, EToO, EToS = conn
+    exact = exact or ExactSolution
     delta = np.zeros(FTods[-1] - 1)
     for f in range(len(FToB)):
-        if FToB[f] == host.BC_JUMP_INTERFACE:
+        if FToB[f] >= host.BC_JUMP_INTERFACE:
             e1, e2 = FToE[:, f] - 1
             lf1 = FToLF[0, f] - 1
             xf, yf = mets[e1].facecoord[0][lf1], mets[e1].facecoord[1][lf1]
-            delta[FTods[f] - 1:FTods[f + 1] - 1] = ExactSolution.v(xf, yf, dom[e2]) - ExactSolution.v(xf, yf, dom[e1])
+            delta[FTods[f] - 1:FTods[f + 1] - 1] = exact.v(xf, yf, dom[e2]) - exact.v(xf, yf, dom[e1])
     return delta
 
 
-def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p):
+def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p, exact=None):
     """Boundary / jump data of every block face and g_delta, exactly what locbcarray! feeds to F_k (:335-363,
     global_curved.jl:596-623).  taus[e][lf]: penalty vectors, returns (v[e][lf] or None, g_delta)."""
     verts, EToV, EToF, FToB, dom = mesh
     FToE, FToLF, EToO, EToS = conn
     ne = EToV.shape[1]
+    exact = exact or ExactSolution
     gd = np.zeros(FTols[-1] - 1)
     v = [[None] * 4 for _ in range(ne)]
     for e in range(ne):
@@ -147,9 +150,9 @@ def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p):
             bc = FToB[f]
             xf, yf = m.facecoord[0][lf], m.facecoord[1][lf]
             if bc == host.BC_DIRICHLET:
-                v[e][lf] = ExactSolution.v(xf, yf, dom[e])
+                v[e][lf] = exact.v(xf, yf, dom[e])
             elif bc == host.BC_NEUMANN:
-                gN = m.nx[lf] * ExactSolution.vx(xf, yf, dom[e]) + m.ny[lf] * ExactSolution.vy(xf, yf, dom[e])
+                gN = m.nx[lf] * exact.vx(xf, yf, dom[e]) + m.ny[lf] * exact.vy(xf, yf, dom[e])
                 v[e][lf] = m.sJ[lf] * gN / taus[e][lf]
             elif bc >= host.BC_JUMP_INTERFACE:
                 d = delta[FTods[f] - 1:FTods[f + 1] - 1]
@@ -170,13 +173,15 @@ def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p):
     return v, gd
 
 
-def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000):
+def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=None, exact=None, jump_code=None):
     """One refinement level on the GPU.  Returns dict(eps, tau_eps, lam, u, stats, ...)."""
     verts, EToV, EToF, FToB, dom = mesh
     ne, nf = EToV.shape[1], len(FToB)
     conn = host.connectivityarrays(EToV, EToF)
     FToE, FToLF, EToO, EToS = conn
-    mets = geometry(mesh, p, N)
+    exact = exact or ExactSolution
+    jump_code = host.BC_JUMP_INTERFACE if jump_code is None else jump_code
+    mets = geometry(mesh, p, N, maps)
     fl = lambda a: np.asarray(a).reshape(-1, order="F")
     blk = Blocks(ctx, p, [N] * ne, [N] * ne)
     blk.set_metrics(np.concatenate([fl(m.crr) for m in mets]), np.concatenate([fl(m.css) for m in mets]),
@@ -189,11 +194,12 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000):
     blk.local_setup(local_mode, tol=1e-14, maxit=200000)
     tr = Trace(blk, FToB, FToE, FToLF, EToO, EToS)
     FTols = tr.FTolambdastarts
-    FTods = host.bcstarts(FToB, FToE, FToLF, host.BC_JUMP_INTERFACE, [N] * ne, [N] * ne)
+    jump_codes = tuple(sorted(set(int(b) for b in FToB if b >= host.BC_JUMP_INTERFACE))) or (jump_code,)
+    FTods = host.bcstarts(FToB, FToE, FToLF, jump_codes, [N] * ne, [N] * ne)
     tau = blk.get_tau()
     taus = [[tau[blk.face_slice(e, lf + 1)] for lf in range(4)] for e in range(ne)]
-    delta = jump_data(mesh, conn, mets, FTods, N)
-    v, gd = face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p)
+    delta = jump_data(mesh, conn, mets, FTods, N, exact)
+    v, gd = face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p, exact)
     Hw = host.norm_weights(p, N)
     JH = [(m.J * Hw[:, None] * Hw[None, :]).reshape(-1, order="F") for m in mets]      # global_curved.jl:491
     # g = - sum_k F_k v_k  (device)  +  JH * source  (host, elementwise)
@@ -205,7 +211,7 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000):
     g = np.zeros(blk.VNp)
     for e in range(ne):
         x, y = mets[e].coord
-        g[blk.vol_slice(e)] = JH[e] * (-ExactSolution.laplace(fl(x), fl(y), dom[e]))      # :364-365
+        g[blk.vol_slice(e)] = JH[e] * (-exact.laplace(fl(x), fl(y), dom[e]))      # :364-365
     dg = ctx.array(g)
     dv = ctx.array(vface)
     blk.face_F_add(dv, -1.0, dg)
@@ -216,18 +222,18 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000):
     eps2 = 0.0
     for e in range(ne):
         x, y = mets[e].coord
-        d = u[blk.vol_slice(e)] - ExactSolution.v(fl(x), fl(y), dom[e])
+        d = u[blk.vol_slice(e)] - exact.v(fl(x), fl(y), dom[e])
         eps2 += d @ (JH[e] * d)
     dtr = ctx.empty(blk.FNp)
     blk.face_traction(du, dtr)
     trv = dtr.get()
     teps2 = 0.0
     for f in range(nf):
-        if FToB[f] == host.BC_JUMP_INTERFACE:
+        if FToB[f] >= host.BC_JUMP_INTERFACE:
             e1, lf1 = FToE[0, f] - 1, FToLF[0, f] - 1
             m = mets[e1]
             xf, yf = m.facecoord[0][lf1], m.facecoord[1][lf1]
-            tex = m.nx[lf1] * ExactSolution.vx(xf, yf, dom[e1]) + m.ny[lf1] * ExactSolution.vy(xf, yf, dom[e1])
+            tex = m.nx[lf1] * exact.vx(xf, yf, dom[e1]) + m.ny[lf1] * exact.vy(xf, yf, dom[e1])
             lamf = lam[FTols[f] - 1:FTols[f + 1] - 1]
             df = delta[FTods[f] - 1:FTods[f + 1] - 1]
             t = (trv[blk.face_slice(e1, lf1 + 1)] + taus[e1][lf1] * (lamf - df / 2)) / m.sJ[lf1]     # computetraction
