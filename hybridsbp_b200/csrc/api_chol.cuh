@@ -4,8 +4,9 @@
 // (global_curved.jl:698, 734; plugin at square_circle.jl:299, BP1.jl:78) where a dense factor fits:
 //   setup   dense M-tilde_e is formed on the device by applying the matrix-free operator to unit vectors
 //           (one apply per column index, all blocks at once), then factorised in place, one CTA per block,
-//           right-looking in panels of 32: diagonal block on CUDA cores in shared memory, panel TRSM one row
-//           per thread, trailing update C -= L21 L21^T on the fp64 tensor pipe (mma.sync m8n8k4 f64, DMMA)
+//           right-looking in panels of 32: per panel one kernel for the diagonal block (CUDA cores, shared memory)
+//           and the panel TRSM (one row per thread), and one kernel with a CTA per 32 x 32 tile of the trailing matrix
+//           of every block for C -= L21 L21^T on the fp64 tensor pipe (mma.sync m8n8k4 f64, DMMA)
 //           -- the only place tensor cores are used, as BASELINE.json's north star asks.
 //   solve   L y = g, L^T x = y, one CTA per block, panels of 32 (column reads are coalesced).
 // Storage: block e at chol_off[e], column-major, leading dimension ld_e = Np_e rounded up to 32 (the pad is an
@@ -48,92 +49,91 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// in-place lower Cholesky of every block; flag[e] = 1 if a pivot was not positive
+// One panel step of the in-place lower Cholesky of every block (right-looking, panel width 32):
+//   k_chol_panel   diagonal block (CUDA cores, shared memory) and the panel below it (X L^T = A21, one row per thread)
+//   k_chol_update  trailing update C[ti][tj] -= L21[ti] L21[tj]^T, one CTA per 32 x 32 tile of the lower triangle of
+//                  every block, on the fp64 tensor pipe (mma.sync m8n8k4 f64)
+// flag[e] = 1 if a pivot was not positive.
 __global__ void __launch_bounds__(CH_THREADS)
-k_chol_factor(const CholBlock *__restrict__ cb, double *__restrict__ Aall, int *__restrict__ flag) {
+k_chol_panel(const CholBlock *__restrict__ cb, double *__restrict__ Aall, int k0, int *__restrict__ flag) {
   __shared__ double D[CH_NB][CH_NB + 1];            // diagonal block / its factor
-  __shared__ double Ti[CH_NB][CH_NB + 1];           // L21 tiles of the trailing update, [row][k]
-  __shared__ double Tj[CH_NB][CH_NB + 1];
   const CholBlock b = cb[blockIdx.x];
+  if (k0 >= b.ld) return;
   double *A = Aall + b.off;
   const int ld = b.ld, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   bool bad = false;
-  for (int k0 = 0; k0 < ld; k0 += CH_NB) {
-    // ---- diagonal block: load, factor (warp 0), store ------------------------------------------------
-    for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
-      const int i = idx % CH_NB, j = idx / CH_NB;
-      D[i][j] = A[(int64_t)(k0 + j) * ld + k0 + i];
-    }
-    __syncthreads();
-    if (wid == 0) {
-      for (int j = 0; j < CH_NB; ++j) {
-        const double djj = D[j][j];
-        if (!(djj > 0.0)) bad = true;
-        const double l = sqrt(djj);
-        __syncwarp();
-        if (lane >= j) D[lane][j] = (lane == j) ? l : D[lane][j] / l;
-        __syncwarp();
-        for (int c = j + 1; c < CH_NB; ++c)
-          if (lane >= c) D[lane][c] -= D[lane][j] * D[c][j];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
-      const int i = idx % CH_NB, j = idx / CH_NB;
-      A[(int64_t)(k0 + j) * ld + k0 + i] = (i >= j) ? D[i][j] : 0.0;
-    }
-    // ---- panel: X L^T = A21, one row per thread -------------------------------------------------------
-    const int m0 = k0 + CH_NB;
-    for (int i = m0 + tid; i < ld; i += CH_THREADS) {
-      double x[CH_NB];
-#pragma unroll
-      for (int j = 0; j < CH_NB; ++j) x[j] = A[(int64_t)(k0 + j) * ld + i];
-#pragma unroll
-      for (int j = 0; j < CH_NB; ++j) {
-        double s = x[j];
-#pragma unroll
-        for (int c = 0; c < j; ++c) s -= x[c] * D[j][c];
-        x[j] = s / D[j][j];
-      }
-#pragma unroll
-      for (int j = 0; j < CH_NB; ++j) A[(int64_t)(k0 + j) * ld + i] = x[j];
-    }
-    __syncthreads();
-    // ---- trailing update (lower triangle): C[ti][tj] -= L21[ti] L21[tj]^T on the fp64 tensor pipe ------
-    const int nt = (ld - m0) / CH_NB;
-    for (int ti = 0; ti < nt; ++ti) {
-      for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
-        const int i = idx % CH_NB, k = idx / CH_NB;
-        Ti[i][k] = A[(int64_t)(k0 + k) * ld + m0 + ti * CH_NB + i];
-      }
-      for (int tj = 0; tj <= ti; ++tj) {
-        __syncthreads();
-        for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
-          const int i = idx % CH_NB, k = idx / CH_NB;
-          Tj[i][k] = A[(int64_t)(k0 + k) * ld + m0 + tj * CH_NB + i];
-        }
-        __syncthreads();
-        // 16 sub-tiles of 8 x 8, two per warp
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int st = wid * 2 + s, si = (st >> 2) * 8, sj = (st & 3) * 8;
-          double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-          for (int k = 0; k < CH_NB; k += 4)
-            dmma_m8n8k4(c0, c1, Ti[si + (lane >> 2)][k + (lane & 3)], Tj[sj + (lane >> 2)][k + (lane & 3)]);
-          const int gi = m0 + ti * CH_NB + si + (lane >> 2);
-          const int gj = m0 + tj * CH_NB + sj + (lane & 3) * 2;
-          double *c = A + (int64_t)gj * ld + gi;
-          c[0] -= c0;
-          c[ld] -= c1;
-        }
-      }
-      __syncthreads();
-    }
-    __syncthreads();
+  for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
+    const int i = idx % CH_NB, j = idx / CH_NB;
+    D[i][j] = A[(int64_t)(k0 + j) * ld + k0 + i];
   }
-  if (bad) flag[blockIdx.x] = 1;
+  __syncthreads();
+  if (wid == 0) {
+    for (int j = 0; j < CH_NB; ++j) {
+      const double djj = D[j][j];
+      if (!(djj > 0.0)) bad = true;
+      const double l = sqrt(djj);
+      __syncwarp();
+      if (lane >= j) D[lane][j] = (lane == j) ? l : D[lane][j] / l;
+      __syncwarp();
+      for (int c = j + 1; c < CH_NB; ++c)
+        if (lane >= c) D[lane][c] -= D[lane][j] * D[c][j];
+      __syncwarp();
+    }
+    if (bad) flag[blockIdx.x] = 1;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
+    const int i = idx % CH_NB, j = idx / CH_NB;
+    A[(int64_t)(k0 + j) * ld + k0 + i] = (i >= j) ? D[i][j] : 0.0;
+  }
+  for (int i = k0 + CH_NB + tid; i < ld; i += CH_THREADS) {
+    double x[CH_NB];
+#pragma unroll
+    for (int j = 0; j < CH_NB; ++j) x[j] = A[(int64_t)(k0 + j) * ld + i];
+#pragma unroll
+    for (int j = 0; j < CH_NB; ++j) {
+      double s = x[j];
+#pragma unroll
+      for (int c = 0; c < j; ++c) s -= x[c] * D[j][c];
+      x[j] = s / D[j][j];
+    }
+#pragma unroll
+    for (int j = 0; j < CH_NB; ++j) A[(int64_t)(k0 + j) * ld + i] = x[j];
+  }
+}
+
+// grid = (tiles, tiles, blocks); tile (ti, tj), tj <= ti, of the trailing matrix behind panel k0
+__global__ void __launch_bounds__(CH_THREADS)
+k_chol_update(const CholBlock *__restrict__ cb, double *__restrict__ Aall, int k0) {
+  __shared__ double Ti[CH_NB][CH_NB + 1];           // L21 tiles, [row][k]
+  __shared__ double Tj[CH_NB][CH_NB + 1];
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  if (tj > ti) return;
+  const CholBlock b = cb[blockIdx.z];
+  const int ld = b.ld, m0 = k0 + CH_NB;
+  if (m0 + (ti + 1) * CH_NB > ld) return;
+  double *A = Aall + b.off;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
+    const int i = idx % CH_NB, k = idx / CH_NB;
+    Ti[i][k] = A[(int64_t)(k0 + k) * ld + m0 + ti * CH_NB + i];
+    Tj[i][k] = A[(int64_t)(k0 + k) * ld + m0 + tj * CH_NB + i];
+  }
+  __syncthreads();
+  // 16 sub-tiles of 8 x 8, two per warp
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int st = wid * 2 + s, si = (st >> 2) * 8, sj = (st & 3) * 8;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < CH_NB; k += 4)
+      dmma_m8n8k4(c0, c1, Ti[si + (lane >> 2)][k + (lane & 3)], Tj[sj + (lane >> 2)][k + (lane & 3)]);
+    const int gi = m0 + ti * CH_NB + si + (lane >> 2);
+    const int gj = m0 + tj * CH_NB + sj + (lane & 3) * 2;
+    double *c = A + (int64_t)gj * ld + gi;
+    c[0] -= c0;
+    c[ld] -= c1;
+  }
 }
 
 // x_e = (L L^T)^-1 g_e for every block; work: one padded vector per block (CholBlock::woff)
@@ -250,7 +250,12 @@ int chol_setup(hsbp_blocks *b) {
   cudaError_t e1 = cudaMalloc((void **)&d_flag, b->nblocks * sizeof(int));
   if (rc == HSBP_OK && e1 == cudaSuccess) {
     cudaMemsetAsync(d_flag, 0, b->nblocks * sizeof(int), ctx->stream);
-    k_chol_factor<<<(unsigned)b->nblocks, CH_THREADS, 0, ctx->stream>>>(dcb, b->d_chol, d_flag);
+    for (int k0 = 0; k0 < maxld; k0 += CH_NB) {
+      k_chol_panel<<<(unsigned)b->nblocks, CH_THREADS, 0, ctx->stream>>>(dcb, b->d_chol, k0, d_flag);
+      const int nt = (maxld - k0 - CH_NB) / CH_NB;
+      if (nt > 0)
+        k_chol_update<<<dim3(nt, nt, (unsigned)b->nblocks), CH_THREADS, 0, ctx->stream>>>(dcb, b->d_chol, k0);
+    }
     e1 = cudaGetLastError();
     if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(flag.data(), d_flag, b->nblocks * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);

@@ -733,7 +733,7 @@ k_sweep(const SweepParams prm) {
 // with_faces = 0 leaves the face terms out (volume operator A-tilde only).
 // dynamic shared memory: 2 * (max face points) doubles
 template <int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
             double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
