@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=1024)
     ap.add_argument("--n", type=int, default=255, help="N per block (points = N+1)")
     ap.add_argument("--p", type=int, default=4)
-    ap.add_argument("--cpu-blocks", type=int, default=4)
+    ap.add_argument("--cpu-blocks", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=5.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-trace", action="store_true", help="skip the trace-CG solve-time measurement")
