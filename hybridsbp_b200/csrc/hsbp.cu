@@ -315,6 +315,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "sweep_chunks_per_side") b->sweep_ncs_override = (int)value;
   else if (n == "sweep_points_per_thread") b->sweep_r_override = (int)value;
   else if (n == "sweep_fold_faces") b->sweep_fold_faces = (int)value;
+  else if (n == "sweep_swizzle") b->sweep_swizzle = (int)value;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);
   return HSBP_OK;
 }

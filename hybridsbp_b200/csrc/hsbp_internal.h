@@ -52,6 +52,7 @@ struct hsbp_blocks {
   int max_Nr = 0, max_Ns = 0;
   int force_generic = 0;
   int sweep_r_override = 0;         // points per thread of the line-marching kernel (0 = heuristic, 2 or 4)
+  int sweep_swizzle = 0;            // 1: swizzled tensor-map TMA for the R = 4 layout (conflict-free, but slower: see k_sweep.cuh)
   int sweep_fold_faces = 1;         // fold the face terms into k_sweep (0: separate gather / scatter kernels)
   int sweep_ncs_override = 0;       // chunks per side of the line-marching kernel (0 = heuristic)
   int last_variant = -1;

@@ -28,6 +28,7 @@
 //
 // Algorithmic traffic: 40 B per point (u, crr, css, crs in, y out); DESIGN.md section 4.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "hsbp_internal.h"
 #include "sbp1d.cuh"
 #include "k_generic.cuh"
@@ -77,6 +78,17 @@ __device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 2-D tiled TMA load (cp.async.bulk.tensor): box of the tensor map at coordinates (c0, c1) -> shared memory
+__device__ __forceinline__ void tensor_g2s_s(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// the four fields as 2-D tensors [rows][16 doubles] with the 128-byte swizzle: a line lands in shared memory with its
+// 16-byte chunks XOR-permuted inside every 128-byte row, which makes the 32-byte-per-lane reads of the R = 4 layout
+// bank-conflict free
+struct SweepMaps {
+  CUtensorMap u, crr, css, crs;
+};
 // one lane of a fully active warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -181,9 +193,10 @@ template <int T0, int T1, class F> __device__ __forceinline__ void for_lanes(F &
 
 // NT: upper bound of the CTA size; MINB: CTAs per SM the register allocation is sized for
 // (R = 2: 128 registers per thread, R = 4: 255).
-template <int P, int R, int NT, int MINB>
+// SWZ: lines arrive through tensor-map TMA with the 128-byte swizzle (needs Nr+1 a multiple of 16)
+template <int P, int R, int NT, int MINB, bool SWZ>
 __global__ void __launch_bounds__(NT, MINB)
-k_sweep(const SweepParams prm) {
+k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
   constexpr int H = C::H, W = C::W, LB = C::LB, PAD = C::PAD, CLW = C::CLW, NST = SW_NST;
@@ -195,10 +208,15 @@ k_sweep(const SweepParams prm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int Nr = prm.Nr, Ns = prm.Ns, Nrp = Nr + 1, Nsp = Ns + 1;
-  const int LW = Nrp + 2 * PAD;
+  // A "slot" holds one line of one field: DOFF doubles of zeros (left halo), the Nrp values, zeros again (right halo =
+  // the front of the next slot).  Plain layout: LW = Nrp + 2 PAD, DOFF = PAD.  Swizzled layout: the data start is
+  // 1024-byte aligned (the swizzle pattern is a function of the address), DOFF = 128, LW = Nrp rounded up to 128, + 128.
+  const int LW = SWZ ? ((Nrp + 127) & ~127) + 128 : Nrp + 2 * PAD;
+  const int DOFF = SWZ ? 128 : PAD;
   double *ring = reinterpret_cast<double *>(smem_raw);    // [NST][4][LW]
+  if constexpr (SWZ) ring = reinterpret_cast<double *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   double *wbuf = ring + (size_t)NST * 4 * LW;             // [2][LW]
-  double *clring = wbuf + 2 * LW;                         // [NST][CLR]: r-end table rows of the staged lines
+  double *clring = wbuf + 2 * LW + (SWZ ? 128 : 0);       // [NST][CLR]: r-end table rows of the staged lines
   uint64_t *full = reinterpret_cast<uint64_t *>(clring + (size_t)NST * CLR);
 
   // ---- which chunk --------------------------------------------------------------------------
@@ -222,9 +240,13 @@ k_sweep(const SweepParams prm) {
   const int64_t foff = e * (2 * (int64_t)Nrp + 2 * (int64_t)Nsp);    // block e in the block-face layout
 
   // ---- one-time setup: zero the halos of the shared lines, barriers --------------------------
-  for (int idx = tid; idx < (NST * 4 + 2) * 2 * PAD; idx += nthreads) {
-    const int line = idx / (2 * PAD), k = idx - line * (2 * PAD);
-    ring[(size_t)line * LW + (k < PAD ? k : Nrp + k)] = 0.0;
+  if constexpr (SWZ) {
+    for (int idx = tid; idx < (NST * 4 + 2) * LW + 128; idx += nthreads) ring[idx] = 0.0;     // everything, once
+  } else {
+    for (int idx = tid; idx < (NST * 4 + 2) * 2 * PAD; idx += nthreads) {
+      const int line = idx / (2 * PAD), k = idx - line * (2 * PAD);
+      ring[(size_t)line * LW + (k < PAD ? k : Nrp + k)] = 0.0;
+    }
   }
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
@@ -233,13 +255,22 @@ k_sweep(const SweepParams prm) {
   __syncthreads();
   auto issue = [&](int n) {      // marching line jstart + n into stage n % NST  (thread 0 only)
     const int st = n % NST;
-    double *dst = ring + (size_t)st * 4 * LW + PAD;
+    double *dst = ring + (size_t)st * 4 * LW + DOFF;
     const int64_t g = base + (int64_t)(jstart + n) * lstride;
     mbar_expect_tx(&full[st], 4u * line_bytes + (uint32_t)(CLR * 8));
-    bulk_g2s(dst, prm.u + g, line_bytes, &full[st]);
-    bulk_g2s(dst + LW, prm.crr + g, line_bytes, &full[st]);
-    bulk_g2s(dst + 2 * LW, prm.css + g, line_bytes, &full[st]);
-    bulk_g2s(dst + 3 * LW, prm.crs + g, line_bytes, &full[st]);
+    if constexpr (SWZ) {
+      const uint32_t bar = smem_u32(&full[st]);
+      const int row = (int)(g >> 4);                      // 16 doubles per tensor row
+      tensor_g2s_s(smem_u32(dst), &tm.u, 0, row, bar);
+      tensor_g2s_s(smem_u32(dst + LW), &tm.crr, 0, row, bar);
+      tensor_g2s_s(smem_u32(dst + 2 * LW), &tm.css, 0, row, bar);
+      tensor_g2s_s(smem_u32(dst + 3 * LW), &tm.crs, 0, row, bar);
+    } else {
+      bulk_g2s(dst, prm.u + g, line_bytes, &full[st]);
+      bulk_g2s(dst + LW, prm.crr + g, line_bytes, &full[st]);
+      bulk_g2s(dst + 2 * LW, prm.css + g, line_bytes, &full[st]);
+      bulk_g2s(dst + 3 * LW, prm.crs + g, line_bytes, &full[st]);
+    }
     const int64_t jl = up ? (int64_t)(jstart + n) : (int64_t)Ns - (jstart + n);       // actual line index
     bulk_g2s(clring + (size_t)st * CLR, prm.rtab + ((e * Nsp + jl) * CLR), (uint32_t)(CLR * 8), &full[st]);
   };
@@ -251,6 +282,16 @@ k_sweep(const SweepParams prm) {
   const int i0 = tid * R;
   const bool own = i0 < Nrp;
   const int nown = Nrp / R;                               // threads that own points (Nrp % R == 0)
+  // offset (doubles, from the data start of a slot) of element idx / of the 16-byte chunks this thread looks at
+  auto sel = [&](int idx) -> int {
+    if constexpr (!SWZ) return idx;
+    if (idx < 0 || idx >= Nrp) return idx;                 // halo: zeros wherever one looks
+    const int L = idx >> 1, row = L >> 3;
+    return row * 16 + (((L & 7) ^ (row & 7)) << 1) + (idx & 1);
+  };
+  int so[NV / 2];
+#pragma unroll
+  for (int k = 0; k < NV / 2; ++k) so[k] = sel(i0 - PAD + 2 * k);
   const double *qc = C::Qc();
   const double *gu = prm.u + base + i0;                   // + j*lstride: this thread's points on marching line j
   const double *gss = prm.css + base + i0;
@@ -302,16 +343,16 @@ k_sweep(const SweepParams prm) {
       double U[NV], Bq[NV];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + i0 + 2 * k);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + i0 + 2 * k);
+        const double2 a = *reinterpret_cast<const double2 *>(sb + DOFF + so[k]);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + DOFF + so[k]);
         U[2 * k] = a.x; U[2 * k + 1] = a.y; Bq[2 * k] = b2.x; Bq[2 * k + 1] = b2.y;
       }
 #pragma unroll
       for (int q = 0; q < R; ++q) { uw[SL(W - 1)][q] = U[PAD + q]; acc[SL(W - 1)][q] = 0.0; }
 #pragma unroll
       for (int k = 0; k < R / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + PAD + i0 + 2 * k);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + PAD + i0 + 2 * k);
+        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + DOFF + so[PAD / 2 + k]);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + DOFF + so[PAD / 2 + k]);
         bw[SL(W - 1)][2 * k] = a.x; bw[SL(W - 1)][2 * k + 1] = a.y;
         cw[SL(W - 1)][2 * k] = b2.x; cw[SL(W - 1)][2 * k + 1] = b2.y;
       }
@@ -441,7 +482,7 @@ k_sweep(const SweepParams prm) {
         }
 #pragma unroll
         for (int k = 0; k < R / 2; ++k)
-          *reinterpret_cast<double2 *>(wb + PAD + i0 + 2 * k) =
+          *reinterpret_cast<double2 *>(wb + DOFF + so[PAD / 2 + k]) =
               make_double2(cw[SL(H)][2 * k] * qs[2 * k], cw[SL(H)][2 * k + 1] * qs[2 * k + 1]);
       }
     }
@@ -452,7 +493,7 @@ k_sweep(const SweepParams prm) {
       double Wv[NV], val[R];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(wb + i0 + 2 * k);
+        const double2 a = *reinterpret_cast<const double2 *>(wb + DOFF + so[k]);
         Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
       }
 #pragma unroll
@@ -465,7 +506,9 @@ k_sweep(const SweepParams prm) {
       for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
         constexpr int TL = decltype(Tc)::value;
         if (tid == TL) {
-          const double *w0 = wb + PAD;
+          double w0[BN];
+#pragma unroll
+          for (int k = 0; k < BN; ++k) w0[k] = wb[DOFF + sel(k)];
 #pragma unroll
           for (int q = 0; q < R; ++q)
             if (TL * R + q < BM) val[q] = acc[SL(0)][q] + qt_closure_row<P>(TL * R + q, w0);
@@ -473,7 +516,7 @@ k_sweep(const SweepParams prm) {
         if (tid == nown - 1 - TL) {                       // mirrored, sign flipped
           double wr[BN];
 #pragma unroll
-          for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
+          for (int k = 0; k < BN; ++k) wr[k] = wb[DOFF + sel(Nr - k)];
 #pragma unroll
           for (int q = 0; q < R; ++q)
             if (TL * R + (R - 1 - q) < BM) val[q] = acc[SL(0)][q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
@@ -536,14 +579,14 @@ k_sweep(const SweepParams prm) {
       double U[NV], Bq[NV], bn[R], cn[R], rr[R], qr[R], wout[R];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + i0 + 2 * k);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + i0 + 2 * k);
+        const double2 a = *reinterpret_cast<const double2 *>(sb + DOFF + so[k]);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + DOFF + so[k]);
         U[2 * k] = a.x; U[2 * k + 1] = a.y; Bq[2 * k] = b2.x; Bq[2 * k + 1] = b2.y;
       }
 #pragma unroll
       for (int k = 0; k < R / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + PAD + i0 + 2 * k);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + PAD + i0 + 2 * k);
+        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + DOFF + so[PAD / 2 + k]);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + DOFF + so[PAD / 2 + k]);
         bn[2 * k] = a.x; bn[2 * k + 1] = a.y; cn[2 * k] = b2.x; cn[2 * k + 1] = b2.y;
       }
       for_offsets<1, H>([&](auto Oc) {
@@ -643,20 +686,28 @@ k_sweep(const SweepParams prm) {
       if (outp) {
 #pragma unroll
         for (int k = 0; k < R / 2; ++k)
-          *reinterpret_cast<double2 *>(wb + PAD + i0 + 2 * k) = make_double2(wout[2 * k], wout[2 * k + 1]);
+          *reinterpret_cast<double2 *>(wb + DOFF + so[PAD / 2 + k]) = make_double2(wout[2 * k], wout[2 * k + 1]);
       }
     }
     __syncthreads();
     if ((tid >> 5) == rw && n < nrefill) {                // stage st is free again: line j + NST goes into it
                                                           // (the warps take turns, so no warp is the slow one)
       if (elect_one()) {
-        const uint32_t bar = full_s + 8u * st, dst = ring_s + (uint32_t)(st * 4 * LW + PAD) * 8u;
+        const uint32_t bar = full_s + 8u * st, dst = ring_s + (uint32_t)(st * 4 * LW + DOFF) * 8u;
         const int64_t g = gofs + NST * lstride;
         mbar_expect_tx_s(bar, 4u * line_bytes + (uint32_t)(CLR * 8));
-        bulk_g2s_s(dst, prm.u + g, line_bytes, bar);
-        bulk_g2s_s(dst + (uint32_t)LW * 8u, prm.crr + g, line_bytes, bar);
-        bulk_g2s_s(dst + (uint32_t)LW * 16u, prm.css + g, line_bytes, bar);
-        bulk_g2s_s(dst + (uint32_t)LW * 24u, prm.crs + g, line_bytes, bar);
+        if constexpr (SWZ) {
+          const int row = (int)(g >> 4);
+          tensor_g2s_s(dst, &tm.u, 0, row, bar);
+          tensor_g2s_s(dst + (uint32_t)LW * 8u, &tm.crr, 0, row, bar);
+          tensor_g2s_s(dst + (uint32_t)LW * 16u, &tm.css, 0, row, bar);
+          tensor_g2s_s(dst + (uint32_t)LW * 24u, &tm.crs, 0, row, bar);
+        } else {
+          bulk_g2s_s(dst, prm.u + g, line_bytes, bar);
+          bulk_g2s_s(dst + (uint32_t)LW * 8u, prm.crr + g, line_bytes, bar);
+          bulk_g2s_s(dst + (uint32_t)LW * 16u, prm.css + g, line_bytes, bar);
+          bulk_g2s_s(dst + (uint32_t)LW * 24u, prm.crs + g, line_bytes, bar);
+        }
         bulk_g2s_s(clring_s + (uint32_t)(st * CLR) * 8u, prm.rtab + tofs + NST * tstride, (uint32_t)(CLR * 8), bar);
       }
     }
@@ -665,7 +716,7 @@ k_sweep(const SweepParams prm) {
       double Wv[NV], val[R];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(wb + i0 + 2 * k);
+        const double2 a = *reinterpret_cast<const double2 *>(wb + DOFF + so[k]);
         Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
       }
 #pragma unroll
@@ -679,7 +730,9 @@ k_sweep(const SweepParams prm) {
         for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
           constexpr int TL = decltype(Tc)::value;
           if (tid == TL) {
-            const double *w0 = wb + PAD;
+            double w0[BN];
+#pragma unroll
+            for (int k = 0; k < BN; ++k) w0[k] = wb[DOFF + sel(k)];
 #pragma unroll
             for (int q = 0; q < R; ++q)
               if (TL * R + q < BM) val[q] = accout[q] + qt_closure_row<P>(TL * R + q, w0);
@@ -692,7 +745,7 @@ k_sweep(const SweepParams prm) {
           if (tid == nown - 1 - TL) {
             double wr[BN];
 #pragma unroll
-            for (int k = 0; k < BN; ++k) wr[k] = wb[PAD + Nr - k];
+            for (int k = 0; k < BN; ++k) wr[k] = wb[DOFF + sel(Nr - k)];
 #pragma unroll
             for (int q = 0; q < R; ++q)
               if (TL * R + (R - 1 - q) < BM) val[q] = accout[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
@@ -846,12 +899,42 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
 }
 
 // ---- host side ------------------------------------------------------------------------------
-template <int P> static size_t sweep_smem(int Nrp, int nthreads) {
+template <int P> static size_t sweep_smem(int Nrp, int nthreads, bool swz = false) {
   using C = SweepCfg<P>;
   (void)nthreads;
-  const int LW = Nrp + 2 * C::PAD;
-  return (size_t)(SW_NST * 4 + 2) * LW * sizeof(double) + (size_t)SW_NST * 2 * C::CLW * sizeof(double) +
-         SW_NST * sizeof(uint64_t);
+  const int LW = swz ? ((Nrp + 127) & ~127) + 128 : Nrp + 2 * C::PAD;
+  return (size_t)(SW_NST * 4 + 2) * LW * sizeof(double) + (swz ? 128 * sizeof(double) + 1024 : 0) +
+         (size_t)SW_NST * 2 * C::CLW * sizeof(double) + SW_NST * sizeof(uint64_t);
+}
+
+// tensor map of one field: [VNp / 16 rows][16 doubles], box = one line (Nrp / 16 rows), 128-byte swizzle
+static int sweep_encode_map(hsbp_ctx *ctx, CUtensorMap *tm, const double *field, int64_t VNp, int Nrp) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      ctx->err = "cuTensorMapEncodeTiled is not available";
+      return HSBP_ERR_CUDA;
+    }
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t gdim[2] = {16, (cuuint64_t)(VNp / 16)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {16, (cuuint32_t)(Nrp / 16)};
+  const cuuint32_t estr[2] = {1, 1};
+  const int promo = 2;                                       // L2 promotion 128 B (0 / 1 / 3 measured the same)
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)field, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+    return HSBP_ERR_CUDA;
+  }
+  return HSBP_OK;
 }
 
 static int sweep_points_per_thread(const hsbp_blocks *b) {
@@ -946,8 +1029,8 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   return HSBP_OK;
 }
 
-template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
-                                                        int64_t e0, int64_t ne) {
+template <int P, int R, int NT, bool SWZ> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
+                                                                  int64_t e0, int64_t ne) {
   hsbp_ctx *ctx = b->ctx;
 #ifndef SW_REGS2_P6
 #define SW_REGS2_P6 168
@@ -955,10 +1038,10 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   // register budget per thread: R = 4 takes all 255; R = 2 fits 128 (p = 2, 4) -- p = 6 has 7-line windows and needs more
   constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
   constexpr int MINB = (R == 2 ? 65536 / REGS2 : 256) / NT;
-  auto kern = k_sweep<P, R, NT, MINB>;
+  auto kern = k_sweep<P, R, NT, MINB, SWZ>;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
-  const size_t sm = sweep_smem<P>(Nrp, nthreads);
+  const size_t sm = sweep_smem<P>(Nrp, nthreads, SWZ);
   static bool attr_set = false;
   static int ctas_per_sm = 1;
   if (!attr_set) {
@@ -992,7 +1075,15 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
   prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K; prm.e0 = (int)e0;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
-  kern<<<(unsigned)(ne * 2 * best), nthreads, sm, ctx->stream>>>(prm);
+  SweepMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if constexpr (SWZ) {
+    int rc;
+    if ((rc = sweep_encode_map(ctx, &maps.u, u, b->VNp, Nrp)) || (rc = sweep_encode_map(ctx, &maps.crr, b->d_crr_s, b->VNp, Nrp)) ||
+        (rc = sweep_encode_map(ctx, &maps.css, b->d_css_s, b->VNp, Nrp)) || (rc = sweep_encode_map(ctx, &maps.crs, b->d_crs, b->VNp, Nrp)))
+      return rc;
+  }
+  kern<<<(unsigned)(ne * 2 * best), nthreads, sm, ctx->stream>>>(prm, maps);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_sweep: ") + cudaGetErrorString(e1);
@@ -1003,10 +1094,21 @@ template <int P, int R, int NT> static int sweep_launch(hsbp_blocks *b, const do
 
 template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double *u, double *y, bool with_faces,
                                                    int64_t e0, int64_t ne) {
-  const int nthreads = (((b->max_Nr + 1) / R) + 31) & ~31;
-  if (nthreads <= 64) return sweep_launch<P, R, 64>(b, u, y, with_faces, e0, ne);
-  if (nthreads <= 128) return sweep_launch<P, R, 128>(b, u, y, with_faces, e0, ne);
-  return sweep_launch<P, R, 256>(b, u, y, with_faces, e0, ne);
+  const int Nrp = b->max_Nr + 1;
+  const int nthreads = ((Nrp / R) + 31) & ~31;
+  if constexpr (R == 4) {
+    // Optional: swizzled shared lines through tensor-map TMA make the 32-byte-per-lane reads conflict free, but measured
+    // on B200 the 2-D tiled copies feed the ring more slowly than the 1-D bulk copies (k_sweep 0.74 ms vs 0.68 ms at
+    // p = 4, 0.59 vs 0.44 ms at p = 2), so the plain layout stays the default (profiles/README.md).
+    if (Nrp % 16 == 0 && b->sweep_swizzle && ((uintptr_t)u & 127) == 0) {
+      if (nthreads <= 64) return sweep_launch<P, R, 64, true>(b, u, y, with_faces, e0, ne);
+      if (nthreads <= 128) return sweep_launch<P, R, 128, true>(b, u, y, with_faces, e0, ne);
+      return sweep_launch<P, R, 256, true>(b, u, y, with_faces, e0, ne);
+    }
+  }
+  if (nthreads <= 64) return sweep_launch<P, R, 64, false>(b, u, y, with_faces, e0, ne);
+  if (nthreads <= 128) return sweep_launch<P, R, 128, false>(b, u, y, with_faces, e0, ne);
+  return sweep_launch<P, R, 256, false>(b, u, y, with_faces, e0, ne);
 }
 
 // y = A-tilde u (with_faces = false) or y = M-tilde u with the face terms prepared in d_fa / d_fb by k_face_prep

@@ -110,7 +110,7 @@ int  hsbp_apply_variant(const hsbp_blocks *blocks);
 /* force the generic kernels (testing) */
 int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
 /* tuning / testing knobs: "force_generic" (0/1), "sweep_chunks_per_side" (0 = heuristic),
- * "sweep_points_per_thread" (0 = heuristic, 2, 4)                                       */
+ * "sweep_points_per_thread" (0 = heuristic, 2, 4), "sweep_fold_faces" (1), "sweep_swizzle" (0) */
 int  hsbp_blocks_set_option(hsbp_blocks *blocks, const char *name, int64_t value);
 
 /* face operators of the blocks, block-face layout (no inter-block coupling):
