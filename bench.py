@@ -289,17 +289,25 @@ def run_ours(args):
         peak, peak_src = load_peaks()
         variant = blk.apply_variant()
         achieved = BYTES_PER_DOF * dof / (stage[0] * 1e-3) / 1e9
+        traffic = None                                 # DRAM bytes per k_sweep launch from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "k_sweep_traffic.json")) as f:
+                tj = json.load(f)
+            if variant == 1 and (args.blocks, args.n, args.p) == (1024, 255, 4):
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {"metric": "fp64 SBP operator-apply GDOF/s", "value": world * dof / (ms_step * 1e-3) / 1e9,
                 "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None,
+                             "frac": achieved / peak, "traffic": traffic,
                              "kernel": ("k_sweep (line-marching kernel: volume operator, all closures and the folded face terms in one pass)" if variant == 1 else
                                         "k_cross_pre + k_vol_apply (two-pass generic volume stage)"),
                              "algorithmic_bytes_per_launch": BYTES_PER_DOF * dof,
                              "kernel_ms": float(stage[0]),
-                             "other_kernels_ms": ({"k_face_prep": float(stage[1])} if (variant == 1 and not args.no_fold) else
+                             "other_kernels_ms": ({"k_edge_prep": float(stage[1])} if (variant == 1 and not args.no_fold) else
                                                   {"k_face_gather": float(stage[1]), "k_face_scatter": float(stage[2])}),
                              "peak_source": peak_src},
                 "e2e": {"value": world * dof / e2e_s / 1e9, "unit": "GDOF/s",
