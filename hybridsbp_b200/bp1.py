@@ -21,7 +21,7 @@ import numpy as np
 
 from . import host
 from ._lib import Bp1Params, Bp1Stats, _f64, lib
-from .blocks import Blocks, LOCAL_PCG
+from .blocks import Blocks, LOCAL_PCG, LOCAL_BAND
 
 YEAR_SECONDS = 31556926          # odefun.jl:1
 
@@ -73,7 +73,7 @@ def setup(N=200, SBPp=2, Lx=80.0, Ly=80.0):
 class Fault:
     """Device-resident BP1 right-hand side (hsbp_bp1_*)."""
 
-    def __init__(self, ctx, su: Bp1Setup, local_tol=1e-13, local_maxit=200000):
+    def __init__(self, ctx, su: Bp1Setup, local_tol=1e-13, local_maxit=200000, local_mode=LOCAL_BAND):
         self.su = su
         m = su.metrics
         self.blk = Blocks(ctx, su.p, [su.N], [su.N])
@@ -81,7 +81,9 @@ class Fault:
         self.blk.set_metrics(fl(m.crr), fl(m.css), fl(m.crs))
         self.blk.set_bc(np.asarray(su.LFtoB, dtype=np.int64))
         self.blk.compute_tau(2.0)
-        self.blk.local_setup(LOCAL_PCG, tol=local_tol, maxit=local_maxit)
+        # the reference keeps cholesky(M-tilde) for the whole run (BP1.jl:78) and back-solves in every odefun call
+        # (odefun.jl:43): the banded factorisation is its direct counterpart; LOCAL_PCG is the matrix-free variant
+        self.blk.local_setup(local_mode, tol=local_tol, maxit=local_maxit)
         prm = Bp1Params(**su.params)
         a, pa = _f64(su.RSa)
         sj, psj = _f64(m.sJ[0])

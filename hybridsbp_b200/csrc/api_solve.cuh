@@ -102,6 +102,7 @@ int local_solve_impl(hsbp_blocks *b, const double *g, double *u, hsbp_local_stat
   if (!g || !u || g == u) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_local_solve: bad pointers (in-place solve is not supported)");
   HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
   if (b->local_mode == HSBP_LOCAL_CHOLESKY) return chol_solve(b, g, u, stats);
+  if (b->local_mode == HSBP_LOCAL_BAND) return band_solve(b, g, u, stats);
   return pcg_solve(b, g, u, stats);
 }
 
@@ -181,13 +182,15 @@ int hsbp_local_setup(hsbp_blocks *b, int mode, double tol, int64_t maxit) {
   if (!b) return HSBP_ERR_ARG;
   hsbp_ctx *ctx = b->ctx;
   if (!b->have_metrics || !b->have_tau) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_local_setup: metrics / tau not set");
-  if (mode != HSBP_LOCAL_PCG && mode != HSBP_LOCAL_CHOLESKY) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_local_setup: unknown mode");
+  if (mode != HSBP_LOCAL_PCG && mode != HSBP_LOCAL_CHOLESKY && mode != HSBP_LOCAL_BAND) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_local_setup: unknown mode");
   HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
   b->local_tol = tol > 0 ? tol : 1e-13;
   b->local_maxit = maxit > 0 ? maxit : 100000;
   int rc;
   if (mode == HSBP_LOCAL_CHOLESKY) {
     if ((rc = chol_setup(b))) return rc;
+  } else if (mode == HSBP_LOCAL_BAND) {
+    if ((rc = band_setup(b))) return rc;
   } else {
     if ((rc = local_alloc(b))) return rc;
     rc = dispatch_p(b->p, [&](auto Pc) { return probe_diagonal<decltype(Pc)::value>(b); });

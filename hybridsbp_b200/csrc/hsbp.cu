@@ -210,6 +210,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
   cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off); cudaFree(b->d_chol_work);
+  cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work);
   delete b;
   return HSBP_OK;
 }
@@ -515,5 +516,6 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 }  // extern "C"
 
 #include "api_chol.cuh"
+#include "api_band.cuh"
 #include "api_solve.cuh"
 #include "api_bp1.cuh"

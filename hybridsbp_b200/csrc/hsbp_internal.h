@@ -67,6 +67,9 @@ struct hsbp_blocks {
   std::vector<int64_t> chol_off;
   void *d_chol_off = nullptr;               // CholBlock descriptors
   double *d_chol_work = nullptr;
+  double *d_band = nullptr;                 // banded factors (api_band.cuh), LAPACK lower-band storage per block
+  void *d_band_desc = nullptr;              // BandBlock descriptors
+  double *d_band_work = nullptr;
   // pinned staging for hsbp_apply_host (lazy)
   double *d_stage_u = nullptr, *d_stage_y = nullptr;
   std::vector<cudaEvent_t> pipe_ev;          // per block group: H2D done, kernels done

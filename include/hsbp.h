@@ -127,9 +127,13 @@ int  hsbp_face_traction(hsbp_blocks *blocks, const double *u_dev, double *tr_dev
  * `F \ g` (global_curved.jl:734, square_circle.jl:383, odefun.jl:43).
  *   HSBP_LOCAL_PCG       batched matrix-free Jacobi-PCG on the block operator (any block size)
  *   HSBP_LOCAL_CHOLESKY  batched dense fp64 Cholesky of M-tilde_e (small blocks)
+ *   HSBP_LOCAL_BAND      batched banded fp64 Cholesky of M-tilde_e (points numbered r-fastest, half-bandwidth
+ *                        about WB*(Nr+1), WB = 2 / 5 / 8 for p = 2 / 4 / 6): the direct solver for blocks whose band
+ *                        fits in device memory, e.g. the single 201 x 201 block of seas/BP1 (BP1.jl:78)
  * tol is the relative residual ||g - M u|| / ||g|| per block (PCG only).                         */
 #define HSBP_LOCAL_PCG      1
 #define HSBP_LOCAL_CHOLESKY 2
+#define HSBP_LOCAL_BAND     3
 typedef struct {
   int64_t iterations_max;     /* PCG: largest iteration count over blocks (0 for Cholesky) */
   int64_t iterations_sum;     /* PCG: sum over blocks                                      */

@@ -10,10 +10,11 @@ from oracle.bp1 import OdeFun
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def case(ctx):
+@pytest.fixture(scope="module", params=["band", "pcg"])
+def case(ctx, request):
+    from hybridsbp_b200 import LOCAL_BAND, LOCAL_PCG
     su = bp1.setup(N=40)
-    gpu = bp1.Fault(ctx, su)
+    gpu = bp1.Fault(ctx, su, local_mode=LOCAL_BAND if request.param == "band" else LOCAL_PCG)
     ref = OdeFun(su.p, su.N, su.metrics, su.LFtoB, su.RSa, su.params)
     yield su, gpu, ref
     gpu.close()

@@ -148,6 +148,30 @@ def test_dense_cholesky_local_solver(ctx, p):
         assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), e
 
 
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_banded_cholesky_local_solver(ctx, p):
+    """K2c: the `factorization` plugin as a batched banded Cholesky (global_curved.jl:698, 734): blocks of different
+    shapes, all boundary-condition types (Neumann faces have the widest coupling), sizes beyond the dense solver."""
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(500 + p)
+    N = 3 * p - 1 if p > 2 else 6
+    shapes = [(N, N), (N + 2, N + 5), (40, N + 1), (N + 7, 33), (47, 52)]
+    mets = [random_spd_metrics(p, a, b, rng, scale2=0.2) for a, b in shapes]
+    bcs = [(1, 1, 1, 1), (1, 2, 2, 2), (0, 1, 2, 7), (2, 0, 1, 1), (2, 2, 1, 2)]
+    lops = [orc.locoperator(p, a, b, m, bc) for (a, b), m, bc in zip(shapes, mets, bcs)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    blk.local_setup(hs.LOCAL_BAND)
+    g = rng.uniform(-1, 1, blk.VNp)
+    dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    st = blk.local_solve(dg, dx)
+    assert st["failed_blocks"] == 0 and st["iterations_max"] == 0
+    x = dx.get()
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        xr = orc.default_factorization(lop.Mt).solve(g[sl])
+        assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, np.linalg.norm(x[sl] - xr) / np.linalg.norm(xr))
+
+
 def test_trace_solve_with_cholesky_local_solver(ctx):
     import hybridsbp_b200 as hs
     p = 4
