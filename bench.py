@@ -194,6 +194,7 @@ def run_ours(args):
     blk.compute_tau(2.0)
     blk.set_option("sweep_points_per_thread", args.sweep_r)
     blk.set_option("sweep_chunks_per_side", args.sweep_ncs)
+    blk.set_option("sweep_deep", args.sweep_deep)
     blk.set_option("force_generic", 1 if args.generic else 0)
     try:
         blk.set_option("sweep_fold_faces", 0 if args.no_fold else 1)
@@ -343,6 +344,7 @@ def main():
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")
     ap.add_argument("--trace-tol", type=float, default=1e-10)
     ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")
+    ap.add_argument("--sweep-deep", type=int, default=1, help="1: css / crs windows of k_sweep in shared-memory rings, 0: in registers")
     ap.add_argument("--sweep-ncs", type=int, default=0, help="chunks per side of k_sweep (0 = heuristic)")
     ap.add_argument("--generic", action="store_true", help="force the generic two-pass kernels")
     ap.add_argument("--no-fold", action="store_true", help="face terms by separate gather / scatter kernels")

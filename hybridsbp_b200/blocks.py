@@ -12,6 +12,7 @@ from ._lib import Context, DeviceArray, LocalStats, TraceStats, _f64, _i64, lib
 LOCAL_PCG = 1
 LOCAL_CHOLESKY = 2
 LOCAL_BAND = 3
+LOCAL_FDM = 4
 
 
 class Blocks:

@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++20", "-lineinfo",
            "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC,-O2",
-           "-shared", "-cudart", "shared", "-o", LIB, os.path.join(CSRC, "hsbp.cu"), "-ldl"]
+           "-shared", "-cudart", "shared", "-o", LIB, os.path.join(CSRC, "hsbp.cu"), "-ldl", "-lcublas", "-lcusolver"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,425 @@
+// K2d: batched PCG on M-tilde_e with a fast-diagonalisation (separable) preconditioner -- the local solver for
+// blocks that are too large for a direct factor (256 x 256 points: 65 536 unknowns per block, 1024 blocks).
+//
+// The reference keeps a sparse Cholesky factor of every block (`factorization(M̃_e)`, global_curved.jl:698) and
+// back-solves (`F \ g`, :734, square_circle.jl:383).  Matrix-free, the same solve is a CG on M-tilde_e; Jacobi-PCG needs
+// O(N) iterations per solve.  Here the preconditioner is the exact inverse of the separable part of the operator,
+//     P_e = Ar_e (x) Hs + Hr (x) As_e - c_e Hr (x) Hs                                    (tensor product, r fastest)
+// where Ar_e, As_e are the 1-D operators obtained by collapsing M-tilde_e against the constant in the other
+// direction and c_e removes the doubly counted part:
+//     Ar_e = (I (x) 1^T) M̃_e (I (x) 1) / (1^T Hs 1),   As_e likewise,   c_e = 1^T M̃_e 1 / ((1^T Hr 1)(1^T Hs 1)).
+// For a block whose coefficients do not vary (crr, css constant, crs = 0, tau constant along faces) P_e = M̃_e; on the
+// smoothly warped blocks of the synthetic mesh the coefficients vary by a few per cent inside a block and the mixed
+// term is a fraction of the diagonal ones, so kappa(P^-1 M̃) = O(1) instead of O(N^2).
+// With the generalised eigen-decompositions  Ar Vr = Hr Vr Lr,  Vr^T Hr Vr = I  (and s likewise)
+//     P^-1 = (Vs (x) Vr) diag(1 / (lr_i + ls_j - c)) (Vs (x) Vr)^T,
+// i.e. for the block's residual as an (Nr+1) x (Ns+1) matrix R:  Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T  -- four dense
+// fp64 GEMMs per block, executed as strided-batched DGEMMs (cuBLAS: plain library GEMMs on the fp64 tensor pipe).
+//
+//   setup   4 (2 WB + 1) operator applications with coloured probe vectors (all blocks at once); symmetric
+//           eigen-decompositions with cuSOLVER (syevd on H^-1/2 A H^-1/2).  The collapse against the constant carries the
+//           other direction's face penalties as a large shift sigma Hr, which leaves the eigenvectors alone but would
+//           make lr_i + ls_j - c a difference of large numbers; the eigenvalues are therefore Rayleigh quotients of
+//           the operator collapsed against the other direction's lowest mode (a shift of the smallest eigenvalue only).
+//   solve   PCG per block, all blocks at once: M̃ p (k_sweep), update of x / r, z = P^-1 r, update of p.
+#pragma once
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include "api_band.cuh"
+
+namespace hsbp {
+
+// probe vector: colour (index % C == ci) along direction dir (0: r, 1: s) times a profile in the other direction --
+// constant one (w == nullptr), or the block's vector w[block * ldw + index] (lowest mode of the other direction)
+__global__ void k_fdm_probe(const BlockDesc *__restrict__ desc, int dir, int C, int ci, const double *__restrict__ w,
+                            int64_t ldw, double *__restrict__ u) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int Nrp = d.Nr + 1;
+  const int64_t np = (int64_t)Nrp * (d.Ns + 1);
+  const double *wb = w ? w + (int64_t)blockIdx.x * ldw : nullptr;
+  for (int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; idx < np; idx += (int64_t)gridDim.y * blockDim.x) {
+    const int j = (int)(idx / Nrp), i = (int)(idx - (int64_t)j * Nrp);
+    const double prof = wb ? wb[dir == 0 ? j : i] : 1.0;
+    u[d.voff + idx] = ((dir == 0 ? i : j) % C == ci) ? prof : 0.0;
+  }
+}
+
+// collapse y = M-tilde u of a probe onto direction `dir` against the same profile (scale * 1 or the block's vector w)
+// and store the entries of the 1-D operator it exposes: row l of the collapsed vector belongs to the one probe column
+// l0 = ci (mod C) within WB of l.  A: [block][n x n] column-major (n = Nr+1 or Ns+1).
+__global__ void __launch_bounds__(256)
+k_fdm_collapse(const BlockDesc *__restrict__ desc, int dir, int C, int WB, int ci, const double *__restrict__ w, int64_t ldw,
+               double scale, const double *__restrict__ y, double *__restrict__ A) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
+  const double *yb = y + d.voff;
+  const double *wb = w ? w + (int64_t)blockIdx.x * ldw : nullptr;
+  const int n = dir == 0 ? Nrp : Nsp;
+  double *Ab = A + (int64_t)blockIdx.x * n * n;
+  if (dir == 0) {
+    for (int i = threadIdx.x; i < Nrp; i += blockDim.x) {      // sum over s, coalesced in i
+      double s = 0.0;
+      for (int j = 0; j < Nsp; ++j) s += (wb ? wb[j] : scale) * yb[i + (int64_t)Nrp * j];
+      const int i0 = i - WB + (((ci - (i - WB)) % C) + C) % C;
+      if (i0 >= 0 && i0 < Nrp) Ab[i + (int64_t)n * i0] = s;
+    }
+  } else {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = wid; j < Nsp; j += nw) {                        // sum over r, one warp per line
+      double s = 0.0;
+      for (int i = lane; i < Nrp; i += 32) s += (wb ? wb[i] : scale) * yb[i + (int64_t)Nrp * j];
+      s = warp_sum(s);
+      if (lane == 0) {
+        const int j0 = j - WB + (((ci - (j - WB)) % C) + C) % C;
+        if (j0 >= 0 && j0 < Nsp) Ab[j + (int64_t)n * j0] = s;
+      }
+    }
+  }
+}
+
+// mu[block][a] = V[:, a]^T T[:, a]  with T = A V: the Rayleigh quotients of the (H-orthonormal) columns of V
+__global__ void __launch_bounds__(256)
+k_fdm_rayleigh(int n, const double *__restrict__ V, const double *__restrict__ T, double *__restrict__ mu) {
+  const double *Vb = V + (int64_t)blockIdx.x * n * n, *Tb = T + (int64_t)blockIdx.x * n * n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int a = wid; a < n; a += nw) {
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += Vb[i + (int64_t)n * a] * Tb[i + (int64_t)n * a];
+    s = warp_sum(s);
+    if (lane == 0) mu[(int64_t)blockIdx.x * n + a] = s;
+  }
+}
+
+// A <- H^-1/2 sym(A) H^-1/2 (standard form of the generalised problem A v = l H v); one CTA per block
+template <int P>
+__global__ void k_fdm_standard_form(int n, double *__restrict__ A) {
+  double *Ab = A + (int64_t)blockIdx.x * n * n;
+  const double h = 2.0 / (n - 1);
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx % n, k = idx / n;
+    if (i < k) continue;
+    const double v = 0.5 * (Ab[i + (int64_t)n * k] + Ab[k + (int64_t)n * i]) /
+                     sqrt(h * hweight<P>(i, n - 1) * h * hweight<P>(k, n - 1));
+    Ab[i + (int64_t)n * k] = v;
+    Ab[k + (int64_t)n * i] = v;
+  }
+}
+// eigenvectors of the standard form -> generalised eigenvectors V = H^-1/2 Q
+template <int P>
+__global__ void k_fdm_scale_vectors(int n, double *__restrict__ V) {
+  double *Vb = V + (int64_t)blockIdx.x * n * n;
+  const double h = 2.0 / (n - 1);
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx % n;
+    Vb[idx] /= sqrt(h * hweight<P>(i, n - 1));
+  }
+}
+// Dinv[i, j] = 1 / max(mr_i + ms_j - c, floor),  c = (mr_0 + ms_0) / 2: both mr_0 and ms_0 are the Rayleigh quotient of
+// the lowest tensor-product mode, which the sum would otherwise count twice
+__global__ void k_fdm_dinv(const BlockDesc *__restrict__ desc, const double *__restrict__ mr, const double *__restrict__ ms,
+                           double *__restrict__ dinv) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
+  const double *mrb = mr + (int64_t)blockIdx.x * Nrp, *msb = ms + (int64_t)blockIdx.x * Nsp;
+  const double c = 0.5 * (mrb[0] + msb[0]);
+  const double floor_ = 1e-10 * fabs(mrb[Nrp - 1] + msb[Nsp - 1]);       // ascending eigenvalue order
+  const int64_t np = (int64_t)Nrp * Nsp;
+  for (int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; idx < np; idx += (int64_t)gridDim.y * blockDim.x) {
+    const int j = (int)(idx / Nrp), i = (int)(idx - (int64_t)j * Nrp);
+    dinv[d.voff + idx] = 1.0 / fmax(mrb[i] + msb[j] - c, floor_);
+  }
+}
+
+// PCG with a general preconditioner, part 1 (after Ap = M̃ p): x += alpha p, r -= alpha Ap, rr = r.r
+__global__ void __launch_bounds__(1024)
+k_fpcg_update1(const BlockDesc *__restrict__ desc, const double *__restrict__ Ap, double *__restrict__ x,
+               double *__restrict__ r, const double *__restrict__ p, PcgState *__restrict__ st, double tol2) {
+  __shared__ double scratch[32];
+  const BlockDesc d = desc[blockIdx.x];
+  PcgState s = st[blockIdx.x];
+  if (!s.active) return;
+  const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1), o = d.voff;
+  double pAp = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) pAp += p[o + i] * Ap[o + i];
+  pAp = cta_sum(pAp, scratch);
+  const double alpha = s.rz / pAp;
+  double rr = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+    x[o + i] += alpha * p[o + i];
+    const double ri = r[o + i] - alpha * Ap[o + i];
+    r[o + i] = ri;
+    rr += ri * ri;
+  }
+  rr = cta_sum(rr, scratch);
+  if (threadIdx.x == 0) {
+    s.rr = rr; s.iters += 1;
+    if (!(rr > tol2 * s.g2)) s.active = 2;                       // converged: part 2 retires the block
+    st[blockIdx.x] = s;
+  }
+}
+// part 2 (after z = P^-1 r): beta = r.z / rz_old, p = z + beta p.  init != 0: first direction p = z, rz = r.z
+__global__ void __launch_bounds__(1024)
+k_fpcg_update2(const BlockDesc *__restrict__ desc, const double *__restrict__ r, const double *__restrict__ z,
+               double *__restrict__ p, PcgState *__restrict__ st, int init, int *__restrict__ nactive) {
+  __shared__ double scratch[32];
+  const BlockDesc d = desc[blockIdx.x];
+  PcgState s = st[blockIdx.x];
+  if (!s.active) return;
+  const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1), o = d.voff;
+  if (s.active == 2) {                                           // retire: a zero direction keeps later applies harmless
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) p[o + i] = 0.0;
+    if (threadIdx.x == 0) { s.active = 0; st[blockIdx.x] = s; }
+    return;
+  }
+  double rz = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) rz += r[o + i] * z[o + i];
+  rz = cta_sum(rz, scratch);
+  const double beta = init ? 0.0 : rz / s.rz;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) p[o + i] = z[o + i] + beta * p[o + i];
+  if (threadIdx.x == 0) {
+    s.rz = rz;
+    st[blockIdx.x] = s;
+    atomicAdd(nactive, 1);
+  }
+}
+// x = 0, r = g, g2 = rr = g.g
+__global__ void __launch_bounds__(1024)
+k_fpcg_init(const BlockDesc *__restrict__ desc, const double *__restrict__ g, double *__restrict__ x,
+            double *__restrict__ r, double *__restrict__ p, PcgState *__restrict__ st) {
+  __shared__ double scratch[32];
+  const BlockDesc d = desc[blockIdx.x];
+  const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1), o = d.voff;
+  double gg = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+    const double gi = g[o + i];
+    x[o + i] = 0.0; r[o + i] = gi; p[o + i] = 0.0;
+    gg += gi * gi;
+  }
+  gg = cta_sum(gg, scratch);
+  if (threadIdx.x == 0) {
+    PcgState s; s.rz = 0.0; s.g2 = gg; s.rr = gg; s.iters = 0;
+    s.active = gg > 0.0 ? 1 : 0;                                  // g == 0 -> x = 0 (global_curved.jl:733)
+    st[blockIdx.x] = s;
+  }
+}
+
+}  // namespace hsbp
+
+namespace {
+
+using namespace hsbp;
+
+struct FdmLibs {                 // per-context library handles (created on first use)
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+};
+
+#define HSBP_BLAS(ctx, call)                                                                        \
+  do {                                                                                              \
+    cublasStatus_t _s = (call);                                                                     \
+    if (_s != CUBLAS_STATUS_SUCCESS) {                                                              \
+      (ctx)->err = std::string(#call) + ": cuBLAS status " + std::to_string((int)_s);                 \
+      return HSBP_ERR_CUDA;                                                                         \
+    }                                                                                               \
+  } while (0)
+#define HSBP_SOLVER(ctx, call)                                                                      \
+  do {                                                                                              \
+    cusolverStatus_t _s = (call);                                                                   \
+    if (_s != CUSOLVER_STATUS_SUCCESS) {                                                            \
+      (ctx)->err = std::string(#call) + ": cuSOLVER status " + std::to_string((int)_s);               \
+      return HSBP_ERR_CUDA;                                                                         \
+    }                                                                                               \
+  } while (0)
+
+int fdm_libs(hsbp_ctx *ctx, FdmLibs **out) {
+  if (!ctx->fdm_libs) {
+    FdmLibs *l = new (std::nothrow) FdmLibs();
+    if (!l) HSBP_FAIL(ctx, HSBP_ERR_STATE, "out of host memory");
+    ctx->fdm_libs = l;
+    HSBP_BLAS(ctx, cublasCreate(&l->blas));
+    HSBP_BLAS(ctx, cublasSetStream(l->blas, ctx->stream));
+    HSBP_SOLVER(ctx, cusolverDnCreate(&l->solver));
+    HSBP_SOLVER(ctx, cusolverDnSetStream(l->solver, ctx->stream));
+  }
+  *out = (FdmLibs *)ctx->fdm_libs;
+  return HSBP_OK;
+}
+
+void fdm_libs_destroy(hsbp_ctx *ctx) {
+  FdmLibs *l = (FdmLibs *)ctx->fdm_libs;
+  if (!l) return;
+  if (l->blas) cublasDestroy(l->blas);
+  if (l->solver) cusolverDnDestroy(l->solver);
+  delete l;
+  ctx->fdm_libs = nullptr;
+}
+
+template <int P> int fdm_setup_p(hsbp_blocks *b) {
+  hsbp_ctx *ctx = b->ctx;
+  if (!b->uniform) HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "fast-diagonalisation PCG needs blocks of one size (use HSBP_LOCAL_PCG)");
+  FdmLibs *libs = nullptr;
+  int rc = fdm_libs(ctx, &libs);
+  if (rc) return rc;
+  if ((rc = local_alloc(b))) return rc;
+  const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
+  const int64_t nb = b->nblocks;
+  const size_t vb = (size_t)b->VNp * sizeof(double);
+  if (!b->d_fdm_vr) {
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_fdm_vr, (size_t)nb * Nrp * Nrp * sizeof(double)));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_fdm_vs, (size_t)nb * Nsp * Nsp * sizeof(double)));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_fdm_z, vb));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_fdm_t, vb));
+  }
+  double *d_lr = nullptr, *d_ls = nullptr, *d_work = nullptr, *d_a2 = nullptr, *d_t2 = nullptr;
+  int *d_info = nullptr;
+  auto cleanup = [&]() { cudaFree(d_lr); cudaFree(d_ls); cudaFree(d_work); cudaFree(d_info); cudaFree(d_a2); cudaFree(d_t2); };
+  const int nmax = std::max(Nrp, Nsp);
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_lr, (size_t)nb * Nrp * sizeof(double)));
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_ls, (size_t)nb * Nsp * sizeof(double)));
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_info, sizeof(int)));
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_a2, (size_t)nb * nmax * nmax * sizeof(double)));
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_t2, (size_t)nb * nmax * nmax * sizeof(double)));
+  HSBP_CUDA(ctx, cudaMemsetAsync(b->d_fdm_vr, 0, (size_t)nb * Nrp * Nrp * sizeof(double), ctx->stream));
+  HSBP_CUDA(ctx, cudaMemsetAsync(b->d_fdm_vs, 0, (size_t)nb * Nsp * Nsp * sizeof(double), ctx->stream));
+  // ---- round 1: 1-D operators collapsed against the constant; their eigenvectors are the transform ---------
+  // (Ar + sigma_s Hr and As + sigma_r Hs have the eigenvectors of Ar, As; the shifts sigma -- the collapsed penalty
+  // terms of the other direction's faces -- are large, so the eigenvalues are taken from round 2 instead)
+  constexpr int WB = BandWidth<P>::WB, C = 2 * WB + 1;
+  const dim3 grid = gen_grid(b);
+  double *u = b->d_pp, *y = b->d_pAp;
+  for (int dir = 0; dir < 2 && rc == HSBP_OK; ++dir)
+    for (int ci = 0; ci < C && rc == HSBP_OK; ++ci) {
+      k_fdm_probe<<<grid, GEN_THREADS, 0, ctx->stream>>>(b->d_desc, dir, C, ci, nullptr, 0, u);
+      rc = apply_async(b, u, y);
+      k_fdm_collapse<<<(unsigned)nb, 256, 0, ctx->stream>>>(b->d_desc, dir, C, WB, ci, nullptr, 0, 0.5, y,
+                                                           dir == 0 ? b->d_fdm_vr : b->d_fdm_vs);
+    }
+  if (rc == HSBP_OK) {
+    k_fdm_standard_form<P><<<(unsigned)nb, 256, 0, ctx->stream>>>(Nrp, b->d_fdm_vr);
+    k_fdm_standard_form<P><<<(unsigned)nb, 256, 0, ctx->stream>>>(Nsp, b->d_fdm_vs);
+    rc = check_launch(ctx, "fdm probes");
+  }
+  if (rc) { cleanup(); return rc; }
+  int lwork_r = 0, lwork_s = 0;
+  cusolverStatus_t cs = cusolverDnDsyevd_bufferSize(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nrp,
+                                                    b->d_fdm_vr, Nrp, d_lr, &lwork_r);
+  if (cs == CUSOLVER_STATUS_SUCCESS)
+    cs = cusolverDnDsyevd_bufferSize(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nsp, b->d_fdm_vs, Nsp,
+                                     d_ls, &lwork_s);
+  const int lwork = std::max(lwork_r, lwork_s);
+  cudaError_t e1 = cs == CUSOLVER_STATUS_SUCCESS ? cudaMalloc((void **)&d_work, (size_t)lwork * sizeof(double)) : cudaSuccess;
+  for (int64_t e = 0; e < nb && cs == CUSOLVER_STATUS_SUCCESS && e1 == cudaSuccess; ++e) {
+    cs = cusolverDnDsyevd(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nrp,
+                          b->d_fdm_vr + (size_t)e * Nrp * Nrp, Nrp, d_lr + (size_t)e * Nrp, d_work, lwork, d_info);
+    if (cs == CUSOLVER_STATUS_SUCCESS)
+      cs = cusolverDnDsyevd(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nsp,
+                            b->d_fdm_vs + (size_t)e * Nsp * Nsp, Nsp, d_ls + (size_t)e * Nsp, d_work, lwork, d_info);
+  }
+  if (cs != CUSOLVER_STATUS_SUCCESS || e1 != cudaSuccess) {
+    cleanup();
+    HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: cuSOLVER syevd failed (status " + std::to_string((int)cs) + ")");
+  }
+  k_fdm_scale_vectors<P><<<(unsigned)nb, 256, 0, ctx->stream>>>(Nrp, b->d_fdm_vr);
+  k_fdm_scale_vectors<P><<<(unsigned)nb, 256, 0, ctx->stream>>>(Nsp, b->d_fdm_vs);
+  // ---- round 2: eigenvalues.  Collapse against the lowest mode w0 of the other direction (w0^T H w0 = 1):
+  //   (I (x) w0^T) M̃ (I (x) w0) = Ar + (w0^T As w0) Hr,  a shift of the size of the smallest eigenvalue only;
+  //   mr_a = v_a^T [.] v_a are the Rayleigh quotients of the tensor modes v_a (x) w0 (and ms_a likewise).
+  const double one = 1.0, zero = 0.0;
+  for (int dir = 0; dir < 2 && rc == HSBP_OK; ++dir) {
+    const int n = dir == 0 ? Nrp : Nsp;
+    const double *prof = dir == 0 ? b->d_fdm_vs : b->d_fdm_vr;           // column 0 of the other direction's vectors
+    const int64_t ldw = dir == 0 ? (int64_t)Nsp * Nsp : (int64_t)Nrp * Nrp;
+    double *V = dir == 0 ? b->d_fdm_vr : b->d_fdm_vs;
+    HSBP_CUDA(ctx, cudaMemsetAsync(d_a2, 0, (size_t)nb * n * n * sizeof(double), ctx->stream));
+    for (int ci = 0; ci < C && rc == HSBP_OK; ++ci) {
+      k_fdm_probe<<<grid, GEN_THREADS, 0, ctx->stream>>>(b->d_desc, dir, C, ci, prof, ldw, u);
+      rc = apply_async(b, u, y);
+      k_fdm_collapse<<<(unsigned)nb, 256, 0, ctx->stream>>>(b->d_desc, dir, C, WB, ci, prof, ldw, 1.0, y, d_a2);
+    }
+    if (rc) break;
+    cublasStatus_t bs = cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, d_a2, n, (long long)n * n,
+                                                  V, n, (long long)n * n, &zero, d_t2, n, (long long)n * n, (int)nb);
+    if (bs != CUBLAS_STATUS_SUCCESS) { cleanup(); HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: cuBLAS DGEMM failed"); }
+    k_fdm_rayleigh<<<(unsigned)nb, 256, 0, ctx->stream>>>(n, V, d_t2, dir == 0 ? d_lr : d_ls);
+  }
+  if (rc) { cleanup(); return rc; }
+  k_fdm_dinv<<<dim3((unsigned)nb, 16), 256, 0, ctx->stream>>>(b->d_desc, d_lr, d_ls, b->d_dinv);
+  e1 = cudaGetLastError();
+  if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e1 != cudaSuccess) { ctx->err = std::string("fdm_setup: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
+  return HSBP_OK;
+}
+
+int fdm_setup(hsbp_blocks *b) {
+  return dispatch_p(b->p, [&](auto Pc) { return fdm_setup_p<decltype(Pc)::value>(b); });
+}
+
+// z = P^-1 r for all blocks: Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T
+int fdm_precondition(hsbp_blocks *b, const double *r, double *z) {
+  hsbp_ctx *ctx = b->ctx;
+  FdmLibs *libs = (FdmLibs *)ctx->fdm_libs;
+  const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
+  const int nb = (int)b->nblocks;
+  const long long sv = (long long)Nrp * Nsp, sr = (long long)Nrp * Nrp, ss = (long long)Nsp * Nsp;
+  const double one = 1.0, zero = 0.0;
+  double *t = b->d_fdm_t;
+  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
+                                           r, Nrp, sv, &zero, t, Nrp, sv, nb));
+  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
+                                           b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
+  k_ewise<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, z, b->d_dinv, z, 0);
+  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
+                                           z, Nrp, sv, &zero, t, Nrp, sv, nb));
+  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
+                                           b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
+  return check_launch(ctx, "fdm_precondition");
+}
+
+int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stats) {
+  hsbp_ctx *ctx = b->ctx;
+  if (!b->d_fdm_vr) HSBP_FAIL(ctx, HSBP_ERR_STATE, "fast-diagonalisation PCG: not set up");
+  const double tol2 = b->local_tol * b->local_tol;
+  PcgState *st = (PcgState *)b->d_pcg;
+  double *r = b->d_pr, *p = b->d_pp, *Ap = b->d_pAp, *z = b->d_fdm_z;
+  const unsigned nb = (unsigned)b->nblocks;
+  int rc;
+  k_fpcg_init<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, g, x, r, p, st);
+  if ((rc = fdm_precondition(b, r, z))) return rc;
+  HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive, 0, 2 * sizeof(int), ctx->stream));
+  k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, p, st, 1, b->d_nactive);
+  const int check_every = 4;
+  int h_active = 1;
+  int64_t it = 0;
+  while (it < b->local_maxit) {
+    int slot = 0;
+    for (int k = 0; k < check_every && it < b->local_maxit; ++k, ++it) {
+      if ((rc = apply_async(b, p, Ap))) return rc;
+      k_fpcg_update1<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, Ap, x, r, p, st, tol2);
+      if ((rc = fdm_precondition(b, r, z))) return rc;
+      slot = (int)(it & 1);
+      HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive + slot, 0, sizeof(int), ctx->stream));
+      k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, p, st, 0, b->d_nactive + slot);
+    }
+    if ((rc = check_launch(ctx, "k_fpcg_update"))) return rc;
+    HSBP_CUDA(ctx, cudaMemcpyAsync(&h_active, b->d_nactive + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_active == 0) break;
+  }
+  if (stats) {
+    std::vector<PcgState> hs(b->nblocks);
+    HSBP_CUDA(ctx, cudaMemcpyAsync(hs.data(), st, b->nblocks * sizeof(PcgState), cudaMemcpyDeviceToHost, ctx->stream));
+    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    hsbp_local_stats s = {0, 0, 0, 0.0};
+    for (auto &q : hs) {
+      s.iterations_max = std::max<int64_t>(s.iterations_max, q.iters);
+      s.iterations_sum += q.iters;
+      s.failed_blocks += q.active ? 1 : 0;
+      if (q.g2 > 0) s.max_rel_residual = std::max(s.max_rel_residual, sqrt(q.rr / q.g2));
+    }
+    *stats = s;
+  }
+  return HSBP_OK;
+}
+
+}  // namespace

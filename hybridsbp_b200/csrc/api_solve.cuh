@@ -22,6 +22,9 @@ namespace {
 
 using namespace hsbp;
 
+int fdm_setup(hsbp_blocks *b);                                                        // api_fdm.cuh
+int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stats);
+
 inline dim3 vec_grid(int64_t n) {
   return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + VEC_THREADS - 1) / VEC_THREADS, 148 * 8)));
 }
@@ -103,6 +106,7 @@ int local_solve_impl(hsbp_blocks *b, const double *g, double *u, hsbp_local_stat
   HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
   if (b->local_mode == HSBP_LOCAL_CHOLESKY) return chol_solve(b, g, u, stats);
   if (b->local_mode == HSBP_LOCAL_BAND) return band_solve(b, g, u, stats);
+  if (b->local_mode == HSBP_LOCAL_FDM) return fdm_solve(b, g, u, stats);
   return pcg_solve(b, g, u, stats);
 }
 
@@ -182,7 +186,7 @@ int hsbp_local_setup(hsbp_blocks *b, int mode, double tol, int64_t maxit) {
   if (!b) return HSBP_ERR_ARG;
   hsbp_ctx *ctx = b->ctx;
   if (!b->have_metrics || !b->have_tau) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_local_setup: metrics / tau not set");
-  if (mode != HSBP_LOCAL_PCG && mode != HSBP_LOCAL_CHOLESKY && mode != HSBP_LOCAL_BAND) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_local_setup: unknown mode");
+  if (mode != HSBP_LOCAL_PCG && mode != HSBP_LOCAL_CHOLESKY && mode != HSBP_LOCAL_BAND && mode != HSBP_LOCAL_FDM) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_local_setup: unknown mode");
   HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
   b->local_tol = tol > 0 ? tol : 1e-13;
   b->local_maxit = maxit > 0 ? maxit : 100000;
@@ -191,6 +195,8 @@ int hsbp_local_setup(hsbp_blocks *b, int mode, double tol, int64_t maxit) {
     if ((rc = chol_setup(b))) return rc;
   } else if (mode == HSBP_LOCAL_BAND) {
     if ((rc = band_setup(b))) return rc;
+  } else if (mode == HSBP_LOCAL_FDM) {
+    if ((rc = fdm_setup(b))) return rc;
   } else {
     if ((rc = local_alloc(b))) return rc;
     rc = dispatch_p(b->p, [&](auto Pc) { return probe_diagonal<decltype(Pc)::value>(b); });

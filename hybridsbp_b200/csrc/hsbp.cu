@@ -24,6 +24,8 @@ template <class F> int dispatch_p(int p, F &&f) {
   return HSBP_ERR_UNSUPP;
 }
 
+void fdm_libs_destroy(hsbp_ctx *ctx);      // api_fdm.cuh
+
 int check_launch(hsbp_ctx *ctx, const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -71,6 +73,7 @@ int hsbp_ctx_destroy(hsbp_ctx *ctx) {
   if (!ctx) return HSBP_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  fdm_libs_destroy(ctx);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->copy_ev[0]); cudaEventDestroy(ctx->copy_ev[1]);
   cudaStreamDestroy(ctx->copy_stream[0]); cudaStreamDestroy(ctx->copy_stream[1]);
@@ -211,6 +214,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
   cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off); cudaFree(b->d_chol_work);
   cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work);
+  cudaFree(b->d_fdm_vr); cudaFree(b->d_fdm_vs); cudaFree(b->d_fdm_z); cudaFree(b->d_fdm_t);
   delete b;
   return HSBP_OK;
 }
@@ -316,7 +320,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "sweep_chunks_per_side") b->sweep_ncs_override = (int)value;
   else if (n == "sweep_points_per_thread") b->sweep_r_override = (int)value;
   else if (n == "sweep_fold_faces") b->sweep_fold_faces = (int)value;
-  else if (n == "sweep_swizzle") b->sweep_swizzle = (int)value;
+  else if (n == "sweep_deep") b->sweep_deep = (int)value;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);
   return HSBP_OK;
 }
@@ -518,4 +522,5 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 #include "api_chol.cuh"
 #include "api_band.cuh"
 #include "api_solve.cuh"
+#include "api_fdm.cuh"
 #include "api_bp1.cuh"

@@ -15,6 +15,7 @@ struct hsbp_ctx {
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   int sm_count = 148;
   size_t smem_optin = 0;
+  void *fdm_libs = nullptr;         // cuBLAS / cuSOLVER handles of the fast-diagonalisation preconditioner (api_fdm.cuh)
   std::string err;
 };
 
@@ -52,7 +53,8 @@ struct hsbp_blocks {
   int max_Nr = 0, max_Ns = 0;
   int force_generic = 0;
   int sweep_r_override = 0;         // points per thread of the line-marching kernel (0 = heuristic, 2 or 4)
-  int sweep_swizzle = 0;            // 1: swizzled tensor-map TMA for the R = 4 layout (conflict-free, but slower: see k_sweep.cuh)
+  int sweep_deep = 1;               // 1: css / crs of older lines come from deeper shared-memory rings, 0: register windows (k_sweep.cuh)
+  int last_sweep_ctas_per_sm = 0;
   int sweep_fold_faces = 1;         // fold the face terms into k_sweep (0: separate gather / scatter kernels)
   int sweep_ncs_override = 0;       // chunks per side of the line-marching kernel (0 = heuristic)
   int last_variant = -1;
@@ -70,6 +72,8 @@ struct hsbp_blocks {
   double *d_band = nullptr;                 // banded factors (api_band.cuh), LAPACK lower-band storage per block
   void *d_band_desc = nullptr;              // BandBlock descriptors
   double *d_band_work = nullptr;
+  double *d_fdm_vr = nullptr, *d_fdm_vs = nullptr;   // generalised eigenvectors of the collapsed 1-D operators (api_fdm.cuh)
+  double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   // pinned staging for hsbp_apply_host (lazy)
   double *d_stage_u = nullptr, *d_stage_y = nullptr;
   std::vector<cudaEvent_t> pipe_ev;          // per block group: H2D done, kernels done

@@ -28,7 +28,6 @@
 //
 // Algorithmic traffic: 40 B per point (u, crr, css, crs in, y out); DESIGN.md section 4.
 #pragma once
-#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "hsbp_internal.h"
 #include "sbp1d.cuh"
 #include "k_generic.cuh"
@@ -78,17 +77,24 @@ __device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// 2-D tiled TMA load (cp.async.bulk.tensor): box of the tensor map at coordinates (c0, c1) -> shared memory
-__device__ __forceinline__ void tensor_g2s_s(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+// shared-memory access through 32-bit shared-window addresses
+__device__ __forceinline__ double2 lds128(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
 }
-// the four fields as 2-D tensors [rows][16 doubles] with the 128-byte swizzle: a line lands in shared memory with its
-// 16-byte chunks XOR-permuted inside every 128-byte row, which makes the 32-byte-per-lane reads of the R = 4 layout
-// bank-conflict free
-struct SweepMaps {
-  CUtensorMap u, crr, css, crs;
-};
+__device__ __forceinline__ double lds64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+// hide how a loop invariant was computed: the compiler then keeps it in a register instead of re-deriving it
+__device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ int opaque(int x) { asm volatile("" : "+r"(x)); return x; }
+
 // one lane of a fully active warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -106,7 +112,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 #ifndef SW_NST_OVERRIDE
 #define SW_NST_OVERRIDE 3
 #endif
-constexpr int SW_NST = SW_NST_OVERRIDE;   // ring stages: one being consumed, the others in flight
+constexpr int SW_NST = SW_NST_OVERRIDE;   // ring stages of u and crr: one being consumed, the others in flight
 constexpr int SW_MAX_THREADS = 256;
 
 struct SweepParams {
@@ -136,6 +142,12 @@ template <int P> struct SweepCfg {
   // r-closure table of one (line, end): MCX rows (closure rows of M u, replaced; rows MC..NB-1 only carry the
   // face terms and are added) followed by the BM closure rows of Q u
   static constexpr int CLW = MCX + T::BM;
+  // ring depths (lines) of the four fields.  u and crr are only looked at on the newest line.  DEEP: css and crs
+  // stay in shared memory for as long as the s-direction stencil needs them (css: lines j-2H+1 .. j for the
+  // couplings of the pairs (j-H, j-H+O); crs: line j-H for w) instead of travelling through register windows
+  template <bool DEEP> static constexpr int nsb() { return DEEP ? 2 * T::H + (SW_NST - 1) : SW_NST; }
+  template <bool DEEP> static constexpr int nsc() { return DEEP ? T::H + 1 + (SW_NST - 1) : SW_NST; }
+  template <bool DEEP> static constexpr int nlines() { return 2 * SW_NST + nsb<DEEP>() + nsc<DEEP>() + 2; }
   __device__ static const double *bs() { return Sbp<P>::bs(); }
   __device__ static const double *hw() { return P == 2 ? c_sw_hw2 : (P == 4 ? c_sw_hw4 : c_sw_hw6); }
   __device__ static const double *Qc() { return P == 2 ? c_sw_Qc2 : (P == 4 ? c_sw_Qc4 : c_sw_Qc6); }
@@ -191,32 +203,32 @@ template <int T0, int T1, class F> __device__ __forceinline__ void for_lanes(F &
   }
 }
 
-// NT: upper bound of the CTA size; MINB: CTAs per SM the register allocation is sized for
-// (R = 2: 128 registers per thread, R = 4: 255).
-// SWZ: lines arrive through tensor-map TMA with the 128-byte swizzle (needs Nr+1 a multiple of 16)
-template <int P, int R, int NT, int MINB, bool SWZ>
-__global__ void __launch_bounds__(NT, MINB)
-k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
+// NT: upper bound of the CTA size; MINB: CTAs per SM the register allocation is sized for.
+// DEEP: the steady state reads css / crs of older lines from deeper shared-memory rings instead of register
+// windows (SweepCfg::nsb, nsc): 2H+1 lines of u and 2H+1 accumulators remain as per-point register state.
+template <int P, int R, bool DEEP>
+__device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
-  constexpr int H = C::H, W = C::W, LB = C::LB, PAD = C::PAD, CLW = C::CLW, NST = SW_NST;
-  constexpr int MC = T::MC, NK = T::NK, BM = T::BM, BN = T::BN, MCX = C::MCX, NB = C::NB;
+  constexpr int H = C::H, W = C::W, PAD = C::PAD, CLW = C::CLW, NST = SW_NST;
+  constexpr int NSB = C::template nsb<DEEP>(), NSC = C::template nsc<DEEP>(), NLINES = C::template nlines<DEEP>();
+  constexpr int MC = T::MC, BM = T::BM, BN = T::BN, MCX = C::MCX, NB = C::NB;
   constexpr int NV = R + 2 * PAD;                         // values of a line a thread looks at
   constexpr int CLR = 2 * CLW;                            // r-end table entries per line (both ends); 2*CLW*8 B is a multiple of 16
+  constexpr int DOFF = PAD;
   static_assert(R % 2 == 0 && PAD >= H, "layout");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int Nr = prm.Nr, Ns = prm.Ns, Nrp = Nr + 1, Nsp = Ns + 1;
-  // A "slot" holds one line of one field: DOFF doubles of zeros (left halo), the Nrp values, zeros again (right halo =
-  // the front of the next slot).  Plain layout: LW = Nrp + 2 PAD, DOFF = PAD.  Swizzled layout: the data start is
-  // 1024-byte aligned (the swizzle pattern is a function of the address), DOFF = 128, LW = Nrp rounded up to 128, + 128.
-  const int LW = SWZ ? ((Nrp + 127) & ~127) + 128 : Nrp + 2 * PAD;
-  const int DOFF = SWZ ? 128 : PAD;
-  double *ring = reinterpret_cast<double *>(smem_raw);    // [NST][4][LW]
-  if constexpr (SWZ) ring = reinterpret_cast<double *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  double *wbuf = ring + (size_t)NST * 4 * LW;             // [2][LW]
-  double *clring = wbuf + 2 * LW + (SWZ ? 128 : 0);       // [NST][CLR]: r-end table rows of the staged lines
+  // A "slot" holds one line of one field: PAD doubles of zeros (left halo), the Nrp values, PAD zeros (right halo)
+  const int LW = Nrp + 2 * PAD;
+  double *ring_u = reinterpret_cast<double *>(smem_raw);  // [NST][LW]
+  double *ring_rr = ring_u + (size_t)NST * LW;            // [NST][LW]  crr'
+  double *ring_ss = ring_rr + (size_t)NST * LW;           // [NSB][LW]  css'
+  double *ring_rs = ring_ss + (size_t)NSB * LW;           // [NSC][LW]  crs
+  double *wbuf = ring_rs + (size_t)NSC * LW;              // [2][LW]
+  double *clring = wbuf + 2 * LW;                         // [NST][CLR]: r-end table rows of the staged lines
   uint64_t *full = reinterpret_cast<uint64_t *>(clring + (size_t)NST * CLR);
 
   // ---- which chunk --------------------------------------------------------------------------
@@ -240,37 +252,28 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
   const int64_t foff = e * (2 * (int64_t)Nrp + 2 * (int64_t)Nsp);    // block e in the block-face layout
 
   // ---- one-time setup: zero the halos of the shared lines, barriers --------------------------
-  if constexpr (SWZ) {
-    for (int idx = tid; idx < (NST * 4 + 2) * LW + 128; idx += nthreads) ring[idx] = 0.0;     // everything, once
-  } else {
-    for (int idx = tid; idx < (NST * 4 + 2) * 2 * PAD; idx += nthreads) {
-      const int line = idx / (2 * PAD), k = idx - line * (2 * PAD);
-      ring[(size_t)line * LW + (k < PAD ? k : Nrp + k)] = 0.0;
-    }
+  for (int idx = tid; idx < NLINES * 2 * PAD; idx += nthreads) {
+    const int line = idx / (2 * PAD), k = idx - line * (2 * PAD);
+    ring_u[(size_t)line * LW + (k < PAD ? k : Nrp + k)] = 0.0;
+  }
+  if constexpr (DEEP) {
+    // lines in front of the first staged one are looked at by the first steps of a chunk (their pairs only
+    // touch rows that are not output); keep them finite
+    for (int idx = tid; idx < (NSB + NSC) * LW; idx += nthreads) ring_ss[idx] = 0.0;
   }
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  auto issue = [&](int n) {      // marching line jstart + n into stage n % NST  (thread 0 only)
+  auto issue = [&](int n) {      // marching line jstart + n into its slots  (thread 0 only)
     const int st = n % NST;
-    double *dst = ring + (size_t)st * 4 * LW + DOFF;
     const int64_t g = base + (int64_t)(jstart + n) * lstride;
     mbar_expect_tx(&full[st], 4u * line_bytes + (uint32_t)(CLR * 8));
-    if constexpr (SWZ) {
-      const uint32_t bar = smem_u32(&full[st]);
-      const int row = (int)(g >> 4);                      // 16 doubles per tensor row
-      tensor_g2s_s(smem_u32(dst), &tm.u, 0, row, bar);
-      tensor_g2s_s(smem_u32(dst + LW), &tm.crr, 0, row, bar);
-      tensor_g2s_s(smem_u32(dst + 2 * LW), &tm.css, 0, row, bar);
-      tensor_g2s_s(smem_u32(dst + 3 * LW), &tm.crs, 0, row, bar);
-    } else {
-      bulk_g2s(dst, prm.u + g, line_bytes, &full[st]);
-      bulk_g2s(dst + LW, prm.crr + g, line_bytes, &full[st]);
-      bulk_g2s(dst + 2 * LW, prm.css + g, line_bytes, &full[st]);
-      bulk_g2s(dst + 3 * LW, prm.crs + g, line_bytes, &full[st]);
-    }
+    bulk_g2s(ring_u + (size_t)st * LW + DOFF, prm.u + g, line_bytes, &full[st]);
+    bulk_g2s(ring_rr + (size_t)st * LW + DOFF, prm.crr + g, line_bytes, &full[st]);
+    bulk_g2s(ring_ss + (size_t)(n % NSB) * LW + DOFF, prm.css + g, line_bytes, &full[st]);
+    bulk_g2s(ring_rs + (size_t)(n % NSC) * LW + DOFF, prm.crs + g, line_bytes, &full[st]);
     const int64_t jl = up ? (int64_t)(jstart + n) : (int64_t)Ns - (jstart + n);       // actual line index
     bulk_g2s(clring + (size_t)st * CLR, prm.rtab + ((e * Nsp + jl) * CLR), (uint32_t)(CLR * 8), &full[st]);
   };
@@ -282,16 +285,6 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
   const int i0 = tid * R;
   const bool own = i0 < Nrp;
   const int nown = Nrp / R;                               // threads that own points (Nrp % R == 0)
-  // offset (doubles, from the data start of a slot) of element idx / of the 16-byte chunks this thread looks at
-  auto sel = [&](int idx) -> int {
-    if constexpr (!SWZ) return idx;
-    if (idx < 0 || idx >= Nrp) return idx;                 // halo: zeros wherever one looks
-    const int L = idx >> 1, row = L >> 3;
-    return row * 16 + (((L & 7) ^ (row & 7)) << 1) + (idx & 1);
-  };
-  int so[NV / 2];
-#pragma unroll
-  for (int k = 0; k < NV / 2; ++k) so[k] = sel(i0 - PAD + 2 * k);
   const double *qc = C::Qc();
   const double *gu = prm.u + base + i0;                   // + j*lstride: this thread's points on marching line j
   const double *gss = prm.css + base + i0;
@@ -300,11 +293,16 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
   // s-direction windows.  Logical index k <-> marching line j-(W-1)+k (u, scaled css, crs) or j-H+k
   // (accumulators); the physical slot of logical k in a step with rotation PH is (PH+1+k) % W, so the
   // W-fold unrolled steady-state loop never moves a register.  bw uses k >= 1, cw uses k >= H.
-  double uw[W][R], bw[W][R], cw[W][R], acc[W][R];
+  // (DEEP: no bw / cw, css and crs of older lines are read from the rings.)
+  double uw[W][R], acc[W][R];
+  [[maybe_unused]] double bw[DEEP ? 1 : W][R], cw[DEEP ? 1 : W][R];
 #pragma unroll
   for (int q = 0; q < R; ++q)
 #pragma unroll
-    for (int k = 0; k < W; ++k) { uw[k][q] = 0.0; bw[k][q] = 0.0; cw[k][q] = 0.0; acc[k][q] = 0.0; }
+    for (int k = 0; k < W; ++k) {
+      uw[k][q] = 0.0; acc[k][q] = 0.0;
+      if constexpr (!DEEP) { bw[k][q] = 0.0; cw[k][q] = 0.0; }
+    }
   if (prologue && own) {                                  // lines that collect read-modify-write contributions
     for (int l = 0; l < BM; ++l)
 #pragma unroll
@@ -323,7 +321,10 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
     const bool pro = FAST ? false : prologue;
 
     mbar_wait(&full[st], parity);
-    const double *sb = ring + (size_t)st * 4 * LW;
+    const double *sbu = ring_u + (size_t)st * LW + DOFF + i0 - PAD;           // this thread's NV values of line j
+    const double *sbr = ring_rr + (size_t)st * LW + DOFF + i0 - PAD;
+    const double *sbs = ring_ss + (size_t)(n % NSB) * LW + DOFF + i0;         // its own R values
+    const double *sbc = ring_rs + (size_t)(n % NSC) * LW + DOFF + i0;
     const int jo = j - H;
     const bool outp = (jo >= o0) && (jo < o1);
     double *wb = wbuf + (size_t)(n & 1) * LW;
@@ -335,27 +336,52 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
 #pragma unroll
           for (int k = 0; k < W - 1; ++k) {               // only the slots that are read later (bw: k >= 1, cw: k >= H)
             uw[k][q] = uw[k + 1][q]; acc[k][q] = acc[k + 1][q];
-            if (k >= 1) bw[k][q] = bw[k + 1][q];
-            if (k >= H) cw[k][q] = cw[k + 1][q];
+            if constexpr (!DEEP) {
+              if (k >= 1) bw[k][q] = bw[k + 1][q];
+              if (k >= H) cw[k][q] = cw[k + 1][q];
+            }
           }
       }
       // ---- take in line j -------------------------------------------------------------------
       double U[NV], Bq[NV];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + DOFF + so[k]);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + DOFF + so[k]);
+        const double2 a = *reinterpret_cast<const double2 *>(sbu + 2 * k);
+        const double2 b2 = *reinterpret_cast<const double2 *>(sbr + 2 * k);
         U[2 * k] = a.x; U[2 * k + 1] = a.y; Bq[2 * k] = b2.x; Bq[2 * k + 1] = b2.y;
       }
 #pragma unroll
       for (int q = 0; q < R; ++q) { uw[SL(W - 1)][q] = U[PAD + q]; acc[SL(W - 1)][q] = 0.0; }
+      double cnew[R];                                     // crs on line j
 #pragma unroll
       for (int k = 0; k < R / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + DOFF + so[PAD / 2 + k]);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + DOFF + so[PAD / 2 + k]);
-        bw[SL(W - 1)][2 * k] = a.x; bw[SL(W - 1)][2 * k + 1] = a.y;
-        cw[SL(W - 1)][2 * k] = b2.x; cw[SL(W - 1)][2 * k + 1] = b2.y;
+        const double2 b2 = *reinterpret_cast<const double2 *>(sbc + 2 * k);
+        cnew[2 * k] = b2.x; cnew[2 * k + 1] = b2.y;
+        if constexpr (!DEEP) {
+          const double2 a = *reinterpret_cast<const double2 *>(sbs + 2 * k);
+          bw[SL(W - 1)][2 * k] = a.x; bw[SL(W - 1)][2 * k + 1] = a.y;
+          cw[SL(W - 1)][2 * k] = b2.x; cw[SL(W - 1)][2 * k + 1] = b2.y;
+        }
       }
+      // css' on line j-H+s / crs on line j-H of point q: register windows, or (DEEP) the shared-memory rings
+      auto css_at = [&](int s2, int q) -> double {
+        if constexpr (DEEP) {
+          int sl = (n - H + s2) % NSB;
+          if (sl < 0) sl += NSB;
+          return ring_ss[(size_t)sl * LW + DOFF + i0 + q];
+        } else {
+          return bw[SL(H + s2)][q];
+        }
+      };
+      auto crs_lag = [&](int q) -> double {
+        if constexpr (DEEP) {
+          int sl = (n - H) % NSC;
+          if (sl < 0) sl += NSC;
+          return ring_rs[(size_t)sl * LW + DOFF + i0 + q];
+        } else {
+          return cw[SL(H)][q];
+        }
+      };
 
       // ---- r-direction on line j: rr = M(crr') u (pair form) goes straight into the accumulator of
       //      line j, qr = Qr u ----------------------------------------------------------------------
@@ -406,7 +432,7 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         acc[SL(H)][q] += rr[q];
-        t[q] = cw[SL(W - 1)][q] * qr[q];                  // t = crs o (Qr u) on line j
+        t[q] = cnew[q] * qr[q];                           // t = crs o (Qr u) on line j
       }
       // ---- Qs^T t, pushed from row j: (Qs^T t)(l) += Qs[j][l] t(j) ------------------------------
       if (FAST || j >= BM) {
@@ -447,7 +473,7 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
           if (!(pro && (a + O < MC))) {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-              const double cf = pair_coef<P, O>([&](int s) { return bw[SL(H + s)][q]; });    // line a+s = j-H+s
+              const double cf = pair_coef<P, O>([&](int s) { return css_at(s, q); });        // line a+s = j-H+s
               const double f = cf * (uw[SL(H + O)][q] - uw[SL(H)][q]);
               if (!row_a_closure) acc[SL(0)][q] += f;
               acc[SL(O)][q] -= f;
@@ -482,18 +508,18 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
         }
 #pragma unroll
         for (int k = 0; k < R / 2; ++k)
-          *reinterpret_cast<double2 *>(wb + DOFF + so[PAD / 2 + k]) =
-              make_double2(cw[SL(H)][2 * k] * qs[2 * k], cw[SL(H)][2 * k + 1] * qs[2 * k + 1]);
+          *reinterpret_cast<double2 *>(wb + DOFF + i0 + 2 * k) =
+              make_double2(crs_lag(2 * k) * qs[2 * k], crs_lag(2 * k + 1) * qs[2 * k + 1]);
       }
     }
     __syncthreads();
-    if (tid == 0 && n + NST < nlines) { fence_proxy_async(); issue(n + NST); }    // stage st is free again
+    if (tid == 0 && n + NST < nlines) { fence_proxy_async(); issue(n + NST); }    // the slots of line j are free again
     if (own && outp) {
       // ---- rs = Qr^T w, then the output line ------------------------------------------------
       double Wv[NV], val[R];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(wb + DOFF + so[k]);
+        const double2 a = *reinterpret_cast<const double2 *>(wb + DOFF + i0 - PAD + 2 * k);
         Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
       }
 #pragma unroll
@@ -508,7 +534,7 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
         if (tid == TL) {
           double w0[BN];
 #pragma unroll
-          for (int k = 0; k < BN; ++k) w0[k] = wb[DOFF + sel(k)];
+          for (int k = 0; k < BN; ++k) w0[k] = wb[DOFF + k];
 #pragma unroll
           for (int q = 0; q < R; ++q)
             if (TL * R + q < BM) val[q] = acc[SL(0)][q] + qt_closure_row<P>(TL * R + q, w0);
@@ -516,7 +542,7 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
         if (tid == nown - 1 - TL) {                       // mirrored, sign flipped
           double wr[BN];
 #pragma unroll
-          for (int k = 0; k < BN; ++k) wr[k] = wb[DOFF + sel(Nr - k)];
+          for (int k = 0; k < BN; ++k) wr[k] = wb[DOFF + Nr - k];
 #pragma unroll
           for (int q = 0; q < R; ++q)
             if (TL * R + (R - 1 - q) < BM) val[q] = acc[SL(0)][q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
@@ -559,35 +585,92 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
   // inside the instruction cache: everything that does not touch the register windows (waiting for
   // the line, the r-direction work, the w exchange and the output) exists once; only the short
   // window section is specialised for the W rotations and selected by a uniform branch.
-  int ph = 0;                                             // rotation of the next steady-state step
-  const int nout0 = o0 + H - jstart;                      // first step whose line j-H belongs to the chunk
-  const int nrefill = nlines - NST;                       // steps after which no line is left to fetch
-  double *yout = nullptr;                                 // output line of the next steady-state step
-  int64_t gofs = 0, tofs = 0;                             // offsets of marching line j (volume fields, r-end table)
-  const int64_t tstride = up ? CLR : -CLR;
-  const uint32_t full_s = smem_u32(full), ring_s = smem_u32(ring), clring_s = smem_u32(clring);
-  const int nwarps = nthreads >> 5;
-  int rw = 0;                                             // warp that issues the next refill
-  auto fast_step = [&]() {
-    mbar_wait_s(full_s + 8u * st, parity);
-    const double *sb = ring + (size_t)st * 4 * LW;
-    const bool outp = n >= nout0;                         // line j-H is an output line of this chunk
-    double *wb = wbuf + (size_t)(n & 1) * LW;
+  // All shared-memory traffic of the loop goes through explicit 32-bit shared-window addresses that are advanced
+  // incrementally, and the loop invariants are made opaque to the compiler: left alone it re-derives them from the
+  // kernel parameters in every step (about a quarter of the executed instructions, measured with ncu).
+  using GenericPH = std::integral_constant<int, W - 1>;    // rotation W-1: slot(k) == k (canonical order)
+  const int jfast = prologue ? MCX + H : jstart;           // first step without s-end closure / face logic
+  while (j < jfast && j <= jend) step(GenericPH{}, std::false_type{});
+  if (j > jend) return;
+
+  constexpr int NAS = DEEP ? 2 * H : 1, NAC = DEEP ? H + 1 : 1;
+  constexpr int ELANES = (MCX + R - 1) / R;                // lanes per r-end that patch closure rows
+  const uint32_t LWB = opaque((uint32_t)LW * 8u);
+  const uint32_t full_s = opaque(smem_u32(full));
+  // thread-constant addresses: this thread's NV values (u, crr, w) / its own R values (css, crs) in slot 0 of a ring
+  const uint32_t c_u0 = opaque(smem_u32(ring_u) + (uint32_t)(DOFF + i0 - PAD) * 8u);
+  const uint32_t c_drr = opaque((uint32_t)NST * LWB);                                    // ring_rr - ring_u
+  const uint32_t c_ss0 = opaque(smem_u32(ring_ss) + (uint32_t)(DOFF + i0) * 8u), c_ssE = opaque(c_ss0 + (uint32_t)NSB * LWB);
+  const uint32_t c_rs0 = opaque(smem_u32(ring_rs) + (uint32_t)(DOFF + i0) * 8u), c_rsE = opaque(c_rs0 + (uint32_t)NSC * LWB);
+  const uint32_t c_w0 = smem_u32(wbuf) + (uint32_t)(DOFF + i0 - PAD) * 8u;
+  const uint32_t c_wsum = opaque(2u * c_w0 + LWB);
+  const uint32_t c_cl0 = opaque(smem_u32(clring));
+  const int nout0 = opaque(o0 + H - jstart);               // first step whose line j-H belongs to the chunk
+  const int nrefill = opaque(nlines - NST);                // steps after which no line is left to fetch
+  const int nwarps = opaque(nthreads >> 5);
+  const int mywarp = opaque(tid >> 5);
+  const int edge = opaque((own && (tid < ELANES || tid >= nown - ELANES)) ? 1 : 0);
+  const int ownf = opaque(own ? 1 : 0);
+  const int far0 = opaque(nown - 1);                       // thread that owns the last points of a line
+
+  uint32_t au = c_u0 + (uint32_t)st * LWB, acl = c_cl0 + (uint32_t)(st * CLR) * 8u, abar = full_s + 8u * (uint32_t)st;
+  uint32_t aw = c_w0 + (uint32_t)(n & 1) * LWB;
+  uint32_t as_[NAS], ac_[NAC];                             // css' on lines j, j-1, ..; crs on lines j, .., j-H
+#pragma unroll
+  for (int k = 0; k < NAS; ++k) as_[k] = c_ss0 + (uint32_t)((((n - k) % NSB) + NSB) % NSB) * LWB;
+#pragma unroll
+  for (int k = 0; k < NAC; ++k) ac_[k] = c_rs0 + (uint32_t)((((n - k) % NSC) + NSC) % NSC) * LWB;
+  int ph = 0;                                              // rotation of the next step
+  int rw = 0;                                              // warp that issues the next refill
+  double *yout = gy + (int64_t)(j - H) * lstride;          // output line of the next step
+
+#pragma unroll 1
+  for (int left = nlines - n; left > 0; --left) {
+    mbar_wait_s(abar, parity);
+    const bool outp = n >= nout0;                          // line j-H is an output line of this chunk
     double accout[R];
-    if (own) {
+    if (ownf) {
       // ---- A: line j from shared memory, r-direction work (rotation independent) ---------------
-      double U[NV], Bq[NV], bn[R], cn[R], rr[R], qr[R], wout[R];
+      double U[NV], Bq[NV], cn[R], rr[R], qr[R], wout[R];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + DOFF + so[k]);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + LW + DOFF + so[k]);
+        const double2 a = lds128(au + 16u * k);
+        const double2 b2 = lds128(au + c_drr + 16u * k);
         U[2 * k] = a.x; U[2 * k + 1] = a.y; Bq[2 * k] = b2.x; Bq[2 * k + 1] = b2.y;
       }
 #pragma unroll
       for (int k = 0; k < R / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(sb + 2 * LW + DOFF + so[PAD / 2 + k]);
-        const double2 b2 = *reinterpret_cast<const double2 *>(sb + 3 * LW + DOFF + so[PAD / 2 + k]);
-        bn[2 * k] = a.x; bn[2 * k + 1] = a.y; cn[2 * k] = b2.x; cn[2 * k + 1] = b2.y;
+        const double2 b2 = lds128(ac_[0] + 16u * k);
+        cn[2 * k] = b2.x; cn[2 * k + 1] = b2.y;
+      }
+      // DEEP: couplings of the s-direction pairs (a, a+O), a = j-H, and crs on line j-H, from the rings
+      // (rotation independent); otherwise the newest css line for the register window
+      [[maybe_unused]] double bn[R], cfs[H][R], c2[R];
+      if constexpr (DEEP) {
+        double Bs[2 * H][R];                              // css' on lines j-2H+1 .. j
+#pragma unroll
+        for (int m = 0; m < 2 * H; ++m)
+#pragma unroll
+          for (int k = 0; k < R / 2; ++k) {
+            const double2 a = lds128(as_[2 * H - 1 - m] + 16u * k);
+            Bs[m][2 * k] = a.x; Bs[m][2 * k + 1] = a.y;
+          }
+        for_offsets<1, H>([&](auto Oc) {
+          constexpr int O = decltype(Oc)::value;
+#pragma unroll
+          for (int q = 0; q < R; ++q) cfs[O - 1][q] = pair_coef<P, O>([&](int s2) { return Bs[s2 + H - 1][q]; });
+        });
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+          const double2 a = lds128(ac_[H] + 16u * k);
+          c2[2 * k] = a.x; c2[2 * k + 1] = a.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+          const double2 a = lds128(as_[0] + 16u * k);
+          bn[2 * k] = a.x; bn[2 * k + 1] = a.y;
+        }
       }
       for_offsets<1, H>([&](auto Oc) {
         constexpr int O = decltype(Oc)::value;
@@ -609,31 +692,24 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
           }
         }
       });
-      // closure rows at the r-ends come from the table (lanes known at compile time, predicated)
-      {
-        for_lanes<0, (MCX + R - 1) / R>([&](auto Tc) {
+      // closure rows at the r-ends come from the table (lanes known at compile time); warps without an edge lane skip
+      if (edge) {
+        for_lanes<0, ELANES>([&](auto Tc) {
           constexpr int TL = decltype(Tc)::value;
           if (tid == TL) {
-            const double *cl = clring + (size_t)st * CLR;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-              if (TL * R + q < MC) rr[q] = cl[TL * R + q];
-              else if (TL * R + q < MCX) rr[q] += cl[TL * R + q];
-              if (TL * R + q < BM) qr[q] = cl[MCX + TL * R + q];
+              if (TL * R + q < MC) rr[q] = lds64(acl + 8u * (TL * R + q));
+              else if (TL * R + q < MCX) rr[q] += lds64(acl + 8u * (TL * R + q));
+              if (TL * R + q < BM) qr[q] = lds64(acl + 8u * (MCX + TL * R + q));
             }
           }
-        });
-      }
-      {
-        for_lanes<0, (MCX + R - 1) / R>([&](auto Tc) {
-          constexpr int TL = decltype(Tc)::value;
-          if (tid == nown - 1 - TL) {
-            const double *cl = clring + (size_t)st * CLR + CLW;
+          if (tid == far0 - TL) {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-              if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
-              else if (TL * R + (R - 1 - q) < MCX) rr[q] += cl[TL * R + (R - 1 - q)];
-              if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MCX + TL * R + (R - 1 - q)];
+              if (TL * R + (R - 1 - q) < MC) rr[q] = lds64(acl + 8u * (CLW + TL * R + (R - 1 - q)));
+              else if (TL * R + (R - 1 - q) < MCX) rr[q] += lds64(acl + 8u * (CLW + TL * R + (R - 1 - q)));
+              if (TL * R + (R - 1 - q) < BM) qr[q] = lds64(acl + 8u * (CLW + MCX + TL * R + (R - 1 - q)));
             }
           }
         });
@@ -644,17 +720,18 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
         constexpr auto SL = [](int k) constexpr { return (PH + 1 + k) % W; };
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-          uw[SL(W - 1)][q] = U[PAD + q]; bw[SL(W - 1)][q] = bn[q]; cw[SL(W - 1)][q] = cn[q];
-          acc[SL(W - 1)][q] = 0.0;
+          uw[SL(W - 1)][q] = U[PAD + q];
+          if constexpr (!DEEP) { bw[SL(W - 1)][q] = bn[q]; cw[SL(W - 1)][q] = cn[q]; }
           acc[SL(H)][q] += rr[q];
         }
-        for_offsets<1, H>([&](auto Oc) {                  // Qs^T t pushed from row j
+        for_offsets<1, H>([&](auto Oc) {                  // Qs^T t pushed from row j (row j+H is touched for the first time)
           constexpr int O = decltype(Oc)::value;
           const double d = sig * C::template D<O>();
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             const double t = cn[q] * qr[q];
-            acc[SL(H + O)][q] = fma(d, t, acc[SL(H + O)][q]);
+            if constexpr (O == H) acc[SL(H + O)][q] = d * t;
+            else acc[SL(H + O)][q] = fma(d, t, acc[SL(H + O)][q]);
             acc[SL(H - O)][q] = fma(-d, t, acc[SL(H - O)][q]);
           }
         });
@@ -662,7 +739,9 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
           constexpr int O = decltype(Oc)::value;
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            const double cf = pair_coef<P, O>([&](int s2) { return bw[SL(H + s2)][q]; });
+            double cf;
+            if constexpr (DEEP) cf = cfs[O - 1][q];
+            else cf = pair_coef<P, O>([&](int s2) { return bw[SL(H + s2)][q]; });
             const double f = cf * (uw[SL(H + O)][q] - uw[SL(H)][q]);
             acc[SL(0)][q] += f;
             acc[SL(O)][q] -= f;
@@ -678,45 +757,45 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
           }
         });
 #pragma unroll
-        for (int q = 0; q < R; ++q) { wout[q] *= cw[SL(H)][q]; accout[q] = acc[SL(0)][q]; }
+        for (int q = 0; q < R; ++q) {
+          if constexpr (DEEP) wout[q] *= c2[q];
+          else wout[q] *= cw[SL(H)][q];
+          accout[q] = acc[SL(0)][q];
+        }
       };
       [&]<int... PHs>(std::integer_sequence<int, PHs...>) {
         ((ph == PHs ? (windows(std::integral_constant<int, PHs>{}), 0) : 0), ...);
       }(std::make_integer_sequence<int, W>{});
       if (outp) {
 #pragma unroll
-        for (int k = 0; k < R / 2; ++k)
-          *reinterpret_cast<double2 *>(wb + DOFF + so[PAD / 2 + k]) = make_double2(wout[2 * k], wout[2 * k + 1]);
+        for (int k = 0; k < R / 2; ++k) sts128(aw + 8u * PAD + 16u * k, wout[2 * k], wout[2 * k + 1]);
       }
     }
     __syncthreads();
-    if ((tid >> 5) == rw && n < nrefill) {                // stage st is free again: line j + NST goes into it
+    if (mywarp == rw && n < nrefill) {                     // the slots of line j are free again: line j + NST goes into them
                                                           // (the warps take turns, so no warp is the slow one)
       if (elect_one()) {
-        const uint32_t bar = full_s + 8u * st, dst = ring_s + (uint32_t)(st * 4 * LW + DOFF) * 8u;
-        const int64_t g = gofs + NST * lstride;
-        mbar_expect_tx_s(bar, 4u * line_bytes + (uint32_t)(CLR * 8));
-        if constexpr (SWZ) {
-          const int row = (int)(g >> 4);
-          tensor_g2s_s(dst, &tm.u, 0, row, bar);
-          tensor_g2s_s(dst + (uint32_t)LW * 8u, &tm.crr, 0, row, bar);
-          tensor_g2s_s(dst + (uint32_t)LW * 16u, &tm.css, 0, row, bar);
-          tensor_g2s_s(dst + (uint32_t)LW * 24u, &tm.crs, 0, row, bar);
-        } else {
-          bulk_g2s_s(dst, prm.u + g, line_bytes, bar);
-          bulk_g2s_s(dst + (uint32_t)LW * 8u, prm.crr + g, line_bytes, bar);
-          bulk_g2s_s(dst + (uint32_t)LW * 16u, prm.css + g, line_bytes, bar);
-          bulk_g2s_s(dst + (uint32_t)LW * 24u, prm.crs + g, line_bytes, bar);
-        }
-        bulk_g2s_s(clring_s + (uint32_t)(st * CLR) * 8u, prm.rtab + tofs + NST * tstride, (uint32_t)(CLR * 8), bar);
+        const int nn = n + NST;
+        const int64_t g = base + (int64_t)(jstart + nn) * lstride;
+        const int64_t jl = up ? (int64_t)(jstart + nn) : (int64_t)Ns - (jstart + nn);
+        const uint32_t tofs8 = (uint32_t)(DOFF + i0) * 8u;                 // thread offset inside c_ss0 / c_rs0
+        uint32_t d_ss = as_[0] + (uint32_t)NST * LWB; if (d_ss >= c_ssE) d_ss -= (uint32_t)NSB * LWB;
+        uint32_t d_rs = ac_[0] + (uint32_t)NST * LWB; if (d_rs >= c_rsE) d_rs -= (uint32_t)NSC * LWB;
+        const uint32_t d_u = au + (uint32_t)(PAD - i0) * 8u;               // data start of the slot of line j in ring_u
+        mbar_expect_tx_s(abar, 4u * line_bytes + (uint32_t)(CLR * 8));
+        bulk_g2s_s(d_u, prm.u + g, line_bytes, abar);
+        bulk_g2s_s(d_u + c_drr, prm.crr + g, line_bytes, abar);
+        bulk_g2s_s(d_ss - tofs8 + (uint32_t)DOFF * 8u, prm.css + g, line_bytes, abar);
+        bulk_g2s_s(d_rs - tofs8 + (uint32_t)DOFF * 8u, prm.crs + g, line_bytes, abar);
+        bulk_g2s_s(acl, prm.rtab + (e * Nsp + jl) * CLR, (uint32_t)(CLR * 8), abar);
       }
     }
-    if (own && outp) {
+    if (ownf && outp) {
       // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
       double Wv[NV], val[R];
 #pragma unroll
       for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = *reinterpret_cast<const double2 *>(wb + DOFF + so[k]);
+        const double2 a = lds128(aw + 16u * k);
         Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
       }
 #pragma unroll
@@ -726,26 +805,21 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
 #pragma unroll
         for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
       });
-      {
-        for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
+      if (edge) {
+        for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
           constexpr int TL = decltype(Tc)::value;
-          if (tid == TL) {
+          if (tid == TL) {                                 // w(k) of the line sits at aw + (PAD - i0 + k) * 8, i0 = TL * R
             double w0[BN];
 #pragma unroll
-            for (int k = 0; k < BN; ++k) w0[k] = wb[DOFF + sel(k)];
+            for (int k = 0; k < BN; ++k) w0[k] = lds64(aw + 8u * (PAD - TL * R + k));
 #pragma unroll
             for (int q = 0; q < R; ++q)
               if (TL * R + q < BM) val[q] = accout[q] + qt_closure_row<P>(TL * R + q, w0);
           }
-        });
-      }
-      {
-        for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {
-          constexpr int TL = decltype(Tc)::value;
-          if (tid == nown - 1 - TL) {
+          if (tid == far0 - TL) {                          // mirrored, sign flipped: w(Nr - k), i0 = Nrp - (TL + 1) R
             double wr[BN];
 #pragma unroll
-            for (int k = 0; k < BN; ++k) wr[k] = wb[DOFF + sel(Nr - k)];
+            for (int k = 0; k < BN; ++k) wr[k] = lds64(aw + 8u * (PAD + (TL + 1) * R - 1 - k));
 #pragma unroll
             for (int q = 0; q < R; ++q)
               if (TL * R + (R - 1 - q) < BM) val[q] = accout[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
@@ -757,22 +831,31 @@ k_sweep(const SweepParams prm, const __grid_constant__ SweepMaps tm) {
         *reinterpret_cast<double2 *>(yout + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
     }
     yout += lstride;
-    gofs += lstride; tofs += tstride;
+    ++n;
     if (++rw == nwarps) rw = 0;
-    ++j; ++n;
-    if (++st == NST) { st = 0; parity ^= 1u; }
+    au += LWB; acl += (uint32_t)(CLR * 8); abar += 8u;
+    if (++st == NST) { st = 0; parity ^= 1u; au = c_u0; acl = c_cl0; abar = full_s; }
+#pragma unroll
+    for (int k = NAS - 1; k > 0; --k) as_[k] = as_[k - 1];
+    as_[0] += LWB;
+    if (as_[0] == c_ssE) as_[0] = c_ss0;
+#pragma unroll
+    for (int k = NAC - 1; k > 0; --k) ac_[k] = ac_[k - 1];
+    ac_[0] += LWB;
+    if (ac_[0] == c_rsE) ac_[0] = c_rs0;
+    aw = c_wsum - aw;
     if (++ph == W) ph = 0;
-  };
-
-  using GenericPH = std::integral_constant<int, W - 1>;    // rotation W-1: slot(k) == k (canonical order)
-  const int jfast = prologue ? MCX + H : jstart;           // first step without s-end closure / face logic
-  while (j < jfast && j <= jend) step(GenericPH{}, std::false_type{});
-  yout = gy + (int64_t)(j - H) * lstride;
-  gofs = base + (int64_t)j * lstride;                      // marching line j in the volume fields
-  tofs = (e * Nsp + (up ? (int64_t)j : (int64_t)Ns - j)) * CLR;   // ... and in the r-end table
-#pragma unroll 1
-  while (j <= jend) fast_step();
+  }
 }
+
+// register windows: the register allocation is sized through the CTAs per SM (MINB)
+template <int P, int R, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_sweep(const SweepParams prm) { sweep_body<P, R, false>(prm); }
+// deep rings: explicit register cap (shared memory, not registers, bounds the CTAs per SM)
+template <int P, int R, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
+k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true>(prm); }
 
 // ---- edge preparation ---------------------------------------------------------------------------
 // One CTA per (block, face), launched before k_sweep.  Everything that lives on the rim of a block and
@@ -899,42 +982,11 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
 }
 
 // ---- host side ------------------------------------------------------------------------------
-template <int P> static size_t sweep_smem(int Nrp, int nthreads, bool swz = false) {
+template <int P> static size_t sweep_smem(int Nrp, bool deep) {
   using C = SweepCfg<P>;
-  (void)nthreads;
-  const int LW = swz ? ((Nrp + 127) & ~127) + 128 : Nrp + 2 * C::PAD;
-  return (size_t)(SW_NST * 4 + 2) * LW * sizeof(double) + (swz ? 128 * sizeof(double) + 1024 : 0) +
-         (size_t)SW_NST * 2 * C::CLW * sizeof(double) + SW_NST * sizeof(uint64_t);
-}
-
-// tensor map of one field: [VNp / 16 rows][16 doubles], box = one line (Nrp / 16 rows), 128-byte swizzle
-static int sweep_encode_map(hsbp_ctx *ctx, CUtensorMap *tm, const double *field, int64_t VNp, int Nrp) {
-  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn encode = nullptr;
-  if (!encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-      ctx->err = "cuTensorMapEncodeTiled is not available";
-      return HSBP_ERR_CUDA;
-    }
-    encode = (encode_fn)fn;
-  }
-  const cuuint64_t gdim[2] = {16, (cuuint64_t)(VNp / 16)};
-  const cuuint64_t gstride[1] = {128};
-  const cuuint32_t box[2] = {16, (cuuint32_t)(Nrp / 16)};
-  const cuuint32_t estr[2] = {1, 1};
-  const int promo = 2;                                       // L2 promotion 128 B (0 / 1 / 3 measured the same)
-  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)field, gdim, gstride, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
-    return HSBP_ERR_CUDA;
-  }
-  return HSBP_OK;
+  const int LW = Nrp + 2 * C::PAD;
+  const int nl = deep ? C::template nlines<true>() : C::template nlines<false>();
+  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * 2 * C::CLW * sizeof(double) + SW_NST * sizeof(uint64_t);
 }
 
 static int sweep_points_per_thread(const hsbp_blocks *b) {
@@ -954,7 +1006,7 @@ template <int P> static bool sweep_eligible(const hsbp_blocks *b) {
   const int R = sweep_points_per_thread(b);
   const int nthreads = ((Nrp / R) + 31) & ~31;
   if (nthreads > SW_MAX_THREADS) return false;
-  return sweep_smem<P>(Nrp, nthreads) <= b->ctx->smem_optin;
+  return sweep_smem<P>(Nrp, true) <= b->ctx->smem_optin;
 }
 
 // crr' = crr * Hs[j] / hr, css' = css * Hr[i] / hs for uniform blocks (see SweepParams)
@@ -1029,19 +1081,28 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   return HSBP_OK;
 }
 
-template <int P, int R, int NT, bool SWZ> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
-                                                                  int64_t e0, int64_t ne) {
-  hsbp_ctx *ctx = b->ctx;
 #ifndef SW_REGS2_P6
 #define SW_REGS2_P6 168
 #endif
-  // register budget per thread: R = 4 takes all 255; R = 2 fits 128 (p = 2, 4) -- p = 6 has 7-line windows and needs more
+#ifndef SW_DEEP_REGS4
+#define SW_DEEP_REGS4 200     // register cap of the DEEP, R = 4 variant (5 CTAs of 64 threads per SM)
+#endif
+#ifndef SW_DEEP_REGS2
+#define SW_DEEP_REGS2 128     // register cap of the DEEP, R = 2 variant
+#endif
+template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
+                                                                   int64_t e0, int64_t ne) {
+  hsbp_ctx *ctx = b->ctx;
+  // register budget per thread.  Register windows (DEEP = false): R = 4 takes all 255; R = 2 fits 128 (p = 2, 4) --
+  // p = 6 has 7-line windows and needs more.  DEEP: only u and the accumulators are per-point state.
   constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
   constexpr int MINB = (R == 2 ? 65536 / REGS2 : 256) / NT;
-  auto kern = k_sweep<P, R, NT, MINB, SWZ>;
+  void (*kern)(const SweepParams);
+  if constexpr (DEEP) kern = k_sweep_deep<P, R, (R == 2 ? SW_DEEP_REGS2 : (P == 6 ? 255 : SW_DEEP_REGS4))>;
+  else kern = k_sweep<P, R, NT, MINB>;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
-  const size_t sm = sweep_smem<P>(Nrp, nthreads, SWZ);
+  const size_t sm = sweep_smem<P>(Nrp, DEEP);
   static bool attr_set = false;
   static int ctas_per_sm = 1;
   if (!attr_set) {
@@ -1075,15 +1136,8 @@ template <int P, int R, int NT, bool SWZ> static int sweep_launch(hsbp_blocks *b
   prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K; prm.e0 = (int)e0;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
-  SweepMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  if constexpr (SWZ) {
-    int rc;
-    if ((rc = sweep_encode_map(ctx, &maps.u, u, b->VNp, Nrp)) || (rc = sweep_encode_map(ctx, &maps.crr, b->d_crr_s, b->VNp, Nrp)) ||
-        (rc = sweep_encode_map(ctx, &maps.css, b->d_css_s, b->VNp, Nrp)) || (rc = sweep_encode_map(ctx, &maps.crs, b->d_crs, b->VNp, Nrp)))
-      return rc;
-  }
-  kern<<<(unsigned)(ne * 2 * best), nthreads, sm, ctx->stream>>>(prm, maps);
+  b->last_sweep_ctas_per_sm = ctas_per_sm;
+  kern<<<(unsigned)(ne * 2 * best), nthreads, sm, ctx->stream>>>(prm);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_sweep: ") + cudaGetErrorString(e1);
@@ -1096,16 +1150,7 @@ template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double 
                                                    int64_t e0, int64_t ne) {
   const int Nrp = b->max_Nr + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
-  if constexpr (R == 4) {
-    // Optional: swizzled shared lines through tensor-map TMA make the 32-byte-per-lane reads conflict free, but measured
-    // on B200 the 2-D tiled copies feed the ring more slowly than the 1-D bulk copies (k_sweep 0.74 ms vs 0.68 ms at
-    // p = 4, 0.59 vs 0.44 ms at p = 2), so the plain layout stays the default (profiles/README.md).
-    if (Nrp % 16 == 0 && b->sweep_swizzle && ((uintptr_t)u & 127) == 0) {
-      if (nthreads <= 64) return sweep_launch<P, R, 64, true>(b, u, y, with_faces, e0, ne);
-      if (nthreads <= 128) return sweep_launch<P, R, 128, true>(b, u, y, with_faces, e0, ne);
-      return sweep_launch<P, R, 256, true>(b, u, y, with_faces, e0, ne);
-    }
-  }
+  if (b->sweep_deep) return sweep_launch<P, R, 256, true>(b, u, y, with_faces, e0, ne);
   if (nthreads <= 64) return sweep_launch<P, R, 64, false>(b, u, y, with_faces, e0, ne);
   if (nthreads <= 128) return sweep_launch<P, R, 128, false>(b, u, y, with_faces, e0, ne);
   return sweep_launch<P, R, 256, false>(b, u, y, with_faces, e0, ne);

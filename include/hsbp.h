@@ -110,7 +110,8 @@ int  hsbp_apply_variant(const hsbp_blocks *blocks);
 /* force the generic kernels (testing) */
 int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
 /* tuning / testing knobs: "force_generic" (0/1), "sweep_chunks_per_side" (0 = heuristic),
- * "sweep_points_per_thread" (0 = heuristic, 2, 4), "sweep_fold_faces" (1), "sweep_swizzle" (0) */
+ * "sweep_points_per_thread" (0 = heuristic, 2, 4), "sweep_fold_faces" (1), "sweep_deep" (1: css / crs windows in
+ * shared-memory rings, 0: in registers) */
 int  hsbp_blocks_set_option(hsbp_blocks *blocks, const char *name, int64_t value);
 
 /* face operators of the blocks, block-face layout (no inter-block coupling):
@@ -130,10 +131,15 @@ int  hsbp_face_traction(hsbp_blocks *blocks, const double *u_dev, double *tr_dev
  *   HSBP_LOCAL_BAND      batched banded fp64 Cholesky of M-tilde_e (points numbered r-fastest, half-bandwidth
  *                        about WB*(Nr+1), WB = 2 / 5 / 8 for p = 2 / 4 / 6): the direct solver for blocks whose band
  *                        fits in device memory, e.g. the single 201 x 201 block of seas/BP1 (BP1.jl:78)
- * tol is the relative residual ||g - M u|| / ||g|| per block (PCG only).                         */
+ *   HSBP_LOCAL_FDM       batched matrix-free PCG preconditioned by the exact inverse of the separable part of
+ *                        M-tilde_e (fast diagonalisation: four dense fp64 GEMMs per block and iteration); blocks of one
+ *                        size, meant for large, mildly varying blocks (256 x 256 points) where Jacobi-PCG needs O(N)
+ *                        iterations
+ * tol is the relative residual ||g - M u|| / ||g|| per block (PCG variants only).                         */
 #define HSBP_LOCAL_PCG      1
 #define HSBP_LOCAL_CHOLESKY 2
 #define HSBP_LOCAL_BAND     3
+#define HSBP_LOCAL_FDM      4
 typedef struct {
   int64_t iterations_max;     /* PCG: largest iteration count over blocks (0 for Cholesky) */
   int64_t iterations_sum;     /* PCG: sum over blocks                                      */

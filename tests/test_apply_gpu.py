@@ -151,12 +151,12 @@ def test_apply_marching_equals_generic_at_full_block_size(ctx, p):
     assert blk.apply_variant() == 0
     y0 = dy.get()
     blk.force_generic(False)
-    for R, ncs, swz in ((0, 0, 0), (2, 3, 0), (4, 1, 0), (4, 5, 0), (4, 2, 1)):
+    for R, ncs, deep in ((0, 0, 1), (2, 3, 1), (4, 1, 1), (4, 5, 1), (4, 2, 0), (2, 2, 0)):
         blk.set_option("sweep_points_per_thread", R)
         blk.set_option("sweep_chunks_per_side", ncs)
-        blk.set_option("sweep_swizzle", swz)          # tensor-map TMA with the 128-byte swizzle (optional path)
+        blk.set_option("sweep_deep", deep)           # css / crs windows in shared-memory rings or in registers
         dy.set(np.full(blk.VNp, np.nan))
         blk.apply(du, dy)
         assert blk.apply_variant() == 1
         y1 = dy.get()
-        assert np.max(np.abs(y1 - y0)) <= 1e-12 * np.max(np.abs(y0)), (R, ncs, swz)
+        assert np.max(np.abs(y1 - y0)) <= 1e-12 * np.max(np.abs(y0)), (R, ncs, deep)

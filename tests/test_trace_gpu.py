@@ -172,6 +172,39 @@ def test_banded_cholesky_local_solver(ctx, p):
         assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, np.linalg.norm(x[sl] - xr) / np.linalg.norm(xr))
 
 
+@pytest.mark.parametrize("p,kind", [(2, "warped"), (4, "warped"), (6, "warped"), (4, "random")])
+def test_fast_diagonalisation_pcg_local_solver(ctx, p, kind):
+    """K2d: PCG on M-tilde_e preconditioned by the inverse of its separable part (api_fdm.cuh) against the oracle's
+    direct solve (global_curved.jl:698, 734); on smoothly warped blocks it must need far fewer iterations than
+    Jacobi-PCG, on the random SPD tensors of local_op_eigenvalues.jl:32-38 it only has to stay correct."""
+    import hybridsbp_b200 as hs
+    from tests.util import warped_metrics
+    rng = np.random.default_rng(600 + p)
+    Nr, Ns = 39, 33
+    if kind == "warped":
+        mets = [warped_metrics(p, Nr, Ns, bx, by, 2, 2) for by in range(2) for bx in range(2)]
+    else:
+        mets = [random_spd_metrics(p, Nr, Ns, rng, scale2=0.2) for _ in range(4)]
+    bcs = [(1, 0, 2, 0), (0, 1, 2, 0), (1, 0, 0, 2), (0, 7, 0, 1)]
+    lops = [orc.locoperator(p, Nr, Ns, m, bc) for m, bc in zip(mets, bcs)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    g = rng.uniform(-1, 1, blk.VNp)
+    dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    blk.local_setup(hs.LOCAL_FDM, tol=1e-13, maxit=5000)
+    st = blk.local_solve(dg, dx)
+    assert st["failed_blocks"] == 0, st
+    x = dx.get()
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        xr = orc.default_factorization(lop.Mt).solve(g[sl])
+        assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, st)
+    if kind == "warped":
+        blk.local_setup(hs.LOCAL_PCG, tol=1e-13, maxit=20000)
+        st_j = blk.local_solve(dg, dx)
+        assert st["iterations_max"] * 2 < st_j["iterations_max"], (st, st_j)
+        print("FDM-PCG %d iterations, Jacobi-PCG %d" % (st["iterations_max"], st_j["iterations_max"]))
+
+
 def test_trace_solve_with_cholesky_local_solver(ctx):
     import hybridsbp_b200 as hs
     p = 4

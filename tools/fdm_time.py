@@ -1,0 +1,35 @@
+"""Local solves on blocks of 256 x 256 points (BASELINE config 4 shape): fast-diagonalisation PCG vs Jacobi-PCG."""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+import hybridsbp_b200 as hs
+from hybridsbp_b200 import synthetic
+ctx = hs.Context(0)
+nbx = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+nby = int(sys.argv[2]) if len(sys.argv) > 2 else nbx
+jac = len(sys.argv) > 3 and sys.argv[3] == "jacobi"
+N, p = 255, 4
+crr, css, crs = synthetic.warped_coefficients(nbx, nby, N)
+_, EToV, EToF, FToB = synthetic.block_grid_connectivity(nbx, nby)
+ne = nbx * nby
+blk = hs.Blocks(ctx, p, [N] * ne, [N] * ne)
+blk.set_metrics(crr, css, crs)
+blk.set_bc(synthetic.block_bcs(EToF, FToB))
+blk.compute_tau(2.0)
+x0 = np.random.default_rng(5).uniform(-1, 1, blk.VNp)
+dx0, dg, dx, dr = ctx.array(x0), ctx.empty(blk.VNp), ctx.empty(blk.VNp), ctx.empty(blk.VNp)
+blk.apply(dx0, dg)
+for name, mode in (("FDM-PCG", hs.LOCAL_FDM),) + ((("Jacobi-PCG", hs.LOCAL_PCG),) if jac else ()):
+    t0 = time.time()
+    blk.local_setup(mode, tol=1e-13, maxit=100000)
+    ts = time.time() - t0
+    for rep in range(2):
+        t0 = time.time()
+        st = blk.local_solve(dg, dx)
+        dt = time.time() - t0
+    blk.apply(dx, dr)
+    g, r = dg.get(), dr.get()
+    print("%d blocks of 256x256, %s: setup %.2f s, solve %.3f s, iterations max %d mean %.1f, failed %d, "
+          "true rel residual %.2e, error %.2e" %
+          (ne, name, ts, dt, st["iterations_max"], st["iterations_sum"] / ne, st["failed_blocks"],
+           np.linalg.norm(r - g) / np.linalg.norm(g), np.linalg.norm(dx.get() - x0) / np.linalg.norm(x0)), flush=True)
