@@ -260,31 +260,46 @@ def run_ours(args):
     # (1024 blocks x 18x18 points per GPU, dense Cholesky local solver K2a), weak scaling over strips of blocks;
     # cut-face exchange by NCCL send / recv, CG scalars by all-reduce (hybridsbp_b200/parallel.py).
     trace = None
+    trace_large = None
     if not args.no_trace:
         import torch
         from hybridsbp_b200 import dist_trace
         torch.cuda.set_device(local)
-        tnb = int(round(args.trace_blocks ** 0.5))
-        dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, args.trace_n, p, dist=dist)
-        dt.solve(tg, tgd, tol=1e-2, maxit=20)                      # warm-up
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        lam_t, u_t, st_t = dt.solve(tg, tgd, tol=args.trace_tol, maxit=20000)
-        torch.cuda.synchronize()
-        t_solve = time.perf_counter() - t0
-        if dist is not None:
-            tt = torch.tensor([t_solve], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_solve = float(tt.item())
-        trace = {"seconds": t_solve, "outer_iterations": st_t["outer_iterations"], "converged": st_t["converged"],
-                 "rel_residual": st_t["rel_residual"], "tol": args.trace_tol,
-                 "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s" %
-                           (tinfo["blocks"], args.trace_n + 1, args.trace_n + 1, p,
-                            "batched dense Cholesky (K2a)" if tinfo["local_mode"] == 2 else "batched Jacobi-PCG (K2b)"),
-                 "lambda_points_per_gpu": tinfo["lambda_points"], "cut_faces_per_gpu": tinfo["cut_faces"],
-                 "volume_points_per_gpu": tinfo["volume_points"]}
-        tinfo["tr"].close(); tinfo["blk"].close()
+        names = {1: "batched Jacobi-PCG (K2b)", 2: "batched dense Cholesky (K2a)", 3: "batched banded Cholesky (K2c)",
+                 4: "batched PCG with fast-diagonalisation preconditioner (K2d)"}
+
+        def timed_trace_solve(nblocks, n_per_block):
+            tnb = int(round(nblocks ** 0.5))
+            t0 = time.perf_counter()
+            dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, n_per_block, p, dist=dist)
+            torch.cuda.synchronize()
+            t_setup = time.perf_counter() - t0
+            dt.solve(tg, tgd, tol=1e-2, maxit=5)                       # warm-up
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lam_t, u_t, st_t = dt.solve(tg, tgd, tol=args.trace_tol, maxit=50000)
+            torch.cuda.synchronize()
+            t_solve = time.perf_counter() - t0
+            if dist is not None:
+                tt = torch.tensor([t_solve], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_solve = float(tt.item())
+            out = {"seconds": t_solve, "setup_seconds": t_setup, "outer_iterations": st_t["outer_iterations"],
+                   "converged": st_t["converged"], "rel_residual": st_t["rel_residual"], "tol": args.trace_tol,
+                   "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s" %
+                             (tinfo["blocks"], n_per_block + 1, n_per_block + 1, p, names[tinfo["local_mode"]]),
+                   "lambda_points_per_gpu": tinfo["lambda_points"], "cut_faces_per_gpu": tinfo["cut_faces"],
+                   "volume_points_per_gpu": tinfo["volume_points"]}
+            tinfo["tr"].close(); tinfo["blk"].close()
+            return out
+
+        # (i) small-block variant of SURVEY.md section 8d: 1024 blocks x 18x18 points per GPU, dense Cholesky factors
+        trace = timed_trace_solve(args.trace_blocks, args.trace_n)
+        # (ii) blocks of BASELINE config 4's size (256 x 256 points), a bounded number of them so that the default run
+        #      stays within minutes; the full 1024-block solve is tools/trace_c4.py (profiles/)
+        if args.trace_large_blocks > 0:
+            trace_large = timed_trace_solve(args.trace_large_blocks, args.n)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -316,7 +331,7 @@ def run_ours(args):
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                         "note": "hsbp_apply_host on pinned host buffers: H2D of u, apply, D2H of y inside each call"},
                 "gpu_launches": (args.steps + nrep + e2e_steps + 1) * (2 if variant == 1 else 4),
-                "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum, "trace_solve": trace}
+                "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum, "trace_solve": trace, "trace_solve_large_blocks": trace_large}
         if world == 1 and not args.no_cpu:
             _, base = cpu_baseline(p, N, args.cpu_blocks, args.cpu_seconds, 1)
             line["cpu_baseline"] = base
@@ -343,6 +358,8 @@ def main():
     ap.add_argument("--trace-blocks", type=int, default=1024, help="blocks per GPU of the trace solve (a square number)")
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")
     ap.add_argument("--trace-tol", type=float, default=1e-10)
+    ap.add_argument("--trace-large-blocks", type=int, default=64,
+                    help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")
     ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")
     ap.add_argument("--sweep-deep", type=int, default=1, help="1: css / crs windows of k_sweep in shared-memory rings, 0: in registers")
     ap.add_argument("--sweep-ncs", type=int, default=0, help="chunks per side of k_sweep (0 = heuristic)")

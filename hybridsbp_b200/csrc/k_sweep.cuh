@@ -94,6 +94,8 @@ __device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
 // hide how a loop invariant was computed: the compiler then keeps it in a register instead of re-deriving it
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 __device__ __forceinline__ int opaque(int x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ int64_t opaque(int64_t x) { asm volatile("" : "+l"(x)); return x; }
+__device__ __forceinline__ double opaque(double x) { asm volatile("" : "+d"(x)); return x; }
 
 // one lane of a fully active warp
 __device__ __forceinline__ bool elect_one() {
@@ -612,6 +614,11 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int edge = opaque((own && (tid < ELANES || tid >= nown - ELANES)) ? 1 : 0);
   const int ownf = opaque(own ? 1 : 0);
   const int far0 = opaque(nown - 1);                       // thread that owns the last points of a line
+  const double sgn = opaque(sig);                          // marching direction (the compiler would re-derive it from blockIdx)
+  const int64_t lstr = opaque(lstride);
+  const int64_t g0 = opaque(base + (int64_t)jstart * lstride);          // marching line 0 of this chunk in the volume fields
+  const int64_t t0 = opaque((e * Nsp + (up ? (int64_t)jstart : (int64_t)Ns - jstart)) * CLR);   // ... in the r-end table
+  const int64_t tstr = opaque(up ? (int64_t)CLR : -(int64_t)CLR);
 
   uint32_t au = c_u0 + (uint32_t)st * LWB, acl = c_cl0 + (uint32_t)(st * CLR) * 8u, abar = full_s + 8u * (uint32_t)st;
   uint32_t aw = c_w0 + (uint32_t)(n & 1) * LWB;
@@ -726,7 +733,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         }
         for_offsets<1, H>([&](auto Oc) {                  // Qs^T t pushed from row j (row j+H is touched for the first time)
           constexpr int O = decltype(Oc)::value;
-          const double d = sig * C::template D<O>();
+          const double d = sgn * C::template D<O>();
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             const double t = cn[q] * qr[q];
@@ -749,7 +756,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         });
         for_offsets<1, H>([&](auto Oc) {                  // w = crs o (Qs u) on line jo
           constexpr int O = decltype(Oc)::value;
-          const double d = sig * C::template D<O>();
+          const double d = sgn * C::template D<O>();
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             if constexpr (O == 1) wout[q] = d * (uw[SL(H + O)][q] - uw[SL(H - O)][q]);
@@ -776,8 +783,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
                                                           // (the warps take turns, so no warp is the slow one)
       if (elect_one()) {
         const int nn = n + NST;
-        const int64_t g = base + (int64_t)(jstart + nn) * lstride;
-        const int64_t jl = up ? (int64_t)(jstart + nn) : (int64_t)Ns - (jstart + nn);
+        const int64_t g = g0 + nn * lstr;
         const uint32_t tofs8 = (uint32_t)(DOFF + i0) * 8u;                 // thread offset inside c_ss0 / c_rs0
         uint32_t d_ss = as_[0] + (uint32_t)NST * LWB; if (d_ss >= c_ssE) d_ss -= (uint32_t)NSB * LWB;
         uint32_t d_rs = ac_[0] + (uint32_t)NST * LWB; if (d_rs >= c_rsE) d_rs -= (uint32_t)NSC * LWB;
@@ -787,7 +793,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         bulk_g2s_s(d_u + c_drr, prm.crr + g, line_bytes, abar);
         bulk_g2s_s(d_ss - tofs8 + (uint32_t)DOFF * 8u, prm.css + g, line_bytes, abar);
         bulk_g2s_s(d_rs - tofs8 + (uint32_t)DOFF * 8u, prm.crs + g, line_bytes, abar);
-        bulk_g2s_s(acl, prm.rtab + (e * Nsp + jl) * CLR, (uint32_t)(CLR * 8), abar);
+        bulk_g2s_s(acl, prm.rtab + t0 + nn * tstr, (uint32_t)(CLR * 8), abar);
       }
     }
     if (ownf && outp) {
@@ -830,7 +836,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
       for (int k = 0; k < R / 2; ++k)
         *reinterpret_cast<double2 *>(yout + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
     }
-    yout += lstride;
+    yout += lstr;
     ++n;
     if (++rw == nwarps) rw = 0;
     au += LWB; acl += (uint32_t)(CLR * 8); abar += 8u;
@@ -992,10 +998,16 @@ template <int P> static size_t sweep_smem(int Nrp, bool deep) {
 static int sweep_points_per_thread(const hsbp_blocks *b) {
   const int Nrp = b->max_Nr + 1;
   if (b->sweep_r_override == 2 || (b->sweep_r_override == 4 && Nrp % 4 == 0)) return b->sweep_r_override;
-  // measured on B200 at 256-point lines: R = 4 (252 registers, 8 warps/SM) 0.675 ms, R = 2 (128 registers,
-  // 16 warps/SM, on the edge of spilling) 0.68 - 0.71 ms
+  const bool can4 = Nrp % 4 == 0, can2 = ((Nrp / 2 + 31) & ~31) <= SW_MAX_THREADS;
+  if (b->sweep_deep) {
+    // measured on B200 at 256-point lines (deep rings): p = 4: R = 2 (126 registers, 16 warps/SM) 0.562 ms, R = 4
+    // (195 registers, 10 warps/SM, two-way bank conflicts of the 32-byte-per-lane reads) 0.724 ms; p = 2: 0.42 / 0.47 ms;
+    // p = 6: R = 2 (128 registers, a few spills) 1.13 ms, R = 4 1.20 ms
+    return can2 ? 2 : 4;
+  }
+  // register windows: R = 4 (252 registers, 8 warps/SM) 0.65 ms, R = 2 (128 registers, 16 warps/SM, spilling) 0.67 ms
   if (b->p == 6) return 2;                                    // R = 4 spills heavily with the 7-line windows of p = 6
-  return (Nrp % 4 == 0 && Nrp >= 128) ? 4 : 2;
+  return (can4 && Nrp >= 128) ? 4 : 2;
 }
 
 template <int P> static bool sweep_eligible(const hsbp_blocks *b) {

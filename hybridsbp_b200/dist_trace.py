@@ -4,7 +4,7 @@ interior strip boundary are exchanged point to point, CG scalars are all-reduced
 import numpy as np
 
 from . import parallel, synthetic
-from .blocks import Blocks, Trace, LOCAL_CHOLESKY, LOCAL_PCG
+from .blocks import Blocks, Trace, LOCAL_CHOLESKY, LOCAL_FDM, LOCAL_PCG  # noqa: F401
 from .host import connectivityarrays
 
 
@@ -26,7 +26,8 @@ def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=
     blk.set_bc(lm.FToB[lm.EToF - 1].T.reshape(-1))
     blk.compute_tau(2.0)
     if local_mode is None:
-        local_mode = LOCAL_CHOLESKY if (N + 1) ** 2 <= 1600 else LOCAL_PCG
+        # small blocks: dense Cholesky factors; large, smoothly varying blocks: PCG with the separable preconditioner
+        local_mode = LOCAL_CHOLESKY if (N + 1) ** 2 <= 1600 else LOCAL_FDM
     blk.local_setup(local_mode, tol=local_tol, maxit=200000)
     tr = Trace(blk, lm.FToB, lm.FToE, lm.FToLF, lm.EToO, lm.EToS)
     op = parallel.GpuLocalOperator(blk, tr)
