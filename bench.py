@@ -271,7 +271,8 @@ def run_ours(args):
         def timed_trace_solve(nblocks, n_per_block):
             tnb = int(round(nblocks ** 0.5))
             t0 = time.perf_counter()
-            dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, n_per_block, p, dist=dist)
+            dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, n_per_block, p, dist=dist,
+                                                                condense=not args.no_condense)
             torch.cuda.synchronize()
             t_setup = time.perf_counter() - t0
             dt.solve(tg, tgd, tol=1e-2, maxit=5)                       # warm-up
@@ -287,8 +288,10 @@ def run_ours(args):
                 t_solve = float(tt.item())
             out = {"seconds": t_solve, "setup_seconds": t_setup, "outer_iterations": st_t["outer_iterations"],
                    "converged": st_t["converged"], "rel_residual": st_t["rel_residual"], "tol": args.trace_tol,
-                   "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s" %
-                             (tinfo["blocks"], n_per_block + 1, n_per_block + 1, p, names[tinfo["local_mode"]]),
+                   "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s; %s" %
+                             (tinfo["blocks"], n_per_block + 1, n_per_block + 1, p, names[tinfo["local_mode"]],
+                              "matrix-free Schur matvec (one batched local solve per CG iteration)" if args.no_condense else
+                              "statically condensed (dense S_e = F^T M^-1 F per block formed during setup)"),
                    "lambda_points_per_gpu": tinfo["lambda_points"], "cut_faces_per_gpu": tinfo["cut_faces"],
                    "volume_points_per_gpu": tinfo["volume_points"]}
             tinfo["tr"].close(); tinfo["blk"].close()
@@ -358,6 +361,7 @@ def main():
     ap.add_argument("--trace-blocks", type=int, default=1024, help="blocks per GPU of the trace solve (a square number)")
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")
     ap.add_argument("--trace-tol", type=float, default=1e-10)
+    ap.add_argument("--no-condense", action="store_true", help="trace solves: matrix-free Schur matvec instead of static condensation")
     ap.add_argument("--trace-large-blocks", type=int, default=64,
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")
     ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")

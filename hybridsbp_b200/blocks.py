@@ -184,6 +184,11 @@ class Trace:
     def Fbar_add(self, lam: DeviceArray, alpha, y: DeviceArray):
         self.ctx._check(lib().hsbp_trace_Fbar_add(self.h, lam.ptr, float(alpha), y.ptr))
 
+    def condense(self, enable=True):
+        """Form S_e = F_e^T M-tilde_e^-1 F_e per block (assembleλmatrix's products, global_curved.jl:759-790); later
+        schur_apply / solve calls use them instead of local solves."""
+        self.ctx._check(lib().hsbp_trace_condense(self.h, 1 if enable else 0))
+
     def schur_apply(self, lam: DeviceArray, out: DeviceArray):
         self.ctx._check(lib().hsbp_trace_schur_apply(self.h, lam.ptr, out.ptr))
 

@@ -152,15 +152,19 @@ k_fpcg_update1(const BlockDesc *__restrict__ desc, const double *__restrict__ Ap
   }
   rr = cta_sum(rr, scratch);
   if (threadIdx.x == 0) {
-    s.rr = rr; s.iters += 1;
+    s.rr = rr; s.iters += 1; s.alpha = alpha;
     if (!(rr > tol2 * s.g2)) s.active = 2;                       // converged: part 2 retires the block
     st[blockIdx.x] = s;
   }
 }
-// part 2 (after z = P^-1 r): beta = r.z / rz_old, p = z + beta p.  init != 0: first direction p = z, rz = r.z
+// part 2 (after z = P^-1 r): p = z + beta p with the flexible (Polak-Ribiere) beta
+//   beta = z_new . (r_new - r_old) / (z_old . r_old) = -alpha (z_new . A p) / rz_old,
+// which equals r_new.z_new / rz_old for an exact, fixed preconditioner and stays a descent direction when the
+// preconditioner is applied in reduced precision.  init != 0: first direction p = z, rz = r.z
 __global__ void __launch_bounds__(1024)
 k_fpcg_update2(const BlockDesc *__restrict__ desc, const double *__restrict__ r, const double *__restrict__ z,
-               double *__restrict__ p, PcgState *__restrict__ st, int init, int *__restrict__ nactive) {
+               const double *__restrict__ Ap, double *__restrict__ p, PcgState *__restrict__ st, int init,
+               int *__restrict__ nactive) {
   __shared__ double scratch[32];
   const BlockDesc d = desc[blockIdx.x];
   PcgState s = st[blockIdx.x];
@@ -171,16 +175,30 @@ k_fpcg_update2(const BlockDesc *__restrict__ desc, const double *__restrict__ r,
     if (threadIdx.x == 0) { s.active = 0; st[blockIdx.x] = s; }
     return;
   }
-  double rz = 0;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) rz += r[o + i] * z[o + i];
-  rz = cta_sum(rz, scratch);
-  const double beta = init ? 0.0 : rz / s.rz;
+  double rz = 0, zAp = 0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+    const double zi = z[o + i];
+    rz += r[o + i] * zi;
+    if (!init) zAp += zi * Ap[o + i];
+  }
+  rz = cta_sum(rz, scratch); zAp = cta_sum(zAp, scratch);
+  const double beta = init ? 0.0 : -s.alpha * zAp / s.rz;
   for (int64_t i = threadIdx.x; i < np; i += blockDim.x) p[o + i] = z[o + i] + beta * p[o + i];
   if (threadIdx.x == 0) {
     s.rz = rz;
     st[blockIdx.x] = s;
     atomicAdd(nactive, 1);
   }
+}
+// fp64 <-> fp32 copies for the reduced-precision preconditioner
+__global__ void k_f64_to_f32(int64_t n, const double *__restrict__ x, float *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = (float)x[i];
+}
+__global__ void k_f32_to_f64(int64_t n, const float *__restrict__ x, double *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = (double)x[i];
+}
+__global__ void k_mul_f32(int64_t n, float *__restrict__ x, const float *__restrict__ d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= d[i];
 }
 // x = 0, r = g, g2 = rr = g.g
 __global__ void __launch_bounds__(1024)
@@ -344,6 +362,22 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
   }
   if (rc) { cleanup(); return rc; }
   k_fdm_dinv<<<dim3((unsigned)nb, 16), 256, 0, ctx->stream>>>(b->d_desc, d_lr, d_ls, b->d_dinv);
+  if (b->fdm_gemm != 0) {                                        // fp32 copies for the reduced-precision application
+    if (!b->d_fdm_vr32) {
+      cudaMalloc((void **)&b->d_fdm_vr32, (size_t)nb * Nrp * Nrp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_vs32, (size_t)nb * Nsp * Nsp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_dinv32, (size_t)b->VNp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_a32, (size_t)b->VNp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_b32, (size_t)b->VNp * sizeof(float));
+    }
+    if (!b->d_fdm_vr32 || !b->d_fdm_vs32 || !b->d_fdm_dinv32 || !b->d_fdm_a32 || !b->d_fdm_b32) {
+      cleanup();
+      HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: out of device memory (fp32 copies)");
+    }
+    k_f64_to_f32<<<vec_grid((int64_t)nb * Nrp * Nrp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nrp * Nrp, b->d_fdm_vr, b->d_fdm_vr32);
+    k_f64_to_f32<<<vec_grid((int64_t)nb * Nsp * Nsp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nsp * Nsp, b->d_fdm_vs, b->d_fdm_vs32);
+    k_f64_to_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, b->d_dinv, b->d_fdm_dinv32);
+  }
   e1 = cudaGetLastError();
   if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
   cleanup();
@@ -356,24 +390,50 @@ int fdm_setup(hsbp_blocks *b) {
 }
 
 // z = P^-1 r for all blocks: Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T
+//   fdm_gemm = 0  fp64 DGEMMs (fp64 tensor pipe)
+//            = 1  fp32 SGEMMs;  = 2  fp32 emulated with 3 x BF16 splits on the BF16 tensor cores (fp32-accurate);
+//            = 3  TF32 tensor cores (10-bit mantissa).  r is rounded to fp32 first, z is widened back; PCG itself (x, r, p,
+//            the operator) stays fp64, and the flexible beta keeps it convergent with an inexactly applied preconditioner.
 int fdm_precondition(hsbp_blocks *b, const double *r, double *z) {
   hsbp_ctx *ctx = b->ctx;
   FdmLibs *libs = (FdmLibs *)ctx->fdm_libs;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nb = (int)b->nblocks;
   const long long sv = (long long)Nrp * Nsp, sr = (long long)Nrp * Nrp, ss = (long long)Nsp * Nsp;
-  const double one = 1.0, zero = 0.0;
-  double *t = b->d_fdm_t;
-  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
-                                           r, Nrp, sv, &zero, t, Nrp, sv, nb));
-  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
-                                           b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
-  k_ewise<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, z, b->d_dinv, z, 0);
-  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
-                                           z, Nrp, sv, &zero, t, Nrp, sv, nb));
-  HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
-                                           b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
-  return check_launch(ctx, "fdm_precondition");
+  if (b->fdm_gemm == 0) {
+    const double one = 1.0, zero = 0.0;
+    double *t = b->d_fdm_t;
+    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
+                                             r, Nrp, sv, &zero, t, Nrp, sv, nb));
+    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
+                                             b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
+    k_ewise<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, z, b->d_dinv, z, 0);
+    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
+                                             z, Nrp, sv, &zero, t, Nrp, sv, nb));
+    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
+                                             b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
+    return check_launch(ctx, "fdm_precondition");
+  }
+  const cublasComputeType_t ct = b->fdm_gemm == 2 ? CUBLAS_COMPUTE_32F_EMULATED_16BFX9
+                                                  : (b->fdm_gemm == 3 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F);
+  const float one = 1.0f, zero = 0.0f;
+  float *a = b->d_fdm_a32, *t = b->d_fdm_b32;
+  k_f64_to_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, r, a);
+  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr32, CUDA_R_32F,
+                                            Nrp, sr, a, CUDA_R_32F, Nrp, sv, &zero, t, CUDA_R_32F, Nrp, sv, nb, ct,
+                                            CUBLAS_GEMM_DEFAULT));
+  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, CUDA_R_32F, Nrp, sv,
+                                            b->d_fdm_vs32, CUDA_R_32F, Nsp, ss, &zero, a, CUDA_R_32F, Nrp, sv, nb, ct,
+                                            CUBLAS_GEMM_DEFAULT));
+  k_mul_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, a, b->d_fdm_dinv32);
+  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr32, CUDA_R_32F,
+                                            Nrp, sr, a, CUDA_R_32F, Nrp, sv, &zero, t, CUDA_R_32F, Nrp, sv, nb, ct,
+                                            CUBLAS_GEMM_DEFAULT));
+  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, CUDA_R_32F, Nrp, sv,
+                                            b->d_fdm_vs32, CUDA_R_32F, Nsp, ss, &zero, a, CUDA_R_32F, Nrp, sv, nb, ct,
+                                            CUBLAS_GEMM_DEFAULT));
+  k_f32_to_f64<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, a, z);
+  return check_launch(ctx, "fdm_precondition (fp32)");
 }
 
 int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stats) {
@@ -387,7 +447,7 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
   k_fpcg_init<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, g, x, r, p, st);
   if ((rc = fdm_precondition(b, r, z))) return rc;
   HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive, 0, 2 * sizeof(int), ctx->stream));
-  k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, p, st, 1, b->d_nactive);
+  k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, Ap, p, st, 1, b->d_nactive);
   const int check_every = 4;
   int h_active = 1;
   int64_t it = 0;
@@ -399,7 +459,7 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
       if ((rc = fdm_precondition(b, r, z))) return rc;
       slot = (int)(it & 1);
       HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive + slot, 0, sizeof(int), ctx->stream));
-      k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, p, st, 0, b->d_nactive + slot);
+      k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, Ap, p, st, 0, b->d_nactive + slot);
     }
     if ((rc = check_launch(ctx, "k_fpcg_update"))) return rc;
     HSBP_CUDA(ctx, cudaMemcpyAsync(&h_active, b->d_nactive + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

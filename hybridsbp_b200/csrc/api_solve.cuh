@@ -16,6 +16,10 @@ struct hsbp_trace {
   double *d_partial = nullptr, *d_dots = nullptr;
   hsbp_local_stats acc = {0, 0, 0, 0.0};
   int64_t local_solves = 0;
+  // static condensation (hsbp_trace_condense): dense S_e = F_e^T M̃_e^-1 F_e of every block
+  double *d_S = nullptr;
+  int64_t *d_S_off = nullptr;
+  int max_nf = 0;
 };
 
 namespace {
@@ -153,6 +157,16 @@ void accumulate(hsbp_trace *t, const hsbp_local_stats &s) {
 int schur_apply(hsbp_trace *t, const double *lam, double *out) {
   hsbp_blocks *b = t->blocks;
   hsbp_ctx *ctx = b->ctx;
+  if (t->d_S) {                      // condensed: scatter, one dense matrix-vector product per block, gather
+    HSBP_CUDA(ctx, cudaMemsetAsync(t->d_fv, 0, (size_t)b->FNp * sizeof(double), ctx->stream));
+    if (t->nlam_faces) k_lam_scatter<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_faces, lam, t->d_fv);
+    k_cond_gemv<<<dim3(16, (unsigned)b->nblocks), 256, (size_t)t->max_nf * sizeof(double), ctx->stream>>>(
+        b->d_desc, t->d_S_off, t->d_S, t->d_fv, t->d_ft);
+    if (t->nlam_faces) k_lam_gather<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_faces, t->d_ft, out);
+    k_ewise<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, t->d_D, lam, t->d_zz, 0);
+    k_axpby<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, 1.0, t->d_zz, -1.0, out, out);
+    return check_launch(ctx, "schur_apply (condensed)");
+  }
   HSBP_CUDA(ctx, cudaMemsetAsync(t->d_w, 0, (size_t)b->VNp * sizeof(double), ctx->stream));
   int rc = trace_Fbar_add(t, lam, 1.0, t->d_w);
   if (rc) return rc;
@@ -164,6 +178,50 @@ int schur_apply(hsbp_trace *t, const double *lam, double *out) {
   k_ewise<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, t->d_D, lam, t->d_zz, 0);
   k_axpby<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, 1.0, t->d_zz, -1.0, out, out);
   return check_launch(ctx, "schur_apply");
+}
+
+// S_e = F_e^T M̃_e^-1 F_e column by column, all blocks in lockstep: one local solve per face point of a block
+int trace_condense(hsbp_trace *t) {
+  hsbp_blocks *b = t->blocks;
+  hsbp_ctx *ctx = b->ctx;
+  if (b->local_mode == 0) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_trace_condense: call hsbp_local_setup first");
+  std::vector<int64_t> off(b->nblocks);
+  int64_t total = 0;
+  int max_nf = 0;
+  for (int64_t e = 0; e < b->nblocks; ++e) {
+    const BlockDesc &d = b->h_desc[e];
+    const int nf = 2 * (d.Ns + 1) + 2 * (d.Nr + 1);
+    off[e] = total; total += (int64_t)nf * nf; max_nf = std::max(max_nf, nf);
+  }
+  size_t free_b = 0, total_b = 0;
+  HSBP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  if ((size_t)total * sizeof(double) > free_b / 2 || (size_t)max_nf * sizeof(double) > 48 * 1024)
+    HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "hsbp_trace_condense: the condensed blocks do not fit");
+  cudaFree(t->d_S); cudaFree(t->d_S_off); t->d_S = nullptr; t->d_S_off = nullptr;
+  double *S = nullptr;
+  int64_t *S_off = nullptr;
+  HSBP_CUDA(ctx, cudaMalloc((void **)&S, (size_t)total * sizeof(double)));
+  if (cudaMalloc((void **)&S_off, b->nblocks * sizeof(int64_t)) != cudaSuccess) { cudaFree(S); HSBP_FAIL(ctx, HSBP_ERR_CUDA, "out of device memory"); }
+  auto fail = [&](int rc) { cudaFree(S); cudaFree(S_off); return rc; };
+  if (cudaMemcpyAsync(S_off, off.data(), b->nblocks * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaMemsetAsync(t->d_fv, 0, (size_t)b->FNp * sizeof(double), ctx->stream) != cudaSuccess)
+    return fail(HSBP_ERR_CUDA);
+  int rc;
+  for (int c = 0; c < max_nf; ++c) {
+    k_cond_unit<<<(unsigned)((b->nblocks + 127) / 128), 128, 0, ctx->stream>>>(b->d_desc, b->nblocks, c, t->d_fv);
+    if (cudaMemsetAsync(t->d_w, 0, (size_t)b->VNp * sizeof(double), ctx->stream) != cudaSuccess) return fail(HSBP_ERR_CUDA);
+    if ((rc = hsbp_face_F_add(b, t->d_fv, 1.0, t->d_w))) return fail(rc);
+    hsbp_local_stats s;
+    if ((rc = local_solve_impl(b, t->d_w, t->d_z, &s))) return fail(rc);
+    accumulate(t, s);
+    if ((rc = hsbp_face_FT(b, t->d_z, t->d_ft))) return fail(rc);
+    k_cond_store<<<(unsigned)b->nblocks, 256, 0, ctx->stream>>>(b->d_desc, S_off, c, t->d_ft, S);
+  }
+  k_cond_sym<<<dim3((unsigned)b->nblocks, 16), 256, 0, ctx->stream>>>(b->d_desc, S_off, S);
+  if ((rc = check_launch(ctx, "trace_condense"))) return fail(rc);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(HSBP_ERR_CUDA);
+  t->d_S = S; t->d_S_off = S_off; t->max_nf = max_nf;
+  return HSBP_OK;
 }
 
 int trace_rhs(hsbp_trace *t, const double *g, const double *gd, double *bl) {
@@ -295,6 +353,7 @@ int hsbp_trace_destroy(hsbp_trace *t) {
   cudaStreamSynchronize(t->blocks->ctx->stream);
   cudaFree(t->d_faces); cudaFree(t->d_D); cudaFree(t->d_ft); cudaFree(t->d_fv); cudaFree(t->d_w); cudaFree(t->d_z);
   cudaFree(t->d_r); cudaFree(t->d_p); cudaFree(t->d_q); cudaFree(t->d_zz); cudaFree(t->d_partial); cudaFree(t->d_dots);
+  cudaFree(t->d_S); cudaFree(t->d_S_off);
   delete t;
   return HSBP_OK;
 }
@@ -335,6 +394,18 @@ int hsbp_trace_schur_apply(hsbp_trace *t, const double *lam_dev, double *out_dev
   if (!out_dev || !lam_dev || out_dev == lam_dev) HSBP_FAIL(t->blocks->ctx, HSBP_ERR_ARG, "hsbp_trace_schur_apply: bad pointers");
   HSBP_CUDA(t->blocks->ctx, cudaSetDevice(t->blocks->ctx->device));
   return schur_apply(t, lam_dev, out_dev);
+}
+
+int hsbp_trace_condense(hsbp_trace *t, int enable) {
+  if (!t) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = t->blocks->ctx;
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!enable) {
+    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(t->d_S); cudaFree(t->d_S_off); t->d_S = nullptr; t->d_S_off = nullptr;
+    return HSBP_OK;
+  }
+  return trace_condense(t);
 }
 
 int hsbp_trace_rhs(hsbp_trace *t, const double *g_dev, const double *gd_dev, double *b_dev) {

@@ -98,6 +98,7 @@ __global__ void k_color_pick(const BlockDesc *__restrict__ desc, int c, int ci, 
 // ---- batched PCG, one CTA per block ---------------------------------------------------------
 struct PcgState {      // per block
   double rz, g2, rr;
+  double alpha;        // last step length (flexible beta of the FDM-preconditioned variant)
   int32_t active, iters;
 };
 
@@ -197,6 +198,62 @@ __global__ void k_lam_D(const LamFace *__restrict__ lf, const BlockDesc *__restr
     if (f.em >= 0) t = tau[f.fm + n];
     if (f.ep >= 0) t += tau[f.fp + (f.flip ? f.nl - 1 - n : n)];
     D[f.loff + n] = fg.ht * hweight<P>(n, fg.Nt) * t;            // the norm weights are mirror symmetric
+  }
+}
+
+// ---- static condensation: dense S_e = F_e^T M̃_e^-1 F_e per block ---------------------------------------------
+// (what assembleλmatrix forms block by block, global_curved.jl:743-797: F' \ F slices and their products)
+__device__ __forceinline__ int block_nf(const BlockDesc &d) { return 2 * (d.Ns + 1) + 2 * (d.Nr + 1); }
+// block-face vector with a one at local face point c of every block (the previous one is cleared)
+__global__ void k_cond_unit(const BlockDesc *__restrict__ desc, int64_t nblocks, int c, double *__restrict__ v) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nblocks) return;
+  const BlockDesc d = desc[e];
+  const int nf = block_nf(d);
+  if (c > 0 && c - 1 < nf) v[d.foff + c - 1] = 0.0;
+  if (c < nf) v[d.foff + c] = 1.0;
+}
+__global__ void k_cond_store(const BlockDesc *__restrict__ desc, const int64_t *__restrict__ soff, int c,
+                             const double *__restrict__ ft, double *__restrict__ S) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int nf = block_nf(d);
+  if (c >= nf) return;
+  double *col = S + soff[blockIdx.x] + (int64_t)c * nf;
+  for (int r = threadIdx.x; r < nf; r += blockDim.x) col[r] = ft[d.foff + r];
+}
+// S <- (S + S^T) / 2: the columns come from iterative solves, the matrix-vector kernel reads rows as columns
+__global__ void k_cond_sym(const BlockDesc *__restrict__ desc, const int64_t *__restrict__ soff, double *__restrict__ S) {
+  const BlockDesc d = desc[blockIdx.x];
+  const int nf = block_nf(d);
+  double *Sb = S + soff[blockIdx.x];
+  for (int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; idx < (int64_t)nf * nf; idx += (int64_t)gridDim.y * blockDim.x) {
+    const int r = (int)(idx % nf), c = (int)(idx / nf);
+    if (r <= c) continue;
+    const double v = 0.5 * (Sb[r + (int64_t)nf * c] + Sb[c + (int64_t)nf * r]);
+    Sb[r + (int64_t)nf * c] = v;
+    Sb[c + (int64_t)nf * r] = v;
+  }
+}
+// y_e = S_e v_e in the block-face layout: one warp per row (= column, S is symmetric), coalesced 8-byte reads;
+// grid = (row groups, blocks).  Algorithmic traffic: 8 nf^2 bytes per block.
+__global__ void __launch_bounds__(256)
+k_cond_gemv(const BlockDesc *__restrict__ desc, const int64_t *__restrict__ soff, const double *__restrict__ S,
+            const double *__restrict__ v, double *__restrict__ y) {
+  extern __shared__ double sv[];
+  const BlockDesc d = desc[blockIdx.y];
+  const int nf = block_nf(d);
+  const double *Sb = S + soff[blockIdx.y];
+  for (int c = threadIdx.x; c < nf; c += blockDim.x) sv[c] = v[d.foff + c];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = blockIdx.x * nw + wid; r < nf; r += gridDim.x * nw) {
+    const double *col = Sb + (int64_t)nf * r;
+    double s0 = 0.0, s1 = 0.0;
+    int c = lane;
+    for (; c + 32 < nf; c += 64) { s0 += col[c] * sv[c]; s1 += col[c + 32] * sv[c + 32]; }
+    if (c < nf) s0 += col[c] * sv[c];
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) y[d.foff + r] = s;
   }
 }
 

@@ -8,7 +8,8 @@ from .blocks import Blocks, Trace, LOCAL_CHOLESKY, LOCAL_FDM, LOCAL_PCG  # noqa:
 from .host import connectivityarrays
 
 
-def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=None, local_tol=1e-13, seed=1234):
+def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=None, local_tol=1e-13, seed=1234,
+                        condense=False, fdm_gemm=3):
     """-> (DistributedTrace, g, gd, info).  g, gd are torch tensors on the rank's GPU; the right-hand sides are
     seeded per global block / face so that every world size solves the same global problem on the same mesh."""
     import torch
@@ -28,8 +29,11 @@ def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=
     if local_mode is None:
         # small blocks: dense Cholesky factors; large, smoothly varying blocks: PCG with the separable preconditioner
         local_mode = LOCAL_CHOLESKY if (N + 1) ** 2 <= 1600 else LOCAL_FDM
+    blk.set_option("fdm_gemm", fdm_gemm)
     blk.local_setup(local_mode, tol=local_tol, maxit=200000)
     tr = Trace(blk, lm.FToB, lm.FToE, lm.FToLF, lm.EToO, lm.EToS)
+    if condense:
+        tr.condense()
     op = parallel.GpuLocalOperator(blk, tr)
     dev = torch.device("cuda", ctx.device)
     dt = parallel.DistributedTrace(op, tr.FTolambdastarts, lm, dist=dist, device=dev)

@@ -168,6 +168,13 @@ int  hsbp_trace_get_D(hsbp_trace *trace, double *D);                          /*
  * layer (hybridsbp_b200/parallel.py) exchanges and adds the partner's.  D is the sum of both sides' penalties:
  * read the partial D, complete it with the partner's, write it back.                                           */
 int  hsbp_trace_set_D(hsbp_trace *trace, const double *D);
+/* Static condensation: form the dense per-block matrices S_e = F_e^T M̃_e^-1 F_e (F_e = [F_1 .. F_4] of block e, size
+ * 2(Nr+1) + 2(Ns+1)) once, with one batched local solve per face point -- the products assembleλmatrix computes block by
+ * block (global_curved.jl:759-790, `F' \ F` slices) without assembling the global sparse B.  Afterwards every
+ * hsbp_trace_schur_apply / CG iteration of hsbp_trace_solve is scatter + one dense matrix-vector product per block +
+ * gather instead of a local solve; the right-hand side and the back-substitution still use the local solver.
+ * enable = 0 frees the matrices and returns to the matrix-free path.  Call after hsbp_local_setup.               */
+int  hsbp_trace_condense(hsbp_trace *trace, int enable);
 int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u   */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
 int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam      */

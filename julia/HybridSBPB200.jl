@@ -112,6 +112,8 @@ end
 # batched call, so the per-block object is a view into a shared batch solver.
 const LOCAL_PCG = 1
 const LOCAL_CHOLESKY = 2
+const LOCAL_BAND = 3      # banded Cholesky (blocks beyond the dense solver, e.g. the 201 x 201 block of BP1)
+const LOCAL_FDM = 4       # PCG with the fast-diagonalisation preconditioner (uniform, large blocks)
 struct LocalStats
   iterations_max::Int64
   iterations_sum::Int64
@@ -166,6 +168,10 @@ struct TraceStats
   inner_iterations_max::Int64
   local_solves::Int64
 end
+"form the dense per-block S_e = F_eᵀ M̃_e⁻¹ F_e (assembleλmatrix's products, global_curved.jl:759-790); later solves use them"
+condense!(t::Trace; enable::Bool = true) =
+  check(t.blocks.ctx, ccall((:hsbp_trace_condense, libhsbp), Cint, (Ptr{Cvoid}, Cint), t.h, enable ? 1 : 0))
+
 "λ = B⁻¹(gδ − F̄ᵀM̃⁻¹g), u = M̃⁻¹(g − F̄λ)   (square_circle.jl:376-388); returns (λ, u, stats)"
 function trace_solve(t::Trace, g::Vector{Float64}, gδ::Vector{Float64}; tol = 1e-10, maxit = 10_000)
   ctx = t.blocks.ctx

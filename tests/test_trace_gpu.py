@@ -172,8 +172,9 @@ def test_banded_cholesky_local_solver(ctx, p):
         assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, np.linalg.norm(x[sl] - xr) / np.linalg.norm(xr))
 
 
-@pytest.mark.parametrize("p,kind", [(2, "warped"), (4, "warped"), (6, "warped"), (4, "random")])
-def test_fast_diagonalisation_pcg_local_solver(ctx, p, kind):
+@pytest.mark.parametrize("p,kind,gemm", [(2, "warped", 0), (4, "warped", 0), (6, "warped", 0), (4, "random", 0),
+                                         (4, "warped", 1), (4, "warped", 2), (4, "warped", 3), (4, "random", 3)])
+def test_fast_diagonalisation_pcg_local_solver(ctx, p, kind, gemm):
     """K2d: PCG on M-tilde_e preconditioned by the inverse of its separable part (api_fdm.cuh) against the oracle's
     direct solve (global_curved.jl:698, 734); on smoothly warped blocks it must need far fewer iterations than
     Jacobi-PCG, on the random SPD tensors of local_op_eigenvalues.jl:32-38 it only has to stay correct."""
@@ -190,6 +191,7 @@ def test_fast_diagonalisation_pcg_local_solver(ctx, p, kind):
     blk = upload_blocks(hs, ctx, p, mets, bcs)
     g = rng.uniform(-1, 1, blk.VNp)
     dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    blk.set_option("fdm_gemm", gemm)      # preconditioner GEMMs: 0 fp64, 1 fp32, 2 fp32 emulated on BF16 tensor cores, 3 TF32
     blk.local_setup(hs.LOCAL_FDM, tol=1e-13, maxit=5000)
     st = blk.local_solve(dg, dx)
     assert st["failed_blocks"] == 0, st
@@ -224,3 +226,37 @@ def test_trace_solve_with_cholesky_local_solver(ctx):
     assert st["converged"] == 1 and st["inner_iterations_sum"] == 0, st
     assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
     assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
+
+
+def test_condensed_trace_solve_matches_matrix_free_and_oracle(ctx):
+    """Static condensation (hsbp_trace_condense): the dense S_e = F_e^T M̃_e^-1 F_e reproduce the oracle's assembled
+    B = D - Fbar^T M̃^-1 Fbar (assembleλmatrix, global_curved.jl:743-797) and the solve agrees with the direct one."""
+    import hybridsbp_b200 as hs
+    p = 4
+    rng = np.random.default_rng(78)
+    c = build_case(hs, ctx, p, 3 * p - 1, flipped_four_block_mesh(), rng)
+    blk, tr, FbarT = c["blk"], c["tr"], c["FbarT"]
+    blk.local_setup(hs.LOCAL_CHOLESKY)
+    B = orc.assemblelambdamatrix(c["Fl"], c["vstarts"], c["EToF"], c["FToB"], c["M"].F, c["D"], FbarT).toarray()
+    lam = rng.uniform(-1, 1, tr.lNp)
+    dl, dq0, dq1 = ctx.array(lam), ctx.empty(tr.lNp), ctx.empty(tr.lNp)
+    tr.schur_apply(dl, dq0)
+    tr.condense()
+    tr.schur_apply(dl, dq1)
+    ref = B @ lam
+    assert np.linalg.norm(dq0.get() - ref) <= 1e-11 * np.linalg.norm(ref)
+    assert np.linalg.norm(dq1.get() - ref) <= 1e-11 * np.linalg.norm(ref)
+    g = rng.uniform(-1, 1, blk.VNp); gd = rng.uniform(-1, 1, tr.lNp)
+    bl = np.zeros(tr.lNp); uu = np.zeros(blk.VNp)
+    orc.LocalToGLobalRHS(bl, g, gd, uu, c["M"].F, FbarT, c["vstarts"])
+    lam_ref = np.linalg.solve(B, bl)
+    rhs = g - FbarT.T @ lam_ref
+    u_ref = np.concatenate([c["M"].F[e].solve(rhs[blk.vol_slice(e)]) for e in range(blk.nblocks)])
+    dg, dgd, dlam, dsol = ctx.array(g), ctx.array(gd), ctx.empty(tr.lNp), ctx.empty(blk.VNp)
+    st = tr.solve(dg, dgd, dlam, dsol, tol=1e-13, maxit=2000)
+    assert st["converged"] == 1 and st["local_solves"] == 2, st          # rhs + back-substitution only
+    assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
+    assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
+    tr.condense(False)
+    tr.schur_apply(dl, dq1)
+    assert np.linalg.norm(dq1.get() - dq0.get()) == 0.0

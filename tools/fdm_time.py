@@ -19,9 +19,12 @@ blk.compute_tau(2.0)
 x0 = np.random.default_rng(5).uniform(-1, 1, blk.VNp)
 dx0, dg, dx, dr = ctx.array(x0), ctx.empty(blk.VNp), ctx.empty(blk.VNp), ctx.empty(blk.VNp)
 blk.apply(dx0, dg)
-for name, mode in (("FDM-PCG", hs.LOCAL_FDM),) + ((("Jacobi-PCG", hs.LOCAL_PCG),) if jac else ()):
+for name, mode, gemm in (("FDM-PCG fp64 GEMM", hs.LOCAL_FDM, 0), ("FDM-PCG fp32 GEMM", hs.LOCAL_FDM, 1),
+                         ("FDM-PCG BF16x9 GEMM", hs.LOCAL_FDM, 2), ("FDM-PCG TF32 GEMM", hs.LOCAL_FDM, 3)) + \
+        ((("Jacobi-PCG", hs.LOCAL_PCG, 0),) if jac else ()):
     t0 = time.time()
-    blk.local_setup(mode, tol=1e-13, maxit=100000)
+    blk.set_option("fdm_gemm", gemm)
+    blk.local_setup(mode, tol=1e-13, maxit=2000)
     ts = time.time() - t0
     for rep in range(2):
         t0 = time.time()
