@@ -189,6 +189,13 @@ class Trace:
         schur_apply / solve calls use them instead of local solves."""
         self.ctx._check(lib().hsbp_trace_condense(self.h, 1 if enable else 0))
 
+    def precond_setup(self, kind=1):
+        """0: Jacobi (D); 1: block-Jacobi with the exact diagonal blocks of B (needs condense())."""
+        self.ctx._check(lib().hsbp_trace_precond_setup(self.h, int(kind)))
+
+    def precond_apply(self, r: DeviceArray, z: DeviceArray):
+        self.ctx._check(lib().hsbp_trace_precond_apply(self.h, r.ptr, z.ptr))
+
     def schur_apply(self, lam: DeviceArray, out: DeviceArray):
         self.ctx._check(lib().hsbp_trace_schur_apply(self.h, lam.ptr, out.ptr))
 

@@ -20,6 +20,9 @@ struct hsbp_trace {
   double *d_S = nullptr;
   int64_t *d_S_off = nullptr;
   int max_nf = 0;
+  // face-block preconditioner (hsbp_trace_precond_setup): Cholesky factors of the diagonal blocks B_ff
+  double *d_pc = nullptr, *d_pc_work = nullptr;
+  void *d_pc_desc = nullptr;
 };
 
 namespace {
@@ -224,6 +227,65 @@ int trace_condense(hsbp_trace *t) {
   return HSBP_OK;
 }
 
+void precond_free(hsbp_trace *t) {
+  cudaFree(t->d_pc); cudaFree(t->d_pc_work); cudaFree(t->d_pc_desc);
+  t->d_pc = nullptr; t->d_pc_work = nullptr; t->d_pc_desc = nullptr;
+}
+
+// dense Cholesky of every B_ff (batched, the panel / DMMA trailing-update kernels of the dense local solver)
+int precond_faceblocks(hsbp_trace *t) {
+  hsbp_blocks *b = t->blocks;
+  hsbp_ctx *ctx = b->ctx;
+  if (!t->d_S) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_trace_precond_setup: the face-block preconditioner needs hsbp_trace_condense first");
+  precond_free(t);
+  const int64_t nf = t->nlam_faces;
+  if (nf == 0) return HSBP_OK;
+  static_assert(sizeof(FaceBlock) == sizeof(CholBlock), "descriptor layout");
+  std::vector<FaceBlock> fbs(nf);
+  int64_t off = 0, woff = 0;
+  int maxld = 0;
+  for (int64_t i = 0; i < nf; ++i) {
+    const LamFace &f = t->h_faces[i];
+    const int ld = (f.nl + CH_NB - 1) / CH_NB * CH_NB;
+    fbs[i].off = off; fbs[i].np = f.nl; fbs[i].ld = ld; fbs[i].voff = f.loff; fbs[i].woff = woff;
+    off += (int64_t)ld * ld; woff += ld; maxld = std::max(maxld, ld);
+  }
+  HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc, (size_t)off * sizeof(double)));
+  HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc_work, (size_t)woff * sizeof(double)));
+  HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc_desc, nf * sizeof(FaceBlock)));
+  HSBP_CUDA(ctx, cudaMemcpyAsync(t->d_pc_desc, fbs.data(), nf * sizeof(FaceBlock), cudaMemcpyHostToDevice, ctx->stream));
+  k_faceblock_fill<<<(unsigned)nf, 256, 0, ctx->stream>>>(t->d_faces, (const FaceBlock *)t->d_pc_desc, b->d_desc, t->d_S_off, t->d_S,
+                                                         t->d_D, t->d_pc);
+  int *d_flag = nullptr;
+  std::vector<int> flag(nf, 0);
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_flag, nf * sizeof(int)));
+  cudaMemsetAsync(d_flag, 0, nf * sizeof(int), ctx->stream);
+  const CholBlock *dcb = (const CholBlock *)t->d_pc_desc;
+  for (int k0 = 0; k0 < maxld; k0 += CH_NB) {
+    k_chol_panel<<<(unsigned)nf, CH_THREADS, 0, ctx->stream>>>(dcb, t->d_pc, k0, d_flag);
+    const int nt = (maxld - k0 - CH_NB) / CH_NB;
+    if (nt > 0) k_chol_update<<<dim3(nt, nt, (unsigned)nf), CH_THREADS, 0, ctx->stream>>>(dcb, t->d_pc, k0);
+  }
+  cudaError_t e1 = cudaGetLastError();
+  if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(flag.data(), d_flag, nf * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_flag);
+  if (e1 != cudaSuccess) { precond_free(t); ctx->err = std::string("precond_faceblocks: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
+  for (int64_t i = 0; i < nf; ++i)
+    if (flag[i]) { precond_free(t); HSBP_FAIL(ctx, HSBP_ERR_ARG, "face-block preconditioner: a diagonal block of B is not positive definite"); }
+  return HSBP_OK;
+}
+
+// z = preconditioner^-1 r: Cholesky solves with the face blocks, or r / D (Jacobi)
+int precond_apply(hsbp_trace *t, const double *r, double *z) {
+  hsbp_ctx *ctx = t->blocks->ctx;
+  if (t->d_pc && t->nlam_faces)
+    k_chol_solve<<<(unsigned)t->nlam_faces, CH_THREADS, 0, ctx->stream>>>((const CholBlock *)t->d_pc_desc, t->d_pc, r, z, t->d_pc_work);
+  else
+    k_ewise<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, r, t->d_D, z, 1);
+  return check_launch(ctx, "precond_apply");
+}
+
 int trace_rhs(hsbp_trace *t, const double *g, const double *gd, double *bl) {
   hsbp_blocks *b = t->blocks;
   hsbp_ctx *ctx = b->ctx;
@@ -354,6 +416,7 @@ int hsbp_trace_destroy(hsbp_trace *t) {
   cudaFree(t->d_faces); cudaFree(t->d_D); cudaFree(t->d_ft); cudaFree(t->d_fv); cudaFree(t->d_w); cudaFree(t->d_z);
   cudaFree(t->d_r); cudaFree(t->d_p); cudaFree(t->d_q); cudaFree(t->d_zz); cudaFree(t->d_partial); cudaFree(t->d_dots);
   cudaFree(t->d_S); cudaFree(t->d_S_off);
+  precond_free(t);
   delete t;
   return HSBP_OK;
 }
@@ -405,7 +468,29 @@ int hsbp_trace_condense(hsbp_trace *t, int enable) {
     cudaFree(t->d_S); cudaFree(t->d_S_off); t->d_S = nullptr; t->d_S_off = nullptr;
     return HSBP_OK;
   }
+  precond_free(t);                   // factors of an older S
   return trace_condense(t);
+}
+
+int hsbp_trace_precond_setup(hsbp_trace *t, int kind) {
+  if (!t) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = t->blocks->ctx;
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (kind == HSBP_PRECOND_JACOBI) {
+    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    precond_free(t);
+    return HSBP_OK;
+  }
+  if (kind != HSBP_PRECOND_FACE_BLOCKS) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup: unknown kind");
+  return precond_faceblocks(t);
+}
+
+int hsbp_trace_precond_apply(hsbp_trace *t, const double *r_dev, double *z_dev) {
+  if (!t) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = t->blocks->ctx;
+  if (!r_dev || !z_dev || r_dev == z_dev) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_apply: bad pointers");
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  return precond_apply(t, r_dev, z_dev);
 }
 
 int hsbp_trace_rhs(hsbp_trace *t, const double *g_dev, const double *gd_dev, double *b_dev) {
@@ -432,7 +517,7 @@ int hsbp_trace_solve(hsbp_trace *t, const double *g_dev, const double *gd_dev, d
   if (n > 0) {
     if ((rc = trace_rhs(t, g_dev, gd_dev, r))) return rc;                  // r = b (lambda0 = 0)
     HSBP_CUDA(ctx, cudaMemsetAsync(lam, 0, n * sizeof(double), ctx->stream));
-    k_ewise<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, r, t->d_D, p, 1);       // p = z = r / D
+    if ((rc = precond_apply(t, r, p))) return rc;                          // p = z = preconditioned residual
     double d3[3];
     if ((rc = dots(t, n, r, p, r, r, nullptr, nullptr, d3))) return rc;
     double rz = d3[0];
@@ -445,7 +530,7 @@ int hsbp_trace_solve(hsbp_trace *t, const double *g_dev, const double *gd_dev, d
         const double alpha = rz / d3[0];
         k_axpby<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, 1.0, lam, alpha, p, lam);
         k_axpby<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, 1.0, r, -alpha, q, r);
-        k_ewise<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, r, t->d_D, z, 1);
+        if ((rc = precond_apply(t, r, z))) return rc;
         if ((rc = dots(t, n, r, z, r, r, nullptr, nullptr, d3))) return rc;
         st.outer_iterations += 1;
         rr = d3[1];

@@ -257,4 +257,46 @@ k_cond_gemv(const BlockDesc *__restrict__ desc, const int64_t *__restrict__ soff
   }
 }
 
+// ---- face-block preconditioner of the trace system ----------------------------------------------------------
+// A_f = B_ff = D_f - S_{e-}[f, f] - orient(S_{e+}[f, f]): the diagonal block of B = D - Fbar^T M̃^-1 Fbar that belongs to
+// face f, from the condensed blocks; padded to ld with the identity.  A cut face of a partitioned mesh (one side on another
+// device) keeps only D_f: both devices must apply the same preconditioner to their copies of lambda.
+struct FaceBlock {      // layout-compatible with CholBlock (api_chol.cuh): off, np, ld, voff, woff
+  int64_t off;
+  int32_t np, ld;
+  int64_t voff;
+  int64_t woff;
+};
+__global__ void __launch_bounds__(256)
+k_faceblock_fill(const LamFace *__restrict__ lf, const FaceBlock *__restrict__ fb, const BlockDesc *__restrict__ desc,
+                 const int64_t *__restrict__ soff, const double *__restrict__ S, const double *__restrict__ D,
+                 double *__restrict__ A) {
+  const LamFace f = lf[blockIdx.x];
+  const FaceBlock q = fb[blockIdx.x];
+  double *Ab = A + q.off;
+  const bool cut = f.em < 0 || f.ep < 0;
+  const double *Sm = nullptr, *Sp = nullptr;
+  int nfm = 0, nfp = 0, om = 0, op = 0;
+  if (!cut) {
+    const BlockDesc dm = desc[f.em], dp = desc[f.ep];
+    nfm = block_nf(dm); nfp = block_nf(dp);
+    om = (int)(f.fm - dm.foff); op = (int)(f.fp - dp.foff);
+    Sm = S + soff[f.em]; Sp = S + soff[f.ep];
+  }
+  for (int idx = threadIdx.x; idx < q.ld * q.ld; idx += blockDim.x) {
+    const int i = idx % q.ld, j = idx / q.ld;
+    double v = 0.0;
+    if (i < q.np && j < q.np) {
+      if (i == j) v = D[f.loff + i];
+      if (!cut) {
+        const int ip = f.flip ? q.np - 1 - i : i, jp = f.flip ? q.np - 1 - j : j;
+        v -= Sm[(om + i) + (int64_t)nfm * (om + j)] + Sp[(op + ip) + (int64_t)nfp * (op + jp)];
+      }
+    } else if (i == j) {
+      v = 1.0;
+    }
+    Ab[idx] = v;
+  }
+}
+
 }  // namespace hsbp

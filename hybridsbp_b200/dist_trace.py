@@ -9,7 +9,7 @@ from .host import connectivityarrays
 
 
 def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=None, local_tol=1e-13, seed=1234,
-                        condense=False, fdm_gemm=3):
+                        condense=False, fdm_gemm=3, face_blocks=None):
     """-> (DistributedTrace, g, gd, info).  g, gd are torch tensors on the rank's GPU; the right-hand sides are
     seeded per global block / face so that every world size solves the same global problem on the same mesh."""
     import torch
@@ -37,6 +37,11 @@ def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=
     op = parallel.GpuLocalOperator(blk, tr)
     dev = torch.device("cuda", ctx.device)
     dt = parallel.DistributedTrace(op, tr.FTolambdastarts, lm, dist=dist, device=dev)
+    if face_blocks is None:
+        face_blocks = condense
+    if face_blocks:                      # after DistributedTrace has completed D on the cut faces
+        tr.precond_setup(1)
+        op.has_precond = True
     npb = (N + 1) ** 2
     g = np.concatenate([np.random.default_rng(seed + int(e)).uniform(-1, 1, npb) for e in lm.blocks])
     gd = np.concatenate([np.random.default_rng(seed + 10 ** 6 + int(f)).uniform(-1, 1, tr.FTolambdastarts[i + 1] - tr.FTolambdastarts[i])

@@ -136,12 +136,19 @@ class DistributedTrace:
         b = self.op.rhs(g, gd)                            # gd - (local side of Fbar^T M^-1 g); gd is replicated
         return self._exchange_add(b, gd)
 
+    def precond(self, r):
+        """z = P^-1 r: the local operator's preconditioner (face blocks; cut faces use the completed D on every rank that
+        holds them, so the copies of lambda stay identical) or Jacobi with the completed D."""
+        if getattr(self.op, "has_precond", False):
+            return self.op.precond(r)
+        return r / self.D
+
     def solve(self, g, gd, tol=1e-10, maxit=10000):
         """-> (lambda, u, stats); same iteration as hsbp_trace_solve."""
         torch = self.torch
         r = self.rhs(g, gd)
         lam = torch.zeros_like(r)
-        p = r / self.D
+        p = self.precond(r)
         rz, b2 = self.dots([(r, p), (r, r)])
         it, rr, converged = 0, b2, b2 == 0.0
         while not converged and it < maxit:
@@ -150,7 +157,7 @@ class DistributedTrace:
             alpha = rz / pq
             lam += alpha * p
             r -= alpha * q
-            z = r / self.D
+            z = self.precond(r)
             rz_new, rr = self.dots([(r, z), (r, r)])
             it += 1
             if np.sqrt(rr / b2) <= tol:
@@ -194,6 +201,15 @@ class GpuLocalOperator:
         out = self.torch.empty_like(lam)
         self._sync()
         self.tr.schur_apply(_Ptr(lam), _Ptr(out))
+        self.blk.ctx.sync()
+        return out
+
+    has_precond = False
+
+    def precond(self, r):
+        out = self.torch.empty_like(r)
+        self._sync()
+        self.tr.precond_apply(_Ptr(r), _Ptr(out))
         self.blk.ctx.sync()
         return out
 

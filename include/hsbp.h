@@ -175,6 +175,15 @@ int  hsbp_trace_set_D(hsbp_trace *trace, const double *D);
  * gather instead of a local solve; the right-hand side and the back-substitution still use the local solver.
  * enable = 0 frees the matrices and returns to the matrix-free path.  Call after hsbp_local_setup.               */
 int  hsbp_trace_condense(hsbp_trace *trace, int enable);
+/* Preconditioner of the CG on B (the reference factorises B directly, square_circle.jl:314; here B is only applied):
+ *   HSBP_PRECOND_JACOBI       D = Hf (tau- + tau+)                      (default)
+ *   HSBP_PRECOND_FACE_BLOCKS  block-Jacobi with the exact diagonal blocks B_ff = D_f - S_e-[f,f] - S_e+[f,f] (dense
+ *                             Cholesky per face); needs hsbp_trace_condense.  Cut faces of a partitioned mesh keep D_f.
+ * hsbp_trace_precond_apply: z = P^-1 r (used by hsbp_trace_solve and by the host-side distributed CG).             */
+#define HSBP_PRECOND_JACOBI      0
+#define HSBP_PRECOND_FACE_BLOCKS 1
+int  hsbp_trace_precond_setup(hsbp_trace *trace, int kind);
+int  hsbp_trace_precond_apply(hsbp_trace *trace, const double *r_dev, double *z_dev);
 int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u   */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
 int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam      */

@@ -257,6 +257,23 @@ def test_condensed_trace_solve_matches_matrix_free_and_oracle(ctx):
     assert st["converged"] == 1 and st["local_solves"] == 2, st          # rhs + back-substitution only
     assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
     assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
+    # face-block preconditioner from the diagonal blocks of B: same solution, fewer iterations
+    it_jacobi = st["outer_iterations"]
+    tr.precond_setup(1)
+    Bd = np.zeros_like(B)
+    starts = np.asarray(tr.FTolambdastarts) - 1
+    for a, b_ in zip(starts[:-1], starts[1:]):
+        Bd[a:b_, a:b_] = B[a:b_, a:b_]
+    r = rng.uniform(-1, 1, tr.lNp)
+    dr, dz = ctx.array(r), ctx.empty(tr.lNp)
+    tr.precond_apply(dr, dz)
+    z_ref = np.linalg.solve(Bd, r)
+    assert np.linalg.norm(dz.get() - z_ref) <= 1e-9 * np.linalg.norm(z_ref)
+    st = tr.solve(dg, dgd, dlam, dsol, tol=1e-13, maxit=2000)
+    assert st["converged"] == 1 and st["outer_iterations"] < it_jacobi, (st, it_jacobi)
+    assert np.linalg.norm(dlam.get() - lam_ref) <= 1e-10 * np.linalg.norm(lam_ref), st
+    assert np.linalg.norm(dsol.get() - u_ref) <= 1e-10 * np.linalg.norm(u_ref), st
+    tr.precond_setup(0)
     tr.condense(False)
     tr.schur_apply(dl, dq1)
     assert np.linalg.norm(dq1.get() - dq0.get()) == 0.0
