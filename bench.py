@@ -195,6 +195,7 @@ def run_ours(args):
     blk.set_option("sweep_points_per_thread", args.sweep_r)
     blk.set_option("sweep_chunks_per_side", args.sweep_ncs)
     blk.set_option("sweep_deep", args.sweep_deep)
+    blk.set_option("sweep_p6_regs", args.sweep_p6_regs)
     blk.set_option("force_generic", 1 if args.generic else 0)
     try:
         blk.set_option("sweep_fold_faces", 0 if args.no_fold else 1)
@@ -366,6 +367,7 @@ def main():
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")
     ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")
     ap.add_argument("--sweep-deep", type=int, default=1, help="1: css / crs windows of k_sweep in shared-memory rings, 0: in registers")
+    ap.add_argument("--sweep-p6-regs", type=int, default=128)
     ap.add_argument("--sweep-ncs", type=int, default=0, help="chunks per side of k_sweep (0 = heuristic)")
     ap.add_argument("--generic", action="store_true", help="force the generic two-pass kernels")
     ap.add_argument("--no-fold", action="store_true", help="face terms by separate gather / scatter kernels")

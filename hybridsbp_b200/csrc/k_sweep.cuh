@@ -1110,19 +1110,27 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
   constexpr int MINB = (R == 2 ? 65536 / REGS2 : 256) / NT;
   void (*kern)(const SweepParams);
-  if constexpr (DEEP) kern = k_sweep_deep<P, R, (R == 2 ? SW_DEEP_REGS2 : (P == 6 ? 255 : SW_DEEP_REGS4))>;
-  else kern = k_sweep<P, R, NT, MINB>;
+  if constexpr (DEEP) {
+    if constexpr (P == 6 && R == 2) {    // 7-line windows: 128 registers spill a little, 168 cost a CTA per SM
+      if (b->sweep_p6_regs == 168) kern = k_sweep_deep<P, R, 168>;
+      else kern = k_sweep_deep<P, R, SW_DEEP_REGS2>;
+    } else {
+      kern = k_sweep_deep<P, R, (R == 2 ? SW_DEEP_REGS2 : (P == 6 ? 255 : SW_DEEP_REGS4))>;
+    }
+  } else {
+    kern = k_sweep<P, R, NT, MINB>;
+  }
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
   const size_t sm = sweep_smem<P>(Nrp, DEEP);
-  static bool attr_set = false;
+  static void (*attr_set_for)(const SweepParams) = nullptr;
   static int ctas_per_sm = 1;
-  if (!attr_set) {
+  if (attr_set_for != kern) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
       ctx->err = "cudaFuncSetAttribute(max dynamic shared memory) failed";
       return HSBP_ERR_CUDA;
     }
-    attr_set = true;
+    attr_set_for = kern;
   }
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, nthreads, sm) != cudaSuccess || ctas_per_sm < 1)
     ctas_per_sm = 1;
