@@ -27,6 +27,7 @@ struct BandBlock {
   int32_t Nrp, Nsp;
   int64_t voff;      // offset of the block in volume vectors
   int64_t woff;      // offset of the block's padded work vector
+  int64_t ioff;      // offset of the block's inverted diagonal blocks (npad / BS_PB panels of BS_PB x BS_PB)
 };
 
 template <int P> struct BandWidth {
@@ -228,6 +229,152 @@ k_band_solve(const BandBlock *__restrict__ bb, const double *__restrict__ AB, co
   for (int i = tid; i < b.np; i += CH_THREADS) x[b.voff + i] = r[i];
 }
 
+// ---- streamed solve ---------------------------------------------------------------------------------------------
+// The solve above touches the band through ordinary loads with several block-wide barriers per panel: 30 ms for the single
+// 201 x 201 block of BP1 (134 MB of band, read twice).  k_band_solve_stream keeps the same data layout -- the BS_PB columns
+// of a panel are contiguous in memory -- and streams the panels through a shared-memory ring with bulk copies (TMA) that
+// run ahead of the arithmetic; the active part of the right-hand side lives in a circular shared-memory window, and the
+// triangular solves with the diagonal blocks are matrix-vector products with their precomputed inverses, so the only
+// serial chain per panel is one 16-term dot product per lane.
+constexpr int BS_PB = 16;             // panel width of the streamed solve
+constexpr int BS_THREADS = 512;
+constexpr int BS_WIN = 2048;          // circular window of the right-hand side / solution (doubles); needs kd + 2 BS_PB <= BS_WIN
+
+// inverse of every BS_PB x BS_PB lower-triangular diagonal block of the factor, row-major [i][j]
+__global__ void __launch_bounds__(BS_PB)
+k_band_invdiag(const BandBlock *__restrict__ bb, const double *__restrict__ AB, double *__restrict__ inv) {
+  __shared__ double D[BS_PB][BS_PB + 1];
+  const BandBlock b = bb[blockIdx.y];
+  const int k0 = blockIdx.x * BS_PB;
+  if (k0 >= b.npad) return;
+  const double *A = AB + b.off;
+  const int c = threadIdx.x;
+  for (int i = 0; i < BS_PB; ++i) D[i][c] = band_get(A, b.ld, b.kd, k0 + i, k0 + c);
+  __syncthreads();
+  double x[BS_PB];                    // column c of the inverse: D x = e_c
+#pragma unroll
+  for (int i = 0; i < BS_PB; ++i) {
+    double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < BS_PB; ++j)
+      if (j < i) s -= D[i][j] * x[j];
+    x[i] = (i >= c) ? s / D[i][i] : 0.0;
+  }
+  double *out = inv + b.ioff + (int64_t)blockIdx.x * BS_PB * BS_PB;
+#pragma unroll
+  for (int i = 0; i < BS_PB; ++i) out[i * BS_PB + c] = x[i];
+}
+
+// x_e = (L L^T)^-1 g_e, one CTA per block.  Dynamic shared memory: nst panel stages of BS_PB * ld doubles, nst inverse
+// blocks, the window, 2 * BS_PB doubles, nst mbarriers.
+__global__ void __launch_bounds__(BS_THREADS, 1)
+k_band_solve_stream(const BandBlock *__restrict__ bb, const double *__restrict__ AB, const double *__restrict__ inv,
+                    const double *__restrict__ g, double *__restrict__ x, double *__restrict__ work, int nst, int maxld) {
+  extern __shared__ __align__(128) unsigned char band_smem[];
+  const BandBlock b = bb[blockIdx.x];
+  const double *A = AB + b.off;
+  const double *Iv = inv + b.ioff;
+  double *y = work + b.woff;                                  // forward result (global, npad doubles)
+  const int ld = b.ld, kd = b.kd, npad = b.npad, np = b.np, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int npan = npad / BS_PB;
+  double *pan = reinterpret_cast<double *>(band_smem);        // [nst][BS_PB * maxld]
+  double *ivs = pan + (size_t)nst * BS_PB * maxld;            // [nst][BS_PB * BS_PB]
+  double *win = ivs + (size_t)nst * BS_PB * BS_PB;            // [BS_WIN]
+  double *pv = win + BS_WIN;                                  // [2 * BS_PB]: panel solution / column dots
+  uint64_t *full = reinterpret_cast<uint64_t *>(pv + 2 * BS_PB);
+  const uint32_t pan_bytes = (uint32_t)(BS_PB * ld) * 8u, inv_bytes = (uint32_t)(BS_PB * BS_PB) * 8u;
+  if (tid == 0) {
+    for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k, int st) {                           // panel k into stage st (thread 0)
+    mbar_expect_tx(&full[st], pan_bytes + inv_bytes);
+    bulk_g2s(pan + (size_t)st * BS_PB * maxld, A + (int64_t)k * BS_PB * ld, pan_bytes, &full[st]);
+    bulk_g2s(ivs + (size_t)st * BS_PB * BS_PB, Iv + (int64_t)k * BS_PB * BS_PB, inv_bytes, &full[st]);
+  };
+  // ================= L y = g: panels in increasing order =================
+  if (tid == 0) {
+    fence_proxy_async();
+    for (int k = 0; k < nst && k < npan; ++k) issue(k, k);
+  }
+  for (int i = tid; i < BS_PB + kd && i < BS_WIN; i += BS_THREADS) win[i] = (i < np) ? g[b.voff + i] : 0.0;
+  __syncthreads();
+  int st = 0;
+  uint32_t parity = 0;
+  for (int k = 0; k < npan; ++k) {
+    const int k0 = k * BS_PB;
+    // rows that enter the window for the next panel: k0 + BS_PB + kd .. + BS_PB - 1 (loaded early, stored late)
+    double gnew = 0.0;
+    const int inew = k0 + BS_PB + kd + (tid - 32);
+    if (wid == 1 && lane < BS_PB && inew < np) gnew = g[b.voff + inew];
+    mbar_wait(&full[st], parity);
+    const double *P = pan + (size_t)st * BS_PB * maxld;
+    const double *Iq = ivs + (size_t)st * BS_PB * BS_PB;
+    if (wid == 0 && lane < BS_PB) {                           // y_panel = inv(D) r_panel
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < BS_PB; ++j) s += Iq[lane * BS_PB + j] * win[(k0 + j) & (BS_WIN - 1)];
+      pv[lane] = s;
+      y[k0 + lane] = s;
+    }
+    __syncthreads();
+    for (int t = tid; t < kd; t += BS_THREADS) {              // r_i -= sum_j L[i][k0+j] y_j, i = k0 + BS_PB + t
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < BS_PB; ++j) {
+        const int d = t + BS_PB - j;
+        if (d <= kd) s += P[j * ld + d] * pv[j];
+      }
+      win[(k0 + BS_PB + t) & (BS_WIN - 1)] -= s;
+    }
+    if (wid == 1 && lane < BS_PB) win[inew & (BS_WIN - 1)] = gnew;
+    __syncthreads();
+    if (tid == 0 && k + nst < npan) { fence_proxy_async(); issue(k + nst, st); }
+    if (++st == nst) { st = 0; parity ^= 1u; }
+  }
+  // ================= L^T x = y: panels in decreasing order =================
+  __syncthreads();
+  for (int i = tid; i < BS_WIN; i += BS_THREADS) win[i] = 0.0;   // x beyond the last row is zero
+  // the stage / parity sequence simply continues: panel (npan - 1 - m) is the (npan + m)-th use of the ring
+  if (tid == 0) {
+    fence_proxy_async();
+    int s2 = st;
+    for (int m = 0; m < nst && m < npan; ++m) { issue(npan - 1 - m, s2); if (++s2 == nst) s2 = 0; }
+  }
+  __syncthreads();
+  for (int m = 0; m < npan; ++m) {
+    const int k = npan - 1 - m, k0 = k * BS_PB;
+    double yv = 0.0;
+    if (wid == 0 && lane < BS_PB) yv = y[k0 + lane];           // early load
+    mbar_wait(&full[st], parity);
+    const double *P = pan + (size_t)st * BS_PB * maxld;
+    const double *Iq = ivs + (size_t)st * BS_PB * BS_PB;
+    {                                                           // s_j = L[k0+BS_PB.., k0+j] . x[k0+BS_PB..], one warp per column
+      const int j = wid;                                        // BS_THREADS / 32 == BS_PB warps
+      double s = 0.0;
+      const int tend = kd - BS_PB + j;                          // d = t + BS_PB - j <= kd
+      for (int t = lane; t <= tend; t += 32) s += P[j * ld + t + BS_PB - j] * win[(k0 + BS_PB + t) & (BS_WIN - 1)];
+      s = warp_sum(s);
+      if (lane == 0) pv[BS_PB + j] = s;
+    }
+    __syncthreads();
+    if (wid == 0 && lane < BS_PB) {                             // x_panel = inv(D)^T (y_panel - s)
+      pv[lane] = yv - pv[BS_PB + lane];
+      __syncwarp((1u << BS_PB) - 1u);
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < BS_PB; ++j)
+        if (j >= lane) s += Iq[j * BS_PB + lane] * pv[j];
+      win[(k0 + lane) & (BS_WIN - 1)] = s;
+      if (k0 + lane < np) x[b.voff + k0 + lane] = s;
+    }
+    __syncthreads();
+    if (tid == 0 && m + nst < npan) { fence_proxy_async(); issue(npan - 1 - (m + nst), st); }
+    if (++st == nst) { st = 0; parity ^= 1u; }
+  }
+}
+
 }  // namespace hsbp
 
 namespace {
@@ -238,8 +385,8 @@ template <int P> int band_setup_p(hsbp_blocks *b) {
   hsbp_ctx *ctx = b->ctx;
   constexpr int WB = BandWidth<P>::WB, C = 2 * WB + 1;
   std::vector<BandBlock> bbs(b->nblocks);
-  int64_t off = 0, woff = 0;
-  int maxnpad = 0, maxkd = 0;
+  int64_t off = 0, woff = 0, ioff = 0;
+  int maxnpad = 0, maxkd = 0, minkd = 1 << 30, maxld = 0;
   for (int64_t e = 0; e < b->nblocks; ++e) {
     const BlockDesc &d = b->h_desc[e];
     BandBlock &q = bbs[e];
@@ -249,15 +396,27 @@ template <int P> int band_setup_p(hsbp_blocks *b) {
     q.kd = std::min(q.np - 1, WB * q.Nrp + WB);
     q.ld = (q.kd + 1 + 31) / 32 * 32;
     q.off = off; q.woff = woff; q.voff = d.voff;
-    off += (int64_t)q.npad * q.ld; woff += q.npad;
-    maxnpad = std::max(maxnpad, q.npad); maxkd = std::max(maxkd, q.kd);
+    q.ioff = ioff;
+    off += (int64_t)q.npad * q.ld; woff += q.npad; ioff += (int64_t)q.npad * BS_PB;
+    maxnpad = std::max(maxnpad, q.npad); maxkd = std::max(maxkd, q.kd); minkd = std::min(minkd, q.kd);
+    maxld = std::max(maxld, q.ld);
   }
   size_t free_b = 0, total_b = 0;
   HSBP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   if ((size_t)off * sizeof(double) > free_b / 2)
     HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "banded Cholesky local solver: the bands do not fit in device memory (use HSBP_LOCAL_PCG)");
-  cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work);
-  b->d_band = nullptr; b->d_band_desc = nullptr; b->d_band_work = nullptr;
+  cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work); cudaFree(b->d_band_inv);
+  b->d_band = nullptr; b->d_band_desc = nullptr; b->d_band_work = nullptr; b->d_band_inv = nullptr;
+  HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_band_inv, (size_t)ioff * sizeof(double)));
+  // streamed solve: at least two panel stages must fit in shared memory, the window must hold a panel's rows
+  {
+    const size_t fixed = (size_t)BS_WIN * 8 + 2 * BS_PB * 8 + 64;
+    const size_t per_stage = (size_t)BS_PB * maxld * 8 + (size_t)BS_PB * BS_PB * 8;
+    int nst = (int)std::min<size_t>(4, (ctx->smem_optin > fixed ? (ctx->smem_optin - fixed) / per_stage : 0));
+    b->band_stream_stages = (nst >= 2 && minkd >= BS_PB && maxkd + 2 * BS_PB <= BS_WIN) ? nst : 0;
+    b->band_maxld = maxld;
+    b->band_maxnpad = maxnpad;
+  }
   HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_band, (size_t)off * sizeof(double)));
   HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_band_desc, b->nblocks * sizeof(BandBlock)));
   HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_band_work, (size_t)woff * sizeof(double)));
@@ -287,6 +446,7 @@ template <int P> int band_setup_p(hsbp_blocks *b) {
       if (nt > 0)
         k_band_update<<<dim3(nt, nt, (unsigned)b->nblocks), CH_THREADS, 0, ctx->stream>>>(dbb, b->d_band, k0);
     }
+    k_band_invdiag<<<dim3((unsigned)(maxnpad / BS_PB), (unsigned)b->nblocks), BS_PB, 0, ctx->stream>>>(dbb, b->d_band, b->d_band_inv);
     e1 = cudaGetLastError();
     if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(flag.data(), d_flag, b->nblocks * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
@@ -306,8 +466,21 @@ int band_setup(hsbp_blocks *b) {
 int band_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stats) {
   hsbp_ctx *ctx = b->ctx;
   if (!b->d_band) HSBP_FAIL(ctx, HSBP_ERR_STATE, "banded Cholesky local solver: not set up");
-  k_band_solve<<<(unsigned)b->nblocks, CH_THREADS, 0, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band, g, x,
-                                                                    b->d_band_work);
+  if (b->band_stream_stages >= 2 && !b->band_no_stream) {
+    const int nst = b->band_stream_stages;
+    const size_t sm = (size_t)nst * BS_PB * b->band_maxld * 8 + (size_t)nst * BS_PB * BS_PB * 8 + (size_t)BS_WIN * 8 +
+                      2 * BS_PB * 8 + nst * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      HSBP_CUDA(ctx, cudaFuncSetAttribute(k_band_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+      attr_set = true;
+    }
+    k_band_solve_stream<<<(unsigned)b->nblocks, BS_THREADS, sm, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band,
+                                                                                b->d_band_inv, g, x, b->d_band_work, nst, b->band_maxld);
+  } else {
+    k_band_solve<<<(unsigned)b->nblocks, CH_THREADS, 0, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band, g, x,
+                                                                      b->d_band_work);
+  }
   if (stats) { stats->iterations_max = 0; stats->iterations_sum = 0; stats->failed_blocks = 0; stats->max_rel_residual = 0.0; }
   return check_launch(ctx, "k_band_solve");
 }

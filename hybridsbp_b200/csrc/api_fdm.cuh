@@ -3,18 +3,17 @@
 //
 // The reference keeps a sparse Cholesky factor of every block (`factorization(M̃_e)`, global_curved.jl:698) and
 // back-solves (`F \ g`, :734, square_circle.jl:383).  Matrix-free, the same solve is a CG on M-tilde_e; Jacobi-PCG needs
-// O(N) iterations per solve.  Here the preconditioner is the exact inverse of the separable part of the operator,
-//     P_e = Ar_e (x) Hs + Hr (x) As_e - c_e Hr (x) Hs                                    (tensor product, r fastest)
-// where Ar_e, As_e are the 1-D operators obtained by collapsing M-tilde_e against the constant in the other
-// direction and c_e removes the doubly counted part:
-//     Ar_e = (I (x) 1^T) M̃_e (I (x) 1) / (1^T Hs 1),   As_e likewise,   c_e = 1^T M̃_e 1 / ((1^T Hr 1)(1^T Hs 1)).
+// O(N) iterations per solve.  Here the preconditioner is the exact inverse of a separable operator
+//     P_e = Ar_e (x) Hs + Hr (x) As_e                                                   (tensor product, r fastest)
+// whose 1-D factors are read off the matrix-free operator by collapsing it against a profile w in the other direction,
+//     (I (x) w^T) M̃_e (I (x) w)   ( = Ar_e (w^T Hs w) + Hr (w^T As_e w) when M̃_e is separable ).
 // For a block whose coefficients do not vary (crr, css constant, crs = 0, tau constant along faces) P_e = M̃_e; on the
 // smoothly warped blocks of the synthetic mesh the coefficients vary by a few per cent inside a block and the mixed
-// term is a fraction of the diagonal ones, so kappa(P^-1 M̃) = O(1) instead of O(N^2).
+// term is a fraction of the diagonal ones, so kappa(P^-1 M̃) = O(1) (measured 4 - 10) instead of O(N^2).
 // With the generalised eigen-decompositions  Ar Vr = Hr Vr Lr,  Vr^T Hr Vr = I  (and s likewise)
-//     P^-1 = (Vs (x) Vr) diag(1 / (lr_i + ls_j - c)) (Vs (x) Vr)^T,
+//     P^-1 = (Vs (x) Vr) diag(1 / d_ij) (Vs (x) Vr)^T,   d_ij = mr_i + ms_j - c,
 // i.e. for the block's residual as an (Nr+1) x (Ns+1) matrix R:  Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T  -- four dense
-// fp64 GEMMs per block, executed as strided-batched DGEMMs (cuBLAS: plain library GEMMs on the fp64 tensor pipe).
+// GEMMs per block, executed as strided-batched cuBLAS GEMMs (plain library GEMMs; fp64 or, by default, TF32 tensor cores).
 //
 //   setup   4 (2 WB + 1) operator applications with coloured probe vectors (all blocks at once); symmetric
 //           eigen-decompositions with cuSOLVER (syevd on H^-1/2 A H^-1/2).  The collapse against the constant carries the

@@ -213,7 +213,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);
   cudaFree(b->d_dinv); cudaFree(b->d_pr); cudaFree(b->d_pp); cudaFree(b->d_pAp); cudaFree(b->d_pcg);
   cudaFree(b->d_nactive); cudaFree(b->d_chol); cudaFree(b->d_chol_off); cudaFree(b->d_chol_work);
-  cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work);
+  cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work); cudaFree(b->d_band_inv);
   cudaFree(b->d_fdm_vr); cudaFree(b->d_fdm_vs); cudaFree(b->d_fdm_z); cudaFree(b->d_fdm_t);
   cudaFree(b->d_fdm_vr32); cudaFree(b->d_fdm_vs32); cudaFree(b->d_fdm_dinv32); cudaFree(b->d_fdm_a32); cudaFree(b->d_fdm_b32);
   delete b;
@@ -324,6 +324,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "sweep_deep") b->sweep_deep = (int)value;
   else if (n == "fdm_gemm") b->fdm_gemm = (int)value;
   else if (n == "sweep_p6_regs") b->sweep_p6_regs = (int)value;
+  else if (n == "band_no_stream") b->band_no_stream = (int)value;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);
   return HSBP_OK;
 }

@@ -73,6 +73,8 @@ struct hsbp_blocks {
   double *d_band = nullptr;                 // banded factors (api_band.cuh), LAPACK lower-band storage per block
   void *d_band_desc = nullptr;              // BandBlock descriptors
   double *d_band_work = nullptr;
+  double *d_band_inv = nullptr;             // inverted diagonal blocks of the banded factors (streamed solve)
+  int band_stream_stages = 0, band_maxld = 0, band_maxnpad = 0, band_no_stream = 0;
   double *d_fdm_vr = nullptr, *d_fdm_vs = nullptr;   // generalised eigenvectors of the collapsed 1-D operators (api_fdm.cuh)
   double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   float *d_fdm_vr32 = nullptr, *d_fdm_vs32 = nullptr, *d_fdm_dinv32 = nullptr, *d_fdm_a32 = nullptr, *d_fdm_b32 = nullptr;

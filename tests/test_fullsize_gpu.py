@@ -71,3 +71,39 @@ def test_apply_then_local_solve_round_trip_at_full_block_size(ctx):
     assert np.linalg.norm(r - g) <= 1e-10 * np.linalg.norm(g), st
     assert np.linalg.norm(dx.get() - x0) <= 1e-6 * np.linalg.norm(x0), st
     blk.close()
+
+
+def test_condensed_trace_solve_on_large_blocks(ctx):
+    """2 x 2 blocks of 128 x 128 points, FDM-PCG local solver (TF32 preconditioner GEMMs), static condensation and the
+    face-block preconditioner: the solution must satisfy the coupled system [M Fbar; Fbar^T D][u; lam] = [g; gd]
+    evaluated with the matrix-free operators, and agree with the matrix-free Jacobi-preconditioned solve."""
+    from hybridsbp_b200.host import connectivityarrays
+    nbx, nby, N, p = 2, 2, 127, 4
+    crr, css, crs = synthetic.warped_coefficients(nbx, nby, N)
+    _, EToV, EToF, FToB = synthetic.block_grid_connectivity(nbx, nby)
+    FToE, FToLF, EToO, EToS = connectivityarrays(EToV, EToF)
+    blk = hs.Blocks(ctx, p, [N] * 4, [N] * 4)
+    blk.set_metrics(crr, css, crs)
+    blk.set_bc(synthetic.block_bcs(EToF, FToB))
+    blk.compute_tau(2.0)
+    blk.local_setup(hs.LOCAL_FDM, tol=1e-13, maxit=5000)
+    tr = hs.Trace(blk, FToB, FToE, FToLF, EToO, EToS)
+    rng = np.random.default_rng(11)
+    g, gd = rng.uniform(-1, 1, blk.VNp), rng.uniform(-1, 1, tr.lNp)
+    dg, dgd = ctx.array(g), ctx.array(gd)
+    lam0, u0 = ctx.empty(tr.lNp), ctx.empty(blk.VNp)
+    st0 = tr.solve(dg, dgd, lam0, u0, tol=1e-11, maxit=5000)           # matrix-free, Jacobi
+    assert st0["converged"] == 1, st0
+    tr.condense()
+    tr.precond_setup(1)
+    lam1, u1 = ctx.empty(tr.lNp), ctx.empty(blk.VNp)
+    st1 = tr.solve(dg, dgd, lam1, u1, tol=1e-11, maxit=5000)
+    assert st1["converged"] == 1 and st1["local_solves"] == 2 and st1["outer_iterations"] < st0["outer_iterations"], (st0, st1)
+    l0, l1, v0, v1 = lam0.get(), lam1.get(), u0.get(), u1.get()
+    assert np.linalg.norm(l1 - l0) <= 1e-8 * np.linalg.norm(l0), (st0, st1)
+    assert np.linalg.norm(v1 - v0) <= 1e-8 * np.linalg.norm(v0), (st0, st1)
+    Mu, Fl, FTu = ctx.empty(blk.VNp), ctx.array(np.zeros(blk.VNp)), ctx.empty(tr.lNp)
+    blk.apply(u1, Mu); tr.Fbar_add(lam1, 1.0, Fl); tr.FbarT(u1, FTu)
+    assert np.linalg.norm(g - Mu.get() - Fl.get()) <= 1e-9 * np.linalg.norm(g)
+    assert np.linalg.norm(gd - FTu.get() - tr.D() * l1) <= 1e-7 * np.linalg.norm(gd)
+    tr.close(); blk.close()

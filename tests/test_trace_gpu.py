@@ -148,8 +148,8 @@ def test_dense_cholesky_local_solver(ctx, p):
         assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), e
 
 
-@pytest.mark.parametrize("p", [2, 4, 6])
-def test_banded_cholesky_local_solver(ctx, p):
+@pytest.mark.parametrize("p,stream", [(2, 1), (4, 1), (6, 1), (4, 0)])
+def test_banded_cholesky_local_solver(ctx, p, stream):
     """K2c: the `factorization` plugin as a batched banded Cholesky (global_curved.jl:698, 734): blocks of different
     shapes, all boundary-condition types (Neumann faces have the widest coupling), sizes beyond the dense solver."""
     import hybridsbp_b200 as hs
@@ -160,6 +160,7 @@ def test_banded_cholesky_local_solver(ctx, p):
     bcs = [(1, 1, 1, 1), (1, 2, 2, 2), (0, 1, 2, 7), (2, 0, 1, 1), (2, 2, 1, 2)]
     lops = [orc.locoperator(p, a, b, m, bc) for (a, b), m, bc in zip(shapes, mets, bcs)]
     blk = upload_blocks(hs, ctx, p, mets, bcs)
+    blk.set_option("band_no_stream", 0 if stream else 1)      # streamed (TMA ring) or plain solve kernel
     blk.local_setup(hs.LOCAL_BAND)
     g = rng.uniform(-1, 1, blk.VNp)
     dg, dx = ctx.array(g), ctx.empty(blk.VNp)
