@@ -134,7 +134,8 @@ _B5 = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0])
 _B4 = np.array([5179 / 57600, 0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40])
 
 
-def integrate(rhs, y0, t0, t1, dt0, abstol=1e-6, reltol=1e-3, max_steps=10 ** 9, qmin=0.2, qmax=10.0, safety=0.9):
+def integrate(rhs, y0, t0, t1, dt0, abstol=1e-6, reltol=1e-3, max_steps=10 ** 9, qmin=0.2, qmax=10.0, safety=0.9,
+              stop_on_underflow=False):
     """Integrate y' = rhs(t, y) -> (dy, rejected).  A step is rejected when the error test fails or when any
     stage reports `rejected` (the reference's isoutofdomain / reject_step mechanism, BP1.jl:149-159).
     Returns (ts, ys, nrejected)."""
@@ -173,6 +174,9 @@ def integrate(rhs, y0, t0, t1, dt0, abstol=1e-6, reltol=1e-3, max_steps=10 ** 9,
         else:
             dt *= 0.5
         nrej += 1
-        if dt < 1e-12 * max(1.0, abs(t)):
+        if dt <= 4.0 * np.spacing(max(1.0, abs(t))):     # dtmin of the reference's integrator: the resolution of t (coseismic
+                                                          # steps are milliseconds at t ~ 1e10 s)
+            if stop_on_underflow:            # return the series up to here (the caller reports the stop time)
+                break
             raise RuntimeError("step size underflow at t = %g" % t)
     return np.array(ts), np.array(ys), nrej

@@ -59,3 +59,22 @@ def test_short_cycle_integration(case):
     V_g = np.array([gpu.rhs(t, y)[0][n:] for t, y in zip(ts_g, ys_g)])
     V_r = np.array([ref(t, y)[0][n:] for t, y in zip(ts_r, ys_r)])
     assert np.max(np.abs(V_g - V_r) / np.abs(V_r)) <= 1e-6
+
+
+@pytest.mark.parametrize("mode", ["band", "pcg"])
+def test_rhs_at_reference_resolution_matches_stored_oracle_output(ctx, mode):
+    """N = 200 (the reference's BP1 resolution, BP1.jl:8): odefun at five states of the first earthquake cycle, including
+    the coseismic phase, against the oracle's stored output (tests/golden/bp1)."""
+    import os
+    from hybridsbp_b200 import LOCAL_BAND, LOCAL_PCG
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "bp1", "states_N200.npz"))
+    su = bp1.setup(N=200)
+    n = su.N + 1
+    f = bp1.Fault(ctx, su, local_tol=1e-13, local_mode=LOCAL_BAND if mode == "band" else LOCAL_PCG)
+    for t, y, d_ref in zip(gold["t"], gold["y"], gold["dpsiV"]):
+        d, rej = f.rhs(float(t), y)
+        assert not rej
+        tol = 1e-9 if mode == "band" else 1e-7
+        assert np.max(np.abs(d[n:] - d_ref[n:])) <= tol * np.max(np.abs(d_ref[n:]))
+        assert np.max(np.abs(d[:n] - d_ref[:n])) <= tol * max(np.max(np.abs(d_ref[:n])), 1e-300)
+    f.close()
