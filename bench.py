@@ -334,7 +334,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                         "note": "hsbp_apply_host on pinned host buffers: H2D of u, apply, D2H of y inside each call"},
-                "gpu_launches": (args.steps + nrep + e2e_steps + 1) * (2 if variant == 1 else 4),
+                "gpu_launches": args.steps * (2 if variant == 1 else 4),      # kernels of the timed region (k_edge_prep + k_sweep per apply)
                 "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum, "trace_solve": trace, "trace_solve_large_blocks": trace_large}
         if world == 1 and not args.no_cpu:
             _, base = cpu_baseline(p, N, args.cpu_blocks, args.cpu_seconds, 1)

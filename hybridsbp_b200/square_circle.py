@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 from . import host
-from .blocks import Blocks, Trace, LOCAL_CHOLESKY, LOCAL_PCG
+from .blocks import Blocks, Trace, LOCAL_BAND, LOCAL_CHOLESKY, LOCAL_PCG  # noqa: F401
 
 BC_MAP = [host.BC_DIRICHLET, host.BC_DIRICHLET, host.BC_NEUMANN, host.BC_NEUMANN, host.BC_JUMP_INTERFACE]   # :11-12
 
@@ -173,7 +173,8 @@ def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p, exact=None):
     return v, gd
 
 
-def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=None, exact=None, jump_code=None):
+def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=None, exact=None, jump_code=None,
+                condense=True):
     """One refinement level on the GPU.  Returns dict(eps, tau_eps, lam, u, stats, ...)."""
     verts, EToV, EToF, FToB, dom = mesh
     ne, nf = EToV.shape[1], len(FToB)
@@ -190,9 +191,16 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=No
     blk.set_bc(bcs.reshape(-1))
     blk.compute_tau(2.0)
     if local_mode is None:
-        local_mode = LOCAL_CHOLESKY if (N + 1) ** 2 <= 2500 else LOCAL_PCG
+        # the reference factorises every block (cholesky(M-tilde), square_circle.jl:299): dense factors for small
+        # blocks, banded factors beyond
+        local_mode = LOCAL_CHOLESKY if (N + 1) ** 2 <= 2500 else LOCAL_BAND
     blk.local_setup(local_mode, tol=1e-14, maxit=200000)
     tr = Trace(blk, FToB, FToE, FToLF, EToO, EToS)
+    if condense:
+        # ... and forms B from per-block products (assembleλmatrix, :313): here the dense S_e stay block-wise and B is
+        # applied inside a CG preconditioned with its exact diagonal blocks
+        tr.condense()
+        tr.precond_setup(1)
     FTols = tr.FTolambdastarts
     jump_codes = tuple(sorted(set(int(b) for b in FToB if b >= host.BC_JUMP_INTERFACE))) or (jump_code,)
     FTods = host.bcstarts(FToB, FToE, FToLF, jump_codes, [N] * ne, [N] * ne)

@@ -111,7 +111,9 @@ int  hsbp_apply_variant(const hsbp_blocks *blocks);
 int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
 /* tuning / testing knobs: "force_generic" (0/1), "sweep_chunks_per_side" (0 = heuristic),
  * "sweep_points_per_thread" (0 = heuristic, 2, 4), "sweep_fold_faces" (1), "sweep_deep" (1: css / crs windows in
- * shared-memory rings, 0: in registers) */
+ * shared-memory rings, 0: in registers), "sweep_p6_regs" (128 / 168), "fdm_gemm" (arithmetic of the fast-diagonalisation
+ * preconditioner's GEMMs: 0 fp64, 1 fp32, 2 fp32 emulated with BF16 x 9, 3 TF32; set before hsbp_local_setup),
+ * "band_no_stream" (1: plain-load banded solve kernel) */
 int  hsbp_blocks_set_option(hsbp_blocks *blocks, const char *name, int64_t value);
 
 /* face operators of the blocks, block-face layout (no inter-block coupling):
