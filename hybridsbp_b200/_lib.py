@@ -91,6 +91,8 @@ def lib():
         "hsbp_trace_condense": (cint, [vp, cint]),
         "hsbp_trace_precond_setup": (cint, [vp, cint]),
         "hsbp_trace_precond_apply": (cint, [vp, dp, dp]),
+        "hsbp_trace_precond_cut_own": (cint, [vp, i64, i64p, dp]),
+        "hsbp_trace_precond_setup_cut": (cint, [vp, i64, i64p, dp]),
         "hsbp_trace_rhs": (cint, [vp, dp, dp, dp]),
         "hsbp_trace_solve": (cint, [vp, dp, dp, dp, dp, dbl, i64, vp]),
         "hsbp_bp1_create": (cint, [vp, i64, i64, i64, dp, dp, vp, C.POINTER(vp)]),

@@ -193,6 +193,16 @@ class Trace:
         """0: Jacobi (D); 1: block-Jacobi with the exact diagonal blocks of B (needs condense())."""
         self.ctx._check(lib().hsbp_trace_precond_setup(self.h, int(kind)))
 
+    def precond_cut_own(self, faces, out):
+        """this device's S_e[f, f] of the cut faces `faces` (1-based ids), packed into the device buffer `out`"""
+        faces = np.ascontiguousarray(faces, dtype=np.int64)
+        self.ctx._check(lib().hsbp_trace_precond_cut_own(self.h, len(faces), faces.ctypes.data_as(C.POINTER(C.c_int64)), out.ptr))
+
+    def precond_setup_cut(self, faces, partner):
+        """face-block preconditioner with the partner devices' blocks of the cut faces `faces` (same packing)"""
+        faces = np.ascontiguousarray(faces, dtype=np.int64)
+        self.ctx._check(lib().hsbp_trace_precond_setup_cut(self.h, len(faces), faces.ctypes.data_as(C.POINTER(C.c_int64)), partner.ptr))
+
     def precond_apply(self, r: DeviceArray, z: DeviceArray):
         self.ctx._check(lib().hsbp_trace_precond_apply(self.h, r.ptr, z.ptr))
 

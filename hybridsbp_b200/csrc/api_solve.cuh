@@ -233,7 +233,7 @@ void precond_free(hsbp_trace *t) {
 }
 
 // dense Cholesky of every B_ff (batched, the panel / DMMA trailing-update kernels of the dense local solver)
-int precond_faceblocks(hsbp_trace *t) {
+int precond_faceblocks(hsbp_trace *t, int64_t ncut = 0, const int64_t *cut_faces = nullptr, const double *partner_dev = nullptr) {
   hsbp_blocks *b = t->blocks;
   hsbp_ctx *ctx = b->ctx;
   if (!t->d_S) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_trace_precond_setup: the face-block preconditioner needs hsbp_trace_condense first");
@@ -254,8 +254,23 @@ int precond_faceblocks(hsbp_trace *t) {
   HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc_work, (size_t)woff * sizeof(double)));
   HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc_desc, nf * sizeof(FaceBlock)));
   HSBP_CUDA(ctx, cudaMemcpyAsync(t->d_pc_desc, fbs.data(), nf * sizeof(FaceBlock), cudaMemcpyHostToDevice, ctx->stream));
+  // cut faces whose partner contribution is known: map lambda-face index -> offset into partner_dev
+  int64_t *d_pidx = nullptr;
+  if (ncut > 0) {
+    std::vector<int64_t> pidx(nf, -1);
+    int64_t po = 0;
+    for (int64_t c = 0; c < ncut; ++c) {
+      const int64_t lfi = cut_faces[c];
+      if (lfi < 0 || lfi >= nf) { precond_free(t); HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup_cut: bad face index"); }
+      pidx[lfi] = po;
+      po += (int64_t)t->h_faces[lfi].nl * t->h_faces[lfi].nl;
+    }
+    HSBP_CUDA(ctx, cudaMalloc((void **)&d_pidx, nf * sizeof(int64_t)));
+    HSBP_CUDA(ctx, cudaMemcpyAsync(d_pidx, pidx.data(), nf * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   k_faceblock_fill<<<(unsigned)nf, 256, 0, ctx->stream>>>(t->d_faces, (const FaceBlock *)t->d_pc_desc, b->d_desc, t->d_S_off, t->d_S,
-                                                         t->d_D, t->d_pc);
+                                                         t->d_D, t->d_pc, d_pidx, partner_dev);
   int *d_flag = nullptr;
   std::vector<int> flag(nf, 0);
   HSBP_CUDA(ctx, cudaMalloc((void **)&d_flag, nf * sizeof(int)));
@@ -269,7 +284,7 @@ int precond_faceblocks(hsbp_trace *t) {
   cudaError_t e1 = cudaGetLastError();
   if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(flag.data(), d_flag, nf * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_flag);
+  cudaFree(d_flag); cudaFree(d_pidx);
   if (e1 != cudaSuccess) { precond_free(t); ctx->err = std::string("precond_faceblocks: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
   for (int64_t i = 0; i < nf; ++i)
     if (flag[i]) { precond_free(t); HSBP_FAIL(ctx, HSBP_ERR_ARG, "face-block preconditioner: a diagonal block of B is not positive definite"); }
@@ -483,6 +498,56 @@ int hsbp_trace_precond_setup(hsbp_trace *t, int kind) {
   }
   if (kind != HSBP_PRECOND_FACE_BLOCKS) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup: unknown kind");
   return precond_faceblocks(t);
+}
+
+// lambda-face index (position among the faces that carry lambda) of face f (0-based position in the FToB order), or -1
+static int64_t lam_face_index(const hsbp_trace *t, int64_t f) {
+  if (f < 0 || f >= t->nfaces || t->starts[f + 1] == t->starts[f]) return -1;
+  int64_t k = 0;
+  for (int64_t g = 0; g < f; ++g) k += t->starts[g + 1] > t->starts[g] ? 1 : 0;
+  return k;
+}
+
+int hsbp_trace_precond_cut_own(hsbp_trace *t, int64_t ncut, const int64_t *faces, double *out_dev) {
+  if (!t) return HSBP_ERR_ARG;
+  hsbp_blocks *b = t->blocks;
+  hsbp_ctx *ctx = b->ctx;
+  if (ncut < 0 || (ncut > 0 && (!faces || !out_dev))) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_cut_own: bad arguments");
+  if (!t->d_S) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_trace_precond_cut_own: needs hsbp_trace_condense first");
+  if (ncut == 0) return HSBP_OK;
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> idx(ncut), ooff(ncut);
+  int64_t o = 0;
+  for (int64_t c = 0; c < ncut; ++c) {
+    const int64_t k = lam_face_index(t, faces[c] - 1);
+    if (k < 0) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_cut_own: face carries no lambda");
+    const LamFace &f = t->h_faces[k];
+    if ((f.em >= 0) == (f.ep >= 0)) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_cut_own: not a cut face");
+    idx[c] = k; ooff[c] = o; o += (int64_t)f.nl * f.nl;
+  }
+  int64_t *d_idx = nullptr;
+  HSBP_CUDA(ctx, cudaMalloc((void **)&d_idx, 2 * ncut * sizeof(int64_t)));
+  cudaMemcpyAsync(d_idx, idx.data(), ncut * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_idx + ncut, ooff.data(), ncut * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+  k_faceblock_own<<<(unsigned)ncut, 256, 0, ctx->stream>>>(t->d_faces, b->d_desc, t->d_S_off, t->d_S, d_idx, d_idx + ncut, out_dev);
+  cudaError_t e1 = cudaGetLastError();
+  if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_idx);
+  if (e1 != cudaSuccess) { ctx->err = std::string("hsbp_trace_precond_cut_own: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
+  return HSBP_OK;
+}
+
+int hsbp_trace_precond_setup_cut(hsbp_trace *t, int64_t ncut, const int64_t *faces, const double *partner_dev) {
+  if (!t) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = t->blocks->ctx;
+  if (ncut < 0 || (ncut > 0 && (!faces || !partner_dev))) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup_cut: bad arguments");
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> idx(ncut);
+  for (int64_t c = 0; c < ncut; ++c) {
+    idx[c] = lam_face_index(t, faces[c] - 1);
+    if (idx[c] < 0) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup_cut: face carries no lambda");
+  }
+  return precond_faceblocks(t, ncut, idx.data(), partner_dev);
 }
 
 int hsbp_trace_precond_apply(hsbp_trace *t, const double *r_dev, double *z_dev) {

@@ -267,35 +267,56 @@ struct FaceBlock {      // layout-compatible with CholBlock (api_chol.cuh): off,
   int64_t voff;
   int64_t woff;
 };
+// partner (optional): for cut faces, the other device's contribution S_{e'}[f, f] in lambda orientation, packed in
+// the order of the cut faces (pidx[face] = offset into partner, -1: none -> the face keeps only D_f)
 __global__ void __launch_bounds__(256)
 k_faceblock_fill(const LamFace *__restrict__ lf, const FaceBlock *__restrict__ fb, const BlockDesc *__restrict__ desc,
                  const int64_t *__restrict__ soff, const double *__restrict__ S, const double *__restrict__ D,
-                 double *__restrict__ A) {
+                 double *__restrict__ A, const int64_t *__restrict__ pidx, const double *__restrict__ partner) {
   const LamFace f = lf[blockIdx.x];
   const FaceBlock q = fb[blockIdx.x];
   double *Ab = A + q.off;
   const bool cut = f.em < 0 || f.ep < 0;
+  const double *Pn = (cut && pidx && pidx[blockIdx.x] >= 0) ? partner + pidx[blockIdx.x] : nullptr;
+  const bool diag_only = cut && !Pn;
   const double *Sm = nullptr, *Sp = nullptr;
   int nfm = 0, nfp = 0, om = 0, op = 0;
-  if (!cut) {
-    const BlockDesc dm = desc[f.em], dp = desc[f.ep];
-    nfm = block_nf(dm); nfp = block_nf(dp);
-    om = (int)(f.fm - dm.foff); op = (int)(f.fp - dp.foff);
-    Sm = S + soff[f.em]; Sp = S + soff[f.ep];
-  }
+  if (f.em >= 0) { const BlockDesc dm = desc[f.em]; nfm = block_nf(dm); om = (int)(f.fm - dm.foff); Sm = S + soff[f.em]; }
+  if (f.ep >= 0) { const BlockDesc dp = desc[f.ep]; nfp = block_nf(dp); op = (int)(f.fp - dp.foff); Sp = S + soff[f.ep]; }
   for (int idx = threadIdx.x; idx < q.ld * q.ld; idx += blockDim.x) {
     const int i = idx % q.ld, j = idx / q.ld;
     double v = 0.0;
     if (i < q.np && j < q.np) {
       if (i == j) v = D[f.loff + i];
-      if (!cut) {
+      if (!diag_only) {                                       // D - (one side + other side): the sum of the two sides is
+                                                              // commutative, so both devices of a cut face build the same block
         const int ip = f.flip ? q.np - 1 - i : i, jp = f.flip ? q.np - 1 - j : j;
-        v -= Sm[(om + i) + (int64_t)nfm * (om + j)] + Sp[(op + ip) + (int64_t)nfp * (op + jp)];
+        const double cm = Sm ? Sm[(om + i) + (int64_t)nfm * (om + j)] : Pn[i + (int64_t)q.np * j];
+        const double cp = Sp ? Sp[(op + ip) + (int64_t)nfp * (op + jp)] : Pn[i + (int64_t)q.np * j];
+        v -= cm + cp;
       }
     } else if (i == j) {
       v = 1.0;
     }
     Ab[idx] = v;
+  }
+}
+// this device's contribution to B_ff of a cut face, in lambda orientation, dense nl x nl
+__global__ void __launch_bounds__(256)
+k_faceblock_own(const LamFace *__restrict__ lf, const BlockDesc *__restrict__ desc, const int64_t *__restrict__ soff,
+                const double *__restrict__ S, const int64_t *__restrict__ faces, const int64_t *__restrict__ ooff,
+                double *__restrict__ out) {
+  const LamFace f = lf[faces[blockIdx.x]];
+  double *O = out + ooff[blockIdx.x];
+  const bool minus = f.em >= 0;
+  const BlockDesc d = desc[minus ? f.em : f.ep];
+  const int nf = block_nf(d), o = (int)((minus ? f.fm : f.fp) - d.foff), nl = f.nl;
+  const double *Sb = S + soff[minus ? f.em : f.ep];
+  const bool flip = !minus && f.flip;
+  for (int idx = threadIdx.x; idx < nl * nl; idx += blockDim.x) {
+    const int i = idx % nl, j = idx / nl;
+    const int ii = flip ? nl - 1 - i : i, jj = flip ? nl - 1 - j : j;
+    O[idx] = Sb[(o + ii) + (int64_t)nf * (o + jj)];
   }
 }
 

@@ -40,7 +40,7 @@ def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=
     if face_blocks is None:
         face_blocks = condense
     if face_blocks:                      # after DistributedTrace has completed D on the cut faces
-        tr.precond_setup(1)
+        parallel.setup_face_block_preconditioner(tr, lm, tr.FTolambdastarts, dist, dev)
         op.has_precond = True
     npb = (N + 1) ** 2
     g = np.concatenate([np.random.default_rng(seed + int(e)).uniform(-1, 1, npb) for e in lm.blocks])

@@ -170,6 +170,35 @@ class DistributedTrace:
                             rel_residual=float(np.sqrt(rr / b2)) if b2 > 0 else 0.0)
 
 
+def setup_face_block_preconditioner(tr, lm, starts, dist, device):
+    """Face-block preconditioner on a partitioned mesh: the diagonal block B_ff of a cut face needs the S_e[f, f] of both
+    ranks.  Every rank packs its own blocks per partner (cut faces in increasing global id, the order both ranks share),
+    exchanges them point to point and builds D_f - (own + partner): the sum is commutative, so both ranks factorise the
+    same matrix and their copies of lambda stay identical."""
+    import torch
+    if dist is None or not lm.cut:
+        tr.precond_setup(1)
+        return
+    starts = np.asarray(starts)
+    ops, parts = [], []
+    for q, faces in sorted(lm.cut.items()):
+        ids = np.asarray(faces, dtype=np.int64) + 1
+        n = int(sum((starts[f + 1] - starts[f]) ** 2 for f in faces))
+        own = torch.empty(n, dtype=torch.float64, device=device)
+        tr.precond_cut_own(ids, _Ptr(own))
+        rec = torch.empty_like(own)
+        ops += [dist.P2POp(dist.isend, own, q), dist.P2POp(dist.irecv, rec, q)]
+        parts.append((ids, own, rec))
+    torch.cuda.synchronize(device)
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    torch.cuda.synchronize(device)
+    ids = np.concatenate([p[0] for p in parts])
+    partner = torch.cat([p[2] for p in parts])
+    torch.cuda.synchronize(device)
+    tr.precond_setup_cut(ids, _Ptr(partner))
+
+
 # ---- local operator over the C-ABI (device pointers of torch tensors) ---------------------------------
 class _Ptr:
     def __init__(self, t):

@@ -186,6 +186,12 @@ int  hsbp_trace_condense(hsbp_trace *trace, int enable);
 #define HSBP_PRECOND_FACE_BLOCKS 1
 int  hsbp_trace_precond_setup(hsbp_trace *trace, int kind);
 int  hsbp_trace_precond_apply(hsbp_trace *trace, const double *r_dev, double *z_dev);
+/* Partitioned meshes: the diagonal block of a cut face needs both devices' contributions.  hsbp_trace_precond_cut_own writes
+ * this device's S_e[f, f] (dense nl x nl, lambda orientation) of the listed cut faces (1-based face ids in this trace's
+ * FToB order) one after the other into out_dev; the host layer exchanges them and hands the partner's blocks, in the same
+ * order, to hsbp_trace_precond_setup_cut, which builds and factorises all face blocks (cut faces not listed keep D_f).     */
+int  hsbp_trace_precond_cut_own(hsbp_trace *trace, int64_t ncut, const int64_t *faces, double *out_dev);
+int  hsbp_trace_precond_setup_cut(hsbp_trace *trace, int64_t ncut, const int64_t *faces, const double *partner_dev);
 int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u   */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
 int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam      */

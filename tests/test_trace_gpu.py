@@ -278,3 +278,39 @@ def test_condensed_trace_solve_matches_matrix_free_and_oracle(ctx):
     tr.condense(False)
     tr.schur_apply(dl, dq1)
     assert np.linalg.norm(dq1.get() - dq0.get()) == 0.0
+
+
+def test_error_paths_report_codes_and_messages(ctx):
+    """The C-ABI never throws or exits: misuse comes back as a status code with a message."""
+    import hybridsbp_b200 as hs
+    from hybridsbp_b200._lib import HsbpError
+    p = 4
+    rng = np.random.default_rng(79)
+    c = build_case(hs, ctx, p, 3 * p - 1, flipped_four_block_mesh(), rng)
+    blk, tr = c["blk"], c["tr"]
+    with pytest.raises(HsbpError) as e:                      # no local solver yet
+        tr.condense()
+    assert e.value.code < 0 and "hsbp_local_setup" in str(e.value)
+    blk.local_setup(hs.LOCAL_CHOLESKY)
+    with pytest.raises(HsbpError) as e:                      # face blocks need the condensed matrices
+        tr.precond_setup(1)
+    assert e.value.code < 0 and "hsbp_trace_condense" in str(e.value)
+    with pytest.raises(HsbpError):
+        tr.precond_setup(7)
+    with pytest.raises(HsbpError):
+        blk.set_option("no_such_option", 1)
+    with pytest.raises(HsbpError):
+        blk.local_setup(99)
+    # FDM needs blocks of one size
+    mets = [random_spd_metrics(p, 12, 12, rng, scale2=0.2), random_spd_metrics(p, 14, 12, rng, scale2=0.2)]
+    b2 = upload_blocks(hs, ctx, p, mets, [(1, 1, 1, 1), (1, 1, 1, 1)])
+    with pytest.raises(HsbpError) as e:
+        b2.local_setup(hs.LOCAL_FDM)
+    assert "one size" in str(e.value)
+    b2.close()
+    # after the failures the objects still work
+    tr.condense(); tr.precond_setup(1)
+    lam = rng.uniform(-1, 1, tr.lNp)
+    dl, dq = ctx.array(lam), ctx.empty(tr.lNp)
+    tr.schur_apply(dl, dq)
+    assert np.all(np.isfinite(dq.get()))
