@@ -180,6 +180,7 @@ def setup_face_block_preconditioner(tr, lm, starts, dist, device):
         tr.precond_setup(1)
         return
     starts = np.asarray(starts)
+    sync = (lambda: torch.cuda.synchronize(device)) if torch.device(device).type == "cuda" else (lambda: None)
     ops, parts = [], []
     for q, faces in sorted(lm.cut.items()):
         ids = np.asarray(faces, dtype=np.int64) + 1
@@ -189,13 +190,13 @@ def setup_face_block_preconditioner(tr, lm, starts, dist, device):
         rec = torch.empty_like(own)
         ops += [dist.P2POp(dist.isend, own, q), dist.P2POp(dist.irecv, rec, q)]
         parts.append((ids, own, rec))
-    torch.cuda.synchronize(device)
+    sync()
     for r in dist.batch_isend_irecv(ops):
         r.wait()
-    torch.cuda.synchronize(device)
+    sync()
     ids = np.concatenate([p[0] for p in parts])
     partner = torch.cat([p[2] for p in parts])
-    torch.cuda.synchronize(device)
+    sync()
     tr.precond_setup_cut(ids, _Ptr(partner))
 
 

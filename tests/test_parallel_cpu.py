@@ -101,7 +101,44 @@ def partial_D(G, owner, rank):
     return Dp
 
 
-def _worker(rank, world, port, owner, out):
+class OracleFaceBlocks:
+    """CPU stand-in for the C-ABI's face-block preconditioner (hsbp_trace_precond_cut_own / _setup_cut / _apply) on top of
+    OracleLocalOperator: exercises parallel.setup_face_block_preconditioner over gloo."""
+
+    def __init__(self, op, lstarts):
+        self.op, self.st = op, np.asarray(lstarts) - 1
+        X = op.M.solve(op.FT.T.toarray())                       # M^-1 Fbar (local columns)
+        self.S = op.FT @ X                                      # this rank's side of Fbar^T M^-1 Fbar
+        self.blocks = None
+
+    def _own(self, f):
+        a, b = self.st[f], self.st[f + 1]
+        return self.S[a:b, a:b]
+
+    def precond_cut_own(self, ids, out):
+        out.t[:] = out.t.new_tensor(np.concatenate([self._own(f - 1).reshape(-1, order="F") for f in ids]))
+
+    def precond_setup_cut(self, ids, partner):
+        part, o = {}, 0
+        for f in ids:
+            nl = self.st[f] - self.st[f - 1]
+            part[f - 1] = partner.t.numpy()[o:o + nl * nl].reshape(nl, nl, order="F"); o += nl * nl
+        D = self.op.get_D()
+        self.blocks = []
+        for f in range(len(self.st) - 1):
+            a, b = self.st[f], self.st[f + 1]
+            if b > a:
+                Bff = np.diag(D[a:b]) - (self._own(f) + part[f] if f in part else self._own(f))
+                self.blocks.append((a, b, Bff))
+
+    def apply(self, r):
+        z = np.zeros(len(r))
+        for a, b, Bff in self.blocks:
+            z[a:b] = np.linalg.solve(Bff, r.numpy()[a:b])
+        return r.new_tensor(z)
+
+
+def _worker(rank, world, port, owner, out, face_blocks=False):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -114,6 +151,10 @@ def _worker(rank, world, port, owner, out):
         op = OracleLocalOperator(lm, G["lops"], G["FbarT"], G["vstarts"], G["starts"], partial_D(G, owner, rank))
         lstarts = np.concatenate([[1], 1 + np.cumsum([G["starts"][f + 1] - G["starts"][f] for f in lm.faces])])
         dt = parallel.DistributedTrace(op, lstarts, lm, dist=dist)
+        if face_blocks:
+            fb = OracleFaceBlocks(op, lstarts)
+            parallel.setup_face_block_preconditioner(fb, lm, lstarts, dist, "cpu")
+            op.has_precond, op.precond = True, fb.apply
         lam, u, st = dt.solve(torch.from_numpy(G["g"][op.cols]), torch.from_numpy(G["gd"][op.rows]), tol=1e-13, maxit=500)
         np.savez(out % rank, lam=lam.numpy(), u=u.numpy(), rows=op.rows, cols=op.cols, D=dt.D.numpy(),
                  it=st["outer_iterations"], conv=st["converged"], ncut=sum(len(v) for v in lm.cut.values()))
@@ -121,12 +162,12 @@ def _worker(rank, world, port, owner, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("owner", [[0, 0, 1, 1], [0, 1, 1, 0]])
-def test_two_rank_trace_solve_equals_single_process(tmp_path, owner):
+@pytest.mark.parametrize("owner,face_blocks", [([0, 0, 1, 1], False), ([0, 1, 1, 0], False), ([0, 1, 1, 0], True)])
+def test_two_rank_trace_solve_equals_single_process(tmp_path, owner, face_blocks):
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(2, port, np.array(owner), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, np.array(owner), out, face_blocks), nprocs=2, join=True)
     G = build_global()
     B = orc.assemblelambdamatrix(G["starts"], G["vstarts"], G["EToF"], G["FToB"], G["M"].F, G["D"], G["FbarT"])
     bl = np.zeros(G["starts"][-1] - 1); uu = np.zeros(G["vstarts"][-1] - 1)
@@ -134,12 +175,16 @@ def test_two_rank_trace_solve_equals_single_process(tmp_path, owner):
     lam_ref = np.linalg.solve(B.toarray(), bl)
     rhs = G["g"] - G["FbarT"].T @ lam_ref
     u_ref = np.concatenate([G["M"].F[e].solve(rhs[G["vstarts"][e] - 1:G["vstarts"][e + 1] - 1]) for e in range(G["ne"])])
-    cuts = 0
+    cuts, its = 0, []
     for rank in range(2):
         r = np.load(out % rank)
         assert r["conv"] == 1
+        its.append(int(r["it"]))
         assert np.allclose(r["D"], G["D"][r["rows"]], rtol=1e-13)             # completed with the partner's half
         assert np.linalg.norm(r["lam"] - lam_ref[r["rows"]]) <= 1e-10 * np.linalg.norm(lam_ref)
         assert np.linalg.norm(r["u"] - u_ref[r["cols"]]) <= 1e-10 * np.linalg.norm(u_ref)
         cuts += int(r["ncut"])
     assert cuts > 0 and cuts % 2 == 0          # both ranks see the same cut faces
+    assert its[0] == its[1]
+    if face_blocks:                            # exact diagonal blocks, completed across the cut: far fewer iterations
+        assert its[0] < 60, its
