@@ -367,7 +367,7 @@ def main():
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")
     ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")
     ap.add_argument("--sweep-deep", type=int, default=1, help="1: css / crs windows of k_sweep in shared-memory rings, 0: in registers")
-    ap.add_argument("--sweep-p6-regs", type=int, default=128)
+    ap.add_argument("--sweep-p6-regs", type=int, default=168)
     ap.add_argument("--sweep-ncs", type=int, default=0, help="chunks per side of k_sweep (0 = heuristic)")
     ap.add_argument("--generic", action="store_true", help="force the generic two-pass kernels")
     ap.add_argument("--no-fold", action="store_true", help="face terms by separate gather / scatter kernels")

@@ -55,7 +55,7 @@ struct hsbp_blocks {
   int sweep_r_override = 0;         // points per thread of the line-marching kernel (0 = heuristic, 2 or 4)
   int sweep_deep = 1;               // 1: css / crs of older lines come from deeper shared-memory rings, 0: register windows (k_sweep.cuh)
   int last_sweep_ctas_per_sm = 0;
-  int sweep_p6_regs = 128;          // register cap of the p = 6, 2-points-per-thread deep-ring kernel (128 or 168)
+  int sweep_p6_regs = 168;          // register cap of the p = 6, 2-points-per-thread deep-ring kernel (168: 0.98 ms, 128: 1.13 ms)
   int sweep_fold_faces = 1;         // fold the face terms into k_sweep (0: separate gather / scatter kernels)
   int sweep_ncs_override = 0;       // chunks per side of the line-marching kernel (0 = heuristic)
   int last_variant = -1;

@@ -875,7 +875,10 @@ k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true>(prm); }
 // with_faces = 0 leaves the face terms out (volume operator A-tilde only).
 // dynamic shared memory: 2 * (max face points) doubles
 template <int P>
-__global__ void __launch_bounds__(256, 3)
+#ifndef SW_EDGE_MINB
+#define SW_EDGE_MINB 4      // CTAs per SM the register allocation is sized for (measured: 2 -> 0.076, 3 -> 0.068, 4 -> 0.064, 5 -> 0.071 ms)
+#endif
+__global__ void __launch_bounds__(256, SW_EDGE_MINB)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
             double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
@@ -1002,7 +1005,7 @@ static int sweep_points_per_thread(const hsbp_blocks *b) {
   if (b->sweep_deep) {
     // measured on B200 at 256-point lines (deep rings): p = 4: R = 2 (126 registers, 16 warps/SM) 0.562 ms, R = 4
     // (195 registers, 10 warps/SM, two-way bank conflicts of the 32-byte-per-lane reads) 0.724 ms; p = 2: 0.42 / 0.47 ms;
-    // p = 6: R = 2 (128 registers, a few spills) 1.13 ms, R = 4 1.20 ms
+    // p = 6: R = 2 at 168 registers (12 warps/SM, no spills) 0.98 ms, at 128 registers (a few spills) 1.13 ms, R = 4 1.20 ms
     return can2 ? 2 : 4;
   }
   // register windows: R = 4 (252 registers, 8 warps/SM) 0.65 ms, R = 2 (128 registers, 16 warps/SM, spilling) 0.67 ms
