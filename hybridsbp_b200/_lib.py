@@ -6,6 +6,7 @@ between.  There is deliberately no fallback: if the shared library is missing
 or a call fails, an exception is raised.
 """
 import ctypes as C
+import weakref
 import os
 import re
 
@@ -200,6 +201,9 @@ class Context:
             raise HsbpError(rc, "hsbp_ctx_create failed (a B200 / sm_100 GPU is required; no CPU fallback)")
         self.h = h
         self.device = int(device)
+        # objects that hold handles created on this context (Blocks); they are destroyed first: the C objects keep raw
+        # pointers to their parents (hsbp_trace -> hsbp_blocks -> hsbp_ctx), and Python's finalisation order is arbitrary
+        self._children = weakref.WeakSet()
 
     def _check(self, rc):
         if rc != 0:
@@ -233,5 +237,7 @@ class Context:
 
     def close(self):
         if self.h is not None:
+            for child in list(self._children):
+                child.close()
             lib().hsbp_ctx_destroy(self.h)
             self.h = None

@@ -4,6 +4,7 @@ Replaces what the reference's `locoperator` assembles per block -- the sparse
 M-tilde, F_k, HfI_FT_k (global_curved.jl:211-506) -- by matrix-free CUDA kernels.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -35,6 +36,8 @@ class Blocks:
         _, pNs = _i64(self.Ns)
         ctx._check(lib().hsbp_blocks_create(ctx.h, self.p, self.nblocks, pNr, pNs, C.byref(h)))
         self.h = h
+        self._children = weakref.WeakSet()       # Trace / bp1.Fault objects built on these blocks (closed first)
+        ctx._children.add(self)
         self.VNp = lib().hsbp_blocks_num_volume_points(h)
         self.FNp = lib().hsbp_blocks_num_face_points(h)
         npts = (self.Nr + 1) * (self.Ns + 1)
@@ -133,7 +136,10 @@ class Blocks:
 
     def close(self):
         if self.h is not None:
-            lib().hsbp_blocks_destroy(self.h)
+            for child in list(self._children):       # traces / BP1 stages point into this object on the C side
+                child.close()
+            if self.ctx.h is not None:
+                lib().hsbp_blocks_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -163,6 +169,7 @@ class Trace:
         self.ctx._check(lib().hsbp_trace_create(blocks.h, nf, P(FToB), P(fe), P(fl), C.c_void_p(eo.ctypes.data),
                                                 P(es), C.byref(h)))
         self.h = h
+        blocks._children.add(self)
         self.nfaces = nf
         self.lNp = lib().hsbp_trace_num_lambda(h)
         self.FTolambdastarts = np.zeros(nf + 1, dtype=np.int64)
@@ -220,7 +227,8 @@ class Trace:
 
     def close(self):
         if self.h is not None:
-            lib().hsbp_trace_destroy(self.h)
+            if self.blocks.h is not None and self.ctx.h is not None:     # the C object points into its blocks / context
+                lib().hsbp_trace_destroy(self.h)
             self.h = None
 
     def __del__(self):

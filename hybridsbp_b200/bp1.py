@@ -91,6 +91,7 @@ class Fault:
         ctx._check(lib().hsbp_bp1_create(self.blk.h, 1, 1, 2, pa, psj, C.byref(prm), C.byref(h)))
         self.h = h
         self.ctx = ctx
+        self.blk._children.add(self)
         self.n = su.N + 1
         self.last_stats = None
 
@@ -110,8 +111,9 @@ class Fault:
 
     def close(self):
         if self.h is not None:
-            lib().hsbp_bp1_destroy(self.h)
-            self.h = None
+            h, self.h = self.h, None
+            if self.blk.h is not None and self.ctx.h is not None:      # the C object points into its blocks / context
+                lib().hsbp_bp1_destroy(h)
             self.blk.close()
 
     def __del__(self):

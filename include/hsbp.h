@@ -160,7 +160,7 @@ int  hsbp_local_solve(hsbp_blocks *blocks, const double *g_dev, double *u_dev, h
  * FToE, FToLF are 2 x nfaces (column-major), EToO (uint8 / Bool) and EToS are 4 x nblocks.       */
 int  hsbp_trace_create(hsbp_blocks *blocks, int64_t nfaces, const int64_t *FToB, const int64_t *FToE,
                        const int64_t *FToLF, const uint8_t *EToO, const int64_t *EToS, hsbp_trace **trace);
-int  hsbp_trace_destroy(hsbp_trace *trace);
+int  hsbp_trace_destroy(hsbp_trace *trace);     /* before hsbp_blocks_destroy of its blocks: a trace points into them */
 int64_t hsbp_trace_num_lambda(const hsbp_trace *trace);                       /* lambda-Np */
 int  hsbp_trace_get_starts(const hsbp_trace *trace, int64_t *FTolambdastarts);   /* nfaces+1, 1-based */
 int  hsbp_trace_get_D(hsbp_trace *trace, double *D);                          /* host, lambda-Np */
