@@ -114,6 +114,12 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 #ifndef SW_NST_OVERRIDE
 #define SW_NST_OVERRIDE 3
 #endif
+// SW_LAGB = 1: the steady state finishes output line j-H-1 (the Qr^T w part, which needs the neighbours' w) between the arrive
+// and the wait of a split CTA barrier, so that work overlaps the wait for the slowest warp; needs a third w buffer
+#ifndef SW_LAGB
+#define SW_LAGB 0
+#endif
+constexpr int SW_NW = SW_LAGB ? 3 : 2;   // w buffers
 constexpr int SW_NST = SW_NST_OVERRIDE;   // ring stages of u and crr: one being consumed, the others in flight
 constexpr int SW_MAX_THREADS = 256;
 
@@ -149,7 +155,7 @@ template <int P> struct SweepCfg {
   // couplings of the pairs (j-H, j-H+O); crs: line j-H for w) instead of travelling through register windows
   template <bool DEEP> static constexpr int nsb() { return DEEP ? 2 * T::H + (SW_NST - 1) : SW_NST; }
   template <bool DEEP> static constexpr int nsc() { return DEEP ? T::H + 1 + (SW_NST - 1) : SW_NST; }
-  template <bool DEEP> static constexpr int nlines() { return 2 * SW_NST + nsb<DEEP>() + nsc<DEEP>() + 2; }
+  template <bool DEEP> static constexpr int nlines() { return 2 * SW_NST + nsb<DEEP>() + nsc<DEEP>() + SW_NW; }
   __device__ static const double *bs() { return Sbp<P>::bs(); }
   __device__ static const double *hw() { return P == 2 ? c_sw_hw2 : (P == 4 ? c_sw_hw4 : c_sw_hw6); }
   __device__ static const double *Qc() { return P == 2 ? c_sw_Qc2 : (P == 4 ? c_sw_Qc4 : c_sw_Qc6); }
@@ -229,9 +235,9 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   double *ring_rr = ring_u + (size_t)NST * LW;            // [NST][LW]  crr'
   double *ring_ss = ring_rr + (size_t)NST * LW;           // [NSB][LW]  css'
   double *ring_rs = ring_ss + (size_t)NSB * LW;           // [NSC][LW]  crs
-  double *wbuf = ring_rs + (size_t)NSC * LW;              // [2][LW]
-  double *clring = wbuf + 2 * LW;                         // [NST][CLR]: r-end table rows of the staged lines
-  uint64_t *full = reinterpret_cast<uint64_t *>(clring + (size_t)NST * CLR);
+  double *wbuf = ring_rs + (size_t)NSC * LW;              // [SW_NW][LW]
+  double *clring = wbuf + SW_NW * LW;                     // [NST][CLR]: r-end table rows of the staged lines
+  uint64_t *full = reinterpret_cast<uint64_t *>(clring + (size_t)NST * CLR);   // [NST] + 1 (split CTA barrier)
 
   // ---- which chunk --------------------------------------------------------------------------
   const int nch = 2 * prm.ncs;
@@ -265,6 +271,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   }
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+    mbar_init(&full[NST], (uint32_t)(nthreads >> 5));      // split CTA barrier: one arrival per warp
     fence_mbar_init();
   }
   __syncthreads();
@@ -604,8 +611,10 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const uint32_t c_drr = opaque((uint32_t)NST * LWB);                                    // ring_rr - ring_u
   const uint32_t c_ss0 = opaque(smem_u32(ring_ss) + (uint32_t)(DOFF + i0) * 8u), c_ssE = opaque(c_ss0 + (uint32_t)NSB * LWB);
   const uint32_t c_rs0 = opaque(smem_u32(ring_rs) + (uint32_t)(DOFF + i0) * 8u), c_rsE = opaque(c_rs0 + (uint32_t)NSC * LWB);
-  const uint32_t c_w0 = smem_u32(wbuf) + (uint32_t)(DOFF + i0 - PAD) * 8u;
+  const uint32_t c_w0 = opaque(smem_u32(wbuf) + (uint32_t)(DOFF + i0 - PAD) * 8u);
   const uint32_t c_wsum = opaque(2u * c_w0 + LWB);
+  [[maybe_unused]] const uint32_t c_wE = opaque(c_w0 + (uint32_t)SW_NW * LWB);
+  [[maybe_unused]] const uint32_t cbar_s = opaque(smem_u32(&full[NST]));
   const uint32_t c_cl0 = opaque(smem_u32(clring));
   const int nout0 = opaque(o0 + H - jstart);               // first step whose line j-H belongs to the chunk
   const int nrefill = opaque(nlines - NST);                // steps after which no line is left to fetch
@@ -621,7 +630,12 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int64_t tstr = opaque(up ? (int64_t)CLR : -(int64_t)CLR);
 
   uint32_t au = c_u0 + (uint32_t)st * LWB, acl = c_cl0 + (uint32_t)(st * CLR) * 8u, abar = full_s + 8u * (uint32_t)st;
-  uint32_t aw = c_w0 + (uint32_t)(n & 1) * LWB;
+  uint32_t aw = c_w0 + (uint32_t)(SW_LAGB ? 0 : (n & 1)) * LWB;
+  [[maybe_unused]] uint32_t awp = aw, cpar = 0;            // previous w buffer, parity of the split barrier
+  [[maybe_unused]] bool outp_prev = false;
+  [[maybe_unused]] double accprev[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) accprev[q] = 0.0;
   uint32_t as_[NAS], ac_[NAC];                             // css' on lines j, j-1, ..; crs on lines j, .., j-H
 #pragma unroll
   for (int k = 0; k < NAS; ++k) as_[k] = c_ss0 + (uint32_t)((((n - k) % NSB) + NSB) % NSB) * LWB;
@@ -631,6 +645,47 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   int rw = 0;                                              // warp that issues the next refill
   double *yout = gy + (int64_t)(j - H) * lstride;          // output line of the next step
 
+  // ---- B: rs = Qr^T w and the output line (w buffer awb, accumulators accv, output line yo) --------------------
+  auto outputB = [&](uint32_t awb, const double (&accv)[R], double *yo) {
+      // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
+    double Wv[NV], val[R];
+#pragma unroll
+    for (int k = 0; k < NV / 2; ++k) {
+      const double2 a = lds128(awb + 16u * k);
+      Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) val[q] = accv[q];
+    for_offsets<1, H>([&](auto Oc) {
+      constexpr int O = decltype(Oc)::value;
+#pragma unroll
+      for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
+    });
+    if (edge) {
+      for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
+        constexpr int TL = decltype(Tc)::value;
+        if (tid == TL) {                                 // w(k) of the line sits at aw + (PAD - i0 + k) * 8, i0 = TL * R
+          double w0[BN];
+#pragma unroll
+          for (int k = 0; k < BN; ++k) w0[k] = lds64(awb + 8u * (PAD - TL * R + k));
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            if (TL * R + q < BM) val[q] = accv[q] + qt_closure_row<P>(TL * R + q, w0);
+        }
+        if (tid == far0 - TL) {                          // mirrored, sign flipped: w(Nr - k), i0 = Nrp - (TL + 1) R
+          double wr[BN];
+#pragma unroll
+          for (int k = 0; k < BN; ++k) wr[k] = lds64(awb + 8u * (PAD + (TL + 1) * R - 1 - k));
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            if (TL * R + (R - 1 - q) < BM) val[q] = accv[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
+        }
+      });
+    }
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k)
+      *reinterpret_cast<double2 *>(yo + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+  };
 #pragma unroll 1
   for (int left = nlines - n; left > 0; --left) {
     mbar_wait_s(abar, parity);
@@ -778,7 +833,15 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         for (int k = 0; k < R / 2; ++k) sts128(aw + 8u * PAD + 16u * k, wout[2 * k], wout[2 * k + 1]);
       }
     }
+#if SW_LAGB
+    __syncwarp();
+    if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cbar_s) : "memory");
+    if (ownf && outp_prev) outputB(awp, accprev, yout - lstr);   // line j-H-1, while the slower warps reach the barrier
+    mbar_wait_s(cbar_s, cpar);
+    cpar ^= 1u;
+#else
     __syncthreads();
+#endif
     if (mywarp == rw && n < nrefill) {                     // the slots of line j are free again: line j + NST goes into them
                                                           // (the warps take turns, so no warp is the slow one)
       if (elect_one()) {
@@ -796,46 +859,13 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         bulk_g2s_s(acl, prm.rtab + t0 + nn * tstr, (uint32_t)(CLR * 8), abar);
       }
     }
-    if (ownf && outp) {
-      // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
-      double Wv[NV], val[R];
+#if !SW_LAGB
+    if (ownf && outp) outputB(aw, accout, yout);
+#else
+    outp_prev = outp;
 #pragma unroll
-      for (int k = 0; k < NV / 2; ++k) {
-        const double2 a = lds128(aw + 16u * k);
-        Wv[2 * k] = a.x; Wv[2 * k + 1] = a.y;
-      }
-#pragma unroll
-      for (int q = 0; q < R; ++q) val[q] = accout[q];
-      for_offsets<1, H>([&](auto Oc) {
-        constexpr int O = decltype(Oc)::value;
-#pragma unroll
-        for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
-      });
-      if (edge) {
-        for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
-          constexpr int TL = decltype(Tc)::value;
-          if (tid == TL) {                                 // w(k) of the line sits at aw + (PAD - i0 + k) * 8, i0 = TL * R
-            double w0[BN];
-#pragma unroll
-            for (int k = 0; k < BN; ++k) w0[k] = lds64(aw + 8u * (PAD - TL * R + k));
-#pragma unroll
-            for (int q = 0; q < R; ++q)
-              if (TL * R + q < BM) val[q] = accout[q] + qt_closure_row<P>(TL * R + q, w0);
-          }
-          if (tid == far0 - TL) {                          // mirrored, sign flipped: w(Nr - k), i0 = Nrp - (TL + 1) R
-            double wr[BN];
-#pragma unroll
-            for (int k = 0; k < BN; ++k) wr[k] = lds64(aw + 8u * (PAD + (TL + 1) * R - 1 - k));
-#pragma unroll
-            for (int q = 0; q < R; ++q)
-              if (TL * R + (R - 1 - q) < BM) val[q] = accout[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
-          }
-        });
-      }
-#pragma unroll
-      for (int k = 0; k < R / 2; ++k)
-        *reinterpret_cast<double2 *>(yout + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
-    }
+    for (int q = 0; q < R; ++q) accprev[q] = accout[q];
+#endif
     yout += lstr;
     ++n;
     if (++rw == nwarps) rw = 0;
@@ -849,9 +879,18 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     for (int k = NAC - 1; k > 0; --k) ac_[k] = ac_[k - 1];
     ac_[0] += LWB;
     if (ac_[0] == c_rsE) ac_[0] = c_rs0;
+#if SW_LAGB
+    awp = aw;
+    aw += LWB;
+    if (aw == c_wE) aw = c_w0;
+#else
     aw = c_wsum - aw;
+#endif
     if (++ph == W) ph = 0;
   }
+#if SW_LAGB
+  if (ownf && outp_prev) outputB(awp, accprev, yout - lstr);      // the last output line (its w is complete: the loop ended on a wait)
+#endif
 }
 
 // register windows: the register allocation is sized through the CTAs per SM (MINB)
@@ -995,7 +1034,7 @@ template <int P> static size_t sweep_smem(int Nrp, bool deep) {
   using C = SweepCfg<P>;
   const int LW = Nrp + 2 * C::PAD;
   const int nl = deep ? C::template nlines<true>() : C::template nlines<false>();
-  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * 2 * C::CLW * sizeof(double) + SW_NST * sizeof(uint64_t);
+  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * 2 * C::CLW * sizeof(double) + (SW_NST + 1) * sizeof(uint64_t);
 }
 
 static int sweep_points_per_thread(const hsbp_blocks *b) {
