@@ -38,3 +38,21 @@ def test_integrator_reproduces_a_known_solution():
     ts, ys, nrej = bp1.integrate(rhs, np.array([1.0, 2.0]), 0.0, 3.0, 0.5, abstol=1e-10, reltol=1e-10)
     assert abs(ts[-1] - 3.0) < 1e-14
     assert np.abs(ys[-1] - np.array([1.0, 2.0]) * np.exp(-3.0)).max() < 1e-9
+
+
+def test_integrator_takes_millisecond_steps_at_late_times():
+    """The smallest step of the restated integrator is the resolution of t (OrdinaryDiffEq's dtmin), not a fraction of t:
+    coseismic steps are milliseconds at t ~ 1e10 s (the first BP1 earthquake at N = 200 starts at 9.7e9 s)."""
+    import numpy as np
+    from hybridsbp_b200 import bp1
+    t0 = 1.0e10
+    rhs = lambda t, y: (-1000.0 * y, False)                       # needs dt < 3e-3 for stability
+    ts, ys, nrej = bp1.integrate(rhs, np.array([1.0]), t0, t0 + 0.05, 1.0e7, abstol=1e-8, reltol=1e-6)
+    assert abs(ts[-1] - (t0 + 0.05)) <= 4 * np.spacing(t0)
+    assert np.min(np.diff(ts)) < 3e-3
+    assert abs(ys[-1][0] - np.exp(-1000.0 * (ts[-1] - t0))) <= 1e-4
+    # a right-hand side that always rejects ends in a reported underflow, not an endless loop
+    with __import__("pytest").raises(RuntimeError):
+        bp1.integrate(lambda t, y: (y, t > t0), np.array([1.0]), t0, t0 + 1.0, 0.5)
+    ts2, _, _ = bp1.integrate(lambda t, y: (y, t > t0), np.array([1.0]), t0, t0 + 1.0, 0.5, stop_on_underflow=True)
+    assert len(ts2) == 1
