@@ -1,4 +1,7 @@
-"""One batched FDM-PCG local solve on 1024 blocks of 256 x 256 points (TF32 preconditioner GEMMs): target of the ncu launch list."""
+"""One batched FDM-PCG local solve on 1024 blocks of 256 x 256 points (TF32 preconditioner GEMMs): target for ncu.
+The setup runs 2048 cuSOLVER syevd calls (about 100 kernels each): profile with a kernel filter and a launch cap, e.g.
+  ncu -k regex:"k_sweep|k_fpcg|gemm|k_edge" --launch-skip 200 -c 400 --metrics gpu__time_duration.sum ...
+(an unfiltered launch list of this script does not finish within a gpurun call)."""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
