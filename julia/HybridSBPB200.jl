@@ -107,6 +107,28 @@ function apply(b::Blocks, u::Vector{Float64})
   y
 end
 
+# ---- options, tau, face operators -----------------------------------------------------------------
+"tuning / solver knobs of include/hsbp.h (\"fdm_gemm\", \"sweep_deep\", ...)"
+set_option!(b::Blocks, name::AbstractString, value::Integer) =
+  check(b.ctx, ccall((:hsbp_blocks_set_option, libhsbp), Cint, (Ptr{Cvoid}, Cstring, Int64), b.h, name, value))
+"tau of faces 1..4 of every block, concatenated (the diagonals of lop[e].τ, global_curved.jl:418-437)"
+function get_tau(b::Blocks)
+  tau = Vector{Float64}(undef, num_face_points(b))
+  check(b.ctx, ccall((:hsbp_blocks_get_tau, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.h, tau))
+  tau
+end
+set_tau!(b::Blocks, tau::Vector{Float64}) =
+  check(b.ctx, ccall((:hsbp_blocks_set_tau, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.h, tau))
+"y += alpha * sum_k F_k v_k per block, block-face vector v (locbcarray!'s products, global_curved.jl:596-623)"
+face_F_add!(y::DeviceVector, b::Blocks, v::DeviceVector, alpha::Real) =
+  check(b.ctx, ccall((:hsbp_face_F_add, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}), b.h, v.ptr, alpha, y.ptr))
+"ft = F_k' u for faces 1..4 of every block (global_curved.jl:455-458)"
+face_FT!(ft::DeviceVector, b::Blocks, u::DeviceVector) =
+  check(b.ctx, ccall((:hsbp_face_FT, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), b.h, u.ptr, ft.ptr))
+"tr = HfI_FT_k u (computetraction's operator, global_curved.jl:460-463, 638-644)"
+face_traction!(tr::DeviceVector, b::Blocks, u::DeviceVector) =
+  check(b.ctx, ccall((:hsbp_face_traction, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), b.h, u.ptr, tr.ptr))
+
 # ---- the `factorization` plugin (global_curved.jl:659, 672, 698, 734) ------------------------------------
 # SBPLocalOperator1 requires `factors[e] <: Factorization` and uses `F \ g`.  All blocks are solved in one
 # batched call, so the per-block object is a view into a shared batch solver.
@@ -171,6 +193,55 @@ end
 "form the dense per-block S_e = F_eᵀ M̃_e⁻¹ F_e (assembleλmatrix's products, global_curved.jl:759-790); later solves use them"
 condense!(t::Trace; enable::Bool = true) =
   check(t.blocks.ctx, ccall((:hsbp_trace_condense, libhsbp), Cint, (Ptr{Cvoid}, Cint), t.h, enable ? 1 : 0))
+
+const PRECOND_JACOBI = 0
+const PRECOND_FACE_BLOCKS = 1
+"preconditioner of the CG on B: D, or the exact diagonal blocks B_ff (needs condense!)"
+precond_setup!(t::Trace; kind::Integer = PRECOND_FACE_BLOCKS) =
+  check(t.blocks.ctx, ccall((:hsbp_trace_precond_setup, libhsbp), Cint, (Ptr{Cvoid}, Cint), t.h, kind))
+
+# ---- SEAS BP1 ODE stage: replaces the body of odefun (seas/BP1/odefun.jl:8-121) ---------------------------
+struct Bp1Params            # layout of hsbp_bp1_params
+  Vp::Float64; mu_shear::Float64; sigma_n::Float64; eta::Float64; V0::Float64; tau_z0::Float64
+  Dc::Float64; f0::Float64; b::Float64; ftol::Float64; atolx::Float64; rtolx::Float64; maxiter::Int64
+end
+struct Bp1Stats             # layout of hsbp_bp1_stats
+  rejected::Int64; failure_bits::Int64; failed_nodes::Int64; newton_iterations_max::Int64; local_iterations::Int64
+end
+mutable struct Bp1Stage
+  blocks::Blocks
+  h::Ptr{Cvoid}
+  function Bp1Stage(b::Blocks, RSa::Vector{Float64}, sJ::Vector{Float64}, prm::Bp1Params;
+                    block::Integer = 1, fault_face::Integer = 1, loading_face::Integer = 2)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(b.ctx, ccall((:hsbp_bp1_create, libhsbp), Cint,
+                       (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Bp1Params}, Ref{Ptr{Cvoid}}),
+                       b.h, block, fault_face, loading_face, RSa, sJ, Ref(prm), h))
+    s = new(b, h[])
+    finalizer(x -> ccall((:hsbp_bp1_destroy, libhsbp), Cint, (Ptr{Cvoid},), x.h), s)
+  end
+end
+"""
+    odefun!(dψV, ψδ, p, t)   with p = (stage = Bp1Stage, reject_step = [false])
+
+Drop-in for the reference's `odefun(dψV, ψδ, p, t)` (odefun.jl:8): boundary scatter, local solve, traction, per-node
+root find and state evolution run on the device; a failure sets `p.reject_step[1] = true` exactly as odefun.jl:74-107 does,
+so the `isoutofdomain = stepcheck` mechanism of BP1.jl:149-159 keeps working.
+"""
+function odefun!(dψV::Vector{Float64}, ψδ::Vector{Float64}, p, t)
+  st = Ref(Bp1Stats(0, 0, 0, 0, 0))
+  s = p.stage
+  check(s.blocks.ctx, ccall((:hsbp_bp1_rhs, libhsbp), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Float64}, Ptr{Float64}, Ref{Bp1Stats}),
+                            s.h, t, ψδ, dψV, st))
+  st[].rejected != 0 && (p.reject_step[1] = true)
+  nothing
+end
+"displacement field of the last odefun! call (u of odefun.jl:43)"
+function displacement(s::Bp1Stage)
+  u = Vector{Float64}(undef, num_volume_points(s.blocks))
+  check(s.blocks.ctx, ccall((:hsbp_bp1_get_u, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.h, u))
+  u
+end
 
 "λ = B⁻¹(gδ − F̄ᵀM̃⁻¹g), u = M̃⁻¹(g − F̄λ)   (square_circle.jl:376-388); returns (λ, u, stats)"
 function trace_solve(t::Trace, g::Vector{Float64}, gδ::Vector{Float64}; tol = 1e-10, maxit = 10_000)
