@@ -273,7 +273,7 @@ def run_ours(args):
             tnb = int(round(nblocks ** 0.5))
             t0 = time.perf_counter()
             dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, n_per_block, p, dist=dist,
-                                                                condense=not args.no_condense)
+                                                                condense=not args.no_condense, coarse_modes=args.trace_coarse_modes)
             torch.cuda.synchronize()
             t_setup = time.perf_counter() - t0
             dt.solve(tg, tgd, tol=1e-2, maxit=5)                       # warm-up
@@ -292,7 +292,8 @@ def run_ours(args):
                    "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s; %s" %
                              (tinfo["blocks"], n_per_block + 1, n_per_block + 1, p, names[tinfo["local_mode"]],
                               "matrix-free Schur matvec (one batched local solve per CG iteration)" if args.no_condense else
-                              "statically condensed (dense S_e = F^T M^-1 F per block formed during setup)"),
+                              "statically condensed (dense S_e = F^T M^-1 F per block formed during setup)") +
+                             ("; coarse space with %d modes per face" % args.trace_coarse_modes if args.trace_coarse_modes else ""),
                    "lambda_points_per_gpu": tinfo["lambda_points"], "cut_faces_per_gpu": tinfo["cut_faces"],
                    "volume_points_per_gpu": tinfo["volume_points"]}
             tinfo["tr"].close(); tinfo["blk"].close()
@@ -362,6 +363,9 @@ def main():
     ap.add_argument("--trace-blocks", type=int, default=1024, help="blocks per GPU of the trace solve (a square number)")
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")
     ap.add_argument("--trace-tol", type=float, default=1e-10)
+    ap.add_argument("--trace-coarse-modes", type=int, default=0,
+                    help="trace solves: Legendre modes per face of an additive coarse space (0 = off; 2 makes the CG iteration "
+                         "count independent of the number of blocks)")
     ap.add_argument("--no-condense", action="store_true", help="trace solves: matrix-free Schur matvec instead of static condensation")
     ap.add_argument("--trace-large-blocks", type=int, default=64,
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")

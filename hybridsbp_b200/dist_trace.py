@@ -9,7 +9,7 @@ from .host import connectivityarrays
 
 
 def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=None, local_tol=1e-13, seed=1234,
-                        condense=False, fdm_gemm=3, face_blocks=None):
+                        condense=False, fdm_gemm=3, face_blocks=None, coarse_modes=0):
     """-> (DistributedTrace, g, gd, info).  g, gd are torch tensors on the rank's GPU; the right-hand sides are
     seeded per global block / face so that every world size solves the same global problem on the same mesh."""
     import torch
@@ -42,6 +42,8 @@ def build_strip_problem(ctx, rank, world, nbx, nby, N, p, dist=None, local_mode=
     if face_blocks:                      # after DistributedTrace has completed D on the cut faces
         parallel.setup_face_block_preconditioner(tr, lm, tr.FTolambdastarts, dist, dev)
         op.has_precond = True
+    if coarse_modes > 0:                 # optional second level (parallel.DistributedTrace.setup_coarse_space)
+        dt.setup_coarse_space(coarse_modes)
     npb = (N + 1) ** 2
     g = np.concatenate([np.random.default_rng(seed + int(e)).uniform(-1, 1, npb) for e in lm.blocks])
     gd = np.concatenate([np.random.default_rng(seed + 10 ** 6 + int(f)).uniform(-1, 1, tr.FTolambdastarts[i + 1] - tr.FTolambdastarts[i])

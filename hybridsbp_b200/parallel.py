@@ -98,6 +98,70 @@ class DistributedTrace:
         op.set_D(D.cpu().numpy())
         self.D = D
         self.messages = sum(len(v) for v in self.cut_idx.values())
+        self.starts = np.asarray(starts)
+        self.coarse = None
+
+    # ---- optional second level: a few polynomial modes per face (tools/proto_coarse_space.py) ----------------
+    def setup_coarse_space(self, modes=2):
+        """Additive coarse correction  Z (Z^T B Z)^-1 Z^T  on top of the first-level preconditioner: Z holds the Legendre
+        modes 0 .. modes-1 of every face that carries lambda.  With two modes the CG iteration count no longer grows with
+        the number of blocks across the mesh (prototype: 12 x 12 blocks 171 -> 37).  The coarse matrix is global and
+        replicated: its columns are B applied to one coarse basis vector each (distributed matvec + all-reduce).  Faces
+        must have one size.  Call after the first-level preconditioner is set up."""
+        torch, dist = self.torch, self.dist
+        st = self.starts
+        lam_faces = [i for i in range(len(self.lm.faces)) if st[i + 1] > st[i]]
+        nls = {int(st[i + 1] - st[i]) for i in lam_faces}
+        if len(nls) != 1:
+            raise ValueError("the coarse space needs faces of one size")
+        nl = nls.pop()
+        # global numbering of the faces that carry lambda (compressed global face ids)
+        gid = np.asarray(self.lm.faces)[lam_faces]
+        nfg = torch.tensor([int(np.max(self.lm.faces)) + 1], device=self.device)
+        if dist is not None:
+            dist.all_reduce(nfg, op=dist.ReduceOp.MAX)
+        mark = torch.zeros(int(nfg.item()), dtype=torch.float64, device=self.device)
+        mark[torch.as_tensor(gid, device=self.device)] = 1.0
+        if dist is not None:
+            dist.all_reduce(mark, op=dist.ReduceOp.MAX)
+        number = (torch.cumsum(mark, 0) - 1).long()
+        nfc = int(mark.sum().item())
+        cidx = number[torch.as_tensor(gid, device=self.device)]                     # coarse face index of every local face
+        s = np.linspace(-1.0, 1.0, nl)
+        Lq = np.stack([np.polynomial.legendre.Legendre.basis(k)(s) for k in range(modes)], axis=1)     # nl x modes
+        Lq = torch.as_tensor(Lq, device=self.device)
+        rows = torch.as_tensor(np.concatenate([np.arange(st[i] - 1, st[i + 1] - 1) for i in lam_faces]), device=self.device)
+        nc = nfc * modes
+        state = dict(nl=nl, modes=modes, Lq=Lq, rows=rows, cidx=cidx, nc=nc, nfl=len(lam_faces))
+        self.coarse = None
+        # A_c = Z^T B Z, one column per coarse basis vector
+        A = torch.zeros(nc, nc, dtype=torch.float64, device=self.device)
+        for j in range(nc):
+            c = torch.zeros(nc, dtype=torch.float64, device=self.device)
+            c[j] = 1.0
+            A[:, j] = self._restrict(state, self.schur_apply(self._prolong(state, c)))
+        A = 0.5 * (A + A.T)
+        state["chol"] = torch.linalg.cholesky(A)
+        self.coarse = state
+
+    def _prolong(self, cs, c):
+        """lam = Z c (every rank fills its own faces, cut faces on both ranks)"""
+        torch = self.torch
+        cf = c.view(-1, cs["modes"])[cs["cidx"]]                                      # local faces x modes
+        lam = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+        lam[cs["rows"]] = (cf @ cs["Lq"].T).reshape(-1)
+        return lam
+
+    def _restrict(self, cs, r):
+        """c = Z^T r over the whole mesh (a cut face is counted by the rank that owns it)"""
+        torch = self.torch
+        rf = (r * self.w)[cs["rows"]].view(cs["nfl"], cs["nl"])
+        c = torch.zeros(cs["nc"] // cs["modes"], cs["modes"], dtype=torch.float64, device=self.device)
+        c.index_add_(0, cs["cidx"], rf @ cs["Lq"])
+        c = c.reshape(-1)
+        if self.dist is not None:
+            self.dist.all_reduce(c)
+        return c
 
     def _exchange_add(self, x, base):
         """On every cut face x_f = base_f + (c_mine + c_partner) with c = x_f - base_f, the part only one rank can
@@ -139,9 +203,12 @@ class DistributedTrace:
     def precond(self, r):
         """z = P^-1 r: the local operator's preconditioner (face blocks; cut faces use the completed D on every rank that
         holds them, so the copies of lambda stay identical) or Jacobi with the completed D."""
-        if getattr(self.op, "has_precond", False):
-            return self.op.precond(r)
-        return r / self.D
+        z = self.op.precond(r) if getattr(self.op, "has_precond", False) else r / self.D
+        if self.coarse is not None:
+            cs = self.coarse
+            c = self.torch.cholesky_solve(self._restrict(cs, r).unsqueeze(1), cs["chol"]).squeeze(1)
+            z = z + self._prolong(cs, c)
+        return z
 
     def solve(self, g, gd, tol=1e-10, maxit=10000):
         """-> (lambda, u, stats); same iteration as hsbp_trace_solve."""

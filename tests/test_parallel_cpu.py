@@ -118,6 +118,9 @@ class OracleFaceBlocks:
     def precond_cut_own(self, ids, out):
         out.t[:] = out.t.new_tensor(np.concatenate([self._own(f - 1).reshape(-1, order="F") for f in ids]))
 
+    def precond_setup(self, kind):
+        self.precond_setup_cut([], None)
+
     def precond_setup_cut(self, ids, partner):
         part, o = {}, 0
         for f in ids:
@@ -138,7 +141,7 @@ class OracleFaceBlocks:
         return r.new_tensor(z)
 
 
-def _worker(rank, world, port, owner, out, face_blocks=False):
+def _worker(rank, world, port, owner, out, face_blocks=False, coarse=0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -155,6 +158,8 @@ def _worker(rank, world, port, owner, out, face_blocks=False):
             fb = OracleFaceBlocks(op, lstarts)
             parallel.setup_face_block_preconditioner(fb, lm, lstarts, dist, "cpu")
             op.has_precond, op.precond = True, fb.apply
+        if coarse:
+            dt.setup_coarse_space(coarse)
         lam, u, st = dt.solve(torch.from_numpy(G["g"][op.cols]), torch.from_numpy(G["gd"][op.rows]), tol=1e-13, maxit=500)
         np.savez(out % rank, lam=lam.numpy(), u=u.numpy(), rows=op.rows, cols=op.cols, D=dt.D.numpy(),
                  it=st["outer_iterations"], conv=st["converged"], ncut=sum(len(v) for v in lm.cut.values()))
@@ -162,12 +167,13 @@ def _worker(rank, world, port, owner, out, face_blocks=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("owner,face_blocks", [([0, 0, 1, 1], False), ([0, 1, 1, 0], False), ([0, 1, 1, 0], True)])
-def test_two_rank_trace_solve_equals_single_process(tmp_path, owner, face_blocks):
+@pytest.mark.parametrize("owner,face_blocks,coarse", [([0, 0, 1, 1], False, 0), ([0, 1, 1, 0], False, 0), ([0, 1, 1, 0], True, 0),
+                                                      ([0, 0, 1, 1], True, 2), ([0, 1, 1, 0], False, 1)])
+def test_two_rank_trace_solve_equals_single_process(tmp_path, owner, face_blocks, coarse):
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(2, port, np.array(owner), out, face_blocks), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, np.array(owner), out, face_blocks, coarse), nprocs=2, join=True)
     G = build_global()
     B = orc.assemblelambdamatrix(G["starts"], G["vstarts"], G["EToF"], G["FToB"], G["M"].F, G["D"], G["FbarT"])
     bl = np.zeros(G["starts"][-1] - 1); uu = np.zeros(G["vstarts"][-1] - 1)
@@ -188,3 +194,42 @@ def test_two_rank_trace_solve_equals_single_process(tmp_path, owner, face_blocks
     assert its[0] == its[1]
     if face_blocks:                            # exact diagonal blocks, completed across the cut: far fewer iterations
         assert its[0] < 60, its
+
+
+def test_coarse_space_makes_the_iteration_count_mesh_independent():
+    """Single process, oracle-backed operator on warped n x n block meshes: face blocks alone need more iterations as the
+    mesh grows, face blocks + two Legendre modes per face do not (tools/proto_coarse_space.py)."""
+    import torch
+    from hybridsbp_b200 import synthetic
+    from hybridsbp_b200.host import connectivityarrays
+    from tests.util import warped_metrics
+    p, N = 2, 9
+    its = {}
+    for nb in (3, 6):
+        _, EToV, EToF, FToB = synthetic.block_grid_connectivity(nb, nb)
+        FToE, FToLF, EToO, EToS = connectivityarrays(EToV, EToF)
+        ne = nb * nb
+        lops = [orc.locoperator(p, N, N, warped_metrics(p, N, N, e % nb, e // nb, nb, nb), FToB[EToF[:, e] - 1]) for e in range(ne)]
+        M, FbarT, D, vstarts, starts = orc.LocalGlobalOperators(lops, [N] * ne, [N] * ne, FToB, FToE, FToLF, EToO, EToS)
+        G = dict(lops=lops, conn=(FToE, FToLF, EToO, EToS), starts=starts, FToB=FToB, EToF=EToF, D=D)
+        owner = np.zeros(ne, dtype=np.int64)
+        lm = parallel.localize(0, owner, EToF, FToB, FToE, FToLF, EToO, EToS)
+        rng = np.random.default_rng(nb)
+        g, gd = rng.uniform(-1, 1, vstarts[-1] - 1), rng.uniform(-1, 1, starts[-1] - 1)
+        for coarse in (0, 2):
+            op = OracleLocalOperator(lm, lops, FbarT, vstarts, starts, partial_D(G, owner, 0))
+            lstarts = np.concatenate([[1], 1 + np.cumsum([starts[f + 1] - starts[f] for f in lm.faces])])
+            dt = parallel.DistributedTrace(op, lstarts, lm, dist=None)
+            fb = OracleFaceBlocks(op, lstarts)
+            parallel.setup_face_block_preconditioner(fb, lm, lstarts, None, "cpu")
+            if fb.blocks is None:                                 # single process: no cut faces, plain setup
+                fb.precond_setup_cut([], None)
+            op.has_precond, op.precond = True, fb.apply
+            if coarse:
+                dt.setup_coarse_space(coarse)
+            lam, u, st = dt.solve(torch.from_numpy(g[op.cols]), torch.from_numpy(gd[op.rows]), tol=1e-10, maxit=2000)
+            assert st["converged"] == 1
+            its[(nb, coarse)] = st["outer_iterations"]
+    assert its[(6, 0)] > 1.4 * its[(3, 0)], its              # first level alone: grows with the mesh
+    assert its[(6, 2)] < 1.6 * its[(3, 2)], its              # with the coarse space: nearly flat (27 -> 80 vs 23 -> 31)
+    assert its[(6, 2)] < 0.5 * its[(6, 0)], its
