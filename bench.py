@@ -273,7 +273,15 @@ def run_ours(args):
             tnb = int(round(nblocks ** 0.5))
             t0 = time.perf_counter()
             dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, n_per_block, p, dist=dist,
-                                                                condense=not args.no_condense, coarse_modes=args.trace_coarse_modes)
+                                                                condense=not args.no_condense, coarse_modes=0)
+            cmodes = args.trace_coarse_modes if args.trace_coarse_modes >= 0 else (2 if (world == 1 and not args.no_condense) else 0)
+            if cmodes > 0:
+                try:
+                    dt.setup_coarse_space(cmodes)
+                except Exception as exc:                               # the second level is optional: report and go on without it
+                    sys.stderr.write("coarse space not set up: %r\n" % (exc,))
+                    dt.coarse = None
+                    cmodes = 0
             torch.cuda.synchronize()
             t_setup = time.perf_counter() - t0
             dt.solve(tg, tgd, tol=1e-2, maxit=5)                       # warm-up
@@ -293,7 +301,7 @@ def run_ours(args):
                              (tinfo["blocks"], n_per_block + 1, n_per_block + 1, p, names[tinfo["local_mode"]],
                               "matrix-free Schur matvec (one batched local solve per CG iteration)" if args.no_condense else
                               "statically condensed (dense S_e = F^T M^-1 F per block formed during setup)") +
-                             ("; coarse space with %d modes per face" % args.trace_coarse_modes if args.trace_coarse_modes else ""),
+                             ("; coarse space with %d modes per face" % cmodes if cmodes else ""),
                    "lambda_points_per_gpu": tinfo["lambda_points"], "cut_faces_per_gpu": tinfo["cut_faces"],
                    "volume_points_per_gpu": tinfo["volume_points"]}
             tinfo["tr"].close(); tinfo["blk"].close()
@@ -363,9 +371,10 @@ def main():
     ap.add_argument("--trace-blocks", type=int, default=1024, help="blocks per GPU of the trace solve (a square number)")
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")
     ap.add_argument("--trace-tol", type=float, default=1e-10)
-    ap.add_argument("--trace-coarse-modes", type=int, default=0,
+    ap.add_argument("--trace-coarse-modes", type=int, default=-1,
                     help="trace solves: Legendre modes per face of an additive coarse space (0 = off; 2 makes the CG iteration "
-                         "count independent of the number of blocks)")
+                         "count independent of the number of blocks; -1 = 2 on one GPU, where the coarse matrix comes out of "
+                         "a few coloured matvecs, and off on partitioned meshes, where it is still built column by column)")
     ap.add_argument("--no-condense", action="store_true", help="trace solves: matrix-free Schur matvec instead of static condensation")
     ap.add_argument("--trace-large-blocks", type=int, default=64,
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")

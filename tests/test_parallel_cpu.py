@@ -227,6 +227,14 @@ def test_coarse_space_makes_the_iteration_count_mesh_independent():
             op.has_precond, op.precond = True, fb.apply
             if coarse:
                 dt.setup_coarse_space(coarse)
+                # the coloured probes reproduce Z^T B Z column by column
+                cs = dt.coarse
+                assert cs["matvecs"] < cs["nc"]
+                Ac = cs["chol"] @ cs["chol"].T
+                for j in (0, 1, cs["nc"] // 2, cs["nc"] - 1):
+                    c = torch.zeros(cs["nc"], dtype=torch.float64); c[j] = 1.0
+                    col = dt._restrict(cs, dt.schur_apply(dt._prolong(cs, c)))
+                    assert torch.allclose(Ac[:, j], col, rtol=1e-9, atol=1e-11 * float(Ac.abs().max()))
             lam, u, st = dt.solve(torch.from_numpy(g[op.cols]), torch.from_numpy(gd[op.rows]), tol=1e-10, maxit=2000)
             assert st["converged"] == 1
             its[(nb, coarse)] = st["outer_iterations"]
