@@ -373,8 +373,8 @@ def main():
     ap.add_argument("--trace-tol", type=float, default=1e-10)
     ap.add_argument("--trace-coarse-modes", type=int, default=-1,
                     help="trace solves: Legendre modes per face of an additive coarse space (0 = off; 2 makes the CG iteration "
-                         "count independent of the number of blocks; -1 = 2 on one GPU, where the coarse matrix comes out of "
-                         "a few coloured matvecs, and off on partitioned meshes, where it is still built column by column)")
+                         "count independent of the number of blocks; -1 = 2 on one GPU and off on partitioned meshes, where "
+                         "the coarse setup is gloo-tested but has not run on NCCL yet)")
     ap.add_argument("--no-condense", action="store_true", help="trace solves: matrix-free Schur matvec instead of static condensation")
     ap.add_argument("--trace-large-blocks", type=int, default=64,
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")

@@ -106,8 +106,8 @@ class DistributedTrace:
         """Additive coarse correction  Z (Z^T B Z)^-1 Z^T  on top of the first-level preconditioner: Z holds the Legendre
         modes 0 .. modes-1 of every face that carries lambda.  With two modes the CG iteration count no longer grows with
         the number of blocks across the mesh (prototype: 12 x 12 blocks 171 -> 37).  The coarse matrix is global and
-        replicated: its columns are B applied to one coarse basis vector each (distributed matvec + all-reduce).  Faces
-        must have one size.  Call after the first-level preconditioner is set up."""
+        replicated; it is probed with coloured coarse vectors (distributed matvec + all-reduce).  Faces must have one
+        size.  Call after the first-level preconditioner is set up."""
         torch, dist = self.torch, self.dist
         st = self.starts
         lam_faces = [i for i in range(len(self.lm.faces)) if st[i + 1] > st[i]]
@@ -134,49 +134,47 @@ class DistributedTrace:
         nc = nfc * modes
         state = dict(nl=nl, modes=modes, Lq=Lq, rows=rows, cidx=cidx, nc=nc, nfl=len(lam_faces))
         self.coarse = None
-        # A_c = Z^T B Z.  B couples a face only to the faces that share a block with it, so on a single device many
-        # columns come out of one matvec: faces of one colour (pairwise without a common neighbour face) are probed
-        # together and their responses are separated by support.  Partitioned meshes: one column per matvec.
+        # A_c = Z^T B Z.  B couples a face only to the faces that share a block with it, so many columns come out of one
+        # matvec: faces of one colour (pairwise without a common neighbour face) are probed together and their responses
+        # are separated by support.  The face graph of the whole mesh is gathered on every rank (4 ids per block), the
+        # greedy colouring is deterministic, and the restricted responses are all-reduced: every rank fills the same A_c.
         A = torch.zeros(nc, nc, dtype=torch.float64, device=self.device)
-        if dist is None:
-            EToF = np.asarray(self.lm.EToF) - 1                                         # local face ids per block
-            pos = {i: k for k, i in enumerate(lam_faces)}                               # local face -> index among lambda faces
-            adj = [set() for _ in lam_faces]
-            for e in range(EToF.shape[1]):
-                fs = [pos[f] for f in EToF[:, e] if f in pos]
-                for a in fs:
-                    adj[a].update(fs)
-            reach = [set().union(*[adj[g] for g in adj[f]]) if adj[f] else {f} for f in range(len(lam_faces))]
-            colour = -np.ones(len(lam_faces), dtype=np.int64)
-            for f in range(len(lam_faces)):
-                used = {colour[g] for g in reach[f] if colour[g] >= 0}
-                c = 0
-                while c in used:
-                    c += 1
-                colour[f] = c
-            cidx_np = cidx.cpu().numpy()
-            for c in range(int(colour.max()) + 1):
-                members = np.where(colour == c)[0]
-                resp_rows, resp_cols = [], []                                           # coarse face g answers to probe face f
-                for f in members:
-                    for g in adj[f]:
-                        resp_rows.append(cidx_np[g]); resp_cols.append(cidx_np[f])
-                rr = torch.as_tensor(np.asarray(resp_rows), device=self.device)
-                rc = torch.as_tensor(np.asarray(resp_cols), device=self.device)
-                mem = torch.as_tensor(cidx_np[members], device=self.device)
-                for k in range(modes):
-                    cv = torch.zeros(nfc, modes, dtype=torch.float64, device=self.device)
-                    cv[mem, k] = 1.0
-                    out = self._restrict(state, self.schur_apply(self._prolong(state, cv.reshape(-1)))).view(nfc, modes)
-                    for m in range(modes):
-                        A[rr * modes + m, rc * modes + k] = out[rr, m]
-            state["matvecs"] = (int(colour.max()) + 1) * modes
-        else:
-            for j in range(nc):
-                c = torch.zeros(nc, dtype=torch.float64, device=self.device)
-                c[j] = 1.0
-                A[:, j] = self._restrict(state, self.schur_apply(self._prolong(state, c)))
-            state["matvecs"] = nc
+        gl = np.asarray(self.lm.faces)[np.asarray(self.lm.EToF) - 1]                    # global face ids, 4 x local blocks
+        if dist is not None:
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, gl)
+            gl = np.concatenate(parts, axis=1)
+        number_np = number.cpu().numpy()
+        mark_np = mark.cpu().numpy() > 0
+        adj = [set() for _ in range(nfc)]
+        for e in range(gl.shape[1]):
+            fs = [int(number_np[f]) for f in gl[:, e] if mark_np[f]]
+            for a_ in fs:
+                adj[a_].update(fs)
+        reach = [set().union(*[adj[g] for g in adj[f]]) if adj[f] else {f} for f in range(nfc)]
+        colour = -np.ones(nfc, dtype=np.int64)
+        for f in range(nfc):
+            used = {colour[g] for g in reach[f] if colour[g] >= 0}
+            c = 0
+            while c in used:
+                c += 1
+            colour[f] = c
+        for c in range(int(colour.max()) + 1):
+            members = np.where(colour == c)[0]
+            resp_rows, resp_cols = [], []                                               # coarse face g answers to probe face f
+            for f in members:
+                for g in adj[f]:
+                    resp_rows.append(g); resp_cols.append(f)
+            rr = torch.as_tensor(np.asarray(resp_rows, dtype=np.int64), device=self.device)
+            rc = torch.as_tensor(np.asarray(resp_cols, dtype=np.int64), device=self.device)
+            mem = torch.as_tensor(members, device=self.device)
+            for k in range(modes):
+                cv = torch.zeros(nfc, modes, dtype=torch.float64, device=self.device)
+                cv[mem, k] = 1.0
+                out = self._restrict(state, self.schur_apply(self._prolong(state, cv.reshape(-1)))).view(nfc, modes)
+                for m in range(modes):
+                    A[rr * modes + m, rc * modes + k] = out[rr, m]
+        state["matvecs"] = (int(colour.max()) + 1) * modes
         A = 0.5 * (A + A.T)
         state["chol"] = torch.linalg.cholesky(A)
         self.coarse = state

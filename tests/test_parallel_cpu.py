@@ -160,6 +160,12 @@ def _worker(rank, world, port, owner, out, face_blocks=False, coarse=0):
             op.has_precond, op.precond = True, fb.apply
         if coarse:
             dt.setup_coarse_space(coarse)
+            cs = dt.coarse                                     # coloured probes == column-by-column Z^T B Z, on every rank
+            Ac = cs["chol"] @ cs["chol"].T
+            for j in (0, cs["nc"] - 1):
+                c = torch.zeros(cs["nc"], dtype=torch.float64); c[j] = 1.0
+                col = dt._restrict(cs, dt.schur_apply(dt._prolong(cs, c)))
+                assert torch.allclose(Ac[:, j], col, rtol=1e-9, atol=1e-11 * float(Ac.abs().max()))
         lam, u, st = dt.solve(torch.from_numpy(G["g"][op.cols]), torch.from_numpy(G["gd"][op.rows]), tol=1e-13, maxit=500)
         np.savez(out % rank, lam=lam.numpy(), u=u.numpy(), rows=op.rows, cols=op.cols, D=dt.D.numpy(),
                  it=st["outer_iterations"], conv=st["converged"], ncut=sum(len(v) for v in lm.cut.values()))
