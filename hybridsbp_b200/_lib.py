@@ -85,15 +85,23 @@ def lib():
         "hsbp_trace_num_lambda": (i64, [vp]),
         "hsbp_trace_get_starts": (cint, [vp, i64p]),
         "hsbp_trace_get_D": (cint, [vp, dp]),
-        "hsbp_trace_set_D": (cint, [vp, dp]),
         "hsbp_trace_FbarT": (cint, [vp, dp, dp]),
         "hsbp_trace_Fbar_add": (cint, [vp, dp, dbl, dp]),
         "hsbp_trace_schur_apply": (cint, [vp, dp, dp]),
         "hsbp_trace_condense": (cint, [vp, cint]),
         "hsbp_trace_precond_setup": (cint, [vp, cint]),
         "hsbp_trace_precond_apply": (cint, [vp, dp, dp]),
-        "hsbp_trace_precond_cut_own": (cint, [vp, i64, i64p, dp]),
-        "hsbp_trace_precond_setup_cut": (cint, [vp, i64, i64p, dp]),
+        "hsbp_trace_coarse_setup": (cint, [vp, cint]),
+        "hsbp_trace_coarse_size": (i64, [vp]),
+        "hsbp_trace_set_option": (cint, [vp, C.c_char_p, i64]),
+        "hsbp_trace_last_local_stats": (cint, [vp, vp]),
+        "hsbp_trace_set_partition": (cint, [vp, i64, i64p, i64p, i64p, i64]),
+        "hsbp_comm_unique_id": (cint, [vp]),
+        "hsbp_comm_init": (cint, [vp, vp, cint, cint]),
+        "hsbp_comm_destroy": (cint, [vp]),
+        "hsbp_comm_rank": (cint, [vp]),
+        "hsbp_comm_world": (cint, [vp]),
+        "hsbp_comm_allreduce_sum": (cint, [vp, dp, i64]),
         "hsbp_trace_rhs": (cint, [vp, dp, dp, dp]),
         "hsbp_trace_solve": (cint, [vp, dp, dp, dp, dp, dbl, i64, vp]),
         "hsbp_bp1_create": (cint, [vp, i64, i64, i64, dp, dp, vp, C.POINTER(vp)]),
@@ -121,7 +129,9 @@ class LocalStats(C.Structure):
 class TraceStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_int64), ("converged", C.c_int64), ("rel_residual", C.c_double),
                 ("inner_iterations_sum", C.c_int64), ("inner_iterations_max", C.c_int64),
-                ("local_solves", C.c_int64)]
+                ("local_solves", C.c_int64), ("true_rel_residual", C.c_double), ("failed_local_blocks", C.c_int64),
+                ("max_local_rel_residual", C.c_double), ("coarse_dofs", C.c_int64), ("issued_iterations", C.c_int64),
+                ("b_norm", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -234,6 +244,38 @@ class Context:
 
     def stream(self):
         return lib().hsbp_stream(self.h)
+
+    # -- multi-GPU: one context = one NCCL rank (hsbp_comm_*) ------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes made by one rank; hand them to every other rank (any transport) and call comm_init everywhere"""
+        buf = C.create_string_buffer(128)
+        rc = lib().hsbp_comm_unique_id(buf)
+        if rc != 0:
+            raise HsbpError(rc, "hsbp_comm_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        assert len(unique_id) == 128
+        self._check(lib().hsbp_comm_init(self.h, C.c_char_p(bytes(unique_id)), int(rank), int(world)))
+
+    def comm_init_torch(self, dist):
+        """communicator over the ranks of an initialised torch.distributed process group (the id travels through it)"""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], rank, world)
+
+    @property
+    def rank(self):
+        return lib().hsbp_comm_rank(self.h)
+
+    @property
+    def world(self):
+        return lib().hsbp_comm_world(self.h)
+
+    def allreduce_sum(self, x: "DeviceArray"):
+        self._check(lib().hsbp_comm_allreduce_sum(self.h, x.ptr, x.n))
 
     def close(self):
         if self.h is not None:

@@ -180,10 +180,12 @@ class Trace:
         self.ctx._check(lib().hsbp_trace_get_D(self.h, C.c_void_p(out.ctypes.data)))
         return out
 
-    def set_D(self, D):
-        a, pa = _f64(D)
-        assert a.size == self.lNp
-        self.ctx._check(lib().hsbp_trace_set_D(self.h, pa))
+    def set_partition(self, faces, partner, gamma, n_gamma_total):
+        """tell the library which local faces are cut by the block partition (parallel.LocalMesh.partition_arrays);
+        collective: completes D on the cut faces with the partner's half"""
+        f, pf = _i64(faces); q, pq = _i64(partner); g, pg = _i64(gamma)
+        assert f.size == q.size == g.size
+        self.ctx._check(lib().hsbp_trace_set_partition(self.h, f.size, pf, pq, pg, int(n_gamma_total)))
 
     def FbarT(self, u: DeviceArray, lam: DeviceArray):
         self.ctx._check(lib().hsbp_trace_FbarT(self.h, u.ptr, lam.ptr))
@@ -197,18 +199,24 @@ class Trace:
         self.ctx._check(lib().hsbp_trace_condense(self.h, 1 if enable else 0))
 
     def precond_setup(self, kind=1):
-        """0: Jacobi (D); 1: block-Jacobi with the exact diagonal blocks of B (needs condense())."""
+        """0: Jacobi (D); 1: block-Jacobi with the exact diagonal blocks of B as explicit inverses (needs condense());
+        collective on a partitioned mesh (the partner's half of a cut face's block is fetched)."""
         self.ctx._check(lib().hsbp_trace_precond_setup(self.h, int(kind)))
 
-    def precond_cut_own(self, faces, out):
-        """this device's S_e[f, f] of the cut faces `faces` (1-based ids), packed into the device buffer `out`"""
-        faces = np.ascontiguousarray(faces, dtype=np.int64)
-        self.ctx._check(lib().hsbp_trace_precond_cut_own(self.h, len(faces), faces.ctypes.data_as(C.POINTER(C.c_int64)), out.ptr))
+    def coarse_setup(self, modes=2):
+        """second level: `modes` Legendre polynomials per face (0 = off); collective on a partitioned mesh"""
+        self.ctx._check(lib().hsbp_trace_coarse_setup(self.h, int(modes)))
 
-    def precond_setup_cut(self, faces, partner):
-        """face-block preconditioner with the partner devices' blocks of the cut faces `faces` (same packing)"""
-        faces = np.ascontiguousarray(faces, dtype=np.int64)
-        self.ctx._check(lib().hsbp_trace_precond_setup_cut(self.h, len(faces), faces.ctypes.data_as(C.POINTER(C.c_int64)), partner.ptr))
+    def coarse_size(self):
+        return lib().hsbp_trace_coarse_size(self.h)
+
+    def set_option(self, name, value):
+        self.ctx._check(lib().hsbp_trace_set_option(self.h, name.encode(), int(value)))
+
+    def last_local_stats(self):
+        st = LocalStats()
+        self.ctx._check(lib().hsbp_trace_last_local_stats(self.h, C.byref(st)))
+        return st.as_dict()
 
     def precond_apply(self, r: DeviceArray, z: DeviceArray):
         self.ctx._check(lib().hsbp_trace_precond_apply(self.h, r.ptr, z.ptr))

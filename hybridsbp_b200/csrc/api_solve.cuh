@@ -2,33 +2,60 @@
 // Included by hsbp.cu (unity build).
 #pragma once
 #include "k_solve.cuh"
+#include "k_cg.cuh"
 
 struct hsbp_trace {
   hsbp_blocks *blocks = nullptr;
   int64_t nfaces = 0, nlam_faces = 0, lNp = 0;
   std::vector<int64_t> starts;          // nfaces + 1, 1-based (FToλstarts)
+  std::vector<int64_t> face2lam;        // per face (FToB order): index among the faces that carry lambda, -1
   std::vector<hsbp::LamFace> h_faces;
   hsbp::LamFace *d_faces = nullptr;
+  std::vector<hsbp::LamFaceX> h_fx;     // partition / preconditioner data of every lambda face (k_cg.cuh)
+  hsbp::LamFaceX *d_fx = nullptr;
+  int64_t *d_f2l = nullptr;             // FNp: lambda index seen from every block-face point (orientation applied), -1
+  int32_t *d_blk_lf = nullptr;          // 4 * nblocks: lambda-face index of every block face, -1
+  int max_nl = 0;
   double *d_D = nullptr;
   double *d_ft = nullptr, *d_fv = nullptr;          // block-face scratch (FNp)
   double *d_w = nullptr, *d_z = nullptr;            // volume scratch (VNp)
-  double *d_r = nullptr, *d_p = nullptr, *d_q = nullptr, *d_zz = nullptr;   // lambda scratch
-  double *d_partial = nullptr, *d_dots = nullptr;
+  double *d_r = nullptr, *d_p = nullptr, *d_q = nullptr, *d_zz = nullptr, *d_b = nullptr;   // lambda scratch
   hsbp_local_stats acc = {0, 0, 0, 0.0};
   int64_t local_solves = 0;
   // static condensation (hsbp_trace_condense): dense S_e = F_e^T M̃_e^-1 F_e of every block
   double *d_S = nullptr;
   int64_t *d_S_off = nullptr;
   int max_nf = 0;
-  // face-block preconditioner (hsbp_trace_precond_setup): Cholesky factors of the diagonal blocks B_ff
-  double *d_pc = nullptr, *d_pc_work = nullptr;
-  void *d_pc_desc = nullptr;
+  // partitioned mesh (hsbp_trace_set_partition): message layout of the cut faces
+  bool partitioned = false;
+  int64_t n_gamma = 0;                  // cut faces of the whole mesh
+  std::vector<int> peers;               // partner ranks, increasing
+  std::vector<int64_t> peer_off, peer_cnt, peer_boff, peer_bcnt;    // per peer: vector message (doubles), face-block message
+  std::vector<int32_t> cut_faces;       // lambda-face indices of this rank's cut faces in message order
+  int64_t msg_len = 0, bmsg_len = 0;
+  double *d_send = nullptr, *d_recv = nullptr;
+  // first level of the preconditioner: explicit inverses of the diagonal blocks B_ff (hsbp_trace_precond_setup)
+  int precond_kind = 0;
+  double *d_binv = nullptr;
+  // second level (hsbp_trace_coarse_setup)
+  int cmodes = 0, nI = 0, ldI = 0, nGq = 0, nGt = 0, ldG = 0;
+  double *d_AII = nullptr, *d_E = nullptr, *d_ET = nullptr, *d_SG = nullptr;
+  int64_t *d_gidx = nullptr;
+  double *d_bI = nullptr, *d_bG = nullptr, *d_t = nullptr, *d_ey = nullptr, *d_cG = nullptr;
+  // CG state
+  double *d_facepart = nullptr, *d_part1 = nullptr, *d_red1 = nullptr, *d_red2_in = nullptr, *d_red2_out = nullptr;
+  hsbp::CgState *d_state = nullptr;
+  hsbp::CgStatus *h_status = nullptr, *d_status = nullptr;
+  int cg_chunk = 4, cg_lookahead = 1;
+  uint64_t blocks_generation = 0;       // generation of the blocks' operator the condensed / preconditioner data belong to
 };
 
 namespace {
 
 using namespace hsbp;
 
+int trace_build_maps(hsbp_trace *t);                                                  // api_cg.cuh
+void trace_free_solver(hsbp_trace *t);
 int fdm_setup(hsbp_blocks *b);                                                        // api_fdm.cuh
 int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stats);
 
@@ -117,18 +144,6 @@ int local_solve_impl(hsbp_blocks *b, const double *g, double *u, hsbp_local_stat
   return pcg_solve(b, g, u, stats);
 }
 
-int dots(hsbp_trace *t, int64_t n, const double *x0, const double *y0, const double *x1, const double *y1,
-         const double *x2, const double *y2, double out[3]) {
-  hsbp_ctx *ctx = t->blocks->ctx;
-  k_dot3_partial<<<DOT_BLOCKS, VEC_THREADS, 0, ctx->stream>>>(n, x0, y0, x1, y1, x2, y2, t->d_partial);
-  k_dot3_final<<<1, 256, 0, ctx->stream>>>(DOT_BLOCKS, t->d_partial, t->d_dots);
-  int rc = check_launch(ctx, "k_dot3");
-  if (rc) return rc;
-  HSBP_CUDA(ctx, cudaMemcpyAsync(out, t->d_dots, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return HSBP_OK;
-}
-
 int trace_FbarT(hsbp_trace *t, const double *u, double *lam) {
   int rc = hsbp_face_FT(t->blocks, u, t->d_ft);
   if (rc) return rc;
@@ -154,33 +169,6 @@ void accumulate(hsbp_trace *t, const hsbp_local_stats &s) {
   t->acc.failed_blocks += s.failed_blocks;
   t->acc.max_rel_residual = std::max(t->acc.max_rel_residual, s.max_rel_residual);
   t->local_solves += 1;
-}
-
-// out = D o lam - Fbar^T M^-1 Fbar lam
-int schur_apply(hsbp_trace *t, const double *lam, double *out) {
-  hsbp_blocks *b = t->blocks;
-  hsbp_ctx *ctx = b->ctx;
-  if (t->d_S) {                      // condensed: scatter, one dense matrix-vector product per block, gather
-    HSBP_CUDA(ctx, cudaMemsetAsync(t->d_fv, 0, (size_t)b->FNp * sizeof(double), ctx->stream));
-    if (t->nlam_faces) k_lam_scatter<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_faces, lam, t->d_fv);
-    k_cond_gemv<<<dim3(16, (unsigned)b->nblocks), 256, (size_t)t->max_nf * sizeof(double), ctx->stream>>>(
-        b->d_desc, t->d_S_off, t->d_S, t->d_fv, t->d_ft);
-    if (t->nlam_faces) k_lam_gather<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_faces, t->d_ft, out);
-    k_ewise<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, t->d_D, lam, t->d_zz, 0);
-    k_axpby<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, 1.0, t->d_zz, -1.0, out, out);
-    return check_launch(ctx, "schur_apply (condensed)");
-  }
-  HSBP_CUDA(ctx, cudaMemsetAsync(t->d_w, 0, (size_t)b->VNp * sizeof(double), ctx->stream));
-  int rc = trace_Fbar_add(t, lam, 1.0, t->d_w);
-  if (rc) return rc;
-  hsbp_local_stats s;
-  if ((rc = local_solve_impl(b, t->d_w, t->d_z, &s))) return rc;
-  accumulate(t, s);
-  if ((rc = trace_FbarT(t, t->d_z, out))) return rc;
-  // out = D*lam - out
-  k_ewise<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, t->d_D, lam, t->d_zz, 0);
-  k_axpby<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, 1.0, t->d_zz, -1.0, out, out);
-  return check_launch(ctx, "schur_apply");
 }
 
 // S_e = F_e^T M̃_e^-1 F_e column by column, all blocks in lockstep: one local solve per face point of a block
@@ -225,92 +213,6 @@ int trace_condense(hsbp_trace *t) {
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(HSBP_ERR_CUDA);
   t->d_S = S; t->d_S_off = S_off; t->max_nf = max_nf;
   return HSBP_OK;
-}
-
-void precond_free(hsbp_trace *t) {
-  cudaFree(t->d_pc); cudaFree(t->d_pc_work); cudaFree(t->d_pc_desc);
-  t->d_pc = nullptr; t->d_pc_work = nullptr; t->d_pc_desc = nullptr;
-}
-
-// dense Cholesky of every B_ff (batched, the panel / DMMA trailing-update kernels of the dense local solver)
-int precond_faceblocks(hsbp_trace *t, int64_t ncut = 0, const int64_t *cut_faces = nullptr, const double *partner_dev = nullptr) {
-  hsbp_blocks *b = t->blocks;
-  hsbp_ctx *ctx = b->ctx;
-  if (!t->d_S) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_trace_precond_setup: the face-block preconditioner needs hsbp_trace_condense first");
-  precond_free(t);
-  const int64_t nf = t->nlam_faces;
-  if (nf == 0) return HSBP_OK;
-  static_assert(sizeof(FaceBlock) == sizeof(CholBlock), "descriptor layout");
-  std::vector<FaceBlock> fbs(nf);
-  int64_t off = 0, woff = 0;
-  int maxld = 0;
-  for (int64_t i = 0; i < nf; ++i) {
-    const LamFace &f = t->h_faces[i];
-    const int ld = (f.nl + CH_NB - 1) / CH_NB * CH_NB;
-    fbs[i].off = off; fbs[i].np = f.nl; fbs[i].ld = ld; fbs[i].voff = f.loff; fbs[i].woff = woff;
-    off += (int64_t)ld * ld; woff += ld; maxld = std::max(maxld, ld);
-  }
-  HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc, (size_t)off * sizeof(double)));
-  HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc_work, (size_t)woff * sizeof(double)));
-  HSBP_CUDA(ctx, cudaMalloc((void **)&t->d_pc_desc, nf * sizeof(FaceBlock)));
-  HSBP_CUDA(ctx, cudaMemcpyAsync(t->d_pc_desc, fbs.data(), nf * sizeof(FaceBlock), cudaMemcpyHostToDevice, ctx->stream));
-  // cut faces whose partner contribution is known: map lambda-face index -> offset into partner_dev
-  int64_t *d_pidx = nullptr;
-  if (ncut > 0) {
-    std::vector<int64_t> pidx(nf, -1);
-    int64_t po = 0;
-    for (int64_t c = 0; c < ncut; ++c) {
-      const int64_t lfi = cut_faces[c];
-      if (lfi < 0 || lfi >= nf) { precond_free(t); HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup_cut: bad face index"); }
-      pidx[lfi] = po;
-      po += (int64_t)t->h_faces[lfi].nl * t->h_faces[lfi].nl;
-    }
-    HSBP_CUDA(ctx, cudaMalloc((void **)&d_pidx, nf * sizeof(int64_t)));
-    HSBP_CUDA(ctx, cudaMemcpyAsync(d_pidx, pidx.data(), nf * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  }
-  k_faceblock_fill<<<(unsigned)nf, 256, 0, ctx->stream>>>(t->d_faces, (const FaceBlock *)t->d_pc_desc, b->d_desc, t->d_S_off, t->d_S,
-                                                         t->d_D, t->d_pc, d_pidx, partner_dev);
-  int *d_flag = nullptr;
-  std::vector<int> flag(nf, 0);
-  HSBP_CUDA(ctx, cudaMalloc((void **)&d_flag, nf * sizeof(int)));
-  cudaMemsetAsync(d_flag, 0, nf * sizeof(int), ctx->stream);
-  const CholBlock *dcb = (const CholBlock *)t->d_pc_desc;
-  for (int k0 = 0; k0 < maxld; k0 += CH_NB) {
-    k_chol_panel<<<(unsigned)nf, CH_THREADS, 0, ctx->stream>>>(dcb, t->d_pc, k0, d_flag);
-    const int nt = (maxld - k0 - CH_NB) / CH_NB;
-    if (nt > 0) k_chol_update<<<dim3(nt, nt, (unsigned)nf), CH_THREADS, 0, ctx->stream>>>(dcb, t->d_pc, k0);
-  }
-  cudaError_t e1 = cudaGetLastError();
-  if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(flag.data(), d_flag, nf * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_flag); cudaFree(d_pidx);
-  if (e1 != cudaSuccess) { precond_free(t); ctx->err = std::string("precond_faceblocks: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
-  for (int64_t i = 0; i < nf; ++i)
-    if (flag[i]) { precond_free(t); HSBP_FAIL(ctx, HSBP_ERR_ARG, "face-block preconditioner: a diagonal block of B is not positive definite"); }
-  return HSBP_OK;
-}
-
-// z = preconditioner^-1 r: Cholesky solves with the face blocks, or r / D (Jacobi)
-int precond_apply(hsbp_trace *t, const double *r, double *z) {
-  hsbp_ctx *ctx = t->blocks->ctx;
-  if (t->d_pc && t->nlam_faces)
-    k_chol_solve<<<(unsigned)t->nlam_faces, CH_THREADS, 0, ctx->stream>>>((const CholBlock *)t->d_pc_desc, t->d_pc, r, z, t->d_pc_work);
-  else
-    k_ewise<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, r, t->d_D, z, 1);
-  return check_launch(ctx, "precond_apply");
-}
-
-int trace_rhs(hsbp_trace *t, const double *g, const double *gd, double *bl) {
-  hsbp_blocks *b = t->blocks;
-  hsbp_ctx *ctx = b->ctx;
-  hsbp_local_stats s;
-  int rc = local_solve_impl(b, g, t->d_z, &s);
-  if (rc) return rc;
-  accumulate(t, s);
-  if ((rc = trace_FbarT(t, t->d_z, bl))) return rc;
-  k_axpby<<<vec_grid(t->lNp), VEC_THREADS, 0, ctx->stream>>>(t->lNp, 1.0, gd, -1.0, bl, bl);
-  return check_launch(ctx, "trace_rhs");
 }
 
 }  // namespace
@@ -361,6 +263,7 @@ int hsbp_trace_create(hsbp_blocks *b, int64_t nfaces, const int64_t *FToB, const
   if (!t) HSBP_FAIL(ctx, HSBP_ERR_STATE, "out of host memory");
   t->blocks = b; t->nfaces = nfaces;
   t->starts.assign(nfaces + 1, 1);
+  t->face2lam.assign(nfaces, -1);
   auto fail = [&](const char *m) { ctx->err = m; delete t; return HSBP_ERR_ARG; };
   auto fstart = [&](int64_t e, int k) {
     const BlockDesc &d = b->h_desc[e];
@@ -391,7 +294,9 @@ int hsbp_trace_create(hsbp_blocks *b, int64_t nfaces, const int64_t *FToB, const
     lf.em = (int32_t)em; lf.km = km; lf.ep = (int32_t)ep; lf.kp = kp;
     lf.flip = (ep >= 0 && !EToO[kp + 4 * ep]) ? 1 : 0; lf.nl = nl;
     lf.loff = t->starts[f] - 1; lf.fm = em >= 0 ? fstart(em, km) : 0; lf.fp = ep >= 0 ? fstart(ep, kp) : 0;
+    t->face2lam[f] = (int64_t)t->h_faces.size();
     t->h_faces.push_back(lf);
+    t->max_nl = std::max(t->max_nl, nl);
     t->starts[f + 1] = t->starts[f] + nl;
   }
   t->nlam_faces = (int64_t)t->h_faces.size();
@@ -403,8 +308,7 @@ int hsbp_trace_create(hsbp_blocks *b, int64_t nfaces, const int64_t *FToB, const
   A((void **)&t->d_faces, t->h_faces.size() * sizeof(LamFace));
   A((void **)&t->d_D, lb); A((void **)&t->d_ft, fb); A((void **)&t->d_fv, fb);
   A((void **)&t->d_w, vb); A((void **)&t->d_z, vb);
-  A((void **)&t->d_r, lb); A((void **)&t->d_p, lb); A((void **)&t->d_q, lb); A((void **)&t->d_zz, lb);
-  A((void **)&t->d_partial, 3 * DOT_BLOCKS * sizeof(double)); A((void **)&t->d_dots, 3 * sizeof(double));
+  A((void **)&t->d_r, lb); A((void **)&t->d_p, lb); A((void **)&t->d_q, lb); A((void **)&t->d_zz, lb); A((void **)&t->d_b, lb);
   if (e == cudaSuccess && t->nlam_faces)
     e = cudaMemcpyAsync(t->d_faces, t->h_faces.data(), t->h_faces.size() * sizeof(LamFace), cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) {
@@ -419,7 +323,12 @@ int hsbp_trace_create(hsbp_blocks *b, int64_t nfaces, const int64_t *FToB, const
     });
     if (rc) { hsbp_trace_destroy(t); return rc; }
   }
+  {
+    int rc = trace_build_maps(t);
+    if (rc) { hsbp_trace_destroy(t); return rc; }
+  }
   cudaStreamSynchronize(ctx->stream);
+  t->blocks_generation = b->generation;
   *out = t;
   return HSBP_OK;
 }
@@ -429,9 +338,9 @@ int hsbp_trace_destroy(hsbp_trace *t) {
   cudaSetDevice(t->blocks->ctx->device);
   cudaStreamSynchronize(t->blocks->ctx->stream);
   cudaFree(t->d_faces); cudaFree(t->d_D); cudaFree(t->d_ft); cudaFree(t->d_fv); cudaFree(t->d_w); cudaFree(t->d_z);
-  cudaFree(t->d_r); cudaFree(t->d_p); cudaFree(t->d_q); cudaFree(t->d_zz); cudaFree(t->d_partial); cudaFree(t->d_dots);
+  cudaFree(t->d_r); cudaFree(t->d_p); cudaFree(t->d_q); cudaFree(t->d_zz); cudaFree(t->d_b);
   cudaFree(t->d_S); cudaFree(t->d_S_off);
-  precond_free(t);
+  trace_free_solver(t);
   delete t;
   return HSBP_OK;
 }
@@ -449,11 +358,6 @@ int hsbp_trace_get_D(hsbp_trace *t, double *D) {
   return hsbp_d2h(t->blocks->ctx, D, t->d_D, (size_t)t->lNp * sizeof(double));
 }
 
-int hsbp_trace_set_D(hsbp_trace *t, const double *D) {
-  if (!t || !D) return HSBP_ERR_ARG;
-  return hsbp_h2d(t->blocks->ctx, t->d_D, D, (size_t)t->lNp * sizeof(double));
-}
-
 int hsbp_trace_FbarT(hsbp_trace *t, const double *u_dev, double *lam_dev) {
   if (!t) return HSBP_ERR_ARG;
   if (!u_dev || !lam_dev) HSBP_FAIL(t->blocks->ctx, HSBP_ERR_ARG, "hsbp_trace_FbarT: null pointer");
@@ -465,164 +369,6 @@ int hsbp_trace_Fbar_add(hsbp_trace *t, const double *lam_dev, double alpha, doub
   if (!y_dev || !lam_dev) HSBP_FAIL(t->blocks->ctx, HSBP_ERR_ARG, "hsbp_trace_Fbar_add: null pointer");
   HSBP_CUDA(t->blocks->ctx, cudaSetDevice(t->blocks->ctx->device));
   return trace_Fbar_add(t, lam_dev, alpha, y_dev);
-}
-
-int hsbp_trace_schur_apply(hsbp_trace *t, const double *lam_dev, double *out_dev) {
-  if (!t) return HSBP_ERR_ARG;
-  if (!out_dev || !lam_dev || out_dev == lam_dev) HSBP_FAIL(t->blocks->ctx, HSBP_ERR_ARG, "hsbp_trace_schur_apply: bad pointers");
-  HSBP_CUDA(t->blocks->ctx, cudaSetDevice(t->blocks->ctx->device));
-  return schur_apply(t, lam_dev, out_dev);
-}
-
-int hsbp_trace_condense(hsbp_trace *t, int enable) {
-  if (!t) return HSBP_ERR_ARG;
-  hsbp_ctx *ctx = t->blocks->ctx;
-  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!enable) {
-    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(t->d_S); cudaFree(t->d_S_off); t->d_S = nullptr; t->d_S_off = nullptr;
-    return HSBP_OK;
-  }
-  precond_free(t);                   // factors of an older S
-  return trace_condense(t);
-}
-
-int hsbp_trace_precond_setup(hsbp_trace *t, int kind) {
-  if (!t) return HSBP_ERR_ARG;
-  hsbp_ctx *ctx = t->blocks->ctx;
-  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (kind == HSBP_PRECOND_JACOBI) {
-    HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    precond_free(t);
-    return HSBP_OK;
-  }
-  if (kind != HSBP_PRECOND_FACE_BLOCKS) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup: unknown kind");
-  return precond_faceblocks(t);
-}
-
-// lambda-face index (position among the faces that carry lambda) of face f (0-based position in the FToB order), or -1
-static int64_t lam_face_index(const hsbp_trace *t, int64_t f) {
-  if (f < 0 || f >= t->nfaces || t->starts[f + 1] == t->starts[f]) return -1;
-  int64_t k = 0;
-  for (int64_t g = 0; g < f; ++g) k += t->starts[g + 1] > t->starts[g] ? 1 : 0;
-  return k;
-}
-
-int hsbp_trace_precond_cut_own(hsbp_trace *t, int64_t ncut, const int64_t *faces, double *out_dev) {
-  if (!t) return HSBP_ERR_ARG;
-  hsbp_blocks *b = t->blocks;
-  hsbp_ctx *ctx = b->ctx;
-  if (ncut < 0 || (ncut > 0 && (!faces || !out_dev))) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_cut_own: bad arguments");
-  if (!t->d_S) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_trace_precond_cut_own: needs hsbp_trace_condense first");
-  if (ncut == 0) return HSBP_OK;
-  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
-  std::vector<int64_t> idx(ncut), ooff(ncut);
-  int64_t o = 0;
-  for (int64_t c = 0; c < ncut; ++c) {
-    const int64_t k = lam_face_index(t, faces[c] - 1);
-    if (k < 0) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_cut_own: face carries no lambda");
-    const LamFace &f = t->h_faces[k];
-    if ((f.em >= 0) == (f.ep >= 0)) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_cut_own: not a cut face");
-    idx[c] = k; ooff[c] = o; o += (int64_t)f.nl * f.nl;
-  }
-  int64_t *d_idx = nullptr;
-  HSBP_CUDA(ctx, cudaMalloc((void **)&d_idx, 2 * ncut * sizeof(int64_t)));
-  cudaMemcpyAsync(d_idx, idx.data(), ncut * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-  cudaMemcpyAsync(d_idx + ncut, ooff.data(), ncut * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-  k_faceblock_own<<<(unsigned)ncut, 256, 0, ctx->stream>>>(t->d_faces, b->d_desc, t->d_S_off, t->d_S, d_idx, d_idx + ncut, out_dev);
-  cudaError_t e1 = cudaGetLastError();
-  if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_idx);
-  if (e1 != cudaSuccess) { ctx->err = std::string("hsbp_trace_precond_cut_own: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
-  return HSBP_OK;
-}
-
-int hsbp_trace_precond_setup_cut(hsbp_trace *t, int64_t ncut, const int64_t *faces, const double *partner_dev) {
-  if (!t) return HSBP_ERR_ARG;
-  hsbp_ctx *ctx = t->blocks->ctx;
-  if (ncut < 0 || (ncut > 0 && (!faces || !partner_dev))) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup_cut: bad arguments");
-  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
-  std::vector<int64_t> idx(ncut);
-  for (int64_t c = 0; c < ncut; ++c) {
-    idx[c] = lam_face_index(t, faces[c] - 1);
-    if (idx[c] < 0) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_setup_cut: face carries no lambda");
-  }
-  return precond_faceblocks(t, ncut, idx.data(), partner_dev);
-}
-
-int hsbp_trace_precond_apply(hsbp_trace *t, const double *r_dev, double *z_dev) {
-  if (!t) return HSBP_ERR_ARG;
-  hsbp_ctx *ctx = t->blocks->ctx;
-  if (!r_dev || !z_dev || r_dev == z_dev) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_precond_apply: bad pointers");
-  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
-  return precond_apply(t, r_dev, z_dev);
-}
-
-int hsbp_trace_rhs(hsbp_trace *t, const double *g_dev, const double *gd_dev, double *b_dev) {
-  if (!t) return HSBP_ERR_ARG;
-  if (!g_dev || !gd_dev || !b_dev) HSBP_FAIL(t->blocks->ctx, HSBP_ERR_ARG, "hsbp_trace_rhs: null pointer");
-  HSBP_CUDA(t->blocks->ctx, cudaSetDevice(t->blocks->ctx->device));
-  return trace_rhs(t, g_dev, gd_dev, b_dev);
-}
-
-int hsbp_trace_solve(hsbp_trace *t, const double *g_dev, const double *gd_dev, double *lam, double *u_dev,
-                     double tol, int64_t maxit, hsbp_trace_stats *stats) {
-  if (!t) return HSBP_ERR_ARG;
-  hsbp_blocks *b = t->blocks;
-  hsbp_ctx *ctx = b->ctx;
-  if (!g_dev || !gd_dev || !lam || !u_dev) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_solve: null pointer");
-  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
-  t->acc = {0, 0, 0, 0.0};
-  t->local_solves = 0;
-  const int64_t n = t->lNp;
-  const dim3 lg = vec_grid(n);
-  double *r = t->d_r, *p = t->d_p, *q = t->d_q, *z = t->d_zz;
-  int rc;
-  hsbp_trace_stats st = {0, 0, 0.0, 0, 0, 0};
-  if (n > 0) {
-    if ((rc = trace_rhs(t, g_dev, gd_dev, r))) return rc;                  // r = b (lambda0 = 0)
-    HSBP_CUDA(ctx, cudaMemsetAsync(lam, 0, n * sizeof(double), ctx->stream));
-    if ((rc = precond_apply(t, r, p))) return rc;                          // p = z = preconditioned residual
-    double d3[3];
-    if ((rc = dots(t, n, r, p, r, r, nullptr, nullptr, d3))) return rc;
-    double rz = d3[0];
-    const double b2 = d3[1];
-    double rr = b2;
-    if (b2 > 0) {
-      while (st.outer_iterations < maxit) {
-        if ((rc = schur_apply(t, p, q))) return rc;                        // note: uses t->d_zz as scratch before z is needed
-        if ((rc = dots(t, n, p, q, nullptr, nullptr, nullptr, nullptr, d3))) return rc;
-        const double alpha = rz / d3[0];
-        k_axpby<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, 1.0, lam, alpha, p, lam);
-        k_axpby<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, 1.0, r, -alpha, q, r);
-        if ((rc = precond_apply(t, r, z))) return rc;
-        if ((rc = dots(t, n, r, z, r, r, nullptr, nullptr, d3))) return rc;
-        st.outer_iterations += 1;
-        rr = d3[1];
-        if (sqrt(rr / b2) <= tol) { st.converged = 1; break; }
-        const double beta = d3[0] / rz;
-        rz = d3[0];
-        k_axpby<<<lg, VEC_THREADS, 0, ctx->stream>>>(n, 1.0, z, beta, p, p);
-      }
-      st.rel_residual = sqrt(rr / b2);
-    } else {
-      st.converged = 1;
-    }
-  } else {
-    st.converged = 1;
-  }
-  // u = M^-1 (g - Fbar lambda)
-  HSBP_CUDA(ctx, cudaMemcpyAsync(t->d_w, g_dev, (size_t)b->VNp * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (n > 0 && (rc = trace_Fbar_add(t, lam, -1.0, t->d_w))) return rc;
-  hsbp_local_stats s;
-  if ((rc = local_solve_impl(b, t->d_w, u_dev, &s))) return rc;
-  accumulate(t, s);
-  HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  st.inner_iterations_sum = t->acc.iterations_sum;
-  st.inner_iterations_max = t->acc.iterations_max;
-  st.local_solves = t->local_solves;
-  if (stats) *stats = st;
-  return HSBP_OK;
 }
 
 }  // extern "C"

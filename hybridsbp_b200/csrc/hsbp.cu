@@ -26,6 +26,13 @@ template <class F> int dispatch_p(int p, F &&f) {
 
 void fdm_libs_destroy(hsbp_ctx *ctx);      // api_fdm.cuh
 
+// M-tilde changed (metrics, boundary conditions or tau): everything derived from the old operator is stale -- local
+// factors must be set up again, a trace refuses its condensed blocks / preconditioners until they are rebuilt
+void operator_changed(hsbp_blocks *b) {
+  b->generation += 1;
+  b->local_mode = 0;
+}
+
 int check_launch(hsbp_ctx *ctx, const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -38,7 +45,7 @@ int check_launch(hsbp_ctx *ctx, const char *what) {
 
 extern "C" {
 
-int hsbp_version(void) { return 100; }
+int hsbp_version(void) { return 200; }
 
 int hsbp_ctx_create(int device, hsbp_ctx **out) {
   if (!out) return HSBP_ERR_ARG;
@@ -73,6 +80,7 @@ int hsbp_ctx_destroy(hsbp_ctx *ctx) {
   if (!ctx) return HSBP_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  hsbp_comm_destroy(ctx);
   fdm_libs_destroy(ctx);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->copy_ev[0]); cudaEventDestroy(ctx->copy_ev[1]);
@@ -236,6 +244,7 @@ static int set_metrics(hsbp_blocks *b, const double *crr, const double *css, con
   b->have_metrics = true;
   b->sweep_scaled_valid = false;
   b->rim_valid = false;
+  operator_changed(b);
   return HSBP_OK;
 }
 int hsbp_blocks_set_metrics(hsbp_blocks *b, const double *crr, const double *css, const double *crs) {
@@ -260,6 +269,8 @@ int hsbp_blocks_set_bc(hsbp_blocks *b, const int64_t *bctype) {
   HSBP_CUDA(ctx, cudaMemcpyAsync(b->d_desc, b->h_desc.data(), b->nblocks * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->stream));
   HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   b->have_bc = true;
+  b->rim_valid = false;
+  operator_changed(b);
   return HSBP_OK;
 }
 
@@ -287,6 +298,7 @@ int hsbp_blocks_compute_tau(hsbp_blocks *b, double tauscale) {
   if (bad) HSBP_FAIL(ctx, HSBP_ERR_ARG, "coefficient tensor is not positive definite (psi_min <= 0)");
   b->have_tau = true;
   b->rim_valid = false;
+  operator_changed(b);
   return HSBP_OK;
 }
 
@@ -295,7 +307,7 @@ int hsbp_blocks_set_tau(hsbp_blocks *b, const double *tau) {
   hsbp_ctx *ctx = b->ctx;
   if (!tau) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_tau: null pointer");
   int rc = hsbp_h2d(ctx, b->d_tau, tau, (size_t)b->FNp * sizeof(double));
-  if (rc == HSBP_OK) { b->have_tau = true; b->rim_valid = false; }
+  if (rc == HSBP_OK) { b->have_tau = true; b->rim_valid = false; operator_changed(b); }
   return rc;
 }
 int hsbp_blocks_get_tau(hsbp_blocks *b, double *tau) {
@@ -523,8 +535,11 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 
 }  // extern "C"
 
+#include "api_comm.cuh"
 #include "api_chol.cuh"
+#include "k_dense.cuh"
 #include "api_band.cuh"
 #include "api_solve.cuh"
+#include "api_cg.cuh"
 #include "api_fdm.cuh"
 #include "api_bp1.cuh"

@@ -15,6 +15,8 @@ struct hsbp_ctx {
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   int sm_count = 148;
   size_t smem_optin = 0;
+  void *comm = nullptr;             // ncclComm_t of this context (api_comm.cuh); one rank per context
+  int rank = 0, world = 1;
   void *fdm_libs = nullptr;         // cuBLAS / cuSOLVER handles of the fast-diagonalisation preconditioner (api_fdm.cuh)
   std::string err;
 };
@@ -59,6 +61,8 @@ struct hsbp_blocks {
   int sweep_fold_faces = 1;         // fold the face terms into k_sweep (0: separate gather / scatter kernels)
   int sweep_ncs_override = 0;       // chunks per side of the line-marching kernel (0 = heuristic)
   int last_variant = -1;
+  uint64_t generation = 0;          // bumped whenever the operator changes (metrics, bc, tau): factors, condensed blocks and
+                                    // preconditioners built for an older generation are stale
   // local solves
   int local_mode = 0;
   double local_tol = 1e-13;

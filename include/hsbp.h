@@ -164,48 +164,86 @@ int  hsbp_trace_destroy(hsbp_trace *trace);     /* before hsbp_blocks_destroy of
 int64_t hsbp_trace_num_lambda(const hsbp_trace *trace);                       /* lambda-Np */
 int  hsbp_trace_get_starts(const hsbp_trace *trace, int64_t *FTolambdastarts);   /* nfaces+1, 1-based */
 int  hsbp_trace_get_D(hsbp_trace *trace, double *D);                          /* host, lambda-Np */
-/* Partitioned meshes (blocks of one mesh spread over several devices, one hsbp_trace per device): pass the local
- * connectivity with FToE = 0 for the side of an interface face that lives on another device.  Such a cut face
- * still carries lambda on both devices; every operator below then returns this device's contribution and the host
- * layer (hybridsbp_b200/parallel.py) exchanges and adds the partner's.  D is the sum of both sides' penalties:
- * read the partial D, complete it with the partner's, write it back.                                           */
-int  hsbp_trace_set_D(hsbp_trace *trace, const double *D);
 /* Static condensation: form the dense per-block matrices S_e = F_e^T M̃_e^-1 F_e (F_e = [F_1 .. F_4] of block e, size
  * 2(Nr+1) + 2(Ns+1)) once, with one batched local solve per face point -- the products assembleλmatrix computes block by
  * block (global_curved.jl:759-790, `F' \ F` slices) without assembling the global sparse B.  Afterwards every
- * hsbp_trace_schur_apply / CG iteration of hsbp_trace_solve is scatter + one dense matrix-vector product per block +
- * gather instead of a local solve; the right-hand side and the back-substitution still use the local solver.
- * enable = 0 frees the matrices and returns to the matrix-free path.  Call after hsbp_local_setup.               */
+ * hsbp_trace_schur_apply / CG iteration of hsbp_trace_solve is one dense matrix-vector product per block (scatter and
+ * gather fused) instead of a local solve; the right-hand side and the back-substitution still use the local solver.
+ * enable = 0 frees the matrices and returns to the matrix-free path.  Call after hsbp_local_setup.  Fails (and keeps
+ * nothing) if a local solve did not reach its tolerance.                                                          */
 int  hsbp_trace_condense(hsbp_trace *trace, int enable);
-/* Preconditioner of the CG on B (the reference factorises B directly, square_circle.jl:314; here B is only applied):
+
+/* ---- multi-GPU: one context (= one device, one NCCL rank) per GPU ---------------------------------------------
+ * The reference is single-process, single-thread.  What shards is its block structure: blocks are
+ * independent given lambda (global_curved.jl:732-737) and every face couples exactly two blocks (:525-554).  The host
+ * partitions the blocks, creates one hsbp_blocks / hsbp_trace per device from the *local* connectivity (FToE = 0 for the
+ * side of an interface face that lives on another device: such a cut face carries lambda on both devices) and tells
+ * the library which faces are cut.  From then on every trace call below is collective over the communicator: the
+ * partial Fbar^T contributions of the cut faces travel by ncclSend / ncclRecv (one message per partner), CG scalars
+ * and the coarse-level data by ncclAllReduce, all on the context's stream.
+ *   hsbp_comm_unique_id   128 bytes (an ncclUniqueId) made by one rank; the host hands them to the others
+ *   hsbp_comm_init        every rank, same id
+ * hsbp_trace_set_partition (every rank, right after hsbp_trace_create, also ranks without cut faces):
+ *   faces[c]    1-based id (position in this trace's FToB) of cut face c
+ *   partner[c]  rank that holds the other side
+ *   gamma[c]    0-based index of the face among ALL cut faces of the mesh (any numbering both sides agree on, e.g. by
+ *               increasing global face id); n_gamma_total = number of cut faces of the whole mesh
+ * It completes D = Hf (tau- + tau+) on the cut faces with the partner's half.                                      */
+int  hsbp_comm_unique_id(void *id128);
+int  hsbp_comm_init(hsbp_ctx *ctx, const void *id128, int rank, int world);
+int  hsbp_comm_destroy(hsbp_ctx *ctx);
+int  hsbp_comm_rank(const hsbp_ctx *ctx);
+int  hsbp_comm_world(const hsbp_ctx *ctx);
+int  hsbp_comm_allreduce_sum(hsbp_ctx *ctx, double *x_dev, int64_t n);        /* in place, blocking */
+int  hsbp_trace_set_partition(hsbp_trace *trace, int64_t ncut, const int64_t *faces, const int64_t *partner,
+                              const int64_t *gamma, int64_t n_gamma_total);
+
+/* Preconditioner of the CG on B (the reference factorises B directly, square_circle.jl:314; here B is only applied).
+ * First level:
  *   HSBP_PRECOND_JACOBI       D = Hf (tau- + tau+)                      (default)
- *   HSBP_PRECOND_FACE_BLOCKS  block-Jacobi with the exact diagonal blocks B_ff = D_f - S_e-[f,f] - S_e+[f,f] (dense
- *                             Cholesky per face); needs hsbp_trace_condense.  Cut faces of a partitioned mesh keep D_f.
- * hsbp_trace_precond_apply: z = P^-1 r (used by hsbp_trace_solve and by the host-side distributed CG).             */
+ *   HSBP_PRECOND_FACE_BLOCKS  block-Jacobi with the exact diagonal blocks B_ff = D_f - S_e-[f,f] - S_e+[f,f], kept as
+ *                             explicit inverses (one dense matrix-vector product per face); needs hsbp_trace_condense.
+ *                             On a cut face the partner's S_e[f,f] is fetched by send / recv.
+ * Second level (hsbp_trace_coarse_setup, modes = 1..3, 0 = off): additive coarse space of `modes` Legendre polynomials
+ * per face.  With two modes the CG iteration count no longer grows with the number of blocks across the mesh.  The
+ * coarse matrix Z^T B Z is eliminated rank by rank (dense inverse of the rank-interior part, a small replicated Schur
+ * complement on the cut faces), so its cost per iteration does not grow with the number of GPUs.  Call after the
+ * first level; collective.
+ * hsbp_trace_precond_apply: z = P^-1 r with both levels (collective).                                                */
 #define HSBP_PRECOND_JACOBI      0
 #define HSBP_PRECOND_FACE_BLOCKS 1
 int  hsbp_trace_precond_setup(hsbp_trace *trace, int kind);
+int  hsbp_trace_coarse_setup(hsbp_trace *trace, int modes);
+int64_t hsbp_trace_coarse_size(const hsbp_trace *trace);      /* coarse dofs: this rank's interior ones + all cut-face ones */
 int  hsbp_trace_precond_apply(hsbp_trace *trace, const double *r_dev, double *z_dev);
-/* Partitioned meshes: the diagonal block of a cut face needs both devices' contributions.  hsbp_trace_precond_cut_own writes
- * this device's S_e[f, f] (dense nl x nl, lambda orientation) of the listed cut faces (1-based face ids in this trace's
- * FToB order) one after the other into out_dev; the host layer exchanges them and hands the partner's blocks, in the same
- * order, to hsbp_trace_precond_setup_cut, which builds and factorises all face blocks (cut faces not listed keep D_f).     */
-int  hsbp_trace_precond_cut_own(hsbp_trace *trace, int64_t ncut, const int64_t *faces, double *out_dev);
-int  hsbp_trace_precond_setup_cut(hsbp_trace *trace, int64_t ncut, const int64_t *faces, const double *partner_dev);
-int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u   */
+/* "cg_chunk" (iterations enqueued between two looks at the device's status word, default 4),
+ * "cg_lookahead" (chunks the host runs ahead of the device, default 1) */
+int  hsbp_trace_set_option(hsbp_trace *trace, const char *name, int64_t value);
+int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u (this device's blocks) */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
-int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam      */
-/* b = gdelta - Fbar^T M̃^-1 g   (LocalToGLobalRHS!, global_curved.jl:730-740)                    */
+int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam (collective) */
+/* b = gdelta - Fbar^T M̃^-1 g   (LocalToGLobalRHS!, global_curved.jl:730-740); collective             */
 int  hsbp_trace_rhs(hsbp_trace *trace, const double *g_dev, const double *gdelta_dev, double *b_dev);
+/* statistics of the local solves of the last trace call (rhs, schur_apply, condense, coarse_setup, solve) */
+int  hsbp_trace_last_local_stats(hsbp_trace *trace, hsbp_local_stats *stats);
 typedef struct {
   int64_t outer_iterations;
-  int64_t converged;              /* 1 if ||b - B lambda|| / ||b|| <= tol was reached */
-  double  rel_residual;
+  int64_t converged;              /* 1 if the CG residual reached tol * ||b|| and every local solve reached its tolerance */
+  double  rel_residual;           /* ||r|| / ||b|| of the CG recurrence at exit                                            */
   int64_t inner_iterations_sum;   /* over all local solves of the call (PCG)          */
   int64_t inner_iterations_max;
   int64_t local_solves;
+  double  true_rel_residual;      /* ||b - B lambda|| / ||b|| recomputed with one more application of B after the loop   */
+  int64_t failed_local_blocks;    /* block solves (rhs, matvecs, back-substitution) that missed their tolerance         */
+  double  max_local_rel_residual;
+  int64_t coarse_dofs;            /* size of the second-level problem seen by this rank, 0 = one level                   */
+  int64_t issued_iterations;      /* iterations enqueued; those after convergence return at once on the device           */
+  double  b_norm;                 /* ||b||                                                                               */
 } hsbp_trace_stats;
-/* lambda = B^-1 (gdelta - Fbar^T M̃^-1 g), u = M̃^-1 (g - Fbar lambda)   (square_circle.jl:376-388) */
+/* lambda = B^-1 (gdelta - Fbar^T M̃^-1 g), u = M̃^-1 (g - Fbar lambda)   (square_circle.jl:376-388).
+ * Device-resident preconditioned CG: all scalars stay on the device, the host enqueues iterations ahead and looks at a
+ * mapped status word every "cg_chunk" iterations; two reductions per iteration on a partitioned mesh (p.q, and one
+ * vector with r.z, r.r and the coarse-level data).  Collective.                                                     */
 int  hsbp_trace_solve(hsbp_trace *trace, const double *g_dev, const double *gdelta_dev,
                       double *lambda_dev, double *u_dev, double tol, int64_t maxit, hsbp_trace_stats *stats);
 
