@@ -84,6 +84,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process (and the pages it touches from now on) to the NUMA node of its GPU: host buffers of the end-to-end
+    path are then allocated next to the GPU's PCIe root instead of all ranks sharing node 0."""
+    try:
+        import ctypes
+        cudart = ctypes.CDLL("libcudart.so")
+        buf = ctypes.create_string_buffer(64)
+        if cudart.cudaDeviceGetPCIBusId(buf, 64, int(local)) != 0:
+            return None
+        bus = buf.value.decode().lower()
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -104,7 +129,7 @@ def cpu_baseline(p, N, nblk_sample, seconds, threads):
         mats.append(orc.locoperator(p, N, N, m, (1 if b == 0 else 0, 0, 0, 0)).Mt)
     S = BlockSpMV(mats)
     t_asm = time.time() - t0
-    nthreads = S.max_threads if threads <= 0 else threads
+    nthreads = (os.cpu_count() or S.max_threads) if threads <= 0 else threads      # explicit: torchrun exports OMP_NUM_THREADS=1
     u = np.random.default_rng(778).uniform(-1, 1, S.n)
     y = np.empty(S.n)
     S(u, y, nthreads)
@@ -130,11 +155,12 @@ def run_reference(args):
     S, base = cpu_baseline(p, N, args.cpu_blocks, 0.5, 0)
     u = np.random.default_rng(778).uniform(-1, 1, S.n)
     y = np.empty(S.n)
+    nthr = base["cores"]
     for _ in range(args.warmup):
-        S(u, y, 0)
+        S(u, y, nthr)
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        S(u, y, 0)
+        S(u, y, nthr)
     dt = (time.perf_counter() - t1) / args.steps
     val = S.n / dt / 1e9
     base["value"] = val
@@ -173,6 +199,7 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None
     ctx = hs.Context(local)
     p, N = args.p, args.n
     nbx = nby = int(round(args.blocks ** 0.5))
@@ -256,67 +283,89 @@ def run_ours(args):
         e2e_s = float(t.item())
     checksum = float(np.abs(y_host).sum())
     ctx.host_unregister(u_host); ctx.host_unregister(y_host)
+    variant = blk.apply_variant()
+    u.free(); y.free()
+    blk.close()                                         # the trace solves below build their own blocks
+    del u_host, y_host
 
-    # second half of BASELINE's metric: hybrid trace-CG solve time.  Small-block variant of SURVEY.md section 8d
-    # (1024 blocks x 18x18 points per GPU, dense Cholesky local solver K2a), weak scaling over strips of blocks;
-    # cut-face exchange by NCCL send / recv, CG scalars by all-reduce (hybridsbp_b200/parallel.py).
+    # second half of BASELINE's metric: hybrid trace-CG solve time, through hsbp_trace_solve -- the library's device-resident,
+    # two-level preconditioned CG; on N > 1 GPUs the cut-face exchange (ncclSend / ncclRecv) and the reductions (ncclAllReduce)
+    # run inside the library on its own stream.  Weak scaling over strips of blocks.
     trace = None
+    trace_small = None
     trace_large = None
     if not args.no_trace:
-        import torch
         from hybridsbp_b200 import dist_trace
-        torch.cuda.set_device(local)
+        if dist is not None and ctx.world == 1:
+            ctx.comm_init_torch(dist)
         names = {1: "batched Jacobi-PCG (K2b)", 2: "batched dense Cholesky (K2a)", 3: "batched banded Cholesky (K2c)",
                  4: "batched PCG with fast-diagonalisation preconditioner (K2d)"}
 
         def timed_trace_solve(nblocks, n_per_block):
             tnb = int(round(nblocks ** 0.5))
+            assert tnb * tnb == nblocks, "trace solves need a square number of blocks per GPU"
             t0 = time.perf_counter()
-            dt, tg, tgd, tinfo = dist_trace.build_strip_problem(ctx, rank, world, tnb, tnb, n_per_block, p, dist=dist,
-                                                                condense=not args.no_condense, coarse_modes=0)
-            cmodes = args.trace_coarse_modes if args.trace_coarse_modes >= 0 else (2 if (world == 1 and not args.no_condense) else 0)
-            if cmodes > 0:
-                try:
-                    dt.setup_coarse_space(cmodes)
-                except Exception as exc:                               # the second level is optional: report and go on without it
-                    sys.stderr.write("coarse space not set up: %r\n" % (exc,))
-                    dt.coarse = None
-                    cmodes = 0
-            torch.cuda.synchronize()
+            tm = {}
+            pr = dist_trace.StripProblem(ctx, rank, world, tnb, tnb, n_per_block, p, condense=not args.no_condense,
+                                         coarse_modes=args.trace_coarse_modes, timings=tm)
+            ctx.sync()
             t_setup = time.perf_counter() - t0
-            dt.solve(tg, tgd, tol=1e-2, maxit=5)                       # warm-up
+            pr.solve(tol=1e-2, maxit=4)                                  # warm-up
             barrier()
-            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            lam_t, u_t, st_t = dt.solve(tg, tgd, tol=args.trace_tol, maxit=50000)
-            torch.cuda.synchronize()
+            ctx.timer_start()
+            st_t = pr.solve(tol=args.trace_tol, maxit=20000)
+            ms_dev = ctx.timer_stop()
             t_solve = time.perf_counter() - t0
+            # the CG loop alone (no right-hand side, no back-substitution): a second solve to a tolerance it cannot reach,
+            # stopped after a fixed number of iterations -> device time per iteration
+            nit = max(8, min(64, st_t["outer_iterations"]))
+            barrier()
+            ctx.timer_start()
+            st_i = pr.solve(tol=1e-300, maxit=nit)
+            ms_fixed = ctx.timer_stop()
+            ctx.timer_start()
+            pr.solve(tol=1e-300, maxit=0)
+            ms_zero = ctx.timer_stop()
+            per_it = (ms_fixed - ms_zero) / max(1, st_i["outer_iterations"])
             if dist is not None:
-                tt = torch.tensor([t_solve], dtype=torch.float64, device="cuda")
+                import torch
+                tt = torch.tensor([t_solve, ms_dev, t_setup, per_it], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                t_solve = float(tt.item())
-            out = {"seconds": t_solve, "setup_seconds": t_setup, "outer_iterations": st_t["outer_iterations"],
-                   "converged": st_t["converged"], "rel_residual": st_t["rel_residual"], "tol": args.trace_tol,
-                   "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s; %s" %
-                             (tinfo["blocks"], n_per_block + 1, n_per_block + 1, p, names[tinfo["local_mode"]],
-                              "matrix-free Schur matvec (one batched local solve per CG iteration)" if args.no_condense else
-                              "statically condensed (dense S_e = F^T M^-1 F per block formed during setup)") +
-                             ("; coarse space with %d modes per face" % cmodes if cmodes else ""),
-                   "lambda_points_per_gpu": tinfo["lambda_points"], "cut_faces_per_gpu": tinfo["cut_faces"],
-                   "volume_points_per_gpu": tinfo["volume_points"]}
-            tinfo["tr"].close(); tinfo["blk"].close()
+                t_solve, ms_dev, t_setup, per_it = [float(v) for v in tt]
+            if st_t["converged"] != 1 or not st_t["true_rel_residual"] <= 100 * args.trace_tol:
+                raise RuntimeError("trace solve did not converge: %r" % (st_t,))
+            info = pr.info
+            out = {"seconds": t_solve, "device_ms": ms_dev, "setup_seconds": t_setup,
+                   "setup_breakdown_seconds": {k: round(v, 3) for k, v in tm.items()},
+                   "outer_iterations": st_t["outer_iterations"], "issued_iterations": st_t["issued_iterations"],
+                   "ms_per_iteration": per_it,
+                   "converged": st_t["converged"], "rel_residual": st_t["rel_residual"], "true_rel_residual": st_t["true_rel_residual"],
+                   "failed_local_blocks": st_t["failed_local_blocks"], "tol": args.trace_tol,
+                   "coarse_dofs": st_t["coarse_dofs"],
+                   "config": "%d blocks x %dx%d points per GPU, p=%d, local solver: %s; %s; first level: %s; second level: %s" %
+                             (info["blocks"], n_per_block + 1, n_per_block + 1, p, names[info["local_mode"]],
+                              "statically condensed (dense S_e = F^T M^-1 F per block formed during setup)" if info["condensed"] else
+                              "matrix-free Schur matvec (one batched local solve per CG iteration)",
+                              "exact face blocks B_ff (explicit inverses)" if info["face_blocks"] else "D",
+                              "%d Legendre modes per face" % info["coarse_modes"] if info["coarse_modes"] else "none"),
+                   "lambda_points_per_gpu": info["lambda_points"], "cut_faces_per_gpu": info["cut_faces"],
+                   "volume_points_per_gpu": info["volume_points"],
+                   "communication": "inside libhsbp: ncclSend/ncclRecv of cut-face contributions + 2 ncclAllReduce per iteration" if world > 1 else "none (1 GPU)"}
+            pr.close()
             return out
 
-        # (i) small-block variant of SURVEY.md section 8d: 1024 blocks x 18x18 points per GPU, dense Cholesky factors
-        trace = timed_trace_solve(args.trace_blocks, args.trace_n)
-        # (ii) blocks of BASELINE config 4's size (256 x 256 points), a bounded number of them so that the default run
-        #      stays within minutes; the full 1024-block solve is tools/trace_c4.py (profiles/)
+        # (i) BASELINE config 4 / 5 in full: 1024 blocks x 256x256 points per GPU (507 904 lambda points per GPU)
+        if args.trace_full:
+            trace = timed_trace_solve(args.blocks, args.n)
+        # (ii) small-block variant of SURVEY.md section 8d: 1024 blocks x 18x18 points per GPU, dense Cholesky factors
+        trace_small = timed_trace_solve(args.trace_blocks, args.trace_n)
+        # (iii) optional: a bounded number of blocks of config 4's size
         if args.trace_large_blocks > 0:
             trace_large = timed_trace_solve(args.trace_large_blocks, args.n)
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        variant = blk.apply_variant()
         achieved = BYTES_PER_DOF * dof / (stage[0] * 1e-3) / 1e9
         traffic = None                                 # DRAM bytes per k_sweep launch from the committed ncu capture
         try:
@@ -341,10 +390,11 @@ def run_ours(args):
                              "peak_source": peak_src},
                 "e2e": {"value": world * dof / e2e_s / 1e9, "unit": "GDOF/s",
                         "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
-                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "numa_node_rank0": numa_node,
                         "note": "hsbp_apply_host on pinned host buffers: H2D of u, apply, D2H of y inside each call"},
                 "gpu_launches": args.steps * (2 if variant == 1 else 4),      # kernels of the timed region (k_edge_prep + k_sweep per apply)
-                "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum, "trace_solve": trace, "trace_solve_large_blocks": trace_large}
+                "clocks": clocks, "apply_variant": variant, "checksum_abs_y": checksum, "trace_solve": trace,
+                "trace_solve_small_blocks": trace_small, "trace_solve_large_blocks": trace_large}
         if world == 1 and not args.no_cpu:
             _, base = cpu_baseline(p, N, args.cpu_blocks, args.cpu_seconds, 1)
             line["cpu_baseline"] = base
@@ -371,12 +421,13 @@ def main():
     ap.add_argument("--trace-blocks", type=int, default=1024, help="blocks per GPU of the trace solve (a square number)")
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")
     ap.add_argument("--trace-tol", type=float, default=1e-10)
-    ap.add_argument("--trace-coarse-modes", type=int, default=-1,
-                    help="trace solves: Legendre modes per face of an additive coarse space (0 = off; 2 makes the CG iteration "
-                         "count independent of the number of blocks; -1 = 2 on one GPU and off on partitioned meshes, where "
-                         "the coarse setup is gloo-tested but has not run on NCCL yet)")
+    ap.add_argument("--trace-coarse-modes", type=int, default=2,
+                    help="trace solves: Legendre modes per face of the additive coarse space (0 = off; 2 makes the CG iteration "
+                         "count independent of the number of blocks)")
+    ap.add_argument("--no-trace-full", dest="trace_full", action="store_false",
+                    help="skip the full config-4 trace solve (1024 blocks x 256x256 points per GPU; about two minutes of setup)")
     ap.add_argument("--no-condense", action="store_true", help="trace solves: matrix-free Schur matvec instead of static condensation")
-    ap.add_argument("--trace-large-blocks", type=int, default=64,
+    ap.add_argument("--trace-large-blocks", type=int, default=0,
                     help="blocks per GPU (a square number) of the trace solve at the operator-apply block size; 0 = skip")
     ap.add_argument("--sweep-r", type=int, default=0, help="points per thread of k_sweep (0 = heuristic)")
     ap.add_argument("--sweep-deep", type=int, default=1, help="1: css / crs windows of k_sweep in shared-memory rings, 0: in registers")

@@ -9,10 +9,11 @@ seas/BP1/BP1.jl `main` and odefun.jl).
                                    step rejection through `isoutofdomain`
 
 Integrator note.  The reference calls OrdinaryDiffEq's Tsit5, a dependency that is neither vendored nor
-pinned; its tableau is not part of the reference.  `integrate` is a Dormand-Prince 5(4)
-pair with the same controls (dt0 = one year, infinity norm, rejection callback; abstol 1e-6 / reltol 1e-3,
-which is what `solve` falls back to because BP1.jl:160 passes the unknown keywords atol / rtol).
-Parity for this path is defined against the oracle's odefun driven by this same integrator.
+pinned.  `integrate` restates it from the published tableau (Tsitouras 2011) and the
+package's documented step control (PI controller, infinity norm, dt0 = one year, rejection through
+isoutofdomain; abstol 1e-6 / reltol 1e-3, which is what `solve` falls back to because BP1.jl:160 passes the
+unknown keywords atol / rtol).  Parity for this path is defined against the oracle's odefun driven by the
+oracle's own copy of the same integrator (oracle/bp1.py).
 """
 import ctypes as C
 from dataclasses import dataclass
@@ -123,59 +124,85 @@ class Fault:
             pass
 
 
-# ---- adaptive Runge-Kutta (Dormand-Prince 5(4)) with rejection callback ------------------------------
-_C = np.array([0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1, 1])
-_A = [[],
-      [1 / 5],
-      [3 / 40, 9 / 40],
-      [44 / 45, -56 / 15, 32 / 9],
-      [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
-      [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
-      [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]]
-_B5 = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0])
-_B4 = np.array([5179 / 57600, 0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40])
+# ---- Tsit5: the integrator BP1.jl:159-161 asks OrdinaryDiffEq for --------------------------------------------------
+# Tableau of Ch. Tsitouras, "Runge-Kutta pairs of order 5(4) satisfying only the first column simplifying assumption",
+# Computers & Mathematics with Applications 62 (2011) 770-775 (the pair OrdinaryDiffEq implements as Tsit5; the package
+# itself is not vendored by the reference).  7 stages, first-same-as-last; BT = b - bhat weighs the
+# stages in the error estimate.  tests/test_oracle_bp1.py checks the order conditions and the observed order.
+TSIT5_C = np.array([0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0])
+TSIT5_A = [[],
+           [0.161],
+           [-0.008480655492356989, 0.335480655492357],
+           [2.8971530571054935, -6.359448489975075, 4.3622954328695815],
+           [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525],
+           [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383],
+           [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]]
+TSIT5_BT = np.array([-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                     0.5823571654525552, -0.45808210592918697, 0.015151515151515152])
 
 
-def integrate(rhs, y0, t0, t1, dt0, abstol=1e-6, reltol=1e-3, max_steps=10 ** 9, qmin=0.2, qmax=10.0, safety=0.9,
-              stop_on_underflow=False):
-    """Integrate y' = rhs(t, y) -> (dy, rejected).  A step is rejected when the error test fails or when any
-    stage reports `rejected` (the reference's isoutofdomain / reject_step mechanism, BP1.jl:149-159).
+def integrate(rhs, y0, t0, t1, dt0, abstol=1e-6, reltol=1e-3, max_steps=10 ** 9, qmin=0.2, qmax=10.0, gamma=0.9,
+              beta1=7.0 / 50.0, beta2=2.0 / 25.0, qoldinit=1e-4, stop_on_underflow=False, tstops=None):
+    """Integrate y' = rhs(t, y) -> (dy, rejected) with Tsit5 and the step control `solve(prob, Tsit5(); dt, isoutofdomain,
+    internalnorm = (x, _) -> norm(x, Inf))` runs with (BP1.jl:159-161):
+      * error estimate dt * sum(BT_i k_i) scaled by abstol + reltol * max(|y_old|, |y_new|), infinity norm;
+        abstol = 1e-6, reltol = 1e-3 are the package defaults (BP1.jl:160 passes the unknown keywords atol / rtol);
+      * PI step-size controller with the defaults of a 5th-order pair (beta1 = 7/50, beta2 = 2/25, gamma = 9/10, qmin = 1/5,
+        qmax = 10, steady-state band [1, 1], qoldinit = 1e-4);
+      * a step whose stages set `rejected` (the reference's reject_step flag, read by `stepcheck` = isoutofdomain,
+        BP1.jl:149-159) is redone with dt * qmin;
+      * tstops: times the integration must hit exactly (output times of the parity tests).
     Returns (ts, ys, nrejected)."""
     t, y = float(t0), np.array(y0, dtype=float)
     ts, ys = [t], [y.copy()]
     dt = float(dt0)
     nrej = 0
+    qold = qoldinit
     k1, bad = rhs(t, y)
     if bad:
         raise RuntimeError("right-hand side rejected the initial state")
+    stops = sorted(float(x) for x in tstops) if tstops is not None else []
+    si = 0
     steps = 0
     while t < t1 and steps < max_steps:
-        dt = min(dt, t1 - t)
+        while si < len(stops) and stops[si] <= t:
+            si += 1
+        tend = min(t1, stops[si]) if si < len(stops) else t1
+        clipped = dt >= tend - t
+        h = tend - t if clipped else dt
         K = [k1]
         ok = True
         for s in range(1, 7):
-            ys_ = y + dt * sum(a * k for a, k in zip(_A[s], K))
-            ks, bad = rhs(t + _C[s] * dt, ys_)
+            ys_ = y + h * sum(a * k for a, k in zip(TSIT5_A[s], K))
+            ks, bad = rhs(tend if (clipped and s >= 5) else t + TSIT5_C[s] * h, ys_)
             if bad:
                 ok = False
                 break
             K.append(ks)
-        if ok:
-            y5 = y + dt * sum(b * k for b, k in zip(_B5, K))
-            y4 = y + dt * sum(b * k for b, k in zip(_B4, K))
-            err = np.max(np.abs(y5 - y4) / (abstol + reltol * np.maximum(np.abs(y), np.abs(y5))))   # infinity norm
-            if err <= 1.0:
-                t += dt
-                y = y5
-                k1 = K[6]                      # first-same-as-last
+        if not ok:                                         # isoutofdomain: dt * qmin
+            dt = h * qmin
+            nrej += 1
+        else:
+            ynew = ys_                                     # the last stage point is the new solution (a_7j = b_j)
+            est = h * sum(b * k for b, k in zip(TSIT5_BT, K))
+            EEst = np.max(np.abs(est) / (abstol + reltol * np.maximum(np.abs(y), np.abs(ynew))))   # internalnorm = Inf norm
+            if EEst == 0.0:
+                q11, q = 0.0, 1.0 / qmax
+            else:
+                q11 = EEst ** beta1
+                q = max(1.0 / qmax, min(1.0 / qmin, (q11 / qold ** beta2) / gamma))
+            if EEst <= 1.0:
+                t = tend if clipped else t + h
+                y = ynew
+                k1 = K[6]                                  # first-same-as-last
                 ts.append(t); ys.append(y.copy())
                 steps += 1
-                dt *= min(qmax, max(qmin, safety * err ** -0.2)) if err > 0 else qmax
+                qold = max(EEst, qoldinit)
+                dtn = h / q
+                dt = max(dtn, dt) if clipped else dtn      # a step shortened to hit a stop does not shrink the next one
                 continue
-            dt *= max(qmin, safety * err ** -0.2)
-        else:
-            dt *= 0.5
-        nrej += 1
+            dt = h / min(1.0 / qmin, q11 / gamma)
+            nrej += 1
         if dt <= 4.0 * np.spacing(max(1.0, abs(t))):     # dtmin of the reference's integrator: the resolution of t (coseismic
                                                           # steps are milliseconds at t ~ 1e10 s)
             if stop_on_underflow:            # return the series up to here (the caller reports the stop time)
