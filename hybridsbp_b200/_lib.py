@@ -106,6 +106,7 @@ def lib():
         "hsbp_trace_solve": (cint, [vp, dp, dp, dp, dp, dbl, i64, vp]),
         "hsbp_bp1_create": (cint, [vp, i64, i64, i64, dp, dp, vp, C.POINTER(vp)]),
         "hsbp_bp1_destroy": (cint, [vp]),
+        "hsbp_bp1_condense": (cint, [vp, cint]),
         "hsbp_bp1_rhs": (cint, [vp, dbl, dp, dp, vp]),
         "hsbp_bp1_get_u": (cint, [vp, dp]),
     }

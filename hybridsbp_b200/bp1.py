@@ -74,7 +74,7 @@ def setup(N=200, SBPp=2, Lx=80.0, Ly=80.0):
 class Fault:
     """Device-resident BP1 right-hand side (hsbp_bp1_*)."""
 
-    def __init__(self, ctx, su: Bp1Setup, local_tol=1e-13, local_maxit=200000, local_mode=LOCAL_BAND):
+    def __init__(self, ctx, su: Bp1Setup, local_tol=1e-13, local_maxit=200000, local_mode=LOCAL_BAND, condense=True):
         self.su = su
         m = su.metrics
         self.blk = Blocks(ctx, su.p, [su.N], [su.N])
@@ -95,6 +95,11 @@ class Fault:
         self.blk._children.add(self)
         self.n = su.N + 1
         self.last_stats = None
+        # odefun needs u = M-tilde^-1 ge only through the traction on the fault: condense that map once (N + 2 local
+        # solves), every later right-hand side is one small kernel; displacement() solves on demand
+        if condense:
+            ctx._check(lib().hsbp_bp1_condense(self.h, 1))
+        self.condensed = bool(condense)
 
     def rhs(self, t, y):
         """(dy, rejected) = odefun(y, t)."""

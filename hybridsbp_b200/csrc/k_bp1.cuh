@@ -29,17 +29,14 @@ __device__ __forceinline__ void rateandstate(double V, double psi, double sigma_
 // status bits written per launch (d_flags[0] |= ...), d_flags[1] = max Newton iterations
 enum { BP1_TAU_NAN = 1, BP1_V_FAIL = 2, BP1_PSI_FAIL = 4 };
 
-// tr: HfI_FT_k u on the fault face (k_face_gather, FACE_TRACTION); tau: penalty on that face;
-// state = [psi; delta] (2 nf), out = [dpsi; V] (2 nf)
-__global__ void __launch_bounds__(128)
-k_bp1_fault(int nf, const double *__restrict__ tr, const double *__restrict__ tau, const double *__restrict__ sJ,
-            const double *__restrict__ rsa, const double *__restrict__ state, double *__restrict__ out,
-            Bp1Dev prm, int *__restrict__ flags) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nf) return;
+// One fault node: shear traction -> bracketed Newton for the slip rate -> state evolution.
+// trn: (HfI_FT_k u)_n on the fault face; state = [psi; delta] (2 nf), out = [dpsi; V] (2 nf)
+__device__ __forceinline__ void bp1_fault_node(int n, int nf, double trn, double taupen, double sJn, double a,
+                                               const double *__restrict__ state, double *__restrict__ out,
+                                               const Bp1Dev &prm, int *__restrict__ flags) {
   const double psi = state[n], delta = state[nf + n];
   // computetraction_mod: (HfI_FT u + tau (delta - delta/2)) / sJ ; odefun.jl:59
-  const double T = (tr[n] + tau[n] * (delta - delta / 2.0)) / sJ[n];
+  const double T = (trn + taupen * (delta - delta / 2.0)) / sJn;
   const double dtau = -prm.mu_shear * T;
   const double taun = dtau + prm.tau_z0;
   double Vout = 0.0, dpsi = 0.0;
@@ -47,7 +44,6 @@ k_bp1_fault(int nf, const double *__restrict__ tr, const double *__restrict__ ta
   if (isnan(taun)) {
     fl = BP1_TAU_NAN;                                                     // odefun.jl:73-78
   } else {
-    const double a = rsa[n];
     double xR = fabs(taun / prm.eta), xL = -xR;                         // odefun.jl:80-81
     double x = 0.0;                                                       // initial guess V[n] = 0 (odefun.jl:51, 82)
     double fL, fR, f, df, tmp;
@@ -84,6 +80,39 @@ k_bp1_fault(int nf, const double *__restrict__ tr, const double *__restrict__ ta
   if (fl) atomicOr(&flags[0], fl);
   if (fl) atomicAdd(&flags[2], 1);
   atomicMax(&flags[1], iters);
+}
+
+// tr: HfI_FT_k u on the fault face (k_face_gather, FACE_TRACTION); tau: penalty on that face
+__global__ void __launch_bounds__(128)
+k_bp1_fault(int nf, const double *__restrict__ tr, const double *__restrict__ tau, const double *__restrict__ sJ,
+            const double *__restrict__ rsa, const double *__restrict__ state, double *__restrict__ out,
+            Bp1Dev prm, int *__restrict__ flags) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nf) return;
+  bp1_fault_node(n, nf, tr[n], tau[n], sJ[n], rsa[n], state, out, prm, flags);
+}
+
+// The same stage with the local solve condensed onto the fault (hsbp_bp1_condense): the displacement enters odefun only
+// through the traction on the fault face, and u = M̃^-1 ge is linear in the boundary data (odefun.jl:36-43), so
+//   HfI_FT_1 u = -1/2 Tf delta - (t Vp / 2) tl,   Tf = HfI_FT_1 M̃^-1 F_1 (nf x nf),  tl = HfI_FT_1 M̃^-1 F_2 1
+// (the products assembleλmatrix forms for interface faces, global_curved.jl:759-790, here for the two Dirichlet faces
+// of the BP1 block).  One kernel: a small dense matrix-vector product per node, then the root find.  state / out live
+// in mapped host memory: no copies around the launch.
+__global__ void __launch_bounds__(64)
+k_bp1_fault_condensed(int nf, const double *__restrict__ Tf, const double *__restrict__ tl, double load,
+                      const double *__restrict__ tau, const double *__restrict__ sJ, const double *__restrict__ rsa,
+                      const double *__restrict__ state, double *__restrict__ out, Bp1Dev prm, int *__restrict__ flags) {
+  extern __shared__ double st[];                 // [psi; delta]
+  for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x) st[i] = state[i];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nf) return;
+  double s0 = 0.0, s1 = 0.0;
+  int m = 0;
+  for (; m + 1 < nf; m += 2) { s0 += Tf[n + (int64_t)nf * m] * st[nf + m]; s1 += Tf[n + (int64_t)nf * (m + 1)] * st[nf + m + 1]; }
+  if (m < nf) s0 += Tf[n + (int64_t)nf * m] * st[nf + m];
+  const double trn = -0.5 * (s0 + s1) - load * tl[n];
+  bp1_fault_node(n, nf, trn, tau[n], sJ[n], rsa[n], st, out, prm, flags);
 }
 
 // Dirichlet data of the ODE stage on the block-face vector v (zero elsewhere): fault face <- delta / 2,

@@ -272,6 +272,13 @@ typedef struct {
 int  hsbp_bp1_create(hsbp_blocks *blocks, int64_t block, int64_t fault_face, int64_t loading_face,
                      const double *a, const double *sJ, const hsbp_bp1_params *params, hsbp_bp1 **bp1);
 int  hsbp_bp1_destroy(hsbp_bp1 *bp1);
+/* Condense the local solve onto the fault (optional, after hsbp_local_setup): the displacement enters odefun only through
+ * the traction on the fault face and u = M̃^-1 ge is linear in the boundary data (odefun.jl:36-43), so
+ *   HfI_FT_f u = -1/2 Tf delta - (t Vp / 2) tl,   Tf = HfI_FT_f M̃^-1 F_f,  tl = HfI_FT_f M̃^-1 F_l 1
+ * -- the same per-block products assembleλmatrix forms (global_curved.jl:759-790), for the two Dirichlet faces of the BP1
+ * block.  Costs (fault points + 1) local solves once; afterwards hsbp_bp1_rhs is one small kernel (dense matrix-vector
+ * product + root find per node) and hsbp_bp1_get_u does the local solve on demand.  enable = 0 switches back.         */
+int  hsbp_bp1_condense(hsbp_bp1 *bp1, int enable);
 int  hsbp_bp1_rhs(hsbp_bp1 *bp1, double t, const double *psi_delta, double *dpsi_V, hsbp_bp1_stats *stats);
 int  hsbp_bp1_get_u(hsbp_bp1 *bp1, double *u);      /* displacement of the last rhs call, host array of VNp */
 
