@@ -93,8 +93,9 @@ def test_series_through_the_first_earthquake_matches_the_oracle(ctx):
       * inside the event a fixed-time comparison is ill-posed: the onset time of a frictional instability is
         exponentially sensitive (perturbing the ORACLE's own odefun output by 1e-13 relative moves V at fixed coseismic
         times by 3e-5).  There the two trajectories are compared up to a shift dt_k along the
-        trajectory, y_gpu(t_k) = y_ref(t_k) + dt_k y'_ref(t_k) + residual: slip and state residuals within 1e-6, slip rate
-        within 1e-4 (second order in dt_k / the 50 ms e-folding time of V), and the shift itself below 50 ms after 7.4e9 s."""
+        trajectory, y_gpu(t_k) = y_ref(t_k) + dt_k y'_ref(t_k) + residual: slip, state and slip-rate residuals within 1e-6
+        and the shift itself below a millisecond after 7.4e9 s.  Measured on B200: shift 3.7e-5 s, residuals 1e-14 (slip),
+        2e-13 (state), 3e-11 (slip rate); without the alignment V differs by 7e-6 at fixed coseismic times, 2e-8 before."""
     import os
     from hybridsbp_b200 import LOCAL_BAND
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "bp1", "event_N16.npz"))
@@ -126,8 +127,9 @@ def test_series_through_the_first_earthquake_matches_the_oracle(ctx):
         worst["psi"] = max(worst["psi"], np.abs(r[:n]).max() / np.abs(yr[k][:n]).max())
         worst["V"] = max(worst["V"], (np.abs(Vg[k] - Vr[k] - dt_k * Vdot[k]) / np.abs(Vr[k])).max())
     print("BP1 through the first earthquake, GPU vs oracle:", {k: float("%.3g" % v) for k, v in worst.items()})
-    assert Vr.max() > 1.0                                  # the stored series does contain the earthquake (peak 1.18 m/s)
+    assert Vr.max() > 0.5                                  # the stored series does contain the earthquake (peak 1.18 m/s between samples)
     assert worst["pre_slip"] <= 1e-6 and worst["pre_V"] <= 1e-6, worst
     assert worst["slip"] <= 1e-6 and worst["psi"] <= 1e-6, worst
-    assert worst["V"] <= 1e-4 and worst["shift"] <= 0.05, worst
+    assert worst["V"] <= 1e-6 and worst["shift"] <= 1e-3, worst
+    assert worst["fixed_time_V"] <= 1e-4, worst
     f.close()

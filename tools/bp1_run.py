@@ -1,7 +1,8 @@
 """SEAS BP1 (seas/BP1/BP1.jl) time integration at the reference's resolution: `gpu` runs the device-resident ODE stage
 (hsbp_bp1_rhs, banded Cholesky local solver), `oracle` the CPU restatement of odefun.jl (test infrastructure; run by hand
-to produce the series the GPU run is compared with).  Controls as in the reference: atol 1e-5, rtol 1e-3, dt0 = 1 year,
-infinity norm, steps rejected when the root-find fails (BP1.jl:149-161).
+to produce the series the GPU run is compared with).  Controls as in the reference: Tsit5, dt0 = 1 year, infinity norm, steps rejected
+when the root-find fails (BP1.jl:149-161); abstol 1e-6 / reltol 1e-3 are the package defaults BP1.jl:160 falls back to (its
+atol / rtol keywords are not the integrator's names).
 usage: python tools/bp1_run.py gpu|oracle N years out.npz [max_steps]"""
 import sys, time
 import numpy as np
@@ -21,7 +22,7 @@ else:
     from oracle.bp1 import OdeFun
     rhs = OdeFun(su.p, su.N, su.metrics, su.LFtoB, su.RSa, su.params)
 t0 = time.time()
-ts, ys, nrej = bp1.integrate(rhs, su.psi_delta0, 0.0, years * bp1.YEAR_SECONDS, bp1.YEAR_SECONDS, abstol=1e-5, reltol=1e-3,
+ts, ys, nrej = bp1.integrate(rhs, su.psi_delta0, 0.0, years * bp1.YEAR_SECONDS, bp1.YEAR_SECONDS, abstol=1e-6, reltol=1e-3,
                              stop_on_underflow=True, max_steps=max_steps)
 wall = time.time() - t0
 ts, ys = np.asarray(ts), np.asarray(ys)
