@@ -109,6 +109,9 @@ def lib():
         "hsbp_bp1_condense": (cint, [vp, cint]),
         "hsbp_bp1_rhs": (cint, [vp, dbl, dp, dp, vp]),
         "hsbp_bp1_get_u": (cint, [vp, dp]),
+        "hsbp_peak_fp64_fma": (cint, [vp, C.POINTER(dbl)]),
+        "hsbp_peak_fp64_dmma": (cint, [vp, C.POINTER(dbl)]),
+        "hsbp_peak_dgemm": (cint, [vp, i64, C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -132,7 +135,7 @@ class TraceStats(C.Structure):
                 ("inner_iterations_sum", C.c_int64), ("inner_iterations_max", C.c_int64),
                 ("local_solves", C.c_int64), ("true_rel_residual", C.c_double), ("failed_local_blocks", C.c_int64),
                 ("max_local_rel_residual", C.c_double), ("coarse_dofs", C.c_int64), ("issued_iterations", C.c_int64),
-                ("b_norm", C.c_double)]
+                ("b_norm", C.c_double), ("cg_loop_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -274,6 +277,16 @@ class Context:
     @property
     def world(self):
         return lib().hsbp_comm_world(self.h)
+
+    def fp64_peaks(self, dgemm_n=8192):
+        """measured fp64 denominators of this device in TFLOP/s: CUDA-core FMA, mma.sync f64, cuBLAS DGEMM"""
+        out = {}
+        for name, fn, args in (("fma", lib().hsbp_peak_fp64_fma, ()), ("dmma", lib().hsbp_peak_fp64_dmma, ()),
+                               ("dgemm", lib().hsbp_peak_dgemm, (int(dgemm_n),))):
+            v = C.c_double()
+            self._check(fn(self.h, *args, C.byref(v)))
+            out[name] = v.value
+        return out
 
     def allreduce_sum(self, x: "DeviceArray"):
         self._check(lib().hsbp_comm_allreduce_sum(self.h, x.ptr, x.n))

@@ -26,7 +26,12 @@ template <class T> int upload_vec(hsbp_ctx *ctx, T **dptr, const std::vector<T> 
 
 int upload_fx(hsbp_trace *t) { return upload_vec(t->blocks->ctx, &t->d_fx, t->h_fx); }
 
+void graph_free(hsbp_trace *t) {
+  if (t->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)t->graph_exec); t->graph_exec = nullptr; }
+}
+
 void coarse_free(hsbp_trace *t) {
+  graph_free(t);
   cudaFree(t->d_AII); cudaFree(t->d_E); cudaFree(t->d_ET); cudaFree(t->d_SG); cudaFree(t->d_gidx);
   cudaFree(t->d_bI); cudaFree(t->d_bG); cudaFree(t->d_t); cudaFree(t->d_ey); cudaFree(t->d_cG);
   cudaFree(t->d_red2_in); cudaFree(t->d_red2_out);
@@ -36,6 +41,7 @@ void coarse_free(hsbp_trace *t) {
 }
 
 void precond_free(hsbp_trace *t) {
+  graph_free(t);
   cudaFree(t->d_binv); t->d_binv = nullptr;
   t->precond_kind = HSBP_PRECOND_JACOBI;
   for (auto &x : t->h_fx) { x.binv_off = -1; x.binv_ld = 0; }
@@ -47,6 +53,8 @@ void trace_free_solver(hsbp_trace *t) {
   cudaFree(t->d_send); cudaFree(t->d_recv); cudaFree(t->d_facepart); cudaFree(t->d_part1); cudaFree(t->d_red1);
   cudaFree(t->d_state);
   if (t->h_status) cudaFreeHost(t->h_status);
+  if (t->ev_a) cudaEventDestroy((cudaEvent_t)t->ev_a);
+  if (t->ev_b) cudaEventDestroy((cudaEvent_t)t->ev_b);
 }
 
 // reduction buffers of the second all-reduce: 3 scalars + one entry per coarse dof on a cut face of the whole mesh
@@ -185,7 +193,9 @@ int precond_stages(hsbp_trace *t, int force, int zonly, double *lam, double *r, 
   hsbp_ctx *ctx = t->blocks->ctx;
   const unsigned nf = (unsigned)t->nlam_faces;
   const size_t smem = (2 * (size_t)t->max_nl + 256) * sizeof(double);
-  k_cg_update<<<nf, 256, smem, ctx->stream>>>(t->d_state, force, t->d_faces, t->d_fx, t->d_D, t->d_binv, t->d_red1 + 1, p, q, t->d_send,
+  const bool multi = ctx->world > 1;                 // a single rank reads the reduction inputs directly: nothing to sum
+  const double *red1 = multi ? t->d_red1 + 1 : t->d_red1, *red2 = multi ? t->d_red2_out : t->d_red2_in;
+  k_cg_update<<<nf, 256, smem, ctx->stream>>>(t->d_state, force, t->d_faces, t->d_fx, t->d_D, t->d_binv, red1, p, q, t->d_send,
                                               t->d_recv, lam, r, z, t->cmodes, t->d_bI, t->d_bG, t->d_facepart, t->d_red2_in);
   int rc = check_launch(ctx, "k_cg_update");
   if (rc) return rc;
@@ -196,9 +206,9 @@ int precond_stages(hsbp_trace *t, int force, int zonly, double *lam, double *r, 
                                                                                (int)nf, t->d_red2_in);
     if ((rc = check_launch(ctx, "k_cg_coarse"))) return rc;
   }
-  if ((rc = comm_allreduce(ctx, t->d_red2_in, t->d_red2_out, 3 + (size_t)(t->cmodes > 0 ? t->nGt : 0)))) return rc;
+  if (multi && (rc = comm_allreduce(ctx, t->d_red2_in, t->d_red2_out, 3 + (size_t)(t->cmodes > 0 ? t->nGt : 0)))) return rc;
   const int nGt = t->cmodes > 0 ? t->nGt : 0;
-  k_cg_scalars<<<(unsigned)std::max(1, (nGt + 7) / 8), 256, 0, ctx->stream>>>(t->d_state, force & 1, nGt, t->ldG, t->d_SG, t->d_red2_out, t->d_cG,
+  k_cg_scalars<<<(unsigned)std::max(1, (nGt + 7) / 8), 256, 0, ctx->stream>>>(t->d_state, force & 1, nGt, t->ldG, t->d_SG, red2, t->d_cG,
                                                                              t->d_status);
   if ((rc = check_launch(ctx, "k_cg_scalars"))) return rc;
   k_cg_p<<<nf, 128, 0, ctx->stream>>>(t->d_state, force & 1, zonly, t->d_faces, t->d_fx, t->cmodes, t->nI, t->nGq, t->d_t, t->d_ET, t->d_gidx,
@@ -252,6 +262,46 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
   const bool sync_mode = !t->d_S && (t->blocks->local_mode == HSBP_LOCAL_PCG || t->blocks->local_mode == HSBP_LOCAL_FDM);
   const int K = sync_mode ? 1 : std::max(1, t->cg_chunk), L = sync_mode ? 0 : std::max(0, t->cg_lookahead);
   int64_t issued = 0;
+  if (!t->ev_a) {
+    HSBP_CUDA(ctx, cudaEventCreate((cudaEvent_t *)&t->ev_a));
+    HSBP_CUDA(ctx, cudaEventCreate((cudaEvent_t *)&t->ev_b));
+  }
+  HSBP_CUDA(ctx, cudaEventRecord((cudaEvent_t)t->ev_a, ctx->stream));
+  // one iteration, enqueued: block-face products, q and the local part of p.q, exchange + reduction, the preconditioner stages
+  auto enqueue_iteration = [&]() -> int {
+    int rc_;
+    if ((rc_ = lam_blockface(t, p, 0))) return rc_;
+    k_cg_q<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_state, 0, 0, t->d_faces, t->d_fx, t->d_D, p, nullptr, t->d_ft, q, t->d_send,
+                                                             t->d_part1, t->d_red1);
+    if ((rc_ = check_launch(ctx, "k_cg_q"))) return rc_;
+    if (t->partitioned && (rc_ = exchange_vec(t))) return rc_;
+    if (ctx->world > 1 && (rc_ = comm_allreduce(ctx, t->d_red1, t->d_red1 + 1, 1))) return rc_;
+    return precond_stages(t, 0, 0, lam, r, z, p, q);
+  };
+  // With condensed blocks an iteration is a fixed sequence of kernels and NCCL calls: a chunk of K iterations is captured once
+  // into a CUDA graph and replayed (one launch per chunk instead of 6 + 3 per iteration).
+  const bool want_graph = t->d_S != nullptr && t->cg_graph != 0;
+  if (want_graph && (!t->graph_exec || t->graph_lam != lam || t->graph_K != K)) {
+    if (t->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)t->graph_exec); t->graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rcg = HSBP_OK;
+      for (int k = 0; k < K && rcg == HSBP_OK; ++k) rcg = enqueue_iteration();
+      cudaError_t ec = cudaStreamEndCapture(ctx->stream, &g);
+      cudaGraphExec_t ge = nullptr;
+      if (rcg == HSBP_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+        t->graph_exec = ge; t->graph_lam = lam; t->graph_K = K;
+      } else {
+        t->cg_graph = 0;                      // capture is not possible here (e.g. an NCCL build without graph support): plain launches
+        cudaGetLastError();
+      }
+      if (g) cudaGraphDestroy(g);
+    } else {
+      t->cg_graph = 0;
+      cudaGetLastError();
+    }
+  }
+  const bool use_graph = want_graph && t->cg_graph != 0 && t->graph_exec != nullptr;
   for (int64_t c = 0;; ++c) {
     // every rank takes this decision on the same data: the state of the iteration after (c - L) K iterations
     const int64_t seen = (c - L) * K;
@@ -263,17 +313,21 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
         HSBP_FAIL(ctx, HSBP_ERR_CUDA, "trace CG: the device stopped making progress");
       }
     }
-    for (int k = 0; k < K; ++k, ++issued) {
-      if ((rc = lam_blockface(t, p, 0))) return rc;
-      k_cg_q<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_state, 0, 0, t->d_faces, t->d_fx, t->d_D, p, nullptr, t->d_ft, q, t->d_send,
-                                                               t->d_part1, t->d_red1);
-      if ((rc = check_launch(ctx, "k_cg_q"))) return rc;
-      if (t->partitioned && (rc = exchange_vec(t))) return rc;
-      if ((rc = comm_allreduce(ctx, t->d_red1, t->d_red1 + 1, 1))) return rc;
-      if ((rc = precond_stages(t, 0, 0, lam, r, z, p, q))) return rc;
+    if (use_graph) {
+      HSBP_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)t->graph_exec, ctx->stream));
+      issued += K;
+    } else {
+      for (int k = 0; k < K; ++k, ++issued)
+        if ((rc = enqueue_iteration())) return rc;
     }
   }
+  HSBP_CUDA(ctx, cudaEventRecord((cudaEvent_t)t->ev_b, ctx->stream));
   HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    float ms = 0.f;
+    HSBP_CUDA(ctx, cudaEventElapsedTime(&ms, (cudaEvent_t)t->ev_a, (cudaEvent_t)t->ev_b));
+    st->cg_loop_ms = ms;
+  }
   HSBP_CUDA(ctx, cudaMemcpy(&h, t->d_state, sizeof(h), cudaMemcpyDeviceToHost));
   st->outer_iterations = h.iter;
   st->converged = h.converged;
@@ -300,6 +354,7 @@ int hsbp_trace_set_option(hsbp_trace *t, const char *name, int64_t value) {
   if (!name) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_set_option: null name");
   const std::string n(name);
   if (n == "cg_chunk") t->cg_chunk = (int)std::max<int64_t>(1, value);
+  else if (n == "cg_graph") t->cg_graph = value ? 1 : 0;
   else if (n == "cg_lookahead") t->cg_lookahead = (int)std::max<int64_t>(0, value);
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_set_option: unknown option " + n);
   return HSBP_OK;

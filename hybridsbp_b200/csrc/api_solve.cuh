@@ -46,7 +46,11 @@ struct hsbp_trace {
   double *d_facepart = nullptr, *d_part1 = nullptr, *d_red1 = nullptr, *d_red2_in = nullptr, *d_red2_out = nullptr;
   hsbp::CgState *d_state = nullptr;
   hsbp::CgStatus *h_status = nullptr, *d_status = nullptr;
-  int cg_chunk = 4, cg_lookahead = 1;
+  int cg_chunk = 4, cg_lookahead = 1, cg_graph = 1;
+  void *graph_exec = nullptr;           // cudaGraphExec_t of one chunk of CG iterations (condensed blocks), for graph_lam / graph_K
+  const double *graph_lam = nullptr;
+  int graph_K = 0;
+  void *ev_a = nullptr, *ev_b = nullptr;    // CUDA events around the iteration loop (hsbp_trace_stats::cg_loop_ms)
   uint64_t blocks_generation = 0;       // generation of the blocks' operator the condensed / preconditioner data belong to
 };
 

@@ -543,3 +543,4 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 #include "api_cg.cuh"
 #include "api_fdm.cuh"
 #include "api_bp1.cuh"
+#include "api_peaks.cuh"

@@ -217,7 +217,8 @@ int  hsbp_trace_coarse_setup(hsbp_trace *trace, int modes);
 int64_t hsbp_trace_coarse_size(const hsbp_trace *trace);      /* coarse dofs: this rank's interior ones + all cut-face ones */
 int  hsbp_trace_precond_apply(hsbp_trace *trace, const double *r_dev, double *z_dev);
 /* "cg_chunk" (iterations enqueued between two looks at the device's status word, default 4),
- * "cg_lookahead" (chunks the host runs ahead of the device, default 1) */
+ * "cg_lookahead" (chunks the host runs ahead of the device, default 1), "cg_graph" (1: with condensed blocks a chunk of
+ * iterations -- kernels and NCCL calls -- is captured into a CUDA graph once and replayed; 0: plain launches) */
 int  hsbp_trace_set_option(hsbp_trace *trace, const char *name, int64_t value);
 int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u (this device's blocks) */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
@@ -239,6 +240,7 @@ typedef struct {
   int64_t coarse_dofs;            /* size of the second-level problem seen by this rank, 0 = one level                   */
   int64_t issued_iterations;      /* iterations enqueued; those after convergence return at once on the device           */
   double  b_norm;                 /* ||b||                                                                               */
+  double  cg_loop_ms;             /* device time of the iteration loop alone (CUDA events on the library's stream)       */
 } hsbp_trace_stats;
 /* lambda = B^-1 (gdelta - Fbar^T M̃^-1 g), u = M̃^-1 (g - Fbar lambda)   (square_circle.jl:376-388).
  * Device-resident preconditioned CG: all scalars stay on the device, the host enqueues iterations ahead and looks at a
@@ -281,6 +283,13 @@ int  hsbp_bp1_destroy(hsbp_bp1 *bp1);
 int  hsbp_bp1_condense(hsbp_bp1 *bp1, int enable);
 int  hsbp_bp1_rhs(hsbp_bp1 *bp1, double t, const double *psi_delta, double *dpsi_V, hsbp_bp1_stats *stats);
 int  hsbp_bp1_get_u(hsbp_bp1 *bp1, double *u);      /* displacement of the last rhs call, host array of VNp */
+
+/* ---- measured fp64 denominators of the device (benchmarks; not on the solve path) -------------------------------
+ * sustained fp64 FMA rate of the CUDA cores, sustained mma.sync.m8n8k4.f64 rate (the tensor instruction of the dense and
+ * banded factorisations and of the Gauss-Jordan inversions), cuBLAS DGEMM n^3 (library number, denominator only).       */
+int  hsbp_peak_fp64_fma(hsbp_ctx *ctx, double *tflops);
+int  hsbp_peak_fp64_dmma(hsbp_ctx *ctx, double *tflops);
+int  hsbp_peak_dgemm(hsbp_ctx *ctx, int64_t n, double *tflops);
 
 #ifdef __cplusplus
 }
