@@ -5,7 +5,7 @@ libhsbp.so (include/hsbp.h).  The compute path is hand-written CUDA only; import
 this package never pulls in the CPU oracle.
 """
 from ._lib import Context, DeviceArray, HsbpError, lib, declared_symbols, LIB_PATH  # noqa: F401
-from .blocks import Blocks, Trace, LOCAL_PCG, LOCAL_CHOLESKY, LOCAL_BAND, LOCAL_FDM  # noqa: F401
+from .blocks import Blocks, SpdFactor, Trace, LOCAL_PCG, LOCAL_CHOLESKY, LOCAL_BAND, LOCAL_FDM  # noqa: F401
 
 BC_DIRICHLET = 1
 BC_NEUMANN = 2

@@ -80,6 +80,11 @@ def lib():
         "hsbp_face_traction": (cint, [vp, dp, dp]),
         "hsbp_local_setup": (cint, [vp, cint, dbl, i64]),
         "hsbp_local_solve": (cint, [vp, dp, dp, vp]),
+        "hsbp_factor_create": (cint, [vp, i64, i64p, i64p, dp, cint, C.POINTER(vp)]),
+        "hsbp_factor_destroy": (cint, [vp]),
+        "hsbp_factor_size": (i64, [vp]),
+        "hsbp_factor_solve": (cint, [vp, dp, dp, i64]),
+        "hsbp_factor_solve_dev": (cint, [vp, dp, dp]),
         "hsbp_trace_create": (cint, [vp, i64, i64p, i64p, i64p, vp, i64p, C.POINTER(vp)]),
         "hsbp_trace_destroy": (cint, [vp]),
         "hsbp_trace_num_lambda": (i64, [vp]),

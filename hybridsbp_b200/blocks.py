@@ -244,3 +244,44 @@ class Trace:
             self.close()
         except Exception:
             pass
+
+
+class SpdFactor:
+    """The reference's `factorization` plugin at its own seam (hsbp_factor_*): a device-resident banded Cholesky factor
+    of ONE assembled sparse SPD matrix, e.g. `lop[e].M̃` exactly as locoperator builds it (global_curved.jl:470-486).
+    `F.solve(g)` is the reference's `F \\ g` (global_curved.jl:734); a 1 x 1 matrix -- the probe SBPLocalOperator1 makes to
+    learn the factor type (:681) -- is fine."""
+
+    def __init__(self, ctx: Context, A):
+        import scipy.sparse as sp
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        assert A.shape[0] == A.shape[1]
+        self.ctx, self.n = ctx, A.shape[0]
+        cp, pcp = _i64(A.indptr)
+        ri, pri = _i64(A.indices)
+        nz, pnz = _f64(A.data)
+        h = C.c_void_p()
+        ctx._check(lib().hsbp_factor_create(ctx.h, self.n, pcp, pri, pnz, 0, C.byref(h)))
+        self.h = h
+        ctx._children.add(self)
+
+    def solve(self, g):
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        cols = g.reshape(self.n, -1, order="F") if g.ndim > 1 else g.reshape(self.n, 1)
+        gin = np.ascontiguousarray(cols.T)                          # right-hand sides one after the other
+        out = np.empty_like(gin)
+        self.ctx._check(lib().hsbp_factor_solve(self.h, C.c_void_p(gin.ctypes.data), C.c_void_p(out.ctypes.data), gin.shape[0]))
+        return out.T.reshape(g.shape, order="F") if g.ndim > 1 else out[0]
+
+    def close(self):
+        if self.h is not None:
+            if self.ctx.h is not None:
+                lib().hsbp_factor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -470,11 +470,7 @@ int band_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *sta
     const int nst = b->band_stream_stages;
     const size_t sm = (size_t)nst * BS_PB * b->band_maxld * 8 + (size_t)nst * BS_PB * BS_PB * 8 + (size_t)BS_WIN * 8 +
                       2 * BS_PB * 8 + nst * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-      HSBP_CUDA(ctx, cudaFuncSetAttribute(k_band_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-      attr_set = true;
-    }
+    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_band_solve_stream, ctx->smem_optin));
     k_band_solve_stream<<<(unsigned)b->nblocks, BS_THREADS, sm, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band,
                                                                                 b->d_band_inv, g, x, b->d_band_work, nst, b->band_maxld);
   } else {

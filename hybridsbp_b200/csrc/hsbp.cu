@@ -539,6 +539,7 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 #include "api_chol.cuh"
 #include "k_dense.cuh"
 #include "api_band.cuh"
+#include "api_factor.cuh"
 #include "api_solve.cuh"
 #include "api_cg.cuh"
 #include "api_fdm.cuh"

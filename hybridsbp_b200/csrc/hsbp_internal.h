@@ -15,6 +15,7 @@ struct hsbp_ctx {
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   int sm_count = 148;
   size_t smem_optin = 0;
+  std::vector<const void *> smem_optin_done;   // kernels whose dynamic shared-memory opt-in was made on THIS device
   void *comm = nullptr;             // ncclComm_t of this context (api_comm.cuh); one rank per context
   int rank = 0, world = 1;
   void *fdm_libs = nullptr;         // cuBLAS / cuSOLVER handles of the fast-diagonalisation preconditioner (api_fdm.cuh)
@@ -89,6 +90,16 @@ struct hsbp_blocks {
   double *d_stage_u = nullptr, *d_stage_y = nullptr;
   std::vector<cudaEvent_t> pipe_ev;          // per block group: H2D done, kernels done
 };
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per context which kernels have it
+template <class K> inline cudaError_t hsbp_smem_optin(hsbp_ctx *ctx, K kernel, size_t bytes) {
+  const void *key = reinterpret_cast<const void *>(kernel);
+  for (const void *k : ctx->smem_optin_done)
+    if (k == key) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) ctx->smem_optin_done.push_back(key);
+  return e;
+}
 
 #define HSBP_CUDA(ctx, call)                                                     \
   do {                                                                           \

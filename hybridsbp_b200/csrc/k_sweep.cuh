@@ -1165,14 +1165,10 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
   const size_t sm = sweep_smem<P>(Nrp, DEEP);
-  static void (*attr_set_for)(const SweepParams) = nullptr;
-  static int ctas_per_sm = 1;
-  if (attr_set_for != kern) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
-      ctx->err = "cudaFuncSetAttribute(max dynamic shared memory) failed";
-      return HSBP_ERR_CUDA;
-    }
-    attr_set_for = kern;
+  int ctas_per_sm = 1;
+  if (hsbp_smem_optin(ctx, kern, ctx->smem_optin) != cudaSuccess) {
+    ctx->err = "cudaFuncSetAttribute(max dynamic shared memory) failed";
+    return HSBP_ERR_CUDA;
   }
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, nthreads, sm) != cudaSuccess || ctas_per_sm < 1)
     ctas_per_sm = 1;

@@ -151,6 +151,23 @@ typedef struct {
 int  hsbp_local_setup(hsbp_blocks *blocks, int mode, double tol, int64_t maxit);
 int  hsbp_local_solve(hsbp_blocks *blocks, const double *g_dev, double *u_dev, hsbp_local_stats *stats);
 
+/* ---- the `factorization` plugin at the reference's own seam -------------------------------------------------------
+ * reference: SBPLocalOperator1 calls `factorization(lop[e].M̃)` on the ASSEMBLED sparse matrix of every block, after
+ * probing the plugin with a 1 x 1 matrix to learn the factor type (global_curved.jl:681, 698; plugin supplied as
+ * x -> cholesky(Symmetric(x)) at square_circle.jl:299, BP1.jl:78); later it only uses `F \ g` (:734,
+ * square_circle.jl:383, odefun.jl:43) and `F' \ S` (:774).  hsbp_factor is that object for a host that keeps the
+ * reference's assembly: one symmetric positive definite matrix given by its CSC arrays (index_base 1: straight from
+ * the reference's host language; only the lower triangle is read), stored as a band -- with points numbered r-fastest
+ * M̃_e is banded -- and factorised on the device with the banded Cholesky kernels (DMMA trailing update).  Any size from
+ * the 1 x 1 probe upwards.  hsbp_factor_solve: nrhs right-hand sides one after the other, host arrays.               */
+typedef struct hsbp_factor hsbp_factor;
+int  hsbp_factor_create(hsbp_ctx *ctx, int64_t n, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                        int index_base, hsbp_factor **factor);
+int  hsbp_factor_destroy(hsbp_factor *factor);
+int64_t hsbp_factor_size(const hsbp_factor *factor);
+int  hsbp_factor_solve(hsbp_factor *factor, const double *g, double *u, int64_t nrhs);
+int  hsbp_factor_solve_dev(hsbp_factor *factor, const double *g_dev, double *u_dev);
+
 /* ---- trace (lambda) operators and Schur-complement solve ------------------------------------
  * reference: gloλoperator (global_curved.jl:510-565) builds FToλstarts, the sparse Fbar^T and the
  * diagonal D; assembleλmatrix (:743-797) forms B = D - Fbar^T M̃^-1 Fbar explicitly and
