@@ -213,10 +213,8 @@ def run_ours(args):
                 FToB[EToF[0, 0 + nbx * by] - 1] = 0
             if rank < world - 1:
                 FToB[EToF[1, nbx - 1 + nbx * by] - 1] = 0
-    crr, css, crs = synthetic.warped_coefficients(nbx, nby, N, L=Lglob, A=Lglob / 40.0, bx0=rank * nbx)
     blk = hs.Blocks(ctx, p, [N] * args.blocks, [N] * args.blocks)
-    blk.set_metrics(crr, css, crs)
-    del crr, css, crs
+    blk.set_synthetic_warp(nbx, rank * nbx, Lglob, Lglob / 40.0)      # metrics generated on the device (hsbp_blocks_set_synthetic_warp)
     blk.set_bc(synthetic.block_bcs(EToF, FToB))
     blk.compute_tau(2.0)
     blk.set_option("sweep_points_per_thread", args.sweep_r)

@@ -65,6 +65,9 @@ def lib():
         "hsbp_blocks_num_face_points": (i64, [vp]),
         "hsbp_blocks_set_metrics": (cint, [vp, dp, dp, dp]),
         "hsbp_blocks_set_metrics_dev": (cint, [vp, dp, dp, dp]),
+        "hsbp_blocks_blend_dev": (cint, [vp, dp, dp, dp, dp]),
+        "hsbp_blocks_set_geometry_dev": (cint, [vp, dp, dp, dp, dp, dp, dp, dp, dp]),
+        "hsbp_blocks_set_synthetic_warp": (cint, [vp, i64, i64, dbl, dbl, dp, dp]),
         "hsbp_blocks_set_bc": (cint, [vp, i64p]),
         "hsbp_blocks_compute_tau": (cint, [vp, dbl]),
         "hsbp_blocks_set_tau": (cint, [vp, dp]),

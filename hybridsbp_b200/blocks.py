@@ -54,6 +54,24 @@ class Blocks:
     def set_metrics_dev(self, crr: DeviceArray, css: DeviceArray, crs: DeviceArray):
         self.ctx._check(lib().hsbp_blocks_set_metrics_dev(self.h, crr.ptr, css.ptr, crs.ptr))
 
+    # -- geometry on the device (transfinite_blend / create_metrics, global_curved.jl:19-51, 136-209) ----------
+    def blend_dev(self, edges: DeviceArray, x: DeviceArray, xr: DeviceArray, xs: DeviceArray):
+        """x, x_r, x_s of every block from its edge curves: `edges` holds per block [a1 | a2 | a3 | a4] sampled at the grid
+        points followed by [a1' | a2' | a3' | a4'] (2 * FNp doubles in all)"""
+        assert edges.n == 2 * self.FNp
+        self.ctx._check(lib().hsbp_blocks_blend_dev(self.h, edges.ptr, x.ptr, xr.ptr, xs.ptr))
+
+    def set_geometry_dev(self, xr, xs, yr, ys, J=None, sJ=None, nx=None, ny=None):
+        """create_metrics on the device: coefficient fields from the derivatives of the block maps; optional outputs J
+        (volume layout) and sJ, nx, ny (block-face layout)"""
+        P = lambda a: a.ptr if a is not None else None
+        self.ctx._check(lib().hsbp_blocks_set_geometry_dev(self.h, xr.ptr, xs.ptr, yr.ptr, ys.ptr, P(J), P(sJ), P(nx), P(ny)))
+
+    def set_synthetic_warp(self, nbx, bx0, L, A, x=None, y=None):
+        """metrics of the synthetic warped multiblock mesh generated on the device"""
+        P = lambda a: a.ptr if a is not None else None
+        self.ctx._check(lib().hsbp_blocks_set_synthetic_warp(self.h, int(nbx), int(bx0), float(L), float(A), P(x), P(y)))
+
     def set_bc(self, bctype):
         a, pa = _i64(np.asarray(bctype).reshape(-1))
         assert a.size == 4 * self.nblocks

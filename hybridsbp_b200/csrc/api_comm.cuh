@@ -124,6 +124,17 @@ int hsbp_comm_init(hsbp_ctx *ctx, const void *id128, int rank, int world) {
   ncclComm_t comm = nullptr;
   HSBP_NCCL(ctx, g_nccl.CommInitRank(&comm, world, id, rank));
   ctx->comm = comm; ctx->rank = rank; ctx->world = world;
+  // NCCL sets its channels up lazily, at the first collective (seconds on 8 GPUs): pay that here, not inside the first solve
+  if (world > 1) {
+    double *d = nullptr;
+    HSBP_CUDA(ctx, cudaMalloc((void **)&d, 2 * sizeof(double)));
+    HSBP_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(double), ctx->stream));
+    int rc = comm_allreduce(ctx, d, d + 1, 1);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) { ctx->err = std::string("hsbp_comm_init: ") + cudaGetErrorString(e); return HSBP_ERR_CUDA; }
+  }
   return HSBP_OK;
 }
 

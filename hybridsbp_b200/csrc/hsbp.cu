@@ -535,6 +535,7 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 
 }  // extern "C"
 
+#include "api_geom.cuh"
 #include "api_comm.cuh"
 #include "api_chol.cuh"
 #include "k_dense.cuh"

@@ -15,7 +15,7 @@ class StripProblem:
     """One rank's part of the strip mesh on its GPU: blocks, trace, right-hand sides (device arrays of the library)."""
 
     def __init__(self, ctx, rank, world, nbx, nby, N, p, local_mode=None, local_tol=1e-13, seed=1234, condense=True,
-                 fdm_gemm=3, face_blocks=None, coarse_modes=2, timings=None):
+                 fdm_gemm=3, face_blocks=None, coarse_modes=2, timings=None, device_geometry=True):
         tm = {} if timings is None else timings
         t0 = time.perf_counter()
         gnbx = nbx * world
@@ -25,11 +25,14 @@ class StripProblem:
         owner = (np.arange(ne) % gnbx) // nbx
         lm = parallel.localize(rank, owner, EToF, FToB, FToE, FToLF, EToO, EToS)
         L = float(max(gnbx, nby))
-        crr, css, crs = synthetic.warped_coefficients(nbx, nby, N, L=L, A=L / 40.0, bx0=rank * nbx)
         nloc = len(lm.blocks)
         blk = Blocks(ctx, p, [N] * nloc, [N] * nloc)
-        blk.set_metrics(crr, css, crs)
-        del crr, css, crs
+        if device_geometry:                   # metrics of the analytic warp generated on the device: nothing crosses PCIe
+            blk.set_synthetic_warp(nbx, rank * nbx, L, L / 40.0)
+        else:
+            crr, css, crs = synthetic.warped_coefficients(nbx, nby, N, L=L, A=L / 40.0, bx0=rank * nbx)
+            blk.set_metrics(crr, css, crs)
+            del crr, css, crs
         blk.set_bc(lm.FToB[lm.EToF - 1].T.reshape(-1))
         blk.compute_tau(2.0)
         ctx.sync()

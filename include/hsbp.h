@@ -88,6 +88,20 @@ int  hsbp_blocks_set_metrics(hsbp_blocks *blocks, const double *crr, const doubl
 /* same, from device memory (e.g. synthetic meshes generated on the device) */
 int  hsbp_blocks_set_metrics_dev(hsbp_blocks *blocks, const double *crr_dev,
                                  const double *css_dev, const double *crs_dev);
+/* Geometry on the device.  The reference evaluates transfinite_blend (global_curved.jl:19-51) and
+ * create_metrics (:136-209) on the host with callbacks per block; here the host supplies only the O(N) edge data:
+ *   hsbp_blocks_blend_dev         x, x_r, x_s of every block from its four edge curves sampled at the grid points; edges_dev
+ *                                 holds per block [a1(s_j) | a2(s_j) | a3(r_i) | a4(r_i)] followed by the same four for the
+ *                                 derivatives a1', a2', a3', a4' (twice the block-face layout); corner consistency as :25
+ *   hsbp_blocks_set_geometry_dev  create_metrics: J (> 0 asserted, :157), crr / css / crs into the blocks' coefficient fields
+ *                                 from x_r, x_s, y_r, y_s; optional outputs J (volume layout) and sJ, nx, ny (block-face
+ *                                 layout, :166-200) -- pass NULL to skip
+ *   hsbp_blocks_set_synthetic_warp  the analytic warped mesh of SURVEY.md section 8d for blocks numbered bx + nbx * by, block
+ *                                 columns bx0 .. bx0 + nbx - 1 of a mesh whose warp period is L: nothing crosses PCIe       */
+int  hsbp_blocks_blend_dev(hsbp_blocks *blocks, const double *edges_dev, double *x_dev, double *xr_dev, double *xs_dev);
+int  hsbp_blocks_set_geometry_dev(hsbp_blocks *blocks, const double *xr_dev, const double *xs_dev, const double *yr_dev,
+                                  const double *ys_dev, double *J_dev, double *sJ_dev, double *nx_dev, double *ny_dev);
+int  hsbp_blocks_set_synthetic_warp(hsbp_blocks *blocks, int64_t nbx, int64_t bx0, double L, double A, double *x_dev, double *y_dev);
 /* LFToB of every block: 4 * nblocks codes (argument LFToB of locoperator, :212) */
 int  hsbp_blocks_set_bc(hsbp_blocks *blocks, const int64_t *bctype);
 /* penalty tau_1..4 on the device as global_curved.jl:418-437 (psi_min, l nearest lines) */

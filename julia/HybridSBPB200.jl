@@ -14,13 +14,27 @@
 #     HybridSBPB200.set_bc!(blk, LFToB)                                # 4 x nelems Int matrix
 #     HybridSBPB200.compute_tau!(blk, 2.0)                             # global_curved.jl:418-437
 #     tr  = HybridSBPB200.Trace(blk, FToB, FToE, FToLF, EToO, EToS)    # connectivityarrays' outputs, 1-based
+#     HybridSBPB200.local_setup!(blk; mode = HybridSBPB200.LOCAL_BAND)
+#     HybridSBPB200.condense!(tr); HybridSBPB200.precond_setup!(tr); HybridSBPB200.coarse_setup!(tr; modes = 2)
 #     λ, u, stats = HybridSBPB200.trace_solve(tr, g, gδ; tol = 1e-10)  # square_circle.jl:376-388
+#
+# or, leaving the reference's assembly and drivers untouched, only swap the plugin (square_circle.jl:297-299):
+#
+#     OPTYPE = typeof(HybridSBPB200.b200_factorization(ctx)(sparse([1], [1], [1.0])))
+#     (M, FbarT, D, vstarts, FToλstarts) = LocalGlobalOperators(lop, Nr, Ns, FToB, FToE, FToLF, EToO, EToS,
+#                                                               HybridSBPB200.b200_factorization(ctx))
+#
+# Lifetime.  The C objects keep raw pointers to their parents (trace -> blocks -> context).  Every wrapper therefore
+# (a) holds a reference to its parent, so the parent is never collected first while the child is reachable, and
+# (b) registers itself with the parent; `close(parent)` closes the children first, finalizers only call `close`, and
+# `close` is idempotent -- the order in which the garbage collector runs finalizers no longer matters.
 #
 module HybridSBPB200
 
 using LinearAlgebra
+using SparseArrays
 import LinearAlgebra: Factorization
-import Base: \, size
+import Base: \, size, close, adjoint
 
 const libhsbp = get(ENV, "HSBP_LIB", joinpath(@__DIR__, "..", "hybridsbp_b200", "libhsbp.so"))
 
@@ -29,15 +43,34 @@ struct HsbpError <: Exception
   msg::String
 end
 
+# children are kept as weak references: registering must not keep them alive
+register!(parent, child) = (push!(parent.children, WeakRef(child)); child)
+function close_children!(parent)
+  for w in parent.children
+    c = w.value
+    c === nothing || close(c)
+  end
+  empty!(parent.children)
+end
+
 mutable struct Context
   h::Ptr{Cvoid}
+  children::Vector{WeakRef}
   function Context(device::Integer = 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:hsbp_ctx_create, libhsbp), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h)
     rc == 0 || throw(HsbpError(rc, "hsbp_ctx_create failed (a B200 / sm_100 GPU is required; no CPU fallback)"))
-    ctx = new(h[])
-    finalizer(c -> ccall((:hsbp_ctx_destroy, libhsbp), Cint, (Ptr{Cvoid},), c.h), ctx)
+    ctx = new(h[], WeakRef[])
+    finalizer(close, ctx)
   end
+end
+"destroy the context after everything created on it (blocks, traces, factors, device vectors)"
+function close(c::Context)
+  c.h == C_NULL && return
+  close_children!(c)
+  ccall((:hsbp_ctx_destroy, libhsbp), Cint, (Ptr{Cvoid},), c.h)
+  c.h = C_NULL
+  nothing
 end
 
 lasterror(ctx::Context) = unsafe_string(ccall((:hsbp_last_error, libhsbp), Cstring, (Ptr{Cvoid},), ctx.h))
@@ -51,9 +84,15 @@ mutable struct DeviceVector
   function DeviceVector(ctx::Context, n::Integer)
     p = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx, ccall((:hsbp_malloc, libhsbp), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.h, 8n, p))
-    v = new(ctx, p[], n)
-    finalizer(x -> ccall((:hsbp_free, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, x.ptr), v)
+    v = register!(ctx, new(ctx, p[], n))
+    finalizer(close, v)
   end
+end
+function close(v::DeviceVector)
+  (v.ptr == C_NULL || v.ctx.h == C_NULL) && (v.ptr = C_NULL; return)
+  ccall((:hsbp_free, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.ctx.h, v.ptr)
+  v.ptr = C_NULL
+  nothing
 end
 function DeviceVector(ctx::Context, a::AbstractVector{Float64})
   v = DeviceVector(ctx, length(a)); upload!(v, a); v
@@ -76,15 +115,24 @@ mutable struct Blocks
   Nr::Vector{Int64}
   Ns::Vector{Int64}
   vstarts::Vector{Int64}     # 1-based, as SBPLocalOperator1 builds it (global_curved.jl:685-686)
+  children::Vector{WeakRef}
   function Blocks(ctx::Context, p::Integer, Nr::Vector{<:Integer}, Ns::Vector{<:Integer})
     h = Ref{Ptr{Cvoid}}(C_NULL)
     nr, ns = Int64.(Nr), Int64.(Ns)
     check(ctx, ccall((:hsbp_blocks_create, libhsbp), Cint,
                      (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
                      ctx.h, p, length(nr), nr, ns, h))
-    b = new(ctx, h[], p, nr, ns, cumsum([1; (nr .+ 1) .* (ns .+ 1)]))
-    finalizer(x -> ccall((:hsbp_blocks_destroy, libhsbp), Cint, (Ptr{Cvoid},), x.h), b)
+    b = register!(ctx, new(ctx, h[], p, nr, ns, cumsum([1; (nr .+ 1) .* (ns .+ 1)]), WeakRef[]))
+    finalizer(close, b)
   end
+end
+"destroy the blocks after the traces / BP1 stages built on them"
+function close(b::Blocks)
+  b.h == C_NULL && return
+  close_children!(b)
+  b.ctx.h == C_NULL || ccall((:hsbp_blocks_destroy, libhsbp), Cint, (Ptr{Cvoid},), b.h)
+  b.h = C_NULL
+  nothing
 end
 num_volume_points(b::Blocks) = ccall((:hsbp_blocks_num_volume_points, libhsbp), Int64, (Ptr{Cvoid},), b.h)
 num_face_points(b::Blocks) = ccall((:hsbp_blocks_num_face_points, libhsbp), Int64, (Ptr{Cvoid},), b.h)
@@ -150,7 +198,7 @@ function local_solve!(u::DeviceVector, b::Blocks, g::DeviceVector)
                      b.h, g.ptr, u.ptr, st))
   st[]
 end
-"All-blocks solve as one Factorization: `F \\ g` with g the concatenated volume vector."
+"All-blocks solve as one Factorization: `F \\ g` with g the concatenated volume vector (matrix-free operator inside)."
 struct B200LocalSolve <: Factorization{Float64}
   blocks::Blocks
 end
@@ -158,8 +206,51 @@ size(F::B200LocalSolve) = (n = num_volume_points(F.blocks); (n, n))
 function \(F::B200LocalSolve, g::AbstractVector{Float64})
   dg = DeviceVector(F.blocks.ctx, collect(g)); du = DeviceVector(F.blocks.ctx, length(g))
   st = local_solve!(du, F.blocks, dg)
-  st.failed_blocks == 0 || @warn "local PCG did not converge on $(st.failed_blocks) blocks" st
+  st.failed_blocks == 0 || error("local solve did not converge on $(st.failed_blocks) blocks: $(st)")
   download(du)
+end
+
+# The plugin itself, at the reference's seam: `factorization(x::SparseMatrixCSC)` -> an object `<: Factorization` with
+# `F \ v` (global_curved.jl:734, square_circle.jl:383, odefun.jl:43) and `F' \ S` (global_curved.jl:774).
+# SBPLocalOperator1 first calls the plugin on `sparse([1], [1], [1.0])` and takes `typeof` of the result as the element
+# type of `factors` (global_curved.jl:681): the 1 x 1 probe goes through the same code path and yields the same type.
+mutable struct B200Factorization <: Factorization{Float64}
+  ctx::Context
+  h::Ptr{Cvoid}
+  n::Int
+  function B200Factorization(ctx::Context, A::SparseMatrixCSC{Float64,<:Integer})
+    n = size(A, 1)
+    n == size(A, 2) || throw(DimensionMismatch("matrix is not square"))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:hsbp_factor_create, libhsbp), Cint,
+                     (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
+                     ctx.h, n, Int64.(A.colptr), Int64.(A.rowval), A.nzval, 1, h))      # 1-based arrays, untouched
+    F = register!(ctx, new(ctx, h[], n))
+    finalizer(close, F)
+  end
+end
+B200Factorization(ctx::Context, A::Symmetric) = B200Factorization(ctx, sparse(A))
+function close(F::B200Factorization)
+  F.h == C_NULL && return
+  F.ctx.h == C_NULL || ccall((:hsbp_factor_destroy, libhsbp), Cint, (Ptr{Cvoid},), F.h)
+  F.h = C_NULL
+  nothing
+end
+"`factorization = b200_factorization(ctx)` in place of `x -> cholesky(Symmetric(x))` (square_circle.jl:299, BP1.jl:78)"
+b200_factorization(ctx::Context) = x -> B200Factorization(ctx, x)
+size(F::B200Factorization) = (F.n, F.n)
+adjoint(F::B200Factorization) = F                                   # symmetric: F' \ S is F \ S (global_curved.jl:774)
+function \(F::B200Factorization, g::AbstractVector{<:Real})
+  gin = Vector{Float64}(g)                                          # views (global_curved.jl:734) are copied out
+  u = similar(gin)
+  check(F.ctx, ccall((:hsbp_factor_solve, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), F.h, gin, u, 1))
+  u
+end
+function \(F::B200Factorization, S::AbstractMatrix{<:Real})          # sparse or dense block of right-hand sides -> dense
+  G = Matrix{Float64}(S)
+  U = similar(G)
+  check(F.ctx, ccall((:hsbp_factor_solve, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), F.h, G, U, size(G, 2)))
+  U
 end
 
 # ---- trace (λ) operators and the Schur-complement solve (global_curved.jl:510-565, 730-797) --------------
@@ -173,23 +264,37 @@ mutable struct Trace
                        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
                        b.h, length(FToB), Int64.(FToB), Int64.(vec(FToE)), Int64.(vec(FToLF)),
                        UInt8.(vec(EToO)), Int64.(vec(EToS)), h))
-    t = new(b, h[])
-    finalizer(x -> ccall((:hsbp_trace_destroy, libhsbp), Cint, (Ptr{Cvoid},), x.h), t)
+    t = register!(b, new(b, h[]))
+    finalizer(close, t)
   end
+end
+function close(t::Trace)
+  t.h == C_NULL && return
+  (t.blocks.h == C_NULL || t.blocks.ctx.h == C_NULL) || ccall((:hsbp_trace_destroy, libhsbp), Cint, (Ptr{Cvoid},), t.h)
+  t.h = C_NULL
+  nothing
 end
 num_lambda(t::Trace) = ccall((:hsbp_trace_num_lambda, libhsbp), Int64, (Ptr{Cvoid},), t.h)
 function FToλstarts(t::Trace, nfaces::Integer)
   s = Vector{Int64}(undef, nfaces + 1)
   check(t.blocks.ctx, ccall((:hsbp_trace_get_starts, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Int64}), t.h, s)); s
 end
-struct TraceStats
+struct TraceStats                  # layout of hsbp_trace_stats
   outer_iterations::Int64
   converged::Int64
   rel_residual::Float64
   inner_iterations_sum::Int64
   inner_iterations_max::Int64
   local_solves::Int64
+  true_rel_residual::Float64
+  failed_local_blocks::Int64
+  max_local_rel_residual::Float64
+  coarse_dofs::Int64
+  issued_iterations::Int64
+  b_norm::Float64
+  cg_loop_ms::Float64
 end
+TraceStats() = TraceStats(0, 0, 0.0, 0, 0, 0, 0.0, 0, 0.0, 0, 0, 0.0, 0.0)
 "form the dense per-block S_e = F_eᵀ M̃_e⁻¹ F_e (assembleλmatrix's products, global_curved.jl:759-790); later solves use them"
 condense!(t::Trace; enable::Bool = true) =
   check(t.blocks.ctx, ccall((:hsbp_trace_condense, libhsbp), Cint, (Ptr{Cvoid}, Cint), t.h, enable ? 1 : 0))
@@ -199,6 +304,38 @@ const PRECOND_FACE_BLOCKS = 1
 "preconditioner of the CG on B: D, or the exact diagonal blocks B_ff (needs condense!)"
 precond_setup!(t::Trace; kind::Integer = PRECOND_FACE_BLOCKS) =
   check(t.blocks.ctx, ccall((:hsbp_trace_precond_setup, libhsbp), Cint, (Ptr{Cvoid}, Cint), t.h, kind))
+"second level: `modes` Legendre polynomials per face (0 = off); makes the CG iteration count independent of the number of blocks"
+coarse_setup!(t::Trace; modes::Integer = 2) =
+  check(t.blocks.ctx, ccall((:hsbp_trace_coarse_setup, libhsbp), Cint, (Ptr{Cvoid}, Cint), t.h, modes))
+set_option!(t::Trace, name::AbstractString, value::Integer) =
+  check(t.blocks.ctx, ccall((:hsbp_trace_set_option, libhsbp), Cint, (Ptr{Cvoid}, Cstring, Int64), t.h, name, value))
+function last_local_stats(t::Trace)
+  st = Ref(LocalStats(0, 0, 0, 0.0))
+  check(t.blocks.ctx, ccall((:hsbp_trace_last_local_stats, libhsbp), Cint, (Ptr{Cvoid}, Ref{LocalStats}), t.h, st))
+  st[]
+end
+
+# ---- multi-GPU: one Context per device = one NCCL rank; the library does every exchange (SURVEY.md section 8e) ----------
+"128 bytes made by one rank; hand them to every other rank (MPI.jl, sockets, a file ...) and call comm_init! everywhere"
+function comm_unique_id()
+  id = Vector{UInt8}(undef, 128)
+  rc = ccall((:hsbp_comm_unique_id, libhsbp), Cint, (Ptr{UInt8},), id)
+  rc == 0 || throw(HsbpError(rc, "hsbp_comm_unique_id failed (NCCL not loadable?)"))
+  id
+end
+comm_init!(ctx::Context, id::Vector{UInt8}, rank::Integer, world::Integer) =
+  check(ctx, ccall((:hsbp_comm_init, libhsbp), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), ctx.h, id, rank, world))
+"""
+    set_partition!(t, faces, partner, gamma, n_gamma_total)
+
+After `Trace(...)` on the LOCAL connectivity of this rank's blocks (FToE = 0 for the side of a face that lives on another
+rank): `faces[c]` 1-based local id of cut face c, `partner[c]` the rank holding its other side, `gamma[c]` its 0-based
+index among all cut faces of the mesh.  Every rank calls it (also with no cut faces); afterwards condense!, precond_setup!,
+coarse_setup! and trace_solve are collective.
+"""
+set_partition!(t::Trace, faces::Vector{<:Integer}, partner::Vector{<:Integer}, gamma::Vector{<:Integer}, n_gamma_total::Integer) =
+  check(t.blocks.ctx, ccall((:hsbp_trace_set_partition, libhsbp), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
+                            t.h, length(faces), Int64.(faces), Int64.(partner), Int64.(gamma), n_gamma_total))
 
 # ---- SEAS BP1 ODE stage: replaces the body of odefun (seas/BP1/odefun.jl:8-121) ---------------------------
 struct Bp1Params            # layout of hsbp_bp1_params
@@ -217,10 +354,19 @@ mutable struct Bp1Stage
     check(b.ctx, ccall((:hsbp_bp1_create, libhsbp), Cint,
                        (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Bp1Params}, Ref{Ptr{Cvoid}}),
                        b.h, block, fault_face, loading_face, RSa, sJ, Ref(prm), h))
-    s = new(b, h[])
-    finalizer(x -> ccall((:hsbp_bp1_destroy, libhsbp), Cint, (Ptr{Cvoid},), x.h), s)
+    s = register!(b, new(b, h[]))
+    finalizer(close, s)
   end
 end
+function close(s::Bp1Stage)
+  s.h == C_NULL && return
+  (s.blocks.h == C_NULL || s.blocks.ctx.h == C_NULL) || ccall((:hsbp_bp1_destroy, libhsbp), Cint, (Ptr{Cvoid},), s.h)
+  s.h = C_NULL
+  nothing
+end
+"condense the local solve onto the fault (N + 2 local solves once): every later odefun! is one small kernel"
+condense!(s::Bp1Stage; enable::Bool = true) =
+  check(s.blocks.ctx, ccall((:hsbp_bp1_condense, libhsbp), Cint, (Ptr{Cvoid}, Cint), s.h, enable ? 1 : 0))
 """
     odefun!(dψV, ψδ, p, t)   with p = (stage = Bp1Stage, reject_step = [false])
 
@@ -248,7 +394,7 @@ function trace_solve(t::Trace, g::Vector{Float64}, gδ::Vector{Float64}; tol = 1
   ctx = t.blocks.ctx
   dg, dgd = DeviceVector(ctx, g), DeviceVector(ctx, gδ)
   dl, du = DeviceVector(ctx, length(gδ)), DeviceVector(ctx, length(g))
-  st = Ref(TraceStats(0, 0, 0.0, 0, 0, 0))
+  st = Ref(TraceStats())
   check(ctx, ccall((:hsbp_trace_solve, libhsbp), Cint,
                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ref{TraceStats}),
                    t.h, dg.ptr, dgd.ptr, dl.ptr, du.ptr, tol, maxit, st))
