@@ -220,11 +220,11 @@ int trace_large_smem(hsbp_trace *t) {
   hsbp_ctx *ctx = t->blocks->ctx;
   const size_t smem = (2 * (size_t)t->max_nl + 256) * sizeof(double);
   if (smem > 200 * 1024) HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "trace solve: faces with more than 12 000 points are not supported");
-  HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_cg_update, ctx->smem_optin));
+  HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_cg_update, std::max<size_t>(smem, 48 * 1024)));      // (these kernels also have static shared memory)
   const size_t s2 = (size_t)t->max_nf * sizeof(double);
   if (s2 > 200 * 1024) HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "trace solve: blocks with more than 25 000 face points are not supported");
-  HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_cg_gemv, ctx->smem_optin));
-  HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_cond_gemv, ctx->smem_optin));
+  HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_cg_gemv, std::max<size_t>(s2, 48 * 1024)));
+  HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_cond_gemv, std::max<size_t>(s2, 48 * 1024)));
   return HSBP_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/hsbp.h"
@@ -15,7 +16,7 @@ struct hsbp_ctx {
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   int sm_count = 148;
   size_t smem_optin = 0;
-  std::vector<const void *> smem_optin_done;   // kernels whose dynamic shared-memory opt-in was made on THIS device
+  std::vector<std::pair<const void *, size_t>> smem_optin_done;   // kernels whose dynamic shared-memory opt-in was made on THIS device
   void *comm = nullptr;             // ncclComm_t of this context (api_comm.cuh); one rank per context
   int rank = 0, world = 1;
   void *fdm_libs = nullptr;         // cuBLAS / cuSOLVER handles of the fast-diagonalisation preconditioner (api_fdm.cuh)
@@ -94,10 +95,15 @@ struct hsbp_blocks {
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per context which kernels have it
 template <class K> inline cudaError_t hsbp_smem_optin(hsbp_ctx *ctx, K kernel, size_t bytes) {
   const void *key = reinterpret_cast<const void *>(kernel);
-  for (const void *k : ctx->smem_optin_done)
-    if (k == key) return cudaSuccess;
+  for (auto &k : ctx->smem_optin_done)
+    if (k.first == key) {
+      if (k.second >= bytes) return cudaSuccess;
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e == cudaSuccess) k.second = bytes;
+      return e;
+    }
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) ctx->smem_optin_done.push_back(key);
+  if (e == cudaSuccess) ctx->smem_optin_done.push_back({key, bytes});
   return e;
 }
 
