@@ -117,6 +117,10 @@ def lib():
         "hsbp_bp1_condense": (cint, [vp, cint]),
         "hsbp_bp1_rhs": (cint, [vp, dbl, dp, dp, vp]),
         "hsbp_bp1_get_u": (cint, [vp, dp]),
+        "hsbp_fault_create": (cint, [vp, i64, dp, dp, dp, vp, C.POINTER(vp)]),
+        "hsbp_fault_destroy": (cint, [vp]),
+        "hsbp_fault_rhs": (cint, [vp, dbl, dp, dp, vp]),
+        "hsbp_fault_stage": (cint, [vp, dp, dp, dp, vp]),
         "hsbp_peak_fp64_fma": (cint, [vp, C.POINTER(dbl)]),
         "hsbp_peak_fp64_dmma": (cint, [vp, C.POINTER(dbl)]),
         "hsbp_peak_dgemm": (cint, [vp, i64, C.POINTER(dbl)]),

@@ -545,4 +545,5 @@ int hsbp_face_F_add(hsbp_blocks *b, const double *v_dev, double alpha, double *y
 #include "api_cg.cuh"
 #include "api_fdm.cuh"
 #include "api_bp1.cuh"
+#include "api_fault.cuh"
 #include "api_peaks.cuh"

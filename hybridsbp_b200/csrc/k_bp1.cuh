@@ -30,14 +30,10 @@ __device__ __forceinline__ void rateandstate(double V, double psi, double sigma_
 enum { BP1_TAU_NAN = 1, BP1_V_FAIL = 2, BP1_PSI_FAIL = 4 };
 
 // One fault node: shear traction -> bracketed Newton for the slip rate -> state evolution.
-// trn: (HfI_FT_k u)_n on the fault face; state = [psi; delta] (2 nf), out = [dpsi; V] (2 nf)
-__device__ __forceinline__ void bp1_fault_node(int n, int nf, double trn, double taupen, double sJn, double a,
-                                               const double *__restrict__ state, double *__restrict__ out,
-                                               const Bp1Dev &prm, int *__restrict__ flags) {
-  const double psi = state[n], delta = state[nf + n];
-  // computetraction_mod: (HfI_FT u + tau (delta - delta/2)) / sJ ; odefun.jl:59
-  const double T = (trn + taupen * (delta - delta / 2.0)) / sJn;
-  const double dtau = -prm.mu_shear * T;
+// dtau: change of the shear stress on the fault at this node (odefun.jl:59); state = [psi; delta] (2 nf), out = [dpsi; V] (2 nf)
+__device__ __forceinline__ void bp1_fault_node_dtau(int n, int nf, double dtau, double a, const double *__restrict__ state,
+                                                    double *__restrict__ out, const Bp1Dev &prm, int *__restrict__ flags) {
+  const double psi = state[n];
   const double taun = dtau + prm.tau_z0;
   double Vout = 0.0, dpsi = 0.0;
   int fl = 0, iters = 0;
@@ -82,6 +78,16 @@ __device__ __forceinline__ void bp1_fault_node(int n, int nf, double trn, double
   atomicMax(&flags[1], iters);
 }
 
+// trn: (HfI_FT_k u)_n on the fault face
+__device__ __forceinline__ void bp1_fault_node(int n, int nf, double trn, double taupen, double sJn, double a,
+                                               const double *__restrict__ state, double *__restrict__ out,
+                                               const Bp1Dev &prm, int *__restrict__ flags) {
+  const double delta = state[nf + n];
+  // computetraction_mod: (HfI_FT u + tau (delta - delta/2)) / sJ ; odefun.jl:59
+  const double T = (trn + taupen * (delta - delta / 2.0)) / sJn;
+  bp1_fault_node_dtau(n, nf, -prm.mu_shear * T, a, state, out, prm, flags);
+}
+
 // tr: HfI_FT_k u on the fault face (k_face_gather, FACE_TRACTION); tau: penalty on that face
 __global__ void __launch_bounds__(128)
 k_bp1_fault(int nf, const double *__restrict__ tr, const double *__restrict__ tau, const double *__restrict__ sJ,
@@ -113,6 +119,30 @@ k_bp1_fault_condensed(int nf, const double *__restrict__ Tf, const double *__res
   if (m < nf) s0 += Tf[n + (int64_t)nf * m] * st[nf + m];
   const double trn = -0.5 * (s0 + s1) - load * tl[n];
   bp1_fault_node(n, nf, trn, tau[n], sJ[n], rsa[n], st, out, prm, flags);
+}
+
+// Fault nodes of a multiblock mesh (hsbp_fault_*): the stress change is a given linear function of slip and time,
+// dtau = A delta + t b (condensed trace solve), or comes precomputed (dtau_in, one trace solve per call).
+__global__ void __launch_bounds__(64)
+k_fault_linear(int nf, const double *__restrict__ A, const double *__restrict__ b, double t, const double *__restrict__ dtau_in,
+               const double *__restrict__ rsa, const double *__restrict__ state, double *__restrict__ out, Bp1Dev prm,
+               int *__restrict__ flags) {
+  extern __shared__ double st[];                 // [psi; delta]
+  for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x) st[i] = state[i];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nf) return;
+  double dtau;
+  if (dtau_in) {
+    dtau = dtau_in[n];
+  } else {
+    double s0 = 0.0, s1 = 0.0;
+    int m = 0;
+    for (; m + 1 < nf; m += 2) { s0 += A[n + (int64_t)nf * m] * st[nf + m]; s1 += A[n + (int64_t)nf * (m + 1)] * st[nf + m + 1]; }
+    if (m < nf) s0 += A[n + (int64_t)nf * m] * st[nf + m];
+    dtau = (s0 + s1) + t * b[n];
+  }
+  bp1_fault_node_dtau(n, nf, dtau, rsa[n], st, out, prm, flags);
 }
 
 // Dirichlet data of the ODE stage on the block-face vector v (zero elsewhere): fault face <- delta / 2,

@@ -17,7 +17,7 @@ from . import host, square_circle as sc
 def load_mesh(filename=None):
     if filename is None:
         here = os.path.dirname(os.path.abspath(__file__))
-        filename = os.path.join(os.path.dirname(here), "tests", "golden", "meshes", "flower_v2.inp")
+        filename = os.path.join(os.path.dirname(here), "meshes", "flower_v2.inp")
     return host.read_inp_2d(filename)
 
 

@@ -255,7 +255,7 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=No
 
 def default_mesh_path():
     here = os.path.dirname(os.path.abspath(__file__))
-    return os.path.join(os.path.dirname(here), "tests", "golden", "meshes", "square_circle.inp")
+    return os.path.join(os.path.dirname(here), "meshes", "square_circle.inp")
 
 
 def main(ctx=None, p=4, N0=17, levels=3):

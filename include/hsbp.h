@@ -315,6 +315,20 @@ int  hsbp_bp1_condense(hsbp_bp1 *bp1, int enable);
 int  hsbp_bp1_rhs(hsbp_bp1 *bp1, double t, const double *psi_delta, double *dpsi_V, hsbp_bp1_stats *stats);
 int  hsbp_bp1_get_u(hsbp_bp1 *bp1, double *u);      /* displacement of the last rhs call, host array of VNp */
 
+/* ---- rate-and-state fault stage on a multiblock mesh ---------------------------------------
+ * On a multiblock mesh (seas/BP1/meshes/BP1_v1.inp) the fault is a set of jump interfaces: slip enters through the jump
+ * branch of locbcarray! (global_curved.jl:614-617), the displacement comes from the trace solve (square_circle.jl:376-388)
+ * and the shear stress from computetraction (global_curved.jl:638-644).  The chain is linear in (slip, time): the stress
+ * change at the n fault nodes is dtau = A delta + t b.  hsbp_fault_rhs evaluates [dpsi/dt; V] from [psi; delta] with A, b
+ * formed once by the host layer (n + 1 trace solves); hsbp_fault_stage takes the dtau of one trace solve per call.  The
+ * per-node root find and state evolution are those of hsbp_bp1_rhs (odefun.jl:69-108).  A, b may be NULL (stage only). */
+typedef struct hsbp_fault hsbp_fault;
+int  hsbp_fault_create(hsbp_ctx *ctx, int64_t n, const double *A, const double *b, const double *a,
+                       const hsbp_bp1_params *params, hsbp_fault **fault);
+int  hsbp_fault_destroy(hsbp_fault *fault);
+int  hsbp_fault_rhs(hsbp_fault *fault, double t, const double *psi_delta, double *dpsi_V, hsbp_bp1_stats *stats);
+int  hsbp_fault_stage(hsbp_fault *fault, const double *dtau_dev, const double *psi_delta, double *dpsi_V, hsbp_bp1_stats *stats);
+
 /* ---- measured fp64 denominators of the device (benchmarks; not on the solve path) -------------------------------
  * sustained fp64 FMA rate of the CUDA cores, sustained mma.sync.m8n8k4.f64 rate (the tensor instruction of the dense and
  * banded factorisations and of the Gauss-Jordan inversions), cuBLAS DGEMM n^3 (library number, denominator only).       */

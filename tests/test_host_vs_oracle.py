@@ -11,7 +11,7 @@ import pytest
 from hybridsbp_b200 import host
 from oracle import hybrid as orc
 
-MESH = os.path.join(os.path.dirname(__file__), "golden", "meshes")
+MESH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "meshes")
 MESHES = {"square_circle.inp": [1, 1, 2, 2, 7], "flower_v2.inp": None, "1_1_block.inp": None, "BP1_v1.inp": None}
 
 

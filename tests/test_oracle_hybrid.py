@@ -13,7 +13,7 @@ from oracle import hybrid as orc
 from tests.util import random_spd_metrics
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-MESH = os.path.join(HERE, "golden", "meshes")
+MESH = os.path.join(os.path.dirname(HERE), "meshes")
 
 
 @pytest.mark.parametrize("p", [2, 4, 6])
@@ -97,7 +97,7 @@ MESHES = {
 
 @pytest.mark.parametrize("name", sorted(MESHES))
 def test_read_inp_2d_counts(name):
-    """read_inp_2d (global_curved.jl:802-956) on copies of the reference's mesh files (tests/golden/meshes)."""
+    """read_inp_2d (global_curved.jl:802-956) on copies of the reference's mesh files (meshes/)."""
     bc_map, nv, ne, nf, counts = MESHES[name]
     verts, EToV, EToF, FToB, EToBlock = orc.read_inp_2d(os.path.join(MESH, name), bc_map)
     assert verts.shape == (2, nv) and EToV.shape == (4, ne) and EToF.shape == (4, ne) and FToB.shape == (nf,)
