@@ -83,6 +83,7 @@ def lib():
         "hsbp_face_traction": (cint, [vp, dp, dp]),
         "hsbp_local_setup": (cint, [vp, cint, dbl, i64]),
         "hsbp_local_solve": (cint, [vp, dp, dp, vp]),
+        "hsbp_local_precondition": (cint, [vp, dp, dp]),
         "hsbp_factor_create": (cint, [vp, i64, i64p, i64p, dp, cint, C.POINTER(vp)]),
         "hsbp_factor_destroy": (cint, [vp]),
         "hsbp_factor_size": (i64, [vp]),

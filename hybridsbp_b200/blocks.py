@@ -152,6 +152,10 @@ class Blocks:
         self.ctx._check(lib().hsbp_local_solve(self.h, g.ptr, u.ptr, C.byref(st)))
         return st.as_dict()
 
+    def local_precondition(self, r: DeviceArray, z: DeviceArray):
+        """z = P^-1 r of the fast-diagonalisation preconditioner alone (testing / profiling hook)"""
+        self.ctx._check(lib().hsbp_local_precondition(self.h, r.ptr, z.ptr))
+
     def close(self):
         if self.h is not None:
             for child in list(self._children):       # traces / BP1 stages point into this object on the C side

@@ -25,6 +25,7 @@
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 #include "api_band.cuh"
+#include "k_tcgemm.cuh"
 
 namespace hsbp {
 
@@ -248,6 +249,9 @@ struct FdmLibs {                 // per-context library handles (created on firs
     }                                                                                               \
   } while (0)
 
+// the tcgen05 kernel computes 128 x N tiles with K in blocks of 32
+inline bool fdm_tc_shapes_ok(int Nrp, int Nsp) { return (Nrp == 128 || Nrp == 256) && (Nsp == 128 || Nsp == 256); }
+
 int fdm_libs(hsbp_ctx *ctx, FdmLibs **out) {
   if (!ctx->fdm_libs) {
     FdmLibs *l = new (std::nothrow) FdmLibs();
@@ -341,7 +345,6 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
   // ---- round 2: eigenvalues.  Collapse against the lowest mode w0 of the other direction (w0^T H w0 = 1):
   //   (I (x) w0^T) M̃ (I (x) w0) = Ar + (w0^T As w0) Hr,  a shift of the size of the smallest eigenvalue only;
   //   mr_a = v_a^T [.] v_a are the Rayleigh quotients of the tensor modes v_a (x) w0 (and ms_a likewise).
-  const double one = 1.0, zero = 0.0;
   for (int dir = 0; dir < 2 && rc == HSBP_OK; ++dir) {
     const int n = dir == 0 ? Nrp : Nsp;
     const double *prof = dir == 0 ? b->d_fdm_vs : b->d_fdm_vr;           // column 0 of the other direction's vectors
@@ -354,28 +357,39 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
       k_fdm_collapse<<<(unsigned)nb, 256, 0, ctx->stream>>>(b->d_desc, dir, C, WB, ci, prof, ldw, 1.0, y, d_a2);
     }
     if (rc) break;
-    cublasStatus_t bs = cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, d_a2, n, (long long)n * n,
-                                                  V, n, (long long)n * n, &zero, d_t2, n, (long long)n * n, (int)nb);
-    if (bs != CUBLAS_STATUS_SUCCESS) { cleanup(); HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: cuBLAS DGEMM failed"); }
+    {                                                       // T = A V (fp64, mma.sync.m8n8k4.f64)
+      hsbp::tc::DgemmParams g;
+      g.A = d_a2; g.B = V; g.C = d_t2; g.scale = nullptr; g.strideA = g.strideB = g.strideC = (int64_t)n * n; g.M = g.N = g.K = n;
+      g.sam = 1; g.sak = n; g.sbn = n; g.sbk = 1; g.scm = 1; g.scn = n;
+      hsbp::tc::k_dgemm_batched<<<dim3((unsigned)((n + 63) / 64), (unsigned)((n + 63) / 64), (unsigned)nb), 256, 0, ctx->stream>>>(g);
+    }
     k_fdm_rayleigh<<<(unsigned)nb, 256, 0, ctx->stream>>>(n, V, d_t2, dir == 0 ? d_lr : d_ls);
   }
   if (rc) { cleanup(); return rc; }
   k_fdm_dinv<<<dim3((unsigned)nb, 16), 256, 0, ctx->stream>>>(b->d_desc, d_lr, d_ls, b->d_dinv);
-  if (b->fdm_gemm != 0) {                                        // fp32 copies for the reduced-precision application
+  if (b->fdm_gemm != 0) {                                        // fp32 copies for the TF32 application (and their transposes:
+                                                                 // the tensor-core kernel wants every operand contiguous in k)
     if (!b->d_fdm_vr32) {
       cudaMalloc((void **)&b->d_fdm_vr32, (size_t)nb * Nrp * Nrp * sizeof(float));
       cudaMalloc((void **)&b->d_fdm_vs32, (size_t)nb * Nsp * Nsp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_vrT32, (size_t)nb * Nrp * Nrp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_vsT32, (size_t)nb * Nsp * Nsp * sizeof(float));
       cudaMalloc((void **)&b->d_fdm_dinv32, (size_t)b->VNp * sizeof(float));
+      cudaMalloc((void **)&b->d_fdm_dinvT32, (size_t)b->VNp * sizeof(float));
       cudaMalloc((void **)&b->d_fdm_a32, (size_t)b->VNp * sizeof(float));
       cudaMalloc((void **)&b->d_fdm_b32, (size_t)b->VNp * sizeof(float));
     }
-    if (!b->d_fdm_vr32 || !b->d_fdm_vs32 || !b->d_fdm_dinv32 || !b->d_fdm_a32 || !b->d_fdm_b32) {
+    if (!b->d_fdm_vr32 || !b->d_fdm_vs32 || !b->d_fdm_vrT32 || !b->d_fdm_vsT32 || !b->d_fdm_dinv32 || !b->d_fdm_dinvT32 || !b->d_fdm_a32 ||
+        !b->d_fdm_b32) {
       cleanup();
       HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: out of device memory (fp32 copies)");
     }
     k_f64_to_f32<<<vec_grid((int64_t)nb * Nrp * Nrp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nrp * Nrp, b->d_fdm_vr, b->d_fdm_vr32);
     k_f64_to_f32<<<vec_grid((int64_t)nb * Nsp * Nsp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nsp * Nsp, b->d_fdm_vs, b->d_fdm_vs32);
     k_f64_to_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, b->d_dinv, b->d_fdm_dinv32);
+    hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nrp, Nrp, b->d_fdm_vr32, b->d_fdm_vrT32);
+    hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nsp, Nsp, b->d_fdm_vs32, b->d_fdm_vsT32);
+    hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nrp, Nsp, b->d_fdm_dinv32, b->d_fdm_dinvT32);
   }
   e1 = cudaGetLastError();
   if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
@@ -388,51 +402,81 @@ int fdm_setup(hsbp_blocks *b) {
   return dispatch_p(b->p, [&](auto Pc) { return fdm_setup_p<decltype(Pc)::value>(b); });
 }
 
-// z = P^-1 r for all blocks: Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T
-//   fdm_gemm = 0  fp64 DGEMMs (fp64 tensor pipe)
-//            = 1  fp32 SGEMMs;  = 2  fp32 emulated with 3 x BF16 splits on the BF16 tensor cores (fp32-accurate);
-//            = 3  TF32 tensor cores (10-bit mantissa).  r is rounded to fp32 first, z is widened back; PCG itself (x, r, p,
-//            the operator) stays fp64, and the flexible beta keeps it convergent with an inexactly applied preconditioner.
+// z = P^-1 r for all blocks: Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T -- four batched GEMMs per application, hand-written:
+//   fdm_gemm = 3 (default of the synthetic-mesh drivers)  tcgen05.mma kind::tf32, accumulators in TMEM (k_tcgemm.cuh); r is
+//                 converted to fp32 while it is staged, the `o Dinv` rides in the epilogue of the second GEMM, z comes out
+//                 as fp64; PCG itself (x, r, p, the operator) stays fp64 and the flexible beta keeps it convergent with the
+//                 inexactly applied preconditioner.  Needs Nr+1, Ns+1 in {128, 256}.
+//   fdm_gemm = 0  fp64 on the fp64 tensor pipe (mma.sync.m8n8k4.f64), any block size.
+//   fdm_gemm = -1 the strided-batched cuBLAS TF32 GEMMs of round 1 -- kept only so that tests can compare the hand-written
+//                 kernels with a library result; never a default.
 int fdm_precondition(hsbp_blocks *b, const double *r, double *z) {
   hsbp_ctx *ctx = b->ctx;
-  FdmLibs *libs = (FdmLibs *)ctx->fdm_libs;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nb = (int)b->nblocks;
   const long long sv = (long long)Nrp * Nsp, sr = (long long)Nrp * Nrp, ss = (long long)Nsp * Nsp;
-  if (b->fdm_gemm == 0) {
-    const double one = 1.0, zero = 0.0;
-    double *t = b->d_fdm_t;
-    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
-                                             r, Nrp, sv, &zero, t, Nrp, sv, nb));
-    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
-                                             b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
-    k_ewise<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, z, b->d_dinv, z, 0);
-    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr, Nrp, sr,
-                                             z, Nrp, sv, &zero, t, Nrp, sv, nb));
-    HSBP_BLAS(ctx, cublasDgemmStridedBatched(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, Nrp, sv,
-                                             b->d_fdm_vs, Nsp, ss, &zero, z, Nrp, sv, nb));
-    return check_launch(ctx, "fdm_precondition");
+  if (b->fdm_gemm == 3 && fdm_tc_shapes_ok(Nrp, Nsp)) {
+    using namespace hsbp::tc;
+    float *t1 = b->d_fdm_a32, *t3 = b->d_fdm_b32;
+    auto launch = [&](const void *A, int64_t sA, int lda, const void *B, int64_t sB, int ldb, int bf64, int M, int N, int K, void *out,
+                      int ldo, int mode, const float *scale) {
+      GemmParams g;
+      g.A = A; g.B = B; g.out = out; g.scale = scale; g.strideA = sA; g.strideB = sB; g.strideO = sv;
+      g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldo = ldo; g.b_is_f64 = bf64; g.mode = mode;
+      k_tc_gemm<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_smem_bytes(N), ctx->stream>>>(g);
+    };
+    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_tc_gemm, gemm_smem_bytes(256)));
+    // T1 = Vr^T R            A(m, k) = Vr[k + Nrp m]   B(n, k) = R[k + Nrp n] (fp64)       -> row-major (m, n)
+    launch(b->d_fdm_vr32, sr, Nrp, r, sv, Nrp, 1, Nrp, Nsp, Nrp, t1, Nsp, OUT_ROWMAJOR_F32, nullptr);
+    // T3 = (T1 Vs) o Dinv    A = T1 row-major          B(n, k) = Vs[k + Nsp n]              -> row-major, scaled
+    launch(t1, sv, Nsp, b->d_fdm_vs32, ss, Nsp, 0, Nrp, Nsp, Nsp, t3, Nsp, OUT_ROWMAJOR_F32_SCALED, b->d_fdm_dinvT32);
+    // W = T3 Vs^T            A = T3 row-major          B(n, k) = Vs[n + Nsp k] = VsT[k + Nsp n]   -> column-major (m + Nrp n)
+    launch(t3, sv, Nsp, b->d_fdm_vsT32, ss, Nsp, 0, Nrp, Nsp, Nsp, t1, Nrp, OUT_COLMAJOR_F32, nullptr);
+    // Z = Vr W               A(m, k) = Vr[m + Nrp k] = VrT[k + Nrp m]   B(n, k) = W[k + Nrp n]    -> column-major fp64
+    launch(b->d_fdm_vrT32, sr, Nrp, t1, sv, Nrp, 0, Nrp, Nsp, Nrp, z, Nrp, OUT_COLMAJOR_F64, nullptr);
+    return check_launch(ctx, "fdm_precondition (tcgen05 TF32)");
   }
-  const cublasComputeType_t ct = b->fdm_gemm == 2 ? CUBLAS_COMPUTE_32F_EMULATED_16BFX9
-                                                  : (b->fdm_gemm == 3 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F);
-  const float one = 1.0f, zero = 0.0f;
-  float *a = b->d_fdm_a32, *t = b->d_fdm_b32;
-  k_f64_to_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, r, a);
-  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr32, CUDA_R_32F,
-                                            Nrp, sr, a, CUDA_R_32F, Nrp, sv, &zero, t, CUDA_R_32F, Nrp, sv, nb, ct,
-                                            CUBLAS_GEMM_DEFAULT));
-  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, CUDA_R_32F, Nrp, sv,
-                                            b->d_fdm_vs32, CUDA_R_32F, Nsp, ss, &zero, a, CUDA_R_32F, Nrp, sv, nb, ct,
-                                            CUBLAS_GEMM_DEFAULT));
-  k_mul_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, a, b->d_fdm_dinv32);
-  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr32, CUDA_R_32F,
-                                            Nrp, sr, a, CUDA_R_32F, Nrp, sv, &zero, t, CUDA_R_32F, Nrp, sv, nb, ct,
-                                            CUBLAS_GEMM_DEFAULT));
-  HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, CUDA_R_32F, Nrp, sv,
-                                            b->d_fdm_vs32, CUDA_R_32F, Nsp, ss, &zero, a, CUDA_R_32F, Nrp, sv, nb, ct,
-                                            CUBLAS_GEMM_DEFAULT));
-  k_f32_to_f64<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, a, z);
-  return check_launch(ctx, "fdm_precondition (fp32)");
+  if (b->fdm_gemm == -1) {
+    FdmLibs *libs = nullptr;
+    int rc = fdm_libs(ctx, &libs);
+    if (rc) return rc;
+    const float one = 1.0f, zero = 0.0f;
+    float *a = b->d_fdm_a32, *t = b->d_fdm_b32;
+    const cublasComputeType_t ct = CUBLAS_COMPUTE_32F_FAST_TF32;
+    k_f64_to_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, r, a);
+    HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_T, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr32, CUDA_R_32F,
+                                              Nrp, sr, a, CUDA_R_32F, Nrp, sv, &zero, t, CUDA_R_32F, Nrp, sv, nb, ct,
+                                              CUBLAS_GEMM_DEFAULT));
+    HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nsp, &one, t, CUDA_R_32F, Nrp, sv,
+                                              b->d_fdm_vs32, CUDA_R_32F, Nsp, ss, &zero, a, CUDA_R_32F, Nrp, sv, nb, ct,
+                                              CUBLAS_GEMM_DEFAULT));
+    k_mul_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, a, b->d_fdm_dinv32);
+    HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_N, Nrp, Nsp, Nrp, &one, b->d_fdm_vr32, CUDA_R_32F,
+                                              Nrp, sr, a, CUDA_R_32F, Nrp, sv, &zero, t, CUDA_R_32F, Nrp, sv, nb, ct,
+                                              CUBLAS_GEMM_DEFAULT));
+    HSBP_BLAS(ctx, cublasGemmStridedBatchedEx(libs->blas, CUBLAS_OP_N, CUBLAS_OP_T, Nrp, Nsp, Nsp, &one, t, CUDA_R_32F, Nrp, sv,
+                                              b->d_fdm_vs32, CUDA_R_32F, Nsp, ss, &zero, a, CUDA_R_32F, Nrp, sv, nb, ct,
+                                              CUBLAS_GEMM_DEFAULT));
+    k_f32_to_f64<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, a, z);
+    return check_launch(ctx, "fdm_precondition (cuBLAS, comparison only)");
+  }
+  // fp64 on the fp64 tensor pipe; all four operands are used where they lie (general strides)
+  {
+    using namespace hsbp::tc;
+    double *t = b->d_fdm_t;
+    auto launch = [&](const double *A, int64_t sA, int64_t sam, int64_t sak, const double *B, int64_t sB, int64_t sbn, int64_t sbk, int M,
+                      int N, int K, double *Cc, const double *scale) {
+      DgemmParams g;
+      g.A = A; g.B = B; g.C = Cc; g.scale = scale; g.strideA = sA; g.strideB = sB; g.strideC = sv; g.M = M; g.N = N; g.K = K;
+      g.sam = sam; g.sak = sak; g.sbn = sbn; g.sbk = sbk; g.scm = 1; g.scn = M;
+      k_dgemm_batched<<<dim3((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)nb), 256, 0, ctx->stream>>>(g);
+    };
+    launch(b->d_fdm_vr, sr, Nrp, 1, r, sv, Nrp, 1, Nrp, Nsp, Nrp, t, nullptr);                      // T1 = Vr^T R
+    launch(t, sv, 1, Nrp, b->d_fdm_vs, ss, Nsp, 1, Nrp, Nsp, Nsp, z, b->d_dinv);                  // T3 = (T1 Vs) o Dinv
+    launch(z, sv, 1, Nrp, b->d_fdm_vs, ss, 1, Nsp, Nrp, Nsp, Nsp, t, nullptr);                     // W = T3 Vs^T
+    launch(b->d_fdm_vr, sr, 1, Nrp, t, sv, Nrp, 1, Nrp, Nsp, Nrp, z, nullptr);                     // Z = Vr W
+    return check_launch(ctx, "fdm_precondition (fp64 DMMA)");
+  }
 }
 
 int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stats) {
@@ -482,3 +526,18 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
 }
 
 }  // namespace
+
+extern "C" {
+
+// z = P^-1 r of the fast-diagonalisation preconditioner alone (testing / profiling hook; HSBP_LOCAL_FDM must be set up)
+int hsbp_local_precondition(hsbp_blocks *b, const double *r_dev, double *z_dev) {
+  if (!b) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = b->ctx;
+  if (!r_dev || !z_dev || r_dev == z_dev) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_local_precondition: bad pointers");
+  if (b->local_mode != HSBP_LOCAL_FDM || !b->d_fdm_vr) HSBP_FAIL(ctx, HSBP_ERR_STATE, "hsbp_local_precondition: set up HSBP_LOCAL_FDM first");
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fdm_precondition(b, r_dev, z_dev);
+}
+
+}  // extern "C"
+

@@ -224,6 +224,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaFree(b->d_band); cudaFree(b->d_band_desc); cudaFree(b->d_band_work); cudaFree(b->d_band_inv);
   cudaFree(b->d_fdm_vr); cudaFree(b->d_fdm_vs); cudaFree(b->d_fdm_z); cudaFree(b->d_fdm_t);
   cudaFree(b->d_fdm_vr32); cudaFree(b->d_fdm_vs32); cudaFree(b->d_fdm_dinv32); cudaFree(b->d_fdm_a32); cudaFree(b->d_fdm_b32);
+  cudaFree(b->d_fdm_vrT32); cudaFree(b->d_fdm_vsT32); cudaFree(b->d_fdm_dinvT32);
   delete b;
   return HSBP_OK;
 }

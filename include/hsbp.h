@@ -126,7 +126,9 @@ int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
 /* tuning / testing knobs: "force_generic" (0/1), "sweep_chunks_per_side" (0 = heuristic),
  * "sweep_points_per_thread" (0 = heuristic, 2, 4), "sweep_fold_faces" (1), "sweep_deep" (1: css / crs windows in
  * shared-memory rings, 0: in registers), "sweep_p6_regs" (128 / 168), "fdm_gemm" (arithmetic of the fast-diagonalisation
- * preconditioner's GEMMs: 0 fp64, 1 fp32, 2 fp32 emulated with BF16 x 9, 3 TF32; set before hsbp_local_setup),
+ * preconditioner's GEMMs, hand-written kernels: 0 fp64 on the fp64 tensor pipe (mma.sync f64), 3 TF32 on tcgen05 with TMEM
+ * accumulators (blocks of 128 / 256 points per direction, fp64 otherwise); -1 cuBLAS TF32, for comparison in tests only;
+ * set before hsbp_local_setup),
  * "band_no_stream" (1: plain-load banded solve kernel) */
 int  hsbp_blocks_set_option(hsbp_blocks *blocks, const char *name, int64_t value);
 
@@ -164,6 +166,8 @@ typedef struct {
 } hsbp_local_stats;
 int  hsbp_local_setup(hsbp_blocks *blocks, int mode, double tol, int64_t maxit);
 int  hsbp_local_solve(hsbp_blocks *blocks, const double *g_dev, double *u_dev, hsbp_local_stats *stats);
+/* z = P^-1 r of the fast-diagonalisation preconditioner alone (HSBP_LOCAL_FDM; testing / profiling hook) */
+int  hsbp_local_precondition(hsbp_blocks *blocks, const double *r_dev, double *z_dev);
 
 /* ---- the `factorization` plugin at the reference's own seam -------------------------------------------------------
  * reference: SBPLocalOperator1 calls `factorization(lop[e].M̃)` on the ASSEMBLED sparse matrix of every block, after

@@ -1,0 +1,77 @@
+"""The hand-written GEMMs of the fast-diagonalisation preconditioner (K2d): tcgen05.mma kind::tf32 with TMEM accumulators
+(k_tc_gemm) and mma.sync.m8n8k4.f64 (k_dgemm_batched).  z = Vr [(Vr^T R Vs) o Dinv] Vs^T is compared between the fp64 kernels,
+the TF32 tensor-core kernels and -- as an independent library result -- strided-batched cuBLAS TF32 GEMMs, on blocks of the
+shapes the tensor-core path serves (128 / 256 points per direction); then the PCG solves built on them are checked by an
+apply -> solve round trip at config-4 block size."""
+import numpy as np
+import pytest
+
+import hybridsbp_b200 as hs
+from hybridsbp_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def make_blocks(ctx, nbx, nby, Nr, Ns, p=4):
+    from tests.util import warped_metrics, flat
+    mets = [warped_metrics(p, Nr, Ns, bx, by, nbx, nby) for by in range(nby) for bx in range(nbx)]
+    _, EToV, EToF, FToB = synthetic.block_grid_connectivity(nbx, nby)
+    blk = hs.Blocks(ctx, p, [Nr] * (nbx * nby), [Ns] * (nbx * nby))
+    blk.set_metrics(np.concatenate([flat(m.crr) for m in mets]), np.concatenate([flat(m.css) for m in mets]),
+                    np.concatenate([flat(m.crs) for m in mets]))
+    blk.set_bc(synthetic.block_bcs(EToF, FToB))
+    blk.compute_tau(2.0)
+    return blk
+
+
+@pytest.mark.parametrize("Nr,Ns", [(255, 255), (127, 255), (255, 127)])
+def test_preconditioner_kernels_agree(ctx, Nr, Ns):
+    blk = make_blocks(ctx, 2, 2, Nr, Ns)
+    rng = np.random.default_rng(Nr + Ns)
+    r = rng.uniform(-1, 1, blk.VNp)
+    dr, dz = ctx.array(r), ctx.empty(blk.VNp)
+    z = {}
+    for gemm in (0, 3, -1):
+        blk.set_option("fdm_gemm", gemm)
+        blk.local_setup(hs.LOCAL_FDM, tol=1e-13, maxit=500)
+        blk.local_precondition(dr, dz)
+        z[gemm] = dz.get()
+    n0 = np.linalg.norm(z[0])
+    assert np.all(np.isfinite(z[3])) and n0 > 0
+    # TF32 (10-bit mantissa) against fp64: four chained 256-term contractions -> a few 1e-4 relative
+    assert np.linalg.norm(z[3] - z[0]) <= 3e-3 * n0, np.linalg.norm(z[3] - z[0]) / n0
+    assert np.linalg.norm(z[-1] - z[0]) <= 3e-3 * n0
+    assert np.linalg.norm(z[3] - z[-1]) <= 3e-3 * n0
+    # the preconditioner is symmetric positive definite: r.z > 0, and (with fp64 kernels) u.P^-1 v = v.P^-1 u
+    assert r @ z[3] > 0 and r @ z[0] > 0
+    v = rng.uniform(-1, 1, blk.VNp)
+    blk.set_option("fdm_gemm", 0)
+    blk.local_setup(hs.LOCAL_FDM, tol=1e-13, maxit=500)
+    dv = ctx.array(v)
+    blk.local_precondition(dv, dz)
+    Pv = dz.get()
+    assert abs(r @ Pv - v @ z[0]) <= 1e-11 * np.linalg.norm(r) * np.linalg.norm(Pv)
+    blk.close()
+
+
+@pytest.mark.parametrize("gemm", [3, 0])
+def test_pcg_on_the_hand_written_kernels_round_trip(ctx, gemm):
+    """4 blocks of 256 x 256 points: x = M-tilde^-1 (M-tilde x0) through FDM-PCG with the tensor-core preconditioner"""
+    blk = make_blocks(ctx, 2, 2, 255, 255)
+    blk.set_option("fdm_gemm", gemm)
+    blk.local_setup(hs.LOCAL_FDM, tol=1e-12, maxit=2000)
+    x0 = np.random.default_rng(5).uniform(-1, 1, blk.VNp)
+    dx0, dg, dx, dr = ctx.array(x0), ctx.empty(blk.VNp), ctx.empty(blk.VNp), ctx.empty(blk.VNp)
+    blk.apply(dx0, dg)
+    st = blk.local_solve(dg, dx)
+    assert st["failed_blocks"] == 0 and st["iterations_max"] < 120, st
+    blk.apply(dx, dr)
+    g, r = dg.get(), dr.get()
+    assert np.linalg.norm(r - g) <= 1e-10 * np.linalg.norm(g), st
+    assert np.linalg.norm(dx.get() - x0) <= 1e-6 * np.linalg.norm(x0), st
+    if gemm == 3:                      # the library GEMMs give the same iteration count (+- rounding mode of TF32)
+        blk.set_option("fdm_gemm", -1)
+        blk.local_setup(hs.LOCAL_FDM, tol=1e-12, maxit=2000)
+        st_lib = blk.local_solve(dg, dx)
+        assert abs(st_lib["iterations_max"] - st["iterations_max"]) <= 6, (st, st_lib)
+    blk.close()
