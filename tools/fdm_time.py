@@ -19,8 +19,10 @@ blk.compute_tau(2.0)
 x0 = np.random.default_rng(5).uniform(-1, 1, blk.VNp)
 dx0, dg, dx, dr = ctx.array(x0), ctx.empty(blk.VNp), ctx.empty(blk.VNp), ctx.empty(blk.VNp)
 blk.apply(dx0, dg)
-for name, mode, gemm in (("FDM-PCG fp64 GEMM", hs.LOCAL_FDM, 0), ("FDM-PCG fp32 GEMM", hs.LOCAL_FDM, 1),
-                         ("FDM-PCG BF16x9 GEMM", hs.LOCAL_FDM, 2), ("FDM-PCG TF32 GEMM", hs.LOCAL_FDM, 3)) + \
+dz = ctx.empty(blk.VNp)
+for name, mode, gemm in (("FDM-PCG, fp64 GEMMs (mma.sync f64, own kernel)", hs.LOCAL_FDM, 0),
+                         ("FDM-PCG, TF32 GEMMs (tcgen05 + TMEM, own kernel)", hs.LOCAL_FDM, 3),
+                         ("FDM-PCG, TF32 GEMMs (cuBLAS, comparison only)", hs.LOCAL_FDM, -1)) + \
         ((("Jacobi-PCG", hs.LOCAL_PCG, 0),) if jac else ()):
     t0 = time.time()
     blk.set_option("fdm_gemm", gemm)
@@ -32,7 +34,14 @@ for name, mode, gemm in (("FDM-PCG fp64 GEMM", hs.LOCAL_FDM, 0), ("FDM-PCG fp32 
         dt = time.time() - t0
     blk.apply(dx, dr)
     g, r = dg.get(), dr.get()
-    print("%d blocks of 256x256, %s: setup %.2f s, solve %.3f s, iterations max %d mean %.1f, failed %d, "
+    pre_ms = float("nan")
+    if mode == hs.LOCAL_FDM:                       # the preconditioner application alone (4 batched GEMMs), CUDA events
+        blk.local_precondition(dg, dz)
+        ctx.timer_start()
+        for _ in range(10):
+            blk.local_precondition(dg, dz)
+        pre_ms = ctx.timer_stop() / 10
+    print("%d blocks of 256x256, %s: setup %.2f s, solve %.3f s, preconditioner %.3f ms, iterations max %d mean %.1f, failed %d, "
           "true rel residual %.2e, error %.2e" %
-          (ne, name, ts, dt, st["iterations_max"], st["iterations_sum"] / ne, st["failed_blocks"],
+          (ne, name, ts, dt, pre_ms, st["iterations_max"], st["iterations_sum"] / ne, st["failed_blocks"],
            np.linalg.norm(r - g) / np.linalg.norm(g), np.linalg.norm(dx.get() - x0) / np.linalg.norm(x0)), flush=True)
