@@ -131,7 +131,7 @@ struct SweepParams {
   // face terms of M-tilde, prepared per face point by k_face_prep (k_generic.cuh), block-face layout:
   //   y(point at normal offset m from face point n) += BS[m] * fcn[n] + (m == 0) * fgm[n];   null: volume part only
   const double *fcn, *fgm;
-  // r-end table made by k_edge_prep: [block][line][end (near, far)][CLW], see SweepCfg::CLW
+  // r-end table made by k_edge_prep: [block][line][CLR], see SweepCfg::CLR
   const double *rtab;
   double *y;
   int Nr, Ns;         // uniform block size
@@ -147,9 +147,17 @@ template <int P> struct SweepCfg {
   static constexpr int PAD = (T::H + 1) & ~1;               // halo of a shared line, even (16-byte vectors)
   static constexpr int NB = (P == 2 ? 3 : (P == 4 ? 4 : 5)); // points of the boundary derivative BS (diagonal_sbp.jl:507,511,591)
   static constexpr int MCX = T::MC > NB ? T::MC : NB;       // rows of an r-end that take table values
-  // r-closure table of one (line, end): MCX rows (closure rows of M u, replaced; rows MC..NB-1 only carry the
-  // face terms and are added) followed by the BM closure rows of Q u
-  static constexpr int CLW = MCX + T::BM;
+  // r-end table of one line (k_edge_prep), laid out so that the lanes that own the end points pick their values up
+  // with 16-byte loads in point order:
+  //   [ near: rr(0 .. MCXP-1) | near: qr(0 .. MCXP-1) | far: rr(MCXP-1 .. 0) | far: qr(MCXP-1 .. 0) | 0 0 ]
+  // rr(m) = row m of Hs/hr M(crr) u  +  face terms of faces 1, 2  +  row m of Qr^T w, w = crs o (Qs u)   (replaces the lane's value)
+  // qr(m) = row m of Qr u (closure rows m < BM and the interior rows up to MCX, so that one mask serves both)
+  // rows MCX .. MCXP-1 and the last pair are zero (a lane whose pair sticks out adds them).
+  static constexpr int MCXP = (MCX + 1) & ~1;
+  static constexpr int CLW = 2 * MCXP;                       // one end
+  static constexpr int CLR = 4 * MCXP + 2;                   // one line: CLR * 8 bytes is a multiple of 16
+  static constexpr int NKX = T::NK >= NB ? T::NK : ((NB + 1) & ~1);   // points normal to an r-face that k_edge_prep looks at
+  static constexpr int RIMW = NKX + T::BN + 1;               // rim table entries per (line, end): crr' (NKX), crs (BN), tau Hf
   // ring depths (lines) of the four fields.  u and crr are only looked at on the newest line.  DEEP: css and crs
   // stay in shared memory for as long as the s-direction stencil needs them (css: lines j-2H+1 .. j for the
   // couplings of the pairs (j-H, j-H+O); crs: line j-H for w) instead of travelling through register windows
@@ -218,11 +226,10 @@ template <int P, int R, bool DEEP>
 __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
-  constexpr int H = C::H, W = C::W, PAD = C::PAD, CLW = C::CLW, NST = SW_NST;
+  constexpr int H = C::H, W = C::W, PAD = C::PAD, MCXP = C::MCXP, CLR = C::CLR, NST = SW_NST;
   constexpr int NSB = C::template nsb<DEEP>(), NSC = C::template nsc<DEEP>(), NLINES = C::template nlines<DEEP>();
   constexpr int MC = T::MC, BM = T::BM, BN = T::BN, MCX = C::MCX, NB = C::NB;
   constexpr int NV = R + 2 * PAD;                         // values of a line a thread looks at
-  constexpr int CLR = 2 * CLW;                            // r-end table entries per line (both ends); 2*CLW*8 B is a multiple of 16
   constexpr int DOFF = PAD;
   static_assert(R % 2 == 0 && PAD >= H, "layout");
 
@@ -415,28 +422,16 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
           }
         }
       });
-      // closure rows at the r-ends come from the table; the owning lanes are known at compile time
-      for_lanes<0, (MCX + R - 1) / R>([&](auto Tc) {
-        constexpr int TL = decltype(Tc)::value;
-        if (tid == TL) {                                  // near end: rows TL*R + q
-          const double *cl = clring + (size_t)st * CLR;
+      // rows at the r-ends come from the table (SweepCfg::CLR: M(crr') u with the face terms and Qr^T w, and Qr u)
+      {
+        const double *cl = clring + (size_t)st * CLR;
 #pragma unroll
-          for (int q = 0; q < R; ++q) {
-            if (TL * R + q < MC) rr[q] = cl[TL * R + q];
-              else if (TL * R + q < MCX) rr[q] += cl[TL * R + q];
-            if (TL * R + q < BM) qr[q] = cl[MCX + TL * R + q];
-          }
+        for (int q = 0; q < R; ++q) {
+          const int i = i0 + q, m = Nr - i;
+          if (i < MCX) { rr[q] = cl[i]; qr[q] = cl[MCXP + i]; }
+          else if (m < MCX) { rr[q] = cl[3 * MCXP - 1 - m]; qr[q] = cl[4 * MCXP - 1 - m]; }
         }
-        if (tid == nown - 1 - TL) {                       // far end: rows m = TL*R + (R-1-q) counted from Nr
-          const double *cl = clring + (size_t)st * CLR + CLW;
-#pragma unroll
-          for (int q = 0; q < R; ++q) {
-            if (TL * R + (R - 1 - q) < MC) rr[q] = cl[TL * R + (R - 1 - q)];
-              else if (TL * R + (R - 1 - q) < MCX) rr[q] += cl[TL * R + (R - 1 - q)];
-            if (TL * R + (R - 1 - q) < BM) qr[q] = cl[MCX + TL * R + (R - 1 - q)];
-          }
-        }
-      });
+      }
       double t[R];
 #pragma unroll
       for (int q = 0; q < R; ++q) {
@@ -538,25 +533,9 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
 #pragma unroll
         for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
       });
-      for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
-        constexpr int TL = decltype(Tc)::value;
-        if (tid == TL) {
-          double w0[BN];
 #pragma unroll
-          for (int k = 0; k < BN; ++k) w0[k] = wb[DOFF + k];
-#pragma unroll
-          for (int q = 0; q < R; ++q)
-            if (TL * R + q < BM) val[q] = acc[SL(0)][q] + qt_closure_row<P>(TL * R + q, w0);
-        }
-        if (tid == nown - 1 - TL) {                       // mirrored, sign flipped
-          double wr[BN];
-#pragma unroll
-          for (int k = 0; k < BN; ++k) wr[k] = wb[DOFF + Nr - k];
-#pragma unroll
-          for (int q = 0; q < R; ++q)
-            if (TL * R + (R - 1 - q) < BM) val[q] = acc[SL(0)][q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
-        }
-      });
+      for (int q = 0; q < R; ++q)                         // closure rows of Qr^T at the two r-ends came with the r-end table
+        if (i0 + q < BM || Nr - (i0 + q) < BM) val[q] = acc[SL(0)][q];
       double *yl = gy + jo * lstride;
       if constexpr (!FAST) {
         if (pro && jo < MC) {                             // closure row jo of M(css) u, straight from memory
@@ -621,8 +600,30 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int nwarps = opaque(nthreads >> 5);
   const int mywarp = opaque(tid >> 5);
   const int edge = opaque((own && (tid < ELANES || tid >= nown - ELANES)) ? 1 : 0);
+  // edge lanes: byte offsets of their pairs in a table row (SweepCfg::CLR) and the blend factors; closm: points that are closure
+  // rows of Qr^T (their accumulator already holds the whole row)
+  uint32_t eo_rr[R / 2], eo_qr[R / 2];
+  double keep[R];
+  int closm_ = 0;
+  {
+    const bool nearl = tid < ELANES;
+    const int d = nearl ? tid : nown - 1 - tid;            // distance of the lane from its end, in lanes
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      const int pos = nearl ? d * R + 2 * k : MCXP - (d + 1) * R + 2 * k;      // first entry of the pair inside rr(0 .. MCXP-1)
+      const bool ok = pos >= 0 && pos < MCXP;
+      eo_rr[k] = opaque(8u * (uint32_t)(ok ? (nearl ? pos : 2 * MCXP + pos) : 4 * MCXP));
+      eo_qr[k] = opaque(8u * (uint32_t)(ok ? (nearl ? MCXP + pos : 3 * MCXP + pos) : 4 * MCXP));
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int row = nearl ? d * R + q : d * R + (R - 1 - q);                 // row of the closure this point is
+      keep[q] = opaque((edge && row < MCX) ? 0.0 : 1.0);
+      if (edge && row < BM) closm_ |= 1 << q;
+    }
+  }
+  const int closm = opaque(closm_);
   const int ownf = opaque(own ? 1 : 0);
-  const int far0 = opaque(nown - 1);                       // thread that owns the last points of a line
   const double sgn = opaque(sig);                          // marching direction (the compiler would re-derive it from blockIdx)
   const int64_t lstr = opaque(lstride);
   const int64_t g0 = opaque(base + (int64_t)jstart * lstride);          // marching line 0 of this chunk in the volume fields
@@ -661,26 +662,10 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
 #pragma unroll
       for (int q = 0; q < R; ++q) val[q] = fma(-C::template D<O>(), Wv[PAD + q + O] - Wv[PAD + q - O], val[q]);
     });
-    if (edge) {
-      for_lanes<0, (BM + R - 1) / R>([&](auto Tc) {       // closure rows of Qr^T at the two r-ends
-        constexpr int TL = decltype(Tc)::value;
-        if (tid == TL) {                                 // w(k) of the line sits at aw + (PAD - i0 + k) * 8, i0 = TL * R
-          double w0[BN];
+    if (closm) {                                          // closure rows of Qr^T at the two r-ends came with the r-end table
 #pragma unroll
-          for (int k = 0; k < BN; ++k) w0[k] = lds64(awb + 8u * (PAD - TL * R + k));
-#pragma unroll
-          for (int q = 0; q < R; ++q)
-            if (TL * R + q < BM) val[q] = accv[q] + qt_closure_row<P>(TL * R + q, w0);
-        }
-        if (tid == far0 - TL) {                          // mirrored, sign flipped: w(Nr - k), i0 = Nrp - (TL + 1) R
-          double wr[BN];
-#pragma unroll
-          for (int k = 0; k < BN; ++k) wr[k] = lds64(awb + 8u * (PAD + (TL + 1) * R - 1 - k));
-#pragma unroll
-          for (int q = 0; q < R; ++q)
-            if (TL * R + (R - 1 - q) < BM) val[q] = accv[q] - qt_closure_row<P>(TL * R + (R - 1 - q), wr);
-        }
-      });
+      for (int q = 0; q < R; ++q)
+        if ((closm >> q) & 1) val[q] = accv[q];
     }
 #pragma unroll
     for (int k = 0; k < R / 2; ++k)
@@ -754,27 +739,15 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
           }
         }
       });
-      // closure rows at the r-ends come from the table (lanes known at compile time); warps without an edge lane skip
+      // rows at the r-ends come from the table: one 16-byte load per pair of points for rr and for qr, blended with the
+      // lane's own value through keep (0: row of the table, 1: interior point whose pair partner sticks out, table holds 0)
       if (edge) {
-        for_lanes<0, ELANES>([&](auto Tc) {
-          constexpr int TL = decltype(Tc)::value;
-          if (tid == TL) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-              if (TL * R + q < MC) rr[q] = lds64(acl + 8u * (TL * R + q));
-              else if (TL * R + q < MCX) rr[q] += lds64(acl + 8u * (TL * R + q));
-              if (TL * R + q < BM) qr[q] = lds64(acl + 8u * (MCX + TL * R + q));
-            }
-          }
-          if (tid == far0 - TL) {
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-              if (TL * R + (R - 1 - q) < MC) rr[q] = lds64(acl + 8u * (CLW + TL * R + (R - 1 - q)));
-              else if (TL * R + (R - 1 - q) < MCX) rr[q] += lds64(acl + 8u * (CLW + TL * R + (R - 1 - q)));
-              if (TL * R + (R - 1 - q) < BM) qr[q] = lds64(acl + 8u * (CLW + MCX + TL * R + (R - 1 - q)));
-            }
-          }
-        });
+        for (int k = 0; k < R / 2; ++k) {
+          const double2 tr = lds128(acl + eo_rr[k]), tq = lds128(acl + eo_qr[k]);
+          rr[2 * k] = fma(rr[2 * k], keep[2 * k], tr.x); rr[2 * k + 1] = fma(rr[2 * k + 1], keep[2 * k + 1], tr.y);
+          qr[2 * k] = fma(qr[2 * k], keep[2 * k], tq.x); qr[2 * k + 1] = fma(qr[2 * k + 1], keep[2 * k + 1], tq.y);
+        }
       }
       // ---- S: the register windows, one specialisation per rotation -----------------------------
       auto windows = [&](auto PHc) {
@@ -909,10 +882,12 @@ k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true>(prm); }
 //     g = G u and the face's boundary condition (k_generic.cuh header) the per-face-point quantities
 //       fcn[n] = (Hf/hn) c_nn alpha,   fgm[n] = sgn (Q_t^T (c_x o alpha))_n + beta
 //     with  y(point m deep behind face point n) += BS[m] fcn[n] + (m == 0) fgm[n];
-//   * for the r-faces (k = 1, 2) the table row of every line n: the MCX closure rows of Hs[n]/hr M(crr) u at that
-//     end with the face terms added, and the BM closure rows of Qr u (mirrored and sign-flipped at the far end).
+//   * for the r-faces (k = 1, 2) the table row of every line n (layout: SweepCfg::CLR): the first MCX rows of
+//     Hs[n]/hr M(crr) u at that end with the face terms added, the closure rows of Qr^T w, w = crs o (Qs u) (the s-direction
+//     derivative of the end points goes through shared memory), and the first MCX rows of Qr u (mirrored and sign-flipped
+//     at the far end) -- everything the lanes of k_sweep that own the end points would otherwise have to branch for.
 // with_faces = 0 leaves the face terms out (volume operator A-tilde only).
-// dynamic shared memory: 2 * (max face points) doubles
+// dynamic shared memory: (2 + BN) * (max face points) doubles
 template <int P>
 #ifndef SW_EDGE_MINB
 #define SW_EDGE_MINB 4      // CTAs per SM the register allocation is sized for (measured: 2 -> 0.076, 3 -> 0.068, 4 -> 0.064, 5 -> 0.071 ms)
@@ -926,13 +901,14 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
   // points normal to the face that are looked at: the closure rows need T::NK, the boundary derivative NB
-  constexpr int NK = T::NK >= S::NB ? T::NK : ((S::NB + 1) & ~1);
-  static_assert(NK % 2 == 0 && NK >= S::NB && NK >= T::NK, "normal extent");
+  constexpr int NK = C::NKX, BN = T::BN, BM = T::BM, MCX = C::MCX, MCXP = C::MCXP, H = C::H;
+  static_assert(NK % 2 == 0 && NK >= S::NB && NK >= T::NK && NK >= BN && NK >= MCX + H, "normal extent");
+  static_assert(BM <= T::MC, "the closure rows of Qr^T are rows the table replaces");
   extern __shared__ double sm_face[];
   const int e = e0 + (blockIdx.x >> 2), k = blockIdx.x & 3;
   const BlockDesc d = desc[e];
   const FaceGeom fg = face_geom(d, k);
-  double *sa = sm_face, *sx = sm_face + fg.nf;
+  double *sa = sm_face, *sx = sm_face + fg.nf, *su = sm_face + 2 * fg.nf;      // su[kk][n]: u at the BN end points of line n (r-faces)
   const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
   // One face point per thread and trip; every global load of a trip is issued before its first use.
   // Faces longer than the CTA take several trips: the tangential operators need the whole face in shared
@@ -945,13 +921,14 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
       const bool act = n < fg.nf;
       double b[NK], uu[NK];                    // c_nn and u at normal offsets 0 .. NK-1 behind face point n
       double cxf = 0.0, tauf = 0.0;
+      [[maybe_unused]] double ce[BN];          // crs at the BN end points of line n (r-faces)
       const int64_t fi = d.foff + fg.fstart + n;
       if (act) {
         if (k < 2) {                           // r-faces: u is strided in memory (NK contiguous points per line, 16-byte
                                                // aligned); the static data comes from the rim table, coalesced in n
           const int64_t g0 = d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : Nrp - NK);
           const double2 *pu = reinterpret_cast<const double2 *>(u + g0);
-          const double *pr = rim + (((int64_t)e * 2 + k) * (NK + 2)) * Nsp + n;
+          const double *pr = rim + (((int64_t)e * 2 + k) * C::RIMW) * Nsp + n;
 #pragma unroll
           for (int m = 0; m < NK / 2; ++m) {
             const double2 vu = pu[m];
@@ -960,8 +937,10 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
           }
 #pragma unroll
           for (int m = 0; m < NK; ++m) b[m] = pr[(int64_t)m * Nsp];       // already scaled by Hs[n] / hr
-          cxf = pr[(int64_t)NK * Nsp];
-          tauf = pr[(int64_t)(NK + 1) * Nsp];                              // tau * Hf
+#pragma unroll
+          for (int m = 0; m < BN; ++m) ce[m] = pr[(int64_t)(NK + m) * Nsp];
+          cxf = ce[0];
+          tauf = pr[(int64_t)(NK + BN) * Nsp];                             // tau * Hf
         } else {                               // s-faces: lines 0 .. NB-1 (or Ns .. Ns-NB+1), coalesced along the face
           const int64_t g0 = d.voff + n + (k == 2 ? 0 : (int64_t)Nrp * d.Ns);
           const int64_t ls = k == 2 ? Nrp : -Nrp;
@@ -974,12 +953,18 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
       }
       double cn = 0.0, beta = 0.0, alpha = 0.0;
       const double Hf = fg.ht * hweight<P>(act ? n : 0, fg.Nt);
-      if (with_faces) {
-        if (stage <= 0) {                      // restriction a = L u of the whole face
-          if (act) sa[n] = uu[0];
-          if (stage == 0) continue;
-          __syncthreads();
+      if (stage <= 0) {                        // restriction a = L u of the whole face; u at the end points of every line
+        if (act) {
+          sa[n] = uu[0];
+          if (k < 2) {
+#pragma unroll
+            for (int m = 0; m < BN; ++m) su[m * fg.nf + n] = uu[m];
+          }
         }
+        if (stage == 0) continue;
+        __syncthreads();
+      }
+      if (with_faces) {
         if (stage < 0 || stage == 1) {         // g = G u, then alpha / beta of the boundary condition
           if (act) {
             double bsu = S::bs()[0] * uu[0];
@@ -1003,26 +988,50 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
           beta += fg.sgn * qt_apply<P>(n, fg.Nt, [&](int l) { return sx[l]; });
           if (k >= 2 || stage == 2) { fcn[fi] = cn; fgm[fi] = beta; }   // (r-faces: only needed by the table below)
         }
-      } else if (stage >= 0 && stage < 2) {
+      } else if (stage == 1) {
         continue;
       }
       if (k < 2 && act) {
-        // r-end table row of line n: closure rows of Hs[n]/hr M(crr) u with the face terms, closure rows of Qr u
-        double rows[C::MCX], qq[T::BM];
+        // r-end table row of line n
+        double rows[MCX], qq[MCX];
 #pragma unroll
-        for (int m = 0; m < C::MCX; ++m) rows[m] = 0.0;
+        for (int m = 0; m < MCX; ++m) rows[m] = 0.0;
         d2_closure_rows<P>(b, uu, rows);
+#pragma unroll
+        for (int m = T::MC; m < MCX; ++m)       // (p = 2) interior rows that carry face terms
+          rows[m] = m_apply<P>(m, 2 * NK, [&](int i) { return b[i]; }, [&](int i) { return uu[i]; });
         if (with_faces) {
 #pragma unroll
           for (int m = 0; m < C::NB; ++m) rows[m] = fma(S::bs()[m], cn, rows[m]);
           rows[0] += beta;
         }
+        {                                       // closure rows of Qr^T w, w = crs o (Qs u) at the BN end points of this line
+          double w[BN];
+#pragma unroll
+          for (int m = 0; m < BN; ++m) w[m] = ce[m] * q_apply<P>(n, fg.Nt, [&](int l) { return su[m * fg.nf + l]; });
+#pragma unroll
+          for (int m = 0; m < BM; ++m) rows[m] += (k == 0 ? 1.0 : -1.0) * qt_closure_row<P>(m, w);
+        }
         q_closure_rows<P>(uu, qq);
-        double *out = rtab + (((int64_t)e * Nsp + n) * 2 + k) * C::CLW;
 #pragma unroll
-        for (int m = 0; m < C::MCX; ++m) out[m] = rows[m];
+        for (int m = BM; m < MCX; ++m) {        // interior rows of Qr u
+          double a = 0.0;
 #pragma unroll
-        for (int m = 0; m < T::BM; ++m) out[C::MCX + m] = k == 1 ? -qq[m] : qq[m];
+          for (int o = 1; o <= H; ++o) a = fma(S::d()[H + o], uu[m + o] - uu[m - o], a);
+          qq[m] = a;
+        }
+        double *out = rtab + ((int64_t)e * Nsp + n) * C::CLR;
+        if (k == 0) {
+#pragma unroll
+          for (int m = 0; m < MCXP; ++m) { out[m] = m < MCX ? rows[m] : 0.0; out[MCXP + m] = m < MCX ? qq[m] : 0.0; }
+        } else {                                // far end: mirrored order, Q changes sign
+#pragma unroll
+          for (int m = 0; m < MCXP; ++m) {
+            out[3 * MCXP - 1 - m] = m < MCX ? rows[m] : 0.0;
+            out[4 * MCXP - 1 - m] = m < MCX ? -qq[m] : 0.0;
+          }
+          out[4 * MCXP] = 0.0; out[4 * MCXP + 1] = 0.0;
+        }
       }
     }
     __syncthreads();                           // stage boundary: sa / sx of the whole face are complete
@@ -1034,7 +1043,7 @@ template <int P> static size_t sweep_smem(int Nrp, bool deep) {
   using C = SweepCfg<P>;
   const int LW = Nrp + 2 * C::PAD;
   const int nl = deep ? C::template nlines<true>() : C::template nlines<false>();
-  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * 2 * C::CLW * sizeof(double) + (SW_NST + 1) * sizeof(uint64_t);
+  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * C::CLR * sizeof(double) + (SW_NST + 1) * sizeof(uint64_t);
 }
 
 static int sweep_points_per_thread(const hsbp_blocks *b) {
@@ -1084,15 +1093,16 @@ k_sweep_scale(const double *__restrict__ crr, const double *__restrict__ css, do
 }
 
 // static data of the r-faces for k_edge_prep, laid out [block][end][entry][line] so that threads (= lines) read it
-// coalesced: entries 0..NK-1 = Hs[n]/hr * crr at the NK points behind the face point, NK = crs at the face point,
-// NK+1 = tau * Hf
+// coalesced: entries 0..NK-1 = Hs[n]/hr * crr at the NK points behind the face point, NK..NK+BN-1 = crs at the BN points
+// behind it, NK+BN = tau * Hf
 template <int P>
 __global__ void __launch_bounds__(256)
 k_rim_build(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ crs,
             const double *__restrict__ tau, double *__restrict__ rim) {
   using S = Sbp<P>;
   using T = SweepTab<P>;
-  constexpr int NK = T::NK >= S::NB ? T::NK : ((S::NB + 1) & ~1);
+  using C = SweepCfg<P>;
+  constexpr int NK = C::NKX, BN = T::BN;
   const int e = blockIdx.x >> 1, k = blockIdx.x & 1;
   const BlockDesc d = desc[e];
   const FaceGeom fg = face_geom(d, k);
@@ -1100,10 +1110,10 @@ k_rim_build(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   for (int n = threadIdx.x; n < Nsp; n += blockDim.x) {
     const double Hf = fg.ht * hweight<P>(n, fg.Nt);
     const int64_t g0 = d.voff + (int64_t)Nrp * n;
-    double *pr = rim + (((int64_t)e * 2 + k) * (NK + 2)) * Nsp + n;
+    double *pr = rim + (((int64_t)e * 2 + k) * C::RIMW) * Nsp + n;
     for (int m = 0; m < NK; ++m) pr[(int64_t)m * Nsp] = (Hf / fg.hn) * crr[g0 + (k == 0 ? m : d.Nr - m)];
-    pr[(int64_t)NK * Nsp] = crs[g0 + (k == 0 ? 0 : d.Nr)];
-    pr[(int64_t)(NK + 1) * Nsp] = tau[d.foff + fg.fstart + n] * Hf;
+    for (int m = 0; m < BN; ++m) pr[(int64_t)(NK + m) * Nsp] = crs[g0 + (k == 0 ? m : d.Nr - m)];
+    pr[(int64_t)(NK + BN) * Nsp] = tau[d.foff + fg.fstart + n] * Hf;
   }
 }
 
@@ -1111,12 +1121,11 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   hsbp_ctx *ctx = b->ctx;
   if (b->sweep_scaled_valid && b->rim_valid) return HSBP_OK;
   const size_t vb = (size_t)b->VNp * sizeof(double);
-  constexpr int NKX = SweepTab<P>::NK >= Sbp<P>::NB ? SweepTab<P>::NK : ((Sbp<P>::NB + 1) & ~1);
   if (!b->d_crr_s) {
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crr_s, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_css_s, vb));
-    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * 2 * SweepCfg<P>::CLW * sizeof(double)));
-    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rim, (size_t)b->nblocks * 2 * (NKX + 2) * (b->max_Ns + 1) * sizeof(double)));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * SweepCfg<P>::CLR * sizeof(double)));
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rim, (size_t)b->nblocks * 2 * SweepCfg<P>::RIMW * (b->max_Ns + 1) * sizeof(double)));
   }
   k_sweep_scale<P><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->d_crr, b->d_css, b->d_crr_s, b->d_css_s, b->max_Nr,
                                                               b->max_Ns, b->VNp);
@@ -1226,7 +1235,7 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
   if (ne < 0) ne = b->nblocks - e0;
   int rc = sweep_prepare<P>(b);
   if (rc) return rc;
-  const size_t fsm = 2 * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
+  const size_t fsm = (2 + SweepTab<P>::BN) * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
   k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
       b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim);
   cudaError_t e1 = cudaGetLastError();
