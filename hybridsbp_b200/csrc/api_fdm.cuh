@@ -133,7 +133,8 @@ __global__ void k_fdm_dinv(const BlockDesc *__restrict__ desc, const double *__r
 // PCG with a general preconditioner, part 1 (after Ap = M̃ p): x += alpha p, r -= alpha Ap, rr = r.r
 __global__ void __launch_bounds__(1024)
 k_fpcg_update1(const BlockDesc *__restrict__ desc, const double *__restrict__ Ap, double *__restrict__ x,
-               double *__restrict__ r, const double *__restrict__ p, PcgState *__restrict__ st, double tol2) {
+               double *__restrict__ r, const double *__restrict__ p, PcgState *__restrict__ st, double tol2,
+               float *__restrict__ r32) {      // r32 (optional): r rounded to TF32, the tensor-core operand of z = P^-1 r
   __shared__ double scratch[32];
   const BlockDesc d = desc[blockIdx.x];
   PcgState s = st[blockIdx.x];
@@ -148,6 +149,7 @@ k_fpcg_update1(const BlockDesc *__restrict__ desc, const double *__restrict__ Ap
     x[o + i] += alpha * p[o + i];
     const double ri = r[o + i] - alpha * Ap[o + i];
     r[o + i] = ri;
+    if (r32) r32[o + i] = hsbp::tc::round_tf32((float)ri);
     rr += ri * ri;
   }
   rr = cta_sum(rr, scratch);
@@ -194,6 +196,10 @@ k_fpcg_update2(const BlockDesc *__restrict__ desc, const double *__restrict__ r,
 __global__ void k_f64_to_f32(int64_t n, const double *__restrict__ x, float *__restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = (float)x[i];
 }
+__global__ void k_f64_to_tf32(int64_t n, const double *__restrict__ x, float *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = hsbp::tc::round_tf32((float)x[i]);
+}
 __global__ void k_f32_to_f64(int64_t n, const float *__restrict__ x, double *__restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = (double)x[i];
 }
@@ -203,7 +209,7 @@ __global__ void k_mul_f32(int64_t n, float *__restrict__ x, const float *__restr
 // x = 0, r = g, g2 = rr = g.g
 __global__ void __launch_bounds__(1024)
 k_fpcg_init(const BlockDesc *__restrict__ desc, const double *__restrict__ g, double *__restrict__ x,
-            double *__restrict__ r, double *__restrict__ p, PcgState *__restrict__ st) {
+            double *__restrict__ r, double *__restrict__ p, PcgState *__restrict__ st, float *__restrict__ r32) {
   __shared__ double scratch[32];
   const BlockDesc d = desc[blockIdx.x];
   const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1), o = d.voff;
@@ -211,6 +217,7 @@ k_fpcg_init(const BlockDesc *__restrict__ desc, const double *__restrict__ g, do
   for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
     const double gi = g[o + i];
     x[o + i] = 0.0; r[o + i] = gi; p[o + i] = 0.0;
+    if (r32) r32[o + i] = hsbp::tc::round_tf32((float)gi);
     gg += gi * gi;
   }
   gg = cta_sum(gg, scratch);
@@ -273,6 +280,31 @@ void fdm_libs_destroy(hsbp_ctx *ctx) {
   if (l->solver) cusolverDnDestroy(l->solver);
   delete l;
   ctx->fdm_libs = nullptr;
+}
+
+// 3-D tensor map over a batch of `rows` x `inner` fp32 matrices (inner index contiguous): box = 32 x box_rows x 1 with the
+// 128-byte swizzle the tensor-core descriptors of k_fdm_pair expect
+int fdm_encode_map(hsbp_ctx *ctx, void *tm_out, const float *base, int inner, int rows, int64_t nb, int box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn enc = nullptr;
+  if (!enc) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      HSBP_FAIL(ctx, HSBP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    enc = (encode_fn)fn;
+  }
+  const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb};
+  const cuuint64_t gstr[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * rows * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc((CUtensorMap *)tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSBP_FAIL(ctx, HSBP_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return HSBP_OK;
 }
 
 template <int P> int fdm_setup_p(hsbp_blocks *b) {
@@ -394,6 +426,17 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
     hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nrp, Nrp, b->d_fdm_vr32, b->d_fdm_vrT32);
     hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nsp, Nsp, b->d_fdm_vs32, b->d_fdm_vsT32);
     hsbp::tc::k_transpose_f32<<<dim3(64, (unsigned)nb), 256, 0, ctx->stream>>>(Nrp, Nsp, b->d_fdm_dinv32, b->d_fdm_dinvT32);
+    b->fdm_tm_valid = false;
+    if (b->fdm_gemm == 3 && fdm_tc_shapes_ok(Nrp, Nsp)) {       // tensor maps of k_fdm_pair: (a) Vr, r32, Vs   (b) Vr^T, T3, Vs^T
+      rc = fdm_encode_map(ctx, b->fdm_tm[0], b->d_fdm_vr32, Nrp, Nrp, nb, 128);
+      if (!rc) rc = fdm_encode_map(ctx, b->fdm_tm[1], b->d_fdm_a32, Nrp, Nsp, nb, Nsp);
+      if (!rc) rc = fdm_encode_map(ctx, b->fdm_tm[2], b->d_fdm_vs32, Nsp, Nsp, nb, Nsp);
+      if (!rc) rc = fdm_encode_map(ctx, b->fdm_tm[3], b->d_fdm_vrT32, Nrp, Nrp, nb, 128);
+      if (!rc) rc = fdm_encode_map(ctx, b->fdm_tm[4], b->d_fdm_b32, Nrp, Nsp, nb, Nsp);
+      if (!rc) rc = fdm_encode_map(ctx, b->fdm_tm[5], b->d_fdm_vsT32, Nsp, Nsp, nb, Nsp);
+      if (rc) { cleanup(); return rc; }
+      b->fdm_tm_valid = true;
+    }
   }
   e1 = cudaGetLastError();
   if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
@@ -414,11 +457,29 @@ int fdm_setup(hsbp_blocks *b) {
 //   fdm_gemm = 0  fp64 on the fp64 tensor pipe (mma.sync.m8n8k4.f64), any block size.
 //   fdm_gemm = -1 the strided-batched cuBLAS TF32 GEMMs of round 1 -- kept only so that tests can compare the hand-written
 //                 kernels with a library result; never a default.
-int fdm_precondition(hsbp_blocks *b, const double *r, double *z) {
+int fdm_precondition(hsbp_blocks *b, const double *r, double *z, bool r32_ready = false, const int *active = nullptr,
+                     int active_stride = 0) {
   hsbp_ctx *ctx = b->ctx;
   const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
   const int nb = (int)b->nblocks;
   const long long sv = (long long)Nrp * Nsp, sr = (long long)Nrp * Nrp, ss = (long long)Nsp * Nsp;
+  if (b->fdm_gemm == 3 && b->fdm_tm_valid && b->fdm_tc_variant == 0) {
+    // two launches of k_fdm_pair (k_tcgemm.cuh): T3 = ((Vr^T R) Vs) o Dinv, then Z = (Vr T3) Vs^T; r as TF32-rounded fp32 in
+    // d_fdm_a32 (written by the PCG update kernels, or converted here), T3 in d_fdm_b32
+    using namespace hsbp::tc;
+    if (!r32_ready) k_f64_to_tf32<<<vec_grid(b->VNp), VEC_THREADS, 0, ctx->stream>>>(b->VNp, r, b->d_fdm_a32);
+    PairParams pp;
+    pp.active = active; pp.active_stride = active_stride; pp.M = Nrp; pp.N = Nsp; pp.strideO = sv;
+    const CUtensorMap *tm = reinterpret_cast<const CUtensorMap *>(b->fdm_tm);
+    const dim3 grid((unsigned)(Nrp / BM), (unsigned)nb);
+    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_fdm_pair<false>, pair_smem_bytes()));
+    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_fdm_pair<true>, pair_smem_bytes()));
+    pp.out = b->d_fdm_b32; pp.scale = b->d_fdm_dinv32;
+    k_fdm_pair<false><<<grid, THREADS, pair_smem_bytes(), ctx->stream>>>(tm[0], tm[1], tm[2], pp);
+    pp.out = z; pp.scale = nullptr;
+    k_fdm_pair<true><<<grid, THREADS, pair_smem_bytes(), ctx->stream>>>(tm[3], tm[4], tm[5], pp);
+    return check_launch(ctx, "fdm_precondition (tcgen05 TF32, fused pairs)");
+  }
   if (b->fdm_gemm == 3 && fdm_tc_shapes_ok(Nrp, Nsp)) {
     using namespace hsbp::tc;
     float *t1 = b->d_fdm_a32, *t3 = b->d_fdm_b32;
@@ -495,8 +556,19 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
   double *r = b->d_pr, *p = b->d_pp, *Ap = b->d_pAp, *z = b->d_fdm_z;
   const unsigned nb = (unsigned)b->nblocks;
   int rc;
-  k_fpcg_init<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, g, x, r, p, st);
-  if ((rc = fdm_precondition(b, r, z))) return rc;
+  // converged blocks drop out of every kernel of the iteration: the update kernels, the operator apply and the preconditioner
+  // all look at PcgState::active
+  const int *act = reinterpret_cast<const int *>(reinterpret_cast<const char *>(st) + offsetof(PcgState, active));
+  const int act_stride = (int)(sizeof(PcgState) / sizeof(int));
+  const bool pair = b->fdm_gemm == 3 && b->fdm_tm_valid && b->fdm_tc_variant == 0;
+  float *r32 = pair ? b->d_fdm_a32 : nullptr;
+  struct SkipGuard {                                   // hsbp_apply of other callers must see every block again
+    hsbp_blocks *b;
+    ~SkipGuard() { b->skip_flags = nullptr; b->skip_stride = 0; }
+  } guard{b};
+  k_fpcg_init<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, g, x, r, p, st, r32);
+  if ((rc = fdm_precondition(b, r, z, pair, act, act_stride))) return rc;
+  if (!b->fdm_no_skip) { b->skip_flags = act; b->skip_stride = act_stride; }
   HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive, 0, 2 * sizeof(int), ctx->stream));
   k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, Ap, p, st, 1, b->d_nactive);
   const int check_every = 4;
@@ -506,8 +578,8 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
     int slot = 0;
     for (int k = 0; k < check_every && it < b->local_maxit; ++k, ++it) {
       if ((rc = apply_async(b, p, Ap))) return rc;
-      k_fpcg_update1<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, Ap, x, r, p, st, tol2);
-      if ((rc = fdm_precondition(b, r, z))) return rc;
+      k_fpcg_update1<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, Ap, x, r, p, st, tol2, r32);
+      if ((rc = fdm_precondition(b, r, z, pair, b->fdm_no_skip ? nullptr : act, act_stride))) return rc;
       slot = (int)(it & 1);
       HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive + slot, 0, sizeof(int), ctx->stream));
       k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, Ap, p, st, 0, b->d_nactive + slot);

@@ -337,6 +337,8 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "sweep_deep") b->sweep_deep = (int)value;
   else if (n == "fdm_gemm") b->fdm_gemm = (int)value;
   else if (n == "fdm_tc_sync") b->fdm_tc_sync = (int)value;
+  else if (n == "fdm_tc_variant") b->fdm_tc_variant = (int)value;
+  else if (n == "fdm_no_skip") b->fdm_no_skip = (int)value;
   else if (n == "sweep_p6_regs") b->sweep_p6_regs = (int)value;
   else if (n == "band_no_stream") b->band_no_stream = (int)value;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);

@@ -139,6 +139,9 @@ struct SweepParams {
   int ncs;            // chunks per side (a block is 2*ncs CTAs)
   int K;              // lines [0, K) are marched upwards, lines [K, Ns] downwards
   int per_up, per_dn; // output lines per chunk on either side
+  // optional: blocks whose flag active[e * active_stride] is 0 are skipped (converged blocks of a batched PCG; y is not written)
+  const int *active;
+  int active_stride;
 };
 
 template <int P> struct SweepCfg {
@@ -251,6 +254,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int64_t el = blockIdx.x / nch;
   const int c = (int)(blockIdx.x - el * nch);
   const int64_t e = prm.e0 + el;
+  if (prm.active != nullptr && prm.active[e * prm.active_stride] == 0) return;
   const bool up = c < prm.ncs;
   const int cc = up ? c : c - prm.ncs;
   const int nside = up ? prm.K : Nsp - prm.K;
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(256, SW_EDGE_MINB)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
             double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
-            const double *__restrict__ rim) {
+            const double *__restrict__ rim, const int *__restrict__ active, int active_stride) {
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -906,6 +910,7 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   static_assert(BM <= T::MC, "the closure rows of Qr^T are rows the table replaces");
   extern __shared__ double sm_face[];
   const int e = e0 + (blockIdx.x >> 2), k = blockIdx.x & 3;
+  if (active != nullptr && active[(int64_t)e * active_stride] == 0) return;       // block skipped by the caller (see SweepParams)
   const BlockDesc d = desc[e];
   const FaceGeom fg = face_geom(d, k);
   double *sa = sm_face, *sx = sm_face + fg.nf, *su = sm_face + 2 * fg.nf;      // su[kk][n]: u at the BN end points of line n (r-faces)
@@ -1200,6 +1205,7 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   prm.crr = b->d_crr_s; prm.css = b->d_css_s; prm.crs = b->d_crs; prm.u = u; prm.y = y;
   prm.fcn = with_faces ? b->d_fa : nullptr; prm.fgm = with_faces ? b->d_fb : nullptr;
   prm.rtab = b->d_rtab;
+  prm.active = b->skip_flags; prm.active_stride = b->skip_stride;
   prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K; prm.e0 = (int)e0;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
@@ -1237,7 +1243,8 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
   if (rc) return rc;
   const size_t fsm = (2 + SweepTab<P>::BN) * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
   k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
-      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim);
+      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
+      b->skip_flags, b->skip_stride);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_edge_prep: ") + cudaGetErrorString(e1);

@@ -14,6 +14,7 @@
 // The preconditioner z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T is four launches of this kernel (api_fdm.cuh); the reference has
 // no counterpart -- it factorises M-tilde (global_curved.jl:698) -- this is the engine of the batched PCG local solver.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -393,6 +394,209 @@ k_tc_gemm_async(GemmParams p) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+}
+
+
+// ---- two chained GEMMs per launch: TMA operands, second GEMM reads its A operand from tensor memory ---------------------------
+//   D1[128 x N]  = A1[m-tile, K = M] * B1[N, K = M]^T          both operands from shared memory (SS)
+//   D2[128 x N]  = D1[128, K = N]    * B2[N, K = N]^T          A = the accumulator of the first GEMM, where it lies in TMEM (TS)
+// The preconditioner  Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T  is two launches:
+//   (a)  T3 = ((Vr^T R) Vs) o Dinv      A1 = Vr (rows m, k contiguous), B1 = R as fp32, B2 = Vs;       out fp32, column-major, TF32-rounded
+//   (b)  Z  = (Vr T3) Vs^T              A1 = Vr^T, B1 = T3 (column-major: contiguous in the contraction index), B2 = Vs^T;  out fp64
+// so T1 = Vr^T R and Vr T3 never leave the SM (each is 128 KB of TMEM per CTA).
+// Every operand tile is one 3-D TMA box (32 fp32 = 128 bytes along k, all rows, one block of the batch) written with the 128-byte
+// swizzle the tensor core reads; a 4-stage ring of 48 KB stages, filled by one elected lane of warp 0, drained by one elected
+// lane of warp 1 which issues the MMAs (4 x K = 8 per stage) and commits each stage back to the producer.  TMEM: columns
+// [0, N) hold D1, [N, 2N) D2.  All eight warps run the epilogue (tcgen05.ld, 32 lanes x 32 columns per call), lanes = rows of the
+// tile, so that every store instruction of a warp writes 32 consecutive values of a column.
+constexpr int PSTG = 4;
+constexpr int PA_BYTES = BM * 128;                 // A tile: 128 rows x 128 bytes
+constexpr int PB_BYTES = 256 * 128;                // B tile: up to 256 rows x 128 bytes
+constexpr int PSTAGE_BYTES = PA_BYTES + PB_BYTES;
+__host__ __device__ inline size_t pair_smem_bytes() { return (size_t)PSTG * PSTAGE_BYTES + 1024; }
+
+struct PairParams {
+  void *out;              // (a) fp32 / (b) fp64, [b * strideO + m + M * n]
+  const float *scale;     // (a) Dinv as fp32, indexed like out; (b) unused
+  const int *active;      // optional per-block flag (block b at active[b * active_stride]); blocks with 0 are skipped
+  int active_stride;
+  int M, N;               // block is M x N (M = Nr+1 = rows and K of the first GEMM, N = Ns+1 = columns and K of the second)
+  int64_t strideO;
+};
+
+// K-major operand tile with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+  d |= (uint64_t)1 << 46;                         // descriptor version of sm_100
+  d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one_() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// OUT_F64: launch (b), fp64 output, no scaling.  Between the GEMMs warps 4..7 round the accumulator of the first one to the
+// nearest TF32 in place (tcgen05.ld / tcgen05.st) -- as an operand the tensor core would truncate it -- and the issuing lane
+// waits for them: the second GEMM must not read D1 before the first one has committed (measured: back-to-back issue without
+// the commit / wait reads a partial accumulator).
+template <bool OUT_F64>
+__global__ void __launch_bounds__(THREADS, 1)
+k_fdm_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+           const __grid_constant__ CUtensorMap tmB2, const PairParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t bar_full[PSTG], bar_empty[PSTG], bar_acc1, bar_mid, bar_acc2;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, b = blockIdx.y;
+  if (p.active != nullptr && p.active[(int64_t)b * p.active_stride] == 0) return;       // converged block (uniform per CTA)
+  const int N = p.N, nk1 = p.M / BK, nk2 = N / BK, nit = nk1 + nk2;
+  const uint32_t s0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ncols = 2 * N <= 256 ? 256u : 512u;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < PSTG; ++s) { mbar_init_(&bar_full[s], 1); mbar_init_(&bar_empty[s], 1); }
+    mbar_init_(&bar_acc1, 1); mbar_init_(&bar_mid, 128); mbar_init_(&bar_acc2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_x = tmem_base_s, tmem_y = tmem_base_s + (uint32_t)N;
+
+  if (warp == 0) {
+    if (elect_one_()) {                                            // ---- producer: TMA into the ring ----
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % PSTG;
+        if (it >= PSTG) mbar_wait_(&bar_empty[s], (uint32_t)((it / PSTG - 1) & 1));
+        const uint32_t sa = s0 + (uint32_t)s * PSTAGE_BYTES, sb = sa + PA_BYTES;
+        if (it < nk1) {
+          mbar_expect_tx_(&bar_full[s], (uint32_t)(PA_BYTES + N * 128));
+          tma_load_3d(sa, &tmA1, it * BK, mt * BM, b, &bar_full[s]);
+          tma_load_3d(sb, &tmB1, it * BK, 0, b, &bar_full[s]);
+        } else {
+          mbar_expect_tx_(&bar_full[s], (uint32_t)(N * 128));
+          tma_load_3d(sb, &tmB2, (it - nk1) * BK, 0, b, &bar_full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_()) {                                            // ---- MMA issuer ----
+      const uint32_t idesc = make_idesc(BM, N);
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % PSTG;
+        mbar_wait_(&bar_full[s], (uint32_t)((it / PSTG) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = s0 + (uint32_t)s * PSTAGE_BYTES, sb = sa + PA_BYTES;
+        if (it < nk1) {
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j)
+            mma_tf32(tmem_x, make_desc_sw128(sa + 32u * j), make_desc_sw128(sb + 32u * j), idesc, (it > 0 || j > 0) ? 1u : 0u);
+        } else {
+          const int kk = it - nk1;
+          if (kk == 0) {                                    // D1 rounded in place by warps 4..7
+            mbar_wait_(&bar_mid, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j)
+            mma_tf32_ts(tmem_y, tmem_x + (uint32_t)(kk * BK + 8 * j), make_desc_sw128(sb + 32u * j), idesc, (kk > 0 || j > 0) ? 1u : 0u);
+        }
+        mma_commit(&bar_empty[s]);
+        if (it == nk1 - 1) mma_commit(&bar_acc1);
+        if (it == nit - 1) mma_commit(&bar_acc2);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {                                   // ---- D1 -> nearest TF32, in place ----
+    mbar_wait_(&bar_acc1, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tl = tmem_x + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tl + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(round_tf32(__uint_as_float(v[j])));
+      tmem_st32(tl + (uint32_t)c0, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive_(&bar_mid);
+  }
+
+  // ---- epilogue: D2 -> global, column-major (lanes = rows: coalesced) ----
+  mbar_wait_(&bar_acc2, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int row = mt * BM + (warp & 3) * 32 + lane;
+    const uint32_t tl = tmem_y + ((uint32_t)((warp & 3) * 32) << 16);
+    const int64_t ob = (int64_t)b * p.strideO + row;
+    for (int c0 = (warp >> 2) * 32; c0 < N; c0 += 64) {
+      uint32_t v[32];
+      tmem_ld32(tl + (uint32_t)c0, v);
+      if constexpr (OUT_F64) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double *o = reinterpret_cast<double *>(p.out) + ob + (int64_t)c0 * p.M;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[(int64_t)j * p.M] = (double)__uint_as_float(v[j]);
+      } else {
+        const float *sc = p.scale + ob + (int64_t)c0 * p.M;
+        float q[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) q[j] = __ldg(sc + (int64_t)j * p.M);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float *o = reinterpret_cast<float *>(p.out) + ob + (int64_t)c0 * p.M;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[(int64_t)j * p.M] = round_tf32(__uint_as_float(v[j]) * q[j]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(ncols) : "memory");
 }
 
 }  // namespace tc

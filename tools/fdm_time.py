@@ -20,10 +20,15 @@ x0 = np.random.default_rng(5).uniform(-1, 1, blk.VNp)
 dx0, dg, dx, dr = ctx.array(x0), ctx.empty(blk.VNp), ctx.empty(blk.VNp), ctx.empty(blk.VNp)
 blk.apply(dx0, dg)
 dz = ctx.empty(blk.VNp)
-for name, mode, gemm in (("FDM-PCG, fp64 GEMMs (mma.sync f64, own kernel)", hs.LOCAL_FDM, 0),
-                         ("FDM-PCG, TF32 GEMMs (tcgen05 + TMEM, own kernel)", hs.LOCAL_FDM, 3),
-                         ("FDM-PCG, TF32 GEMMs (cuBLAS, comparison only)", hs.LOCAL_FDM, -1)) + \
-        ((("Jacobi-PCG", hs.LOCAL_PCG, 0),) if jac else ()):
+for name, mode, gemm, opts in (
+        ("FDM-PCG, fp64 GEMMs (mma.sync f64, own kernel)", hs.LOCAL_FDM, 0, {}),
+        ("FDM-PCG, TF32 (tcgen05: two fused GEMM pairs, TMA, TMEM operand)", hs.LOCAL_FDM, 3, {"fdm_tc_variant": 0}),
+        ("FDM-PCG, TF32 (same, converged blocks NOT skipped)", hs.LOCAL_FDM, 3, {"fdm_tc_variant": 0, "fdm_no_skip": 1}),
+        ("FDM-PCG, TF32 (tcgen05: four single-GEMM launches)", hs.LOCAL_FDM, 3, {"fdm_tc_variant": 1, "fdm_no_skip": 0}),
+        ("FDM-PCG, TF32 GEMMs (cuBLAS, comparison only)", hs.LOCAL_FDM, -1, {})) + \
+        ((("Jacobi-PCG", hs.LOCAL_PCG, 0, {}),) if jac else ()):
+    for k, v in opts.items():
+        blk.set_option(k, v)
     t0 = time.time()
     blk.set_option("fdm_gemm", gemm)
     blk.local_setup(mode, tol=1e-13, maxit=2000)
