@@ -197,7 +197,7 @@ int hsbp_blocks_create(hsbp_ctx *ctx, int p, int64_t nblocks, const int64_t *Nr,
   auto A = [&](void **p_, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p_, n); };
   A((void **)&b->d_desc, nblocks * sizeof(BlockDesc));
   A((void **)&b->d_crr, vb); A((void **)&b->d_css, vb); A((void **)&b->d_crs, vb);
-  A((void **)&b->d_tau, fb); A((void **)&b->d_fa, fb); A((void **)&b->d_fb, fb);
+  A((void **)&b->d_tau, fb); A((void **)&b->d_fa, fb + 64); A((void **)&b->d_fb, fb + 64);   // (k_sweep's phantom point reads one entry past a face)
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(b->d_desc, b->h_desc.data(), nblocks * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -216,6 +216,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
   cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab); cudaFree(b->d_rim);
+  cudaFree(b->d_crs_p); cudaFree(b->d_u_p); cudaFree(b->d_y_p);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);

@@ -131,10 +131,11 @@ struct SweepParams {
   // face terms of M-tilde, prepared per face point by k_face_prep (k_generic.cuh), block-face layout:
   //   y(point at normal offset m from face point n) += BS[m] * fcn[n] + (m == 0) * fgm[n];   null: volume part only
   const double *fcn, *fgm;
-  // r-end table made by k_edge_prep: [block][line][CLR], see SweepCfg::CLR
+  // r-end table made by k_edge_prep: [block][line][clr], see SweepCfg::clr
   const double *rtab;
   double *y;
   int Nr, Ns;         // uniform block size
+  int pitch;          // ODD kernels: distance between lines of the volume fields (Nr + 2, even); the pad entry of every line is 0
   int e0;             // first block of this launch (a launch may cover a range of the blocks)
   int ncs;            // chunks per side (a block is 2*ncs CTAs)
   int K;              // lines [0, K) are marched upwards, lines [K, Ns] downwards
@@ -152,13 +153,16 @@ template <int P> struct SweepCfg {
   static constexpr int MCX = T::MC > NB ? T::MC : NB;       // rows of an r-end that take table values
   // r-end table of one line (k_edge_prep), laid out so that the lanes that own the end points pick their values up
   // with 16-byte loads in point order:
-  //   [ near: rr(0 .. MCXP-1) | near: qr(0 .. MCXP-1) | far: rr(MCXP-1 .. 0) | far: qr(MCXP-1 .. 0) | 0 0 ]
+  //   [ near: rr(0 .. MCXP-1) | near: qr(0 .. MCXP-1) | far: rr(.. 1 0) | far: qr(.. 1 0) | 0 0 ]
   // rr(m) = row m of Hs/hr M(crr) u  +  face terms of faces 1, 2  +  row m of Qr^T w, w = crs o (Qs u)   (replaces the lane's value)
   // qr(m) = row m of Qr u (closure rows m < BM and the interior rows up to MCX, so that one mask serves both)
   // rows MCX .. MCXP-1 and the last pair are zero (a lane whose pair sticks out adds them).
+  // ODD (lines with an odd number of points, stored with an even pitch: the last lane owns the last point and a phantom):
+  // the far sections are two entries longer and the rows sit one position lower, so that the pairs stay aligned.
   static constexpr int MCXP = (MCX + 1) & ~1;
-  static constexpr int CLW = 2 * MCXP;                       // one end
-  static constexpr int CLR = 4 * MCXP + 2;                   // one line: CLR * 8 bytes is a multiple of 16
+  template <bool ODD> static constexpr int lf() { return MCXP + (ODD ? 2 : 0); }          // length of a far section
+  template <bool ODD> static constexpr int clr() { return 2 * MCXP + 2 * lf<ODD>() + 2; } // one line: clr * 8 bytes is a multiple of 16
+  template <bool ODD> static constexpr int farpos(int m) { return lf<ODD>() - 1 - (ODD ? 1 : 0) - m; }   // row m inside a far section
   static constexpr int NKX = T::NK >= NB ? T::NK : ((NB + 1) & ~1);   // points normal to an r-face that k_edge_prep looks at
   static constexpr int RIMW = NKX + T::BN + 1;               // rim table entries per (line, end): crr' (NKX), crs (BN), tau Hf
   // ring depths (lines) of the four fields.  u and crr are only looked at on the newest line.  DEEP: css and crs
@@ -225,11 +229,13 @@ template <int T0, int T1, class F> __device__ __forceinline__ void for_lanes(F &
 // NT: upper bound of the CTA size; MINB: CTAs per SM the register allocation is sized for.
 // DEEP: the steady state reads css / crs of older lines from deeper shared-memory rings instead of register
 // windows (SweepCfg::nsb, nsc): 2H+1 lines of u and 2H+1 accumulators remain as per-point register state.
-template <int P, int R, bool DEEP>
+template <int P, int R, bool DEEP, bool ODD = false>
 __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
-  constexpr int H = C::H, W = C::W, PAD = C::PAD, MCXP = C::MCXP, CLR = C::CLR, NST = SW_NST;
+  constexpr int H = C::H, W = C::W, PAD = C::PAD, MCXP = C::MCXP, NST = SW_NST;
+  constexpr int LF = C::template lf<ODD>(), CLR = C::template clr<ODD>(), SODD = ODD ? 1 : 0;
+  static_assert(!ODD || R == 2, "odd line lengths: two points per thread");
   constexpr int NSB = C::template nsb<DEEP>(), NSC = C::template nsc<DEEP>(), NLINES = C::template nlines<DEEP>();
   constexpr int MC = T::MC, BM = T::BM, BN = T::BN, MCX = C::MCX, NB = C::NB;
   constexpr int NV = R + 2 * PAD;                         // values of a line a thread looks at
@@ -238,7 +244,8 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int Nr = prm.Nr, Ns = prm.Ns, Nrp = Nr + 1, Nsp = Ns + 1;
+  // Nrp: length of a stored line (ODD: the pitch, one phantom point behind the last one), Nrt: points of a line
+  const int Nr = prm.Nr, Ns = prm.Ns, Nrt = Nr + 1, Nrp = ODD ? prm.pitch : Nrt, Nsp = Ns + 1;
   // A "slot" holds one line of one field: PAD doubles of zeros (left halo), the Nrp values, PAD zeros (right halo)
   const int LW = Nrp + 2 * PAD;
   double *ring_u = reinterpret_cast<double *>(smem_raw);  // [NST][LW]
@@ -268,7 +275,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int64_t lstride = up ? (int64_t)Nrp : -(int64_t)Nrp;
   const int64_t base = e * (int64_t)Nrp * Nsp + (up ? 0 : (int64_t)Ns * Nrp);   // marching line j starts at base + j*lstride
   const uint32_t line_bytes = (uint32_t)Nrp * 8u;
-  const int64_t foff = e * (2 * (int64_t)Nrp + 2 * (int64_t)Nsp);    // block e in the block-face layout
+  const int64_t foff = e * (2 * (int64_t)Nrt + 2 * (int64_t)Nsp);    // block e in the block-face layout
 
   // ---- one-time setup: zero the halos of the shared lines, barriers --------------------------
   for (int idx = tid; idx < NLINES * 2 * PAD; idx += nthreads) {
@@ -433,7 +440,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         for (int q = 0; q < R; ++q) {
           const int i = i0 + q, m = Nr - i;
           if (i < MCX) { rr[q] = cl[i]; qr[q] = cl[MCXP + i]; }
-          else if (m < MCX) { rr[q] = cl[3 * MCXP - 1 - m]; qr[q] = cl[4 * MCXP - 1 - m]; }
+          else if (m >= 0 && m < MCX) { rr[q] = cl[2 * MCXP + LF - 1 - SODD - m]; qr[q] = cl[2 * MCXP + LF + LF - 1 - SODD - m]; }
         }
       }
       double t[R];
@@ -550,7 +557,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
       }
       if constexpr (!FAST) {
         if (pro && jo < NB && prm.fcn != nullptr) {       // s-face terms: face 3 (line 0 side) / 4 (line Ns side)
-          const int64_t fi = foff + 2 * Nsp + (up ? 0 : Nrp) + i0;
+          const int64_t fi = foff + 2 * Nsp + (up ? 0 : Nrt) + i0;
           const double bsm = C::bs()[jo];
 #pragma unroll
           for (int q = 0; q < R; ++q) {
@@ -603,7 +610,8 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int nrefill = opaque(nlines - NST);                // steps after which no line is left to fetch
   const int nwarps = opaque(nthreads >> 5);
   const int mywarp = opaque(tid >> 5);
-  const int edge = opaque((own && (tid < ELANES || tid >= nown - ELANES)) ? 1 : 0);
+  constexpr int ELF = (MCX + SODD + R - 1) / R;            // lanes at the far end (ODD: the phantom point shifts the rows by one)
+  const int edge = opaque((own && (tid < ELANES || tid >= nown - ELF)) ? 1 : 0);
   // edge lanes: byte offsets of their pairs in a table row (SweepCfg::CLR) and the blend factors; closm: points that are closure
   // rows of Qr^T (their accumulator already holds the whole row)
   uint32_t eo_rr[R / 2], eo_qr[R / 2];
@@ -614,16 +622,16 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     const int d = nearl ? tid : nown - 1 - tid;            // distance of the lane from its end, in lanes
 #pragma unroll
     for (int k = 0; k < R / 2; ++k) {
-      const int pos = nearl ? d * R + 2 * k : MCXP - (d + 1) * R + 2 * k;      // first entry of the pair inside rr(0 .. MCXP-1)
-      const bool ok = pos >= 0 && pos < MCXP;
-      eo_rr[k] = opaque(8u * (uint32_t)(ok ? (nearl ? pos : 2 * MCXP + pos) : 4 * MCXP));
-      eo_qr[k] = opaque(8u * (uint32_t)(ok ? (nearl ? MCXP + pos : 3 * MCXP + pos) : 4 * MCXP));
+      const int pos = nearl ? d * R + 2 * k : LF - (d + 1) * R + 2 * k;        // first entry of the pair inside its section
+      const bool ok = pos >= 0 && pos < (nearl ? MCXP : LF);
+      eo_rr[k] = opaque(8u * (uint32_t)(ok ? (nearl ? pos : 2 * MCXP + pos) : 2 * MCXP + 2 * LF));
+      eo_qr[k] = opaque(8u * (uint32_t)(ok ? (nearl ? MCXP + pos : 2 * MCXP + LF + pos) : 2 * MCXP + 2 * LF));
     }
 #pragma unroll
     for (int q = 0; q < R; ++q) {
-      const int row = nearl ? d * R + q : d * R + (R - 1 - q);                 // row of the closure this point is
-      keep[q] = opaque((edge && row < MCX) ? 0.0 : 1.0);
-      if (edge && row < BM) closm_ |= 1 << q;
+      const int row = nearl ? d * R + q : (d + 1) * R - 1 - SODD - q;          // row of the closure this point is (-1: phantom)
+      keep[q] = opaque((edge && row >= 0 && row < MCX) ? 0.0 : 1.0);
+      if (edge && row >= 0 && row < BM) closm_ |= 1 << q;
     }
   }
   const int closm = opaque(closm_);
@@ -875,9 +883,9 @@ template <int P, int R, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_sweep(const SweepParams prm) { sweep_body<P, R, false>(prm); }
 // deep rings: explicit register cap (shared memory, not registers, bounds the CTAs per SM)
-template <int P, int R, int MAXREG>
+template <int P, int R, int MAXREG, bool ODD = false>
 __global__ void __maxnreg__(MAXREG)
-k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true>(prm); }
+k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true, ODD>(prm); }
 
 // ---- edge preparation ---------------------------------------------------------------------------
 // One CTA per (block, face), launched before k_sweep.  Everything that lives on the rim of a block and
@@ -886,13 +894,13 @@ k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true>(prm); }
 //     g = G u and the face's boundary condition (k_generic.cuh header) the per-face-point quantities
 //       fcn[n] = (Hf/hn) c_nn alpha,   fgm[n] = sgn (Q_t^T (c_x o alpha))_n + beta
 //     with  y(point m deep behind face point n) += BS[m] fcn[n] + (m == 0) fgm[n];
-//   * for the r-faces (k = 1, 2) the table row of every line n (layout: SweepCfg::CLR): the first MCX rows of
+//   * for the r-faces (k = 1, 2) the table row of every line n (layout: SweepCfg::clr): the first MCX rows of
 //     Hs[n]/hr M(crr) u at that end with the face terms added, the closure rows of Qr^T w, w = crs o (Qs u) (the s-direction
 //     derivative of the end points goes through shared memory), and the first MCX rows of Qr u (mirrored and sign-flipped
 //     at the far end) -- everything the lanes of k_sweep that own the end points would otherwise have to branch for.
 // with_faces = 0 leaves the face terms out (volume operator A-tilde only).
 // dynamic shared memory: (2 + BN) * (max face points) doubles
-template <int P>
+template <int P, bool ODD = false>
 #ifndef SW_EDGE_MINB
 #define SW_EDGE_MINB 4      // CTAs per SM the register allocation is sized for (measured: 2 -> 0.076, 3 -> 0.068, 4 -> 0.064, 5 -> 0.071 ms)
 #endif
@@ -900,7 +908,8 @@ __global__ void __launch_bounds__(256, SW_EDGE_MINB)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
             double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
-            const double *__restrict__ rim, const int *__restrict__ active, int active_stride) {
+            const double *__restrict__ rim, const int *__restrict__ active, int active_stride, int upitch) {
+  // ODD: u is the library's pitched copy (lines upitch apart, block e at e * upitch * (Ns+1)); everything else as the caller has it
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -915,6 +924,8 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   const FaceGeom fg = face_geom(d, k);
   double *sa = sm_face, *sx = sm_face + fg.nf, *su = sm_face + 2 * fg.nf;      // su[kk][n]: u at the BN end points of line n (r-faces)
   const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
+  const int64_t up = ODD ? upitch : Nrp, uoff = ODD ? (int64_t)e * upitch * Nsp : d.voff;     // lines of u
+  constexpr int LF = C::template lf<ODD>(), CLR = C::template clr<ODD>();
   // One face point per thread and trip; every global load of a trip is issued before its first use.
   // Faces longer than the CTA take several trips: the tangential operators need the whole face in shared
   // memory, so alpha-dependent data is parked in fcn / fgm between the passes (STAGE 0, 1, 2); a face that
@@ -931,14 +942,19 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
       if (act) {
         if (k < 2) {                           // r-faces: u is strided in memory (NK contiguous points per line, 16-byte
                                                // aligned); the static data comes from the rim table, coalesced in n
-          const int64_t g0 = d.voff + (int64_t)Nrp * n + (k == 0 ? 0 : Nrp - NK);
-          const double2 *pu = reinterpret_cast<const double2 *>(u + g0);
+          const int64_t g0 = uoff + up * n + (k == 0 ? 0 : Nrp - NK);
           const double *pr = rim + (((int64_t)e * 2 + k) * C::RIMW) * Nsp + n;
+          if (ODD && k == 1) {                 // an odd number of points: the far end is not 16-byte aligned
 #pragma unroll
-          for (int m = 0; m < NK / 2; ++m) {
-            const double2 vu = pu[m];
-            if (k == 0) { uu[2 * m] = vu.x; uu[2 * m + 1] = vu.y; }
-            else { uu[NK - 1 - 2 * m] = vu.x; uu[NK - 2 - 2 * m] = vu.y; }
+            for (int m = 0; m < NK; ++m) uu[NK - 1 - m] = u[g0 + m];
+          } else {
+            const double2 *pu = reinterpret_cast<const double2 *>(u + g0);
+#pragma unroll
+            for (int m = 0; m < NK / 2; ++m) {
+              const double2 vu = pu[m];
+              if (k == 0) { uu[2 * m] = vu.x; uu[2 * m + 1] = vu.y; }
+              else { uu[NK - 1 - 2 * m] = vu.x; uu[NK - 2 - 2 * m] = vu.y; }
+            }
           }
 #pragma unroll
           for (int m = 0; m < NK; ++m) b[m] = pr[(int64_t)m * Nsp];       // already scaled by Hs[n] / hr
@@ -948,9 +964,10 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
           tauf = pr[(int64_t)(NK + BN) * Nsp];                             // tau * Hf
         } else {                               // s-faces: lines 0 .. NB-1 (or Ns .. Ns-NB+1), coalesced along the face
           const int64_t g0 = d.voff + n + (k == 2 ? 0 : (int64_t)Nrp * d.Ns);
-          const int64_t ls = k == 2 ? Nrp : -Nrp;
+          const int64_t gu0 = uoff + n + (k == 2 ? 0 : up * d.Ns);
+          const int64_t ls = k == 2 ? up : -up;
 #pragma unroll
-          for (int m = 0; m < S::NB; ++m) uu[m] = u[g0 + ls * m];
+          for (int m = 0; m < S::NB; ++m) uu[m] = u[gu0 + ls * m];
           b[0] = css[g0];
           cxf = crs[g0];
         }
@@ -1025,17 +1042,18 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
           for (int o = 1; o <= H; ++o) a = fma(S::d()[H + o], uu[m + o] - uu[m - o], a);
           qq[m] = a;
         }
-        double *out = rtab + ((int64_t)e * Nsp + n) * C::CLR;
+        double *out = rtab + ((int64_t)e * Nsp + n) * CLR;
         if (k == 0) {
 #pragma unroll
           for (int m = 0; m < MCXP; ++m) { out[m] = m < MCX ? rows[m] : 0.0; out[MCXP + m] = m < MCX ? qq[m] : 0.0; }
-        } else {                                // far end: mirrored order, Q changes sign
+        } else {                                // far end: point order (row m at farpos(m)), Q changes sign
 #pragma unroll
-          for (int m = 0; m < MCXP; ++m) {
-            out[3 * MCXP - 1 - m] = m < MCX ? rows[m] : 0.0;
-            out[4 * MCXP - 1 - m] = m < MCX ? -qq[m] : 0.0;
+          for (int pos = 0; pos < LF; ++pos) {
+            const int m = LF - 1 - (ODD ? 1 : 0) - pos;
+            out[2 * MCXP + pos] = (m >= 0 && m < MCX) ? rows[m >= 0 && m < MCX ? m : 0] : 0.0;
+            out[2 * MCXP + LF + pos] = (m >= 0 && m < MCX) ? -qq[m >= 0 && m < MCX ? m : 0] : 0.0;
           }
-          out[4 * MCXP] = 0.0; out[4 * MCXP + 1] = 0.0;
+          out[2 * MCXP + 2 * LF] = 0.0; out[2 * MCXP + 2 * LF + 1] = 0.0;
         }
       }
     }
@@ -1044,15 +1062,18 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
 }
 
 // ---- host side ------------------------------------------------------------------------------
-template <int P> static size_t sweep_smem(int Nrp, bool deep) {
+// Nrp: stored line length (the even pitch of blocks with an odd number of points per line)
+template <int P> static size_t sweep_smem(int Nrp, bool deep, bool odd = false) {
   using C = SweepCfg<P>;
   const int LW = Nrp + 2 * C::PAD;
   const int nl = deep ? C::template nlines<true>() : C::template nlines<false>();
-  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * C::CLR * sizeof(double) + (SW_NST + 1) * sizeof(uint64_t);
+  const int clr = odd ? C::template clr<true>() : C::template clr<false>();
+  return (size_t)nl * LW * sizeof(double) + (size_t)SW_NST * clr * sizeof(double) + (SW_NST + 1) * sizeof(uint64_t);
 }
 
 static int sweep_points_per_thread(const hsbp_blocks *b) {
   const int Nrp = b->max_Nr + 1;
+  if (Nrp & 1) return 2;                                      // odd line length: the pitched two-point variant
   if (b->sweep_r_override == 2 || (b->sweep_r_override == 4 && Nrp % 4 == 0)) return b->sweep_r_override;
   const bool can4 = Nrp % 4 == 0, can2 = ((Nrp / 2 + 31) & ~31) <= SW_MAX_THREADS;
   if (b->sweep_deep) {
@@ -1068,32 +1089,61 @@ static int sweep_points_per_thread(const hsbp_blocks *b) {
 
 template <int P> static bool sweep_eligible(const hsbp_blocks *b) {
   if (!b->uniform) return false;
-  const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
-  if (Nrp & 1) return false;                                   // 16-byte aligned lines for the bulk copies
-  if (Nrp < 32 || Nsp < 32) return false;                      // room for both closures and a chunk per side
+  const int Nrt = b->max_Nr + 1, Nsp = b->max_Ns + 1;
+  // lines with an odd number of points (N = 34, 68, 136, 200 of the reference's drivers) run on pitched copies: the bulk copies
+  // need 16-byte aligned lines; deep-ring kernels only
+  const bool odd = Nrt & 1;
+  if (odd && !b->sweep_deep) return false;
+  const int Nrp = Nrt + (odd ? 1 : 0);
+  if (Nrt < 32 || Nsp < 32) return false;                      // room for both closures and a chunk per side
   const int R = sweep_points_per_thread(b);
   const int nthreads = ((Nrp / R) + 31) & ~31;
   if (nthreads > SW_MAX_THREADS) return false;
-  return sweep_smem<P>(Nrp, true) <= b->ctx->smem_optin;
+  return sweep_smem<P>(Nrp, true, odd) <= b->ctx->smem_optin;
 }
 
 // crr' = crr * Hs[j] / hr, css' = css * Hr[i] / hs for uniform blocks (see SweepParams)
 template <int P>
 __global__ void __launch_bounds__(256)
-k_sweep_scale(const double *__restrict__ crr, const double *__restrict__ css, double *__restrict__ crr_s,
-              double *__restrict__ css_s, int Nr, int Ns, int64_t total) {
+k_sweep_scale(const double *__restrict__ crr, const double *__restrict__ css, const double *__restrict__ crs,
+              double *__restrict__ crr_s, double *__restrict__ css_s, double *__restrict__ crs_p, int Nr, int Ns, int pitch,
+              int64_t total) {
+  // output lines are `pitch` apart (= Nr + 1, or Nr + 2 with a zero pad entry for odd line lengths; then crs is copied too)
   using C = SweepCfg<P>;
   constexpr int BM = SweepTab<P>::BM;
   const int Nrp = Nr + 1;
-  const int64_t np = (int64_t)Nrp * (Ns + 1);
+  const int64_t np = (int64_t)Nrp * (Ns + 1), npp = (int64_t)pitch * (Ns + 1);
   const double hr = 2.0 / Nr, hs = 2.0 / Ns;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t loc = idx % np;
-    const int jj = (int)(loc / Nrp), i = (int)(loc - (int64_t)jj * Nrp);
+    const int64_t e = idx / npp, loc = idx - e * npp;
+    const int jj = (int)(loc / pitch), i = (int)(loc - (int64_t)jj * pitch);
+    if (i >= Nrp) {
+      crr_s[idx] = 0.0; css_s[idx] = 0.0;
+      if (crs_p) crs_p[idx] = 0.0;
+      continue;
+    }
+    const int64_t src = e * np + (int64_t)jj * Nrp + i;
     const double hwi = i < BM ? C::hw()[i] : (i > Nr - BM ? C::hw()[Nr - i] : 1.0);
     const double hwj = jj < BM ? C::hw()[jj] : (jj > Ns - BM ? C::hw()[Ns - jj] : 1.0);
-    crr_s[idx] = crr[idx] * (hs * hwj / hr);
-    css_s[idx] = css[idx] * (hr * hwi / hs);
+    crr_s[idx] = crr[src] * (hs * hwj / hr);
+    css_s[idx] = css[src] * (hr * hwi / hs);
+    if (crs_p) crs_p[idx] = crs[src];
+  }
+}
+
+// natural <-> pitched copies of a volume vector (odd line lengths): dst lines are dpitch apart, src lines spitch
+__global__ void __launch_bounds__(256)
+k_sweep_repitch(const double *__restrict__ src, double *__restrict__ dst, int n, int Nsp, int spitch, int dpitch, int64_t e0,
+                int64_t ne, const int *__restrict__ active, int active_stride) {
+  const int64_t total = ne * Nsp * (int64_t)dpitch;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t line = idx / dpitch;
+    const int i = (int)(idx - line * dpitch);
+    const int64_t e = e0 + line / Nsp;
+    if (active != nullptr && active[e * active_stride] == 0) continue;
+    const int64_t gl = e0 * Nsp + line;                    // line counted from block 0
+    if (i < n) dst[gl * dpitch + i] = src[gl * spitch + i];
+    else if (i < dpitch && dpitch > spitch) dst[gl * dpitch + i] = 0.0;
   }
 }
 
@@ -1125,15 +1175,24 @@ k_rim_build(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
 template <int P> static int sweep_prepare(hsbp_blocks *b) {
   hsbp_ctx *ctx = b->ctx;
   if (b->sweep_scaled_valid && b->rim_valid) return HSBP_OK;
-  const size_t vb = (size_t)b->VNp * sizeof(double);
+  const bool odd = (b->max_Nr + 1) & 1;
+  const int pitch = b->max_Nr + 1 + (odd ? 1 : 0);
+  const int64_t VNpp = b->nblocks * (int64_t)pitch * (b->max_Ns + 1);      // points of a pitched volume vector
+  const size_t vb = (size_t)VNpp * sizeof(double);
   if (!b->d_crr_s) {
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crr_s, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_css_s, vb));
-    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * SweepCfg<P>::CLR * sizeof(double)));
+    if (odd) {                                                // pitched copies of crs, u, y
+      HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crs_p, vb));
+      HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_u_p, vb));
+      HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_y_p, vb));
+    }
+    const int clr = odd ? SweepCfg<P>::template clr<true>() : SweepCfg<P>::template clr<false>();
+    HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * clr * sizeof(double)));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rim, (size_t)b->nblocks * 2 * SweepCfg<P>::RIMW * (b->max_Ns + 1) * sizeof(double)));
   }
-  k_sweep_scale<P><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->d_crr, b->d_css, b->d_crr_s, b->d_css_s, b->max_Nr,
-                                                              b->max_Ns, b->VNp);
+  k_sweep_scale<P><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->d_crr, b->d_css, b->d_crs, b->d_crr_s, b->d_css_s, b->d_crs_p,
+                                                              b->max_Nr, b->max_Ns, pitch, VNpp);
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_sweep_scale: ") + cudaGetErrorString(e1);
@@ -1161,6 +1220,7 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
 template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
                                                                    int64_t e0, int64_t ne) {
   hsbp_ctx *ctx = b->ctx;
+  const bool odd = (b->max_Nr + 1) & 1;                       // u, y: the pitched copies (vol_sweep)
   // register budget per thread.  Register windows (DEEP = false): R = 4 takes all 255; R = 2 fits 128 (p = 2, 4) --
   // p = 6 has 7-line windows and needs more.  DEEP: only u and the accumulators are per-point state.
   constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
@@ -1168,17 +1228,22 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   void (*kern)(const SweepParams);
   if constexpr (DEEP) {
     if constexpr (P == 6 && R == 2) {    // 7-line windows: 128 registers spill a little, 168 cost a CTA per SM
-      if (b->sweep_p6_regs == 168) kern = k_sweep_deep<P, R, 168>;
+      if (odd) kern = k_sweep_deep<P, R, 168, true>;
+      else if (b->sweep_p6_regs == 168) kern = k_sweep_deep<P, R, 168>;
       else kern = k_sweep_deep<P, R, SW_DEEP_REGS2>;
+    } else if (R == 2 && odd) {
+      if constexpr (R == 2) kern = k_sweep_deep<P, 2, SW_DEEP_REGS2, true>;
+      else kern = nullptr;
     } else {
       kern = k_sweep_deep<P, R, (R == 2 ? SW_DEEP_REGS2 : (P == 6 ? 255 : SW_DEEP_REGS4))>;
     }
   } else {
     kern = k_sweep<P, R, NT, MINB>;
   }
-  const int Nrp = b->max_Nr + 1, Nsp = b->max_Ns + 1;
+  if (odd && (!DEEP || R != 2)) { ctx->err = "k_sweep: odd line lengths need the deep-ring two-point kernel"; return HSBP_ERR_STATE; }
+  const int Nrp = b->max_Nr + 1 + (odd ? 1 : 0), Nsp = b->max_Ns + 1;
   const int nthreads = ((Nrp / R) + 31) & ~31;
-  const size_t sm = sweep_smem<P>(Nrp, DEEP);
+  const size_t sm = sweep_smem<P>(Nrp, DEEP, odd);
   int ctas_per_sm = 1;
   if (hsbp_smem_optin(ctx, kern, ctx->smem_optin) != cudaSuccess) {
     ctx->err = "cudaFuncSetAttribute(max dynamic shared memory) failed";
@@ -1202,7 +1267,7 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   }
   if (b->sweep_ncs_override > 0) best = std::min(b->sweep_ncs_override, std::max(1, K / 16));
   SweepParams prm;
-  prm.crr = b->d_crr_s; prm.css = b->d_css_s; prm.crs = b->d_crs; prm.u = u; prm.y = y;
+  prm.crr = b->d_crr_s; prm.css = b->d_css_s; prm.crs = odd ? b->d_crs_p : b->d_crs; prm.u = u; prm.y = y; prm.pitch = Nrp;
   prm.fcn = with_faces ? b->d_fa : nullptr; prm.fgm = with_faces ? b->d_fb : nullptr;
   prm.rtab = b->d_rtab;
   prm.active = b->skip_flags; prm.active_stride = b->skip_stride;
@@ -1234,7 +1299,7 @@ template <int P, int R> static int sweep_launch_nt(hsbp_blocks *b, const double 
 template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y, bool with_faces,
                                      cudaEvent_t ev_between = nullptr, int64_t e0 = 0, int64_t ne = -1) {
   hsbp_ctx *ctx = b->ctx;
-  if (((uintptr_t)u & 15) || ((uintptr_t)y & 15)) {
+  if (!((b->max_Nr + 1) & 1) && (((uintptr_t)u & 15) || ((uintptr_t)y & 15))) {
     ctx->err = "hsbp_apply: u / y must be 16-byte aligned for the line-marching kernel";
     return HSBP_ERR_ARG;
   }
@@ -1242,17 +1307,34 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
   int rc = sweep_prepare<P>(b);
   if (rc) return rc;
   const size_t fsm = (2 + SweepTab<P>::BN) * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
-  k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
-      b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
-      b->skip_flags, b->skip_stride);
+  const bool odd = (b->max_Nr + 1) & 1;
+  const int Nrt = b->max_Nr + 1, Nsp = b->max_Ns + 1, pitch = Nrt + 1;
+  double *y_user = y;
+  if (odd) {                       // odd line lengths: the kernels work on pitched copies of u and y (16-byte aligned lines)
+    k_sweep_repitch<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(u, b->d_u_p, Nrt, Nsp, Nrt, pitch, e0, ne, b->skip_flags, b->skip_stride);
+    u = b->d_u_p; y = b->d_y_p;
+    k_edge_prep<P, true><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
+        b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
+        b->skip_flags, b->skip_stride, pitch);
+  } else {
+    k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
+        b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
+        b->skip_flags, b->skip_stride, 0);
+  }
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_edge_prep: ") + cudaGetErrorString(e1);
     return HSBP_ERR_CUDA;
   }
   if (ev_between) cudaEventRecord(ev_between, ctx->stream);
-  return sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces, e0, ne)
-                                         : sweep_launch_nt<P, 2>(b, u, y, with_faces, e0, ne);
+  rc = sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces, e0, ne)
+                                       : sweep_launch_nt<P, 2>(b, u, y, with_faces, e0, ne);
+  if (rc == HSBP_OK && odd) {
+    k_sweep_repitch<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(y, y_user, Nrt, Nsp, pitch, Nrt, e0, ne, b->skip_flags, b->skip_stride);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { ctx->err = std::string("k_sweep_repitch: ") + cudaGetErrorString(e2); return HSBP_ERR_CUDA; }
+  }
+  return rc;
 }
 
 }  // namespace hsbp

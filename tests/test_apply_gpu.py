@@ -103,13 +103,16 @@ SWEEP_CASES = [
     (4, 31, 40, 0, 1), (4, 63, 33, 2, 0), (4, 127, 64, 4, 2), (4, 127, 64, 2, 1), (4, 255, 37, 0, 0),
     (4, 259, 50, 4, 0), (4, 255, 255, 0, 0),
     (6, 47, 47, 0, 0), (6, 63, 80, 2, 2), (6, 127, 40, 4, 1), (6, 131, 64, 4, 2),
+    # odd numbers of points per line (N = 34, 68, 136 of square_circle.jl / flower, N = 200 of BP1): pitched copies, phantom point
+    (2, 34, 40, 0, 0), (2, 200, 33, 0, 2), (4, 34, 34, 0, 0), (4, 68, 45, 0, 2), (4, 136, 60, 0, 0), (4, 200, 40, 0, 1),
+    (6, 34, 34, 0, 0), (6, 68, 50, 0, 0), (6, 200, 47, 0, 2),
 ]
 
 
 @pytest.mark.parametrize("p,Nr,Ns,R,ncs", SWEEP_CASES)
 def test_apply_marching_kernel_vs_oracle(ctx, p, Nr, Ns, R, ncs):
-    """uniform blocks with an even number (>= 32) of r-points take the TMA line-marching kernel
-    (k_sweep): every closure, both marching directions, chunk seams, 2 and 4 points per thread"""
+    """uniform blocks with >= 32 points per direction take the TMA line-marching kernel (k_sweep): every closure, both
+    marching directions, chunk seams, 2 and 4 points per thread, even and odd line lengths"""
     import hybridsbp_b200 as hs
     rng = np.random.default_rng(1000 * p + Nr + Ns)
     nb = 3 if Nr * Ns < 40000 else 2
