@@ -286,6 +286,42 @@ def run_ours(args):
     blk.close()                                         # the trace solves below build their own blocks
     del u_host, y_host
 
+    # the same operator apply at the other orders and at a line length of the reference's own drivers (N = 200 per block, BP1:
+    # 201 points per line -- odd, served by the pitched variant of k_sweep); rank 0 only, a few launches each
+    def apply_case(pp, nn, nblocks):
+        tnb = int(round(nblocks ** 0.5))
+        b2 = hs.Blocks(ctx, pp, [nn] * nblocks, [nn] * nblocks)
+        b2.set_synthetic_warp(tnb, 0, float(tnb), tnb / 40.0)
+        _, _, eToF, fToB = synthetic.block_grid_connectivity(tnb, tnb)
+        b2.set_bc(synthetic.block_bcs(eToF, fToB))
+        b2.compute_tau(2.0)
+        uu = ctx.array(np.random.default_rng(5).uniform(-1, 1, b2.VNp))
+        yy = ctx.empty(b2.VNp)
+        for _ in range(3):
+            b2.apply(uu, yy)
+        st2 = np.zeros(3)
+        for _ in range(5):
+            st2 += b2.apply_timed(uu, yy)
+        st2 /= 5
+        ctx.timer_start()
+        for _ in range(10):
+            b2.apply(uu, yy)
+        ms = ctx.timer_stop() / 10
+        out = {"sbp_order": pp, "blocks": nblocks, "points_per_block": (nn + 1) ** 2, "apply_variant": b2.apply_variant(),
+               "gdof_per_s": b2.VNp / (ms * 1e-3) / 1e9, "ms_per_apply": ms, "k_sweep_ms": float(st2[0]),
+               "other_kernels_ms": float(st2[1]),
+               "k_sweep_algorithmic_gbs": BYTES_PER_DOF * b2.VNp / (st2[0] * 1e-3) / 1e9,
+               "whole_apply_algorithmic_gbs": BYTES_PER_DOF * b2.VNp / (ms * 1e-3) / 1e9}
+        uu.free(); yy.free(); b2.close()
+        return out
+
+    other_cases = []
+    if rank == 0 and not args.no_other_orders:
+        for pp, nn, nbk in ((2, args.n, args.blocks), (6, args.n, args.blocks), (4, 200, args.blocks), (6, 136, args.blocks)):
+            if (pp, nn) != (p, N):
+                other_cases.append(apply_case(pp, nn, nbk))
+    barrier()
+
     # second half of BASELINE's metric: hybrid trace-CG solve time, through hsbp_trace_solve -- the library's device-resident,
     # two-level preconditioned CG; on N > 1 GPUs the cut-face exchange (ncclSend / ncclRecv) and the reductions (ncclAllReduce)
     # run inside the library on its own stream.  Weak scaling over strips of blocks.
@@ -376,7 +412,10 @@ def run_ours(args):
                              "kernel_ms": float(stage[0]),
                              "other_kernels_ms": ({"k_edge_prep": float(stage[1])} if (variant == 1 and not args.no_fold) else
                                                   {"k_face_gather": float(stage[1]), "k_face_scatter": float(stage[2])}),
-                             "peak_source": peak_src},
+                             "peak_source": peak_src,
+                             "other_cases": [dict(c, frac_k_sweep=c["k_sweep_algorithmic_gbs"] / peak,
+                                                  frac_whole_apply=c["whole_apply_algorithmic_gbs"] / peak) for c in other_cases],
+                             "frac_whole_apply": BYTES_PER_DOF * dof / (ms_step * 1e-3) / 1e9 / peak},
                 "e2e": {"value": world * dof / e2e_s / 1e9, "unit": "GDOF/s",
                         "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "numa_node_rank0": numa_node,
@@ -406,6 +445,7 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=5.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other-orders", action="store_true", help="skip the p = 2 / 6 and odd-line-length operator-apply entries")
     ap.add_argument("--no-trace", action="store_true", help="skip the trace-CG solve-time measurement")
     ap.add_argument("--trace-blocks", type=int, default=1024, help="blocks per GPU of the trace solve (a square number)")
     ap.add_argument("--trace-n", type=int, default=17, help="N per block of the trace solve")

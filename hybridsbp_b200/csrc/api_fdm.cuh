@@ -22,10 +22,14 @@
 //           the operator collapsed against the other direction's lowest mode (a shift of the smallest eigenvalue only).
 //   solve   PCG per block, all blocks at once: M̃ p (k_sweep), update of x / r, z = P^-1 r, update of p.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 #include "api_band.cuh"
 #include "k_tcgemm.cuh"
+#include "k_eig.cuh"
 
 namespace hsbp {
 
@@ -334,6 +338,13 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
   HSBP_CUDA(ctx, cudaMalloc((void **)&d_t2, (size_t)nb * nmax * nmax * sizeof(double)));
   HSBP_CUDA(ctx, cudaMemsetAsync(b->d_fdm_vr, 0, (size_t)nb * Nrp * Nrp * sizeof(double), ctx->stream));
   HSBP_CUDA(ctx, cudaMemsetAsync(b->d_fdm_vs, 0, (size_t)nb * Nsp * Nsp * sizeof(double), ctx->stream));
+  // HSBP_FDM_TIMING=1: phase times of this setup on stderr (synchronising; diagnostics only)
+  const bool timing = getenv("HSBP_FDM_TIMING") != nullptr;
+  auto tnow = [&]() { if (timing) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+  auto tprint = [&](const char *what, std::chrono::steady_clock::time_point t0) {
+    if (timing) fprintf(stderr, "[fdm_setup] %-28s %8.3f s\n", what, std::chrono::duration<double>(tnow() - t0).count());
+  };
+  auto tph = tnow();
   // ---- round 1: 1-D operators collapsed against the constant; their eigenvectors are the transform ---------
   // (Ar + sigma_s Hr and As + sigma_r Hs have the eigenvectors of Ar, As; the shifts sigma -- the collapsed penalty
   // terms of the other direction's faces -- are large, so the eigenvalues are taken from round 2 instead)
@@ -353,25 +364,49 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
     rc = check_launch(ctx, "fdm probes");
   }
   if (rc) { cleanup(); return rc; }
-  int lwork_r = 0, lwork_s = 0;
-  cusolverStatus_t cs = cusolverDnDsyevd_bufferSize(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nrp,
-                                                    b->d_fdm_vr, Nrp, d_lr, &lwork_r);
-  if (cs == CUSOLVER_STATUS_SUCCESS)
-    cs = cusolverDnDsyevd_bufferSize(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nsp, b->d_fdm_vs, Nsp,
-                                     d_ls, &lwork_s);
-  const int lwork = std::max(lwork_r, lwork_s);
-  cudaError_t e1 = cs == CUSOLVER_STATUS_SUCCESS ? cudaMalloc((void **)&d_work, (size_t)lwork * sizeof(double)) : cudaSuccess;
-  for (int64_t e = 0; e < nb && cs == CUSOLVER_STATUS_SUCCESS && e1 == cudaSuccess; ++e) {
-    cs = cusolverDnDsyevd(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nrp,
-                          b->d_fdm_vr + (size_t)e * Nrp * Nrp, Nrp, d_lr + (size_t)e * Nrp, d_work, lwork, d_info);
+  tprint("round 1 probes", tph); tph = tnow();
+  if (b->fdm_eig_lib == 0) {
+    // hand-written batched Jacobi eigensolver (k_eig.cuh), one CTA per matrix, all blocks of a direction in one launch
+    int *d_bad = d_info;
+    HSBP_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    for (int dir = 0; dir < 2; ++dir) {
+      const int n = dir == 0 ? Nrp : Nsp;
+      if (eig_smem_bytes(n) + 2048 > (size_t)ctx->smem_optin) { cleanup(); HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "fast-diagonalisation setup: block too large for the batched eigensolver"); }
+      HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_jacobi_eig, eig_smem_bytes(std::max(Nrp, Nsp))));
+      k_jacobi_eig<<<(unsigned)nb, EIG_THREADS, eig_smem_bytes(n), ctx->stream>>>(n, dir == 0 ? b->d_fdm_vr : b->d_fdm_vs,
+                                                                                 dir == 0 ? d_lr : d_ls, d_t2, 30, 1e-15, d_bad);
+    }
+    int bad = 0;
+    cudaError_t e2 = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+    if (e2 != cudaSuccess || bad) {
+      cleanup();
+      HSBP_FAIL(ctx, HSBP_ERR_CUDA, e2 != cudaSuccess ? std::string("fast-diagonalisation setup: k_jacobi_eig: ") + cudaGetErrorString(e2)
+                                                      : "fast-diagonalisation setup: " + std::to_string(bad) + " eigen-decompositions did not converge");
+    }
+  } else {
+    // cuSOLVER syevd, one matrix after the other: kept only as a comparison for tests (fdm_eig_lib option)
+    int lwork_r = 0, lwork_s = 0;
+    cusolverStatus_t cs = cusolverDnDsyevd_bufferSize(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nrp,
+                                                      b->d_fdm_vr, Nrp, d_lr, &lwork_r);
     if (cs == CUSOLVER_STATUS_SUCCESS)
-      cs = cusolverDnDsyevd(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nsp,
-                            b->d_fdm_vs + (size_t)e * Nsp * Nsp, Nsp, d_ls + (size_t)e * Nsp, d_work, lwork, d_info);
+      cs = cusolverDnDsyevd_bufferSize(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nsp, b->d_fdm_vs, Nsp,
+                                       d_ls, &lwork_s);
+    const int lwork = std::max(lwork_r, lwork_s);
+    cudaError_t e1 = cs == CUSOLVER_STATUS_SUCCESS ? cudaMalloc((void **)&d_work, (size_t)lwork * sizeof(double)) : cudaSuccess;
+    for (int64_t e = 0; e < nb && cs == CUSOLVER_STATUS_SUCCESS && e1 == cudaSuccess; ++e) {
+      cs = cusolverDnDsyevd(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nrp,
+                            b->d_fdm_vr + (size_t)e * Nrp * Nrp, Nrp, d_lr + (size_t)e * Nrp, d_work, lwork, d_info);
+      if (cs == CUSOLVER_STATUS_SUCCESS)
+        cs = cusolverDnDsyevd(libs->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, Nsp,
+                              b->d_fdm_vs + (size_t)e * Nsp * Nsp, Nsp, d_ls + (size_t)e * Nsp, d_work, lwork, d_info);
+    }
+    if (cs != CUSOLVER_STATUS_SUCCESS || e1 != cudaSuccess) {
+      cleanup();
+      HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: cuSOLVER syevd failed (status " + std::to_string((int)cs) + ")");
+    }
   }
-  if (cs != CUSOLVER_STATUS_SUCCESS || e1 != cudaSuccess) {
-    cleanup();
-    HSBP_FAIL(ctx, HSBP_ERR_CUDA, "fast-diagonalisation setup: cuSOLVER syevd failed (status " + std::to_string((int)cs) + ")");
-  }
+  tprint("eigen-decompositions", tph); tph = tnow();
   k_fdm_scale_vectors<P><<<(unsigned)nb, 256, 0, ctx->stream>>>(Nrp, b->d_fdm_vr);
   k_fdm_scale_vectors<P><<<(unsigned)nb, 256, 0, ctx->stream>>>(Nsp, b->d_fdm_vs);
   // ---- round 2: eigenvalues.  Collapse against the lowest mode w0 of the other direction (w0^T H w0 = 1):
@@ -399,6 +434,7 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
   }
   if (rc) { cleanup(); return rc; }
   k_fdm_dinv<<<dim3((unsigned)nb, 16), 256, 0, ctx->stream>>>(b->d_desc, d_lr, d_ls, b->d_dinv);
+  tprint("round 2 (Rayleigh quotients)", tph); tph = tnow();
   if (b->fdm_gemm != 0) {                                        // fp32 copies for the TF32 application (and their transposes:
                                                                  // the tensor-core kernel wants every operand contiguous in k)
     if (!b->d_fdm_vr32) {
@@ -438,9 +474,11 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
       b->fdm_tm_valid = true;
     }
   }
-  e1 = cudaGetLastError();
+  cudaError_t e1 = cudaGetLastError();
   if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+  tprint("fp32 copies, tensor maps", tph); tph = tnow();
   cleanup();
+  tprint("cleanup (cudaFree)", tph);
   if (e1 != cudaSuccess) { ctx->err = std::string("fdm_setup: ") + cudaGetErrorString(e1); return HSBP_ERR_CUDA; }
   return HSBP_OK;
 }
@@ -488,13 +526,9 @@ int fdm_precondition(hsbp_blocks *b, const double *r, double *z, bool r32_ready 
       GemmParams g;
       g.A = A; g.B = B; g.out = out; g.scale = scale; g.strideA = sA; g.strideB = sB; g.strideO = sv;
       g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldo = ldo; g.b_is_f64 = bf64; g.mode = mode;
-      if (bf64 || b->fdm_tc_sync)                 // fp64 operand: converted while it is staged through registers
-        k_tc_gemm<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_smem_bytes(N), ctx->stream>>>(g);
-      else                                        // fp32 operands: cp.async pipeline
-        k_tc_gemm_async<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_async_smem_bytes(N), ctx->stream>>>(g);
+      k_tc_gemm<<<dim3((unsigned)(M / BM), (unsigned)nb), THREADS, gemm_smem_bytes(N), ctx->stream>>>(g);
     };
     HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_tc_gemm, gemm_smem_bytes(256)));
-    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_tc_gemm_async, gemm_async_smem_bytes(256)));
     // T1 = Vr^T R            A(m, k) = Vr[k + Nrp m]   B(n, k) = R[k + Nrp n] (fp64)       -> row-major (m, n)
     launch(b->d_fdm_vr32, sr, Nrp, r, sv, Nrp, 1, Nrp, Nsp, Nrp, t1, Nsp, OUT_ROWMAJOR_F32, nullptr);
     // T3 = (T1 Vs) o Dinv    A = T1 row-major          B(n, k) = Vs[k + Nsp n]              -> row-major, scaled

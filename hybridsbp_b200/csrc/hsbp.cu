@@ -287,7 +287,10 @@ int hsbp_blocks_compute_tau(hsbp_blocks *b, double tauscale) {
   int rc = dispatch_p(b->p, [&](auto P) {
     k_compute_tau<decltype(P)::value><<<(unsigned)(4 * b->nblocks), 128, 0, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, tauscale, b->d_tau, d_bad);
-    return check_launch(ctx, "k_compute_tau");
+    int rc2 = check_launch(ctx, "k_compute_tau");
+    if (rc2) return rc2;
+    k_psi_min_check<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->VNp, b->d_crr, b->d_css, b->d_crs, d_bad);   // :419, whole block
+    return check_launch(ctx, "k_psi_min_check");
   });
   int bad = 0;
   if (rc == HSBP_OK) {
@@ -337,9 +340,9 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "sweep_fold_faces") b->sweep_fold_faces = (int)value;
   else if (n == "sweep_deep") b->sweep_deep = (int)value;
   else if (n == "fdm_gemm") b->fdm_gemm = (int)value;
-  else if (n == "fdm_tc_sync") b->fdm_tc_sync = (int)value;
   else if (n == "fdm_tc_variant") b->fdm_tc_variant = (int)value;
   else if (n == "fdm_no_skip") b->fdm_no_skip = (int)value;
+  else if (n == "fdm_eig_lib") b->fdm_eig_lib = (int)value;
   else if (n == "sweep_p6_regs") b->sweep_p6_regs = (int)value;
   else if (n == "band_no_stream") b->band_no_stream = (int)value;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_blocks_set_option: unknown option " + n);

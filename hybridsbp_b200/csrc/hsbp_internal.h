@@ -86,9 +86,9 @@ struct hsbp_blocks {
   double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   float *d_fdm_vr32 = nullptr, *d_fdm_vs32 = nullptr, *d_fdm_dinv32 = nullptr, *d_fdm_a32 = nullptr, *d_fdm_b32 = nullptr;
   float *d_fdm_vrT32 = nullptr, *d_fdm_vsT32 = nullptr, *d_fdm_dinvT32 = nullptr;    // transposes: every tensor-core operand contiguous in k
-  int fdm_tc_sync = 0;              // 1: every tensor-core GEMM through the register-staged kernel (testing)
   const int *skip_flags = nullptr;  // set around a batched PCG: blocks with skip_flags[e * skip_stride] == 0 are left out of
   int skip_stride = 0;              // hsbp_apply's sweep kernels and the preconditioner (converged blocks)
+  int fdm_eig_lib = 0;              // 1: eigen-decompositions of the FDM setup by cuSOLVER syevd (comparison only)
   int fdm_no_skip = 0;              // 1: converged blocks stay in the kernels of the FDM-PCG iteration (testing / timing)
   int fdm_tc_variant = 0;           // 0: k_fdm_pair (two fused GEMM pairs, TMA operands); 1: four single-GEMM launches (testing)
   alignas(64) unsigned char fdm_tm[6][128];   // CUtensorMap x 6 (k_fdm_pair operands), valid after hsbp_local_setup(HSBP_LOCAL_FDM)

@@ -224,4 +224,20 @@ k_compute_tau(const BlockDesc *__restrict__ desc, const double *__restrict__ crr
   }
 }
 
+// the reference asserts psi_min > 0 at every point of the block (global_curved.jl:418-419), not only in the layers the face
+// penalties look at: same expression, same operation order, whole volume
+__global__ void __launch_bounds__(256)
+k_psi_min_check(int64_t n, const double *__restrict__ crr, const double *__restrict__ css, const double *__restrict__ crs,
+                int *__restrict__ bad) {
+  bool any = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double a = crr[i], b = css[i], c = crs[i];
+    const double dab = __dsub_rn(a, b);
+    const double disc = __dadd_rn(__dmul_rn(dab, dab), __dmul_rn(4.0, __dmul_rn(c, c)));
+    const double pm = __dmul_rn(__dsub_rn(__dadd_rn(a, b), __dsqrt_rn(disc)), 0.5);
+    any |= !(pm > 0.0);
+  }
+  if (__syncthreads_or(any) && threadIdx.x == 0) atomicExch(bad, 1);
+}
+
 }  // namespace hsbp

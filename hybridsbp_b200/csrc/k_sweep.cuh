@@ -114,12 +114,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 #ifndef SW_NST_OVERRIDE
 #define SW_NST_OVERRIDE 3
 #endif
-// SW_LAGB = 1: the steady state finishes output line j-H-1 (the Qr^T w part, which needs the neighbours' w) between the arrive
-// and the wait of a split CTA barrier, so that work overlaps the wait for the slowest warp; needs a third w buffer
-#ifndef SW_LAGB
-#define SW_LAGB 0
-#endif
-constexpr int SW_NW = SW_LAGB ? 3 : 2;   // w buffers
+constexpr int SW_NW = 2;                  // w buffers
 constexpr int SW_NST = SW_NST_OVERRIDE;   // ring stages of u and crr: one being consumed, the others in flight
 constexpr int SW_MAX_THREADS = 256;
 
@@ -289,7 +284,6 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   }
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
-    mbar_init(&full[NST], (uint32_t)(nthreads >> 5));      // split CTA barrier: one arrival per warp
     fence_mbar_init();
   }
   __syncthreads();
@@ -603,8 +597,6 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const uint32_t c_rs0 = opaque(smem_u32(ring_rs) + (uint32_t)(DOFF + i0) * 8u), c_rsE = opaque(c_rs0 + (uint32_t)NSC * LWB);
   const uint32_t c_w0 = opaque(smem_u32(wbuf) + (uint32_t)(DOFF + i0 - PAD) * 8u);
   const uint32_t c_wsum = opaque(2u * c_w0 + LWB);
-  [[maybe_unused]] const uint32_t c_wE = opaque(c_w0 + (uint32_t)SW_NW * LWB);
-  [[maybe_unused]] const uint32_t cbar_s = opaque(smem_u32(&full[NST]));
   const uint32_t c_cl0 = opaque(smem_u32(clring));
   const int nout0 = opaque(o0 + H - jstart);               // first step whose line j-H belongs to the chunk
   const int nrefill = opaque(nlines - NST);                // steps after which no line is left to fetch
@@ -643,12 +635,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int64_t tstr = opaque(up ? (int64_t)CLR : -(int64_t)CLR);
 
   uint32_t au = c_u0 + (uint32_t)st * LWB, acl = c_cl0 + (uint32_t)(st * CLR) * 8u, abar = full_s + 8u * (uint32_t)st;
-  uint32_t aw = c_w0 + (uint32_t)(SW_LAGB ? 0 : (n & 1)) * LWB;
-  [[maybe_unused]] uint32_t awp = aw, cpar = 0;            // previous w buffer, parity of the split barrier
-  [[maybe_unused]] bool outp_prev = false;
-  [[maybe_unused]] double accprev[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) accprev[q] = 0.0;
+  uint32_t aw = c_w0 + (uint32_t)(n & 1) * LWB;
   uint32_t as_[NAS], ac_[NAC];                             // css' on lines j, j-1, ..; crs on lines j, .., j-H
 #pragma unroll
   for (int k = 0; k < NAS; ++k) as_[k] = c_ss0 + (uint32_t)((((n - k) % NSB) + NSB) % NSB) * LWB;
@@ -818,15 +805,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         for (int k = 0; k < R / 2; ++k) sts128(aw + 8u * PAD + 16u * k, wout[2 * k], wout[2 * k + 1]);
       }
     }
-#if SW_LAGB
-    __syncwarp();
-    if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cbar_s) : "memory");
-    if (ownf && outp_prev) outputB(awp, accprev, yout - lstr);   // line j-H-1, while the slower warps reach the barrier
-    mbar_wait_s(cbar_s, cpar);
-    cpar ^= 1u;
-#else
     __syncthreads();
-#endif
     if (mywarp == rw && n < nrefill) {                     // the slots of line j are free again: line j + NST goes into them
                                                           // (the warps take turns, so no warp is the slow one)
       if (elect_one()) {
@@ -844,13 +823,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         bulk_g2s_s(acl, prm.rtab + t0 + nn * tstr, (uint32_t)(CLR * 8), abar);
       }
     }
-#if !SW_LAGB
     if (ownf && outp) outputB(aw, accout, yout);
-#else
-    outp_prev = outp;
-#pragma unroll
-    for (int q = 0; q < R; ++q) accprev[q] = accout[q];
-#endif
     yout += lstr;
     ++n;
     if (++rw == nwarps) rw = 0;
@@ -864,18 +837,9 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     for (int k = NAC - 1; k > 0; --k) ac_[k] = ac_[k - 1];
     ac_[0] += LWB;
     if (ac_[0] == c_rsE) ac_[0] = c_rs0;
-#if SW_LAGB
-    awp = aw;
-    aw += LWB;
-    if (aw == c_wE) aw = c_w0;
-#else
     aw = c_wsum - aw;
-#endif
     if (++ph == W) ph = 0;
   }
-#if SW_LAGB
-  if (ownf && outp_prev) outputB(awp, accprev, yout - lstr);      // the last output line (its w is complete: the loop ended on a wait)
-#endif
 }
 
 // register windows: the register allocation is sized through the CTAs per SM (MINB)

@@ -299,104 +299,6 @@ k_tc_gemm(GemmParams p) {
 }
 
 
-// ---- the same tile with both operands in fp32: cp.async straight into the operand layout, four stages ------------------------
-// Every thread copies its 16-byte chunks of k-block kb + ASTAGES - 1 while the tensor core works on k-block kb: three k-blocks
-// (144 KB per SM) are in flight, no registers are tied up by the staging.  One CTA per SM (192 KB of shared memory).
-#ifndef HSBP_TC_ASTAGES
-#define HSBP_TC_ASTAGES 2
-#endif
-constexpr int ASTAGES = HSBP_TC_ASTAGES;       // 2 stages: 97 KB, two CTAs per SM (the epilogue of one overlaps the main loop of the other)
-__host__ __device__ inline size_t gemm_async_smem_bytes(int N) { return (size_t)ASTAGES * (BM + N) * BK * 4 + 1024; }
-
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-
-__global__ void __launch_bounds__(THREADS, ASTAGES <= 2 ? 2 : 1)
-k_tc_gemm_async(GemmParams p) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ uint64_t bar_free[ASTAGES];
-  __shared__ uint64_t bar_acc;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, K = p.K;
-  const int mt = blockIdx.x;
-  const int64_t b = blockIdx.y;
-  const uint32_t a_stage_bytes = BM * BK * 4, b_stage_bytes = (uint32_t)N * BK * 4;
-  const uint32_t sA0 = smem_addr(smem_raw), sB0 = sA0 + ASTAGES * a_stage_bytes;
-  uint32_t ncols = 32;
-  while ((int)ncols < N) ncols <<= 1;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    for (int s = 0; s < ASTAGES; ++s) mbar_init_(&bar_free[s], 1);
-    mbar_init_(&bar_acc, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_s;
-  const float *Ag = reinterpret_cast<const float *>(p.A) + b * p.strideA + (int64_t)mt * BM * p.lda;
-  const float *Bg = reinterpret_cast<const float *>(p.B) + b * p.strideB;
-  const uint32_t idesc = make_idesc(BM, N);
-  const int nkb = K / BK;
-  const int lr = lane & 7, lc = lane >> 3;
-  constexpr int NW = THREADS / 32;
-  const int nuA = (BM / 8) * 2, nuB = (N / 8) * 2;
-
-  auto issue = [&](int kb) {                     // all copies of k-block kb into stage kb % ASTAGES
-    const int s = kb % ASTAGES, k0 = kb * BK;
-    const uint32_t sa = sA0 + (uint32_t)s * a_stage_bytes, sb = sB0 + (uint32_t)s * b_stage_bytes;
-    for (int u = warp; u < nuA; u += NW) {
-      const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
-      cp_async16(sa + (uint32_t)c * BM * 16 + (uint32_t)r * 16, Ag + (int64_t)r * p.lda + k0 + c * 4);
-    }
-    for (int u = warp; u < nuB; u += NW) {
-      const int r = (u >> 1) * 8 + lr, c = (u & 1) * 4 + lc;
-      cp_async16(sb + (uint32_t)c * (uint32_t)N * 16 + (uint32_t)r * 16, Bg + (int64_t)r * p.ldb + k0 + c * 4);
-    }
-  };
-  for (int kb = 0; kb < ASTAGES - 1; ++kb) {
-    if (kb < nkb) issue(kb);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % ASTAGES;
-    asm volatile("cp.async.wait_group %0;" ::"n"(ASTAGES - 2) : "memory");     // this thread's copies of k-block kb have landed
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();                                                            // ... and everybody else's
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = sA0 + (uint32_t)s * a_stage_bytes, b0 = sB0 + (uint32_t)s * b_stage_bytes;
-#pragma unroll
-      for (int j = 0; j < BK / 8; ++j) {
-        const uint64_t ad = make_desc(a0 + (uint32_t)(2 * j) * BM * 16, BM * 16, 128);
-        const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j) * (uint32_t)N * 16, (uint32_t)N * 16, 128);
-        mma_tf32(tmem_d, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-      }
-      mma_commit(&bar_free[s]);
-      if (kb == nkb - 1) mma_commit(&bar_acc);
-    }
-    // refill the stage that k-block kb - 1 used (its MMAs were committed one iteration ago)
-    const int nxt = kb + ASTAGES - 1;
-    if (nxt < nkb) {
-      if (kb >= 1) mbar_wait_(&bar_free[(kb - 1) % ASTAGES], (uint32_t)(((kb - 1) / ASTAGES) & 1));
-      issue(nxt);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  mbar_wait_(&bar_acc, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  tc_epilogue(p, tmem_d, mt, b, warp, lane, N);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
-}
-
-
 // ---- two chained GEMMs per launch: TMA operands, second GEMM reads its A operand from tensor memory ---------------------------
 //   D1[128 x N]  = A1[m-tile, K = M] * B1[N, K = M]^T          both operands from shared memory (SS)
 //   D2[128 x N]  = D1[128, K = N]    * B2[N, K = N]^T          A = the accumulator of the first GEMM, where it lies in TMEM (TS)

@@ -163,3 +163,22 @@ def test_apply_marching_equals_generic_at_full_block_size(ctx, p):
         assert blk.apply_variant() == 1
         y1 = dy.get()
         assert np.max(np.abs(y1 - y0)) <= 1e-12 * np.max(np.abs(y0)), (R, ncs, deep)
+
+
+def test_compute_tau_rejects_an_indefinite_tensor_anywhere_in_the_block(ctx):
+    """global_curved.jl:418-419 asserts psi_min > 0 over the whole block, not only in the layers next to the faces"""
+    import hybridsbp_b200 as hs
+    p, N = 4, 20
+    rng = np.random.default_rng(9)
+    m = random_spd_metrics(p, N, N, rng)
+    crr, css, crs = flat(m.crr).copy(), flat(m.css).copy(), flat(m.crs).copy()
+    blk = hs.Blocks(ctx, p, [N], [N])
+    blk.set_metrics(crr, css, crs)
+    blk.set_bc([1, 1, 1, 1])
+    blk.compute_tau(1.0)                                   # fine
+    mid = (N + 1) * (N // 2) + N // 2                      # a point far from every face
+    crs[mid] = 10.0 * max(crr[mid], css[mid])              # indefinite there
+    blk.set_metrics(crr, css, crs)
+    with pytest.raises(hs.HsbpError):
+        blk.compute_tau(1.0)
+    blk.close()

@@ -113,3 +113,23 @@ def test_converged_blocks_drop_out_without_changing_the_result(ctx):
     y = blk.apply_host(np.ones(blk.VNp))              # the skip flags do not leak into later applies
     assert np.all(np.isfinite(y)) and np.abs(y[blk.vol_slice(1)]).max() > 0
     blk.close()
+
+
+def test_batched_jacobi_eigensolver_gives_the_library_preconditioner(ctx):
+    """setup with the hand-written batched Jacobi eigensolver (k_eig.cuh) against cuSOLVER syevd (comparison knob): the fp64
+    preconditioner built on either set of eigenvectors is the same operator"""
+    blk = make_blocks(ctx, 2, 2, 255, 127)
+    rng = np.random.default_rng(77)
+    r = rng.uniform(-1, 1, blk.VNp)
+    dr, dz = ctx.array(r), ctx.empty(blk.VNp)
+    z = []
+    blk.set_option("fdm_gemm", 0)
+    for lib in (0, 1):
+        blk.set_option("fdm_eig_lib", lib)
+        blk.local_setup(hs.LOCAL_FDM, tol=1e-13, maxit=500)
+        blk.local_precondition(dr, dz)
+        z.append(dz.get())
+    blk.set_option("fdm_eig_lib", 0)
+    assert np.all(np.isfinite(z[0]))
+    assert np.linalg.norm(z[0] - z[1]) <= 1e-8 * np.linalg.norm(z[1]), np.linalg.norm(z[0] - z[1]) / np.linalg.norm(z[1])
+    blk.close()

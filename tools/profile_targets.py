@@ -15,8 +15,7 @@ if what == "chol":
     r = sc.solve_level(ctx, mesh, 4, 34, local_mode=hs.LOCAL_CHOLESKY, tol=1e-6, maxit=20)
     print("chol: outer iterations", r["stats"]["outer_iterations"])
 else:
-    import torch
-    torch.cuda.set_device(0)
-    dt, g, gd, info = dist_trace.build_strip_problem(ctx, 0, 1, 8, 8, 63, 4, local_mode=hs.LOCAL_PCG)
-    lam, u, st = dt.solve(g, gd, tol=1e-3, maxit=3)
+    pr = dist_trace.StripProblem(ctx, 0, 1, 8, 8, 63, 4, local_mode=hs.LOCAL_PCG, condense=(what == "trace"),
+                                 coarse_modes=2 if what == "trace" else 0)
+    st = pr.solve(tol=1e-3, maxit=3)
     print("pcg/trace:", st)

@@ -1,9 +1,9 @@
-"""Hybrid trace-CG solve on the synthetic warped mesh with blocks of 256 x 256 points (BASELINE config 4: 32 x 32 blocks).
-usage: python tools/trace_c4.py [nbx] [nby] [tol] [condense 0/1]   -- one GPU; prints one JSON line."""
+"""Hybrid trace-CG solve on the synthetic warped mesh with blocks of 256 x 256 points (BASELINE config 4: 32 x 32 blocks) through
+hsbp_trace_solve.  usage: python tools/trace_c4.py [nbx] [nby] [tol] [condense 0/1]   -- one GPU; prints one JSON line with the
+independent residuals of the coupled system [M Fbar; Fbar^T D][u; lam] = [g; gd] (matrix-free operators, not the condensed S_e)."""
 import json, sys, time
 import numpy as np
 sys.path.insert(0, ".")
-import torch
 import hybridsbp_b200 as hs
 from hybridsbp_b200 import dist_trace
 nbx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
@@ -12,27 +12,26 @@ tol = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-10
 condense = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
 N, p = 255, 4
 ctx = hs.Context(0)
-torch.cuda.set_device(0)
+tm = {}
 t0 = time.perf_counter()
-dt, g, gd, info = dist_trace.build_strip_problem(ctx, 0, 1, nbx, nby, N, p, condense=condense)
-torch.cuda.synchronize()
-t_setup = time.perf_counter() - t0
-t0 = time.perf_counter()
-lam, u, st = dt.solve(g, gd, tol=tol, maxit=100000)
-torch.cuda.synchronize()
-t_solve = time.perf_counter() - t0
-# residuals of the coupled system [M Fbar; Fbar^T D][u; lam] = [g; gd] with the matrix-free operators (independent of S_e)
-blk, tr = info["blk"], info["tr"]
-from hybridsbp_b200.parallel import _Ptr
+pr = dist_trace.StripProblem(ctx, 0, 1, nbx, nby, N, p, condense=condense, timings=tm)
 ctx.sync()
-Mu = torch.empty_like(u); Fl = torch.zeros_like(u); FTu = torch.empty_like(lam)
-torch.cuda.synchronize()
-blk.apply(_Ptr(u), _Ptr(Mu)); tr.Fbar_add(_Ptr(lam), 1.0, _Ptr(Fl)); tr.FbarT(_Ptr(u), _Ptr(FTu)); ctx.sync()
-D = torch.as_tensor(tr.D(), device=u.device)
-res_vol = float(torch.linalg.norm(g - Mu - Fl) / torch.linalg.norm(g))
-res_lam = float(torch.linalg.norm(gd - FTu - D * lam) / torch.linalg.norm(gd))
-print(json.dumps({"blocks": nbx * nby, "points_per_block": (N + 1) ** 2, "p": p, "lambda_points": info["lambda_points"],
-                  "volume_points": info["volume_points"], "setup_seconds": t_setup, "solve_seconds": t_solve,
-                  "outer_iterations": st["outer_iterations"], "converged": st["converged"],
-                  "rel_residual": st["rel_residual"], "tol": tol, "local_solver": info["local_mode"], "condensed": condense,
+t_setup = time.perf_counter() - t0
+pr.solve(tol=1e-2, maxit=4)
+t0 = time.perf_counter()
+st = pr.solve(tol=tol, maxit=100000)
+ctx.sync()
+t_solve = time.perf_counter() - t0
+blk, tr = pr.blk, pr.tr
+Mu, Fl, FTu = ctx.empty(blk.VNp), ctx.array(np.zeros(blk.VNp)), ctx.empty(tr.lNp)
+blk.apply(pr.u, Mu); tr.Fbar_add(pr.lam, 1.0, Fl); tr.FbarT(pr.u, FTu); ctx.sync()
+g, gd, lam = pr.g.get(), pr.gd.get(), pr.lam.get()
+res_vol = float(np.linalg.norm(g - Mu.get() - Fl.get()) / np.linalg.norm(g))
+res_lam = float(np.linalg.norm(gd - FTu.get() - tr.D() * lam) / np.linalg.norm(gd))
+print(json.dumps({"blocks": nbx * nby, "points_per_block": (N + 1) ** 2, "p": p, "lambda_points": pr.info["lambda_points"],
+                  "volume_points": pr.info["volume_points"], "setup_seconds": t_setup,
+                  "setup_breakdown_seconds": {k: round(v, 3) for k, v in tm.items()}, "solve_seconds": t_solve,
+                  "outer_iterations": st["outer_iterations"], "converged": st["converged"], "cg_loop_ms": st["cg_loop_ms"],
+                  "rel_residual": st["rel_residual"], "true_rel_residual": st["true_rel_residual"], "tol": tol,
+                  "local_solver": pr.info["local_mode"], "condensed": condense,
                   "check_rel_residual_volume_equations": res_vol, "check_rel_residual_trace_equations": res_lam}))
