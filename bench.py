@@ -188,6 +188,8 @@ def workload_config(args, world):
 
 def run_ours(args):
     rank, world, local = dist_env()
+    # NCCL writes its version / debug lines to stdout by default; stdout of this program is the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     from hybridsbp_b200 import build as _build
     if rank == 0 or world == 1:
         _build.build()

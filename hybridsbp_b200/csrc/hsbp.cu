@@ -216,7 +216,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
   cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab); cudaFree(b->d_rim);
-  cudaFree(b->d_crs_p); cudaFree(b->d_u_p); cudaFree(b->d_y_p);
+  cudaFree(b->d_crs_p);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);

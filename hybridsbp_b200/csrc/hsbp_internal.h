@@ -47,7 +47,7 @@ struct hsbp_blocks {
   bool rim_valid = false;
   double *d_rtab = nullptr;                        // r-end table of the line-marching kernel (k_edge_prep)
   double *d_crr_s = nullptr, *d_css_s = nullptr;   // norm-weighted copies for the line-marching kernel (lazy)
-  double *d_crs_p = nullptr, *d_u_p = nullptr, *d_y_p = nullptr;   // odd line lengths: pitched copies (even pitch, zero pad) of crs, u, y
+  double *d_crs_p = nullptr;                       // odd line lengths: pitched copy (even pitch, zero pad) of crs
   bool sweep_scaled_valid = false;
   double *d_tau = nullptr;          // FNp
   double *d_fa = nullptr;           // FNp scratch: alpha (or F^T u)

@@ -108,6 +108,13 @@ __device__ __forceinline__ bool elect_one() {
       "}\n" : "=r"(pred));
   return pred != 0;
 }
+// 8-byte asynchronous copy global -> shared and its completion as one (pre-counted) arrival on an mbarrier
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -205,11 +212,11 @@ template <int O, int H, class F> __device__ __forceinline__ void for_offsets(F &
 // marching line 0, lstride: distance between marching lines)
 template <int P>
 __device__ __noinline__ double sweep_sclosure_row(int row, const double *__restrict__ pb, const double *__restrict__ pu,
-                                                  int64_t lstride) {
+                                                  int64_t lstride, int64_t ulstride) {
   using T = SweepTab<P>;
   double b[T::NK], uu[T::NK];
 #pragma unroll
-  for (int k = 0; k < T::NK; ++k) { b[k] = __ldg(pb + k * lstride); uu[k] = __ldg(pu + k * lstride); }
+  for (int k = 0; k < T::NK; ++k) { b[k] = __ldg(pb + k * lstride); uu[k] = __ldg(pu + k * ulstride); }
   return d2_closure_row<P>(row, b, uu);
 }
 
@@ -277,21 +284,26 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     const int line = idx / (2 * PAD), k = idx - line * (2 * PAD);
     ring_u[(size_t)line * LW + (k < PAD ? k : Nrp + k)] = 0.0;
   }
+  if constexpr (ODD) {            // the phantom entry of the u slots: no copy ever writes it
+    if (tid < NST) ring_u[(size_t)tid * LW + PAD + Nrt] = 0.0;
+  }
   if constexpr (DEEP) {
     // lines in front of the first staged one are looked at by the first steps of a chunk (their pairs only
     // touch rows that are not output); keep them finite
     for (int idx = tid; idx < (NSB + NSC) * LW; idx += nthreads) ring_ss[idx] = 0.0;
   }
   if (tid == 0) {
-    for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+    // ODD: u is not bulk-copied (its lines are not 16-byte aligned) -- every owning thread copies its own points with 8-byte
+    // cp.async and arrives on the line's barrier when they have landed
+    for (int s = 0; s < NST; ++s) mbar_init(&full[s], ODD ? 1u + (uint32_t)(Nrp / R) : 1u);
     fence_mbar_init();
   }
   __syncthreads();
   auto issue = [&](int n) {      // marching line jstart + n into its slots  (thread 0 only)
     const int st = n % NST;
     const int64_t g = base + (int64_t)(jstart + n) * lstride;
-    mbar_expect_tx(&full[st], 4u * line_bytes + (uint32_t)(CLR * 8));
-    bulk_g2s(ring_u + (size_t)st * LW + DOFF, prm.u + g, line_bytes, &full[st]);
+    mbar_expect_tx(&full[st], (ODD ? 3u : 4u) * line_bytes + (uint32_t)(CLR * 8));
+    if constexpr (!ODD) bulk_g2s(ring_u + (size_t)st * LW + DOFF, prm.u + g, line_bytes, &full[st]);
     bulk_g2s(ring_rr + (size_t)st * LW + DOFF, prm.crr + g, line_bytes, &full[st]);
     bulk_g2s(ring_ss + (size_t)(n % NSB) * LW + DOFF, prm.css + g, line_bytes, &full[st]);
     bulk_g2s(ring_rs + (size_t)(n % NSC) * LW + DOFF, prm.crs + g, line_bytes, &full[st]);
@@ -307,9 +319,26 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const bool own = i0 < Nrp;
   const int nown = Nrp / R;                               // threads that own points (Nrp % R == 0)
   const double *qc = C::Qc();
-  const double *gu = prm.u + base + i0;                   // + j*lstride: this thread's points on marching line j
+  // u and y of ODD kernels: the caller's vectors (lines Nrt apart); everything else is read from pitched copies
+  const int64_t ylstride = ODD ? (up ? (int64_t)Nrt : -(int64_t)Nrt) : lstride;
+  const int64_t ybase = ODD ? e * (int64_t)Nrt * Nsp + (up ? 0 : (int64_t)Ns * Nrt) : base;
+  const int nq = ODD ? min(R, Nrt - i0) : R;              // points of this thread that exist (own threads: >= 1)
+  const double *gu = prm.u + ybase + i0;                  // + j*ylstride: this thread's points on marching line j
   const double *gss = prm.css + base + i0;
-  double *gy = prm.y + base + i0;
+  auto issue_u = [&](int n) {    // ODD: this thread's points of marching line jstart + n
+    if constexpr (ODD) {
+      if (own) {
+        const int st = n % NST;
+        const double *src = gu + (int64_t)(jstart + n) * ylstride;
+        const uint32_t dst = smem_u32(ring_u + (size_t)st * LW + DOFF + i0);
+        cp_async8(dst, src);
+        if (nq > 1) cp_async8(dst + 8u, src + 1);
+        cp_async_arrive_noinc(smem_u32(&full[st]));
+      }
+    }
+  };
+  for (int n = 0; n < NST && n < nlines; ++n) issue_u(n);
+  double *gy = prm.y + ybase + i0;                         // (ODD: 8-byte stores, the phantom point is left out)
 
   // s-direction windows.  Logical index k <-> marching line j-(W-1)+k (u, scaled css, crs) or j-H+k
   // (accumulators); the physical slot of logical k in a step with rotation PH is (PH+1+k) % W, so the
@@ -327,7 +356,8 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   if (prologue && own) {                                  // lines that collect read-modify-write contributions
     for (int l = 0; l < BM; ++l)
 #pragma unroll
-      for (int q = 0; q < R; ++q) gy[l * lstride + q] = 0.0;
+      for (int q = 0; q < R; ++q)
+        if (q < nq) gy[l * ylstride + q] = 0.0;
   }
 
   int j = jstart, n = 0, st = 0;
@@ -458,9 +488,10 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         for (int l = 0; l < BM; ++l) {                    // dense closure block: straight into y
           const double d = sig * qc[j * BN + l];
           if (d != 0.0) {
-            double *yl = gy + l * lstride;
+            double *yl = gy + l * ylstride;
 #pragma unroll
-            for (int q = 0; q < R; ++q) yl[q] = fma(d, t[q], yl[q]);
+            for (int q = 0; q < R; ++q)
+              if (q < nq) yl[q] = fma(d, t[q], yl[q]);
           }
         }
         for_offsets<1, H>([&](auto Oc) {
@@ -509,9 +540,9 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
           for (int l = 0; l < BN; ++l) {
             const double d = sig * qc[jo * BN + l];
             if (d != 0.0) {
-              const double *ul = gu + l * lstride;
+              const double *ul = gu + l * ylstride;
 #pragma unroll
-              for (int q = 0; q < R; ++q) qs[q] = fma(d, ul[q], qs[q]);
+              for (int q = 0; q < R; ++q) qs[q] = fma(d, q < nq ? ul[q] : 0.0, qs[q]);
             }
           }
         }
@@ -523,6 +554,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     }
     __syncthreads();
     if (tid == 0 && n + NST < nlines) { fence_proxy_async(); issue(n + NST); }    // the slots of line j are free again
+    if (n + NST < nlines) issue_u(n + NST);
     if (own && outp) {
       // ---- rs = Qr^T w, then the output line ------------------------------------------------
       double Wv[NV], val[R];
@@ -541,12 +573,12 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
 #pragma unroll
       for (int q = 0; q < R; ++q)                         // closure rows of Qr^T at the two r-ends came with the r-end table
         if (i0 + q < BM || Nr - (i0 + q) < BM) val[q] = acc[SL(0)][q];
-      double *yl = gy + jo * lstride;
+      double *yl = gy + jo * ylstride;
       if constexpr (!FAST) {
         if (pro && jo < MC) {                             // closure row jo of M(css) u, straight from memory
 #pragma unroll
           for (int q = 0; q < R; ++q)
-            val[q] += sweep_sclosure_row<P>(jo, gss + q, gu + q, lstride);
+            if (q < nq) val[q] += sweep_sclosure_row<P>(jo, gss + q, gu + q, lstride, ylstride);
         }
       }
       if constexpr (!FAST) {
@@ -555,14 +587,21 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
           const double bsm = C::bs()[jo];
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            val[q] = fma(bsm, prm.fcn[fi + q], val[q]);
-            if (jo == 0) val[q] += prm.fgm[fi + q];
+            if (q < nq) {
+              val[q] = fma(bsm, prm.fcn[fi + q], val[q]);
+              if (jo == 0) val[q] += prm.fgm[fi + q];
+            }
           }
         }
       }
       if (!FAST && pro && jo < BM) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) yl[q] += val[q];
+        for (int q = 0; q < R; ++q)
+          if (q < nq) yl[q] += val[q];
+      } else if constexpr (ODD) {
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+          if (q < nq) yl[q] = val[q];
       } else {
 #pragma unroll
         for (int k = 0; k < R / 2; ++k)
@@ -630,6 +669,10 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int ownf = opaque(own ? 1 : 0);
   const double sgn = opaque(sig);                          // marching direction (the compiler would re-derive it from blockIdx)
   const int64_t lstr = opaque(lstride);
+  [[maybe_unused]] const int64_t ylstr = opaque(ylstride);
+  // ODD: u of marching line j + NST relative to the output line j - H of y (both the caller's vectors, same layout)
+  [[maybe_unused]] const int64_t udelta = opaque((int64_t)(prm.u - prm.y) + (int64_t)(NST + H) * ylstride);
+  [[maybe_unused]] const int nq2 = opaque(nq > 1 ? 1 : 0);
   const int64_t g0 = opaque(base + (int64_t)jstart * lstride);          // marching line 0 of this chunk in the volume fields
   const int64_t t0 = opaque((e * Nsp + (up ? (int64_t)jstart : (int64_t)Ns - jstart)) * CLR);   // ... in the r-end table
   const int64_t tstr = opaque(up ? (int64_t)CLR : -(int64_t)CLR);
@@ -643,7 +686,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   for (int k = 0; k < NAC; ++k) ac_[k] = c_rs0 + (uint32_t)((((n - k) % NSC) + NSC) % NSC) * LWB;
   int ph = 0;                                              // rotation of the next step
   int rw = 0;                                              // warp that issues the next refill
-  double *yout = gy + (int64_t)(j - H) * lstride;          // output line of the next step
+  double *yout = gy + (int64_t)(j - H) * ylstride;         // output line of the next step
 
   // ---- B: rs = Qr^T w and the output line (w buffer awb, accumulators accv, output line yo) --------------------
   auto outputB = [&](uint32_t awb, const double (&accv)[R], double *yo) {
@@ -666,9 +709,14 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
       for (int q = 0; q < R; ++q)
         if ((closm >> q) & 1) val[q] = accv[q];
     }
+    if constexpr (ODD) {
+      yo[0] = val[0];
+      if (nq2) yo[1] = val[1];
+    } else {
 #pragma unroll
-    for (int k = 0; k < R / 2; ++k)
-      *reinterpret_cast<double2 *>(yo + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+      for (int k = 0; k < R / 2; ++k)
+        *reinterpret_cast<double2 *>(yo + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+    }
   };
 #pragma unroll 1
   for (int left = nlines - n; left > 0; --left) {
@@ -815,16 +863,24 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         uint32_t d_ss = as_[0] + (uint32_t)NST * LWB; if (d_ss >= c_ssE) d_ss -= (uint32_t)NSB * LWB;
         uint32_t d_rs = ac_[0] + (uint32_t)NST * LWB; if (d_rs >= c_rsE) d_rs -= (uint32_t)NSC * LWB;
         const uint32_t d_u = au + (uint32_t)(PAD - i0) * 8u;               // data start of the slot of line j in ring_u
-        mbar_expect_tx_s(abar, 4u * line_bytes + (uint32_t)(CLR * 8));
-        bulk_g2s_s(d_u, prm.u + g, line_bytes, abar);
+        mbar_expect_tx_s(abar, (ODD ? 3u : 4u) * line_bytes + (uint32_t)(CLR * 8));
+        if constexpr (!ODD) bulk_g2s_s(d_u, prm.u + g, line_bytes, abar);
         bulk_g2s_s(d_u + c_drr, prm.crr + g, line_bytes, abar);
         bulk_g2s_s(d_ss - tofs8 + (uint32_t)DOFF * 8u, prm.css + g, line_bytes, abar);
         bulk_g2s_s(d_rs - tofs8 + (uint32_t)DOFF * 8u, prm.crs + g, line_bytes, abar);
         bulk_g2s_s(acl, prm.rtab + t0 + nn * tstr, (uint32_t)(CLR * 8), abar);
       }
     }
+    if constexpr (ODD) {                                   // this thread's points of u on line j + NST, into the slot of line j
+      if (ownf && n < nrefill) {
+        const double *src = yout + udelta;
+        cp_async8(au + 8u * PAD, src);
+        if (nq2) cp_async8(au + 8u * PAD + 8u, src + 1);
+        cp_async_arrive_noinc(abar);
+      }
+    }
     if (ownf && outp) outputB(aw, accout, yout);
-    yout += lstr;
+    yout += ODD ? ylstr : lstr;
     ++n;
     if (++rw == nwarps) rw = 0;
     au += LWB; acl += (uint32_t)(CLR * 8); abar += 8u;
@@ -868,12 +924,14 @@ template <int P, bool ODD = false>
 #ifndef SW_EDGE_MINB
 #define SW_EDGE_MINB 4      // CTAs per SM the register allocation is sized for (measured: 2 -> 0.076, 3 -> 0.068, 4 -> 0.064, 5 -> 0.071 ms)
 #endif
-__global__ void __launch_bounds__(256, SW_EDGE_MINB)
+#ifndef SW_EDGE_MINB6
+#define SW_EDGE_MINB6 SW_EDGE_MINB
+#endif
+__global__ void __launch_bounds__(256, P == 6 ? SW_EDGE_MINB6 : SW_EDGE_MINB)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
             double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
             const double *__restrict__ rim, const int *__restrict__ active, int active_stride, int upitch) {
-  // ODD: u is the library's pitched copy (lines upitch apart, block e at e * upitch * (Ns+1)); everything else as the caller has it
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -888,7 +946,8 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   const FaceGeom fg = face_geom(d, k);
   double *sa = sm_face, *sx = sm_face + fg.nf, *su = sm_face + 2 * fg.nf;      // su[kk][n]: u at the BN end points of line n (r-faces)
   const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
-  const int64_t up = ODD ? upitch : Nrp, uoff = ODD ? (int64_t)e * upitch * Nsp : d.voff;     // lines of u
+  const int64_t up = Nrp, uoff = d.voff;                  // lines of u (the caller's vector)
+  (void)upitch;
   constexpr int LF = C::template lf<ODD>(), CLR = C::template clr<ODD>();
   // One face point per thread and trip; every global load of a trip is issued before its first use.
   // Faces longer than the CTA take several trips: the tangential operators need the whole face in shared
@@ -908,9 +967,9 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
                                                // aligned); the static data comes from the rim table, coalesced in n
           const int64_t g0 = uoff + up * n + (k == 0 ? 0 : Nrp - NK);
           const double *pr = rim + (((int64_t)e * 2 + k) * C::RIMW) * Nsp + n;
-          if (ODD && k == 1) {                 // an odd number of points: the far end is not 16-byte aligned
+          if constexpr (ODD) {                 // an odd number of points per line: no 16-byte alignment
 #pragma unroll
-            for (int m = 0; m < NK; ++m) uu[NK - 1 - m] = u[g0 + m];
+            for (int m = 0; m < NK; ++m) uu[k == 0 ? m : NK - 1 - m] = u[g0 + m];
           } else {
             const double2 *pu = reinterpret_cast<const double2 *>(u + g0);
 #pragma unroll
@@ -1095,22 +1154,6 @@ k_sweep_scale(const double *__restrict__ crr, const double *__restrict__ css, co
   }
 }
 
-// natural <-> pitched copies of a volume vector (odd line lengths): dst lines are dpitch apart, src lines spitch
-__global__ void __launch_bounds__(256)
-k_sweep_repitch(const double *__restrict__ src, double *__restrict__ dst, int n, int Nsp, int spitch, int dpitch, int64_t e0,
-                int64_t ne, const int *__restrict__ active, int active_stride) {
-  const int64_t total = ne * Nsp * (int64_t)dpitch;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t line = idx / dpitch;
-    const int i = (int)(idx - line * dpitch);
-    const int64_t e = e0 + line / Nsp;
-    if (active != nullptr && active[e * active_stride] == 0) continue;
-    const int64_t gl = e0 * Nsp + line;                    // line counted from block 0
-    if (i < n) dst[gl * dpitch + i] = src[gl * spitch + i];
-    else if (i < dpitch && dpitch > spitch) dst[gl * dpitch + i] = 0.0;
-  }
-}
-
 // static data of the r-faces for k_edge_prep, laid out [block][end][entry][line] so that threads (= lines) read it
 // coalesced: entries 0..NK-1 = Hs[n]/hr * crr at the NK points behind the face point, NK..NK+BN-1 = crs at the BN points
 // behind it, NK+BN = tau * Hf
@@ -1146,10 +1189,8 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
   if (!b->d_crr_s) {
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crr_s, vb));
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_css_s, vb));
-    if (odd) {                                                // pitched copies of crs, u, y
+    if (odd) {                                                // pitched copy of crs
       HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_crs_p, vb));
-      HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_u_p, vb));
-      HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_y_p, vb));
     }
     const int clr = odd ? SweepCfg<P>::template clr<true>() : SweepCfg<P>::template clr<false>();
     HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_rtab, (size_t)b->nblocks * (b->max_Ns + 1) * clr * sizeof(double)));
@@ -1184,7 +1225,7 @@ template <int P> static int sweep_prepare(hsbp_blocks *b) {
 template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *b, const double *u, double *y, bool with_faces,
                                                                    int64_t e0, int64_t ne) {
   hsbp_ctx *ctx = b->ctx;
-  const bool odd = (b->max_Nr + 1) & 1;                       // u, y: the pitched copies (vol_sweep)
+  const bool odd = (b->max_Nr + 1) & 1;
   // register budget per thread.  Register windows (DEEP = false): R = 4 takes all 255; R = 2 fits 128 (p = 2, 4) --
   // p = 6 has 7-line windows and needs more.  DEEP: only u and the accumulators are per-point state.
   constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
@@ -1272,32 +1313,19 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
   if (rc) return rc;
   const size_t fsm = (2 + SweepTab<P>::BN) * (size_t)(std::max(b->max_Nr, b->max_Ns) + 1) * sizeof(double);
   const bool odd = (b->max_Nr + 1) & 1;
-  const int Nrt = b->max_Nr + 1, Nsp = b->max_Ns + 1, pitch = Nrt + 1;
-  double *y_user = y;
-  if (odd) {                       // odd line lengths: the kernels work on pitched copies of u and y (16-byte aligned lines)
-    k_sweep_repitch<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(u, b->d_u_p, Nrt, Nsp, Nrt, pitch, e0, ne, b->skip_flags, b->skip_stride);
-    u = b->d_u_p; y = b->d_y_p;
+  if (odd) {                       // odd line lengths: pitched copies of the coefficient fields (sweep_prepare); u and y are the
+                                   // caller's vectors (u by 8-byte cp.async, y by 8-byte stores)
     k_edge_prep<P, true><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
-        b->skip_flags, b->skip_stride, pitch);
+        b->skip_flags, b->skip_stride, 0);
   } else {
     k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
         b->skip_flags, b->skip_stride, 0);
   }
-  cudaError_t e1 = cudaGetLastError();
-  if (e1 != cudaSuccess) {
-    ctx->err = std::string("k_edge_prep: ") + cudaGetErrorString(e1);
-    return HSBP_ERR_CUDA;
-  }
   if (ev_between) cudaEventRecord(ev_between, ctx->stream);
   rc = sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces, e0, ne)
                                        : sweep_launch_nt<P, 2>(b, u, y, with_faces, e0, ne);
-  if (rc == HSBP_OK && odd) {
-    k_sweep_repitch<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(y, y_user, Nrt, Nsp, pitch, Nrt, e0, ne, b->skip_flags, b->skip_stride);
-    cudaError_t e2 = cudaGetLastError();
-    if (e2 != cudaSuccess) { ctx->err = std::string("k_sweep_repitch: ") + cudaGetErrorString(e2); return HSBP_ERR_CUDA; }
-  }
   return rc;
 }
 
