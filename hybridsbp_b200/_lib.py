@@ -74,6 +74,7 @@ def lib():
         "hsbp_blocks_get_tau": (cint, [vp, dp]),
         "hsbp_apply": (cint, [vp, dp, dp]),
         "hsbp_apply_host": (cint, [vp, dp, dp]),
+        "hsbp_apply_energy": (cint, [vp, dp, dp, dp]),
         "hsbp_apply_timed": (cint, [vp, dp, dp, dp]),
         "hsbp_apply_variant": (cint, [vp]),
         "hsbp_blocks_force_generic": (cint, [vp, cint]),

@@ -113,6 +113,12 @@ class Blocks:
         self.ctx._check(lib().hsbp_apply_host(self.h, pu, C.c_void_p(y.ctypes.data)))
         return y
 
+    def apply_energy(self, u: DeviceArray, y: DeviceArray):
+        """y = M-tilde u; returns u_e . (M-tilde u)_e per block, computed inside the sweep kernel (hsbp_apply_energy)."""
+        en = np.zeros(self.nblocks)
+        self.ctx._check(lib().hsbp_apply_energy(self.h, u.ptr, y.ptr, C.c_void_p(en.ctypes.data)))
+        return en
+
     def apply_timed(self, u: DeviceArray, y: DeviceArray):
         """apply with per-stage CUDA-event times: (volume ms, face gather ms, face scatter ms)."""
         ms = np.zeros(3)

@@ -138,14 +138,26 @@ __global__ void k_fdm_dinv(const BlockDesc *__restrict__ desc, const double *__r
 __global__ void __launch_bounds__(1024)
 k_fpcg_update1(const BlockDesc *__restrict__ desc, const double *__restrict__ Ap, double *__restrict__ x,
                double *__restrict__ r, const double *__restrict__ p, PcgState *__restrict__ st, double tol2,
-               float *__restrict__ r32) {      // r32 (optional): r rounded to TF32, the tensor-core operand of z = P^-1 r
+               float *__restrict__ r32,        // r32 (optional): r rounded to TF32, the tensor-core operand of z = P^-1 r
+               const double *__restrict__ dotpart, int nch, int closure_pts) {
+  // dotpart (optional): p . Ap of every (block, chunk) as k_sweep left it (SweepParams::dot) -- everything but the first
+  // closure_pts points of either s-end of the block, which are summed here: one pass over the vectors instead of two
   __shared__ double scratch[32];
   const BlockDesc d = desc[blockIdx.x];
   PcgState s = st[blockIdx.x];
   if (!s.active) return;
   const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1), o = d.voff;
   double pAp = 0;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) pAp += p[o + i] * Ap[o + i];
+  if (dotpart != nullptr) {
+    for (int64_t i = threadIdx.x; i < 2 * (int64_t)closure_pts; i += blockDim.x) {
+      const int64_t k = i < closure_pts ? i : np - 2 * (int64_t)closure_pts + i;
+      pAp += p[o + k] * Ap[o + k];
+    }
+    if (threadIdx.x == 0)
+      for (int c = 0; c < nch; ++c) pAp += dotpart[(int64_t)blockIdx.x * nch + c];
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) pAp += p[o + i] * Ap[o + i];
+  }
   pAp = cta_sum(pAp, scratch);
   const double alpha = s.rz / pAp;
   double rr = 0;
@@ -598,11 +610,18 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
   float *r32 = pair ? b->d_fdm_a32 : nullptr;
   struct SkipGuard {                                   // hsbp_apply of other callers must see every block again
     hsbp_blocks *b;
-    ~SkipGuard() { b->skip_flags = nullptr; b->skip_stride = 0; }
+    ~SkipGuard() { b->skip_flags = nullptr; b->skip_stride = 0; b->sweep_dot_out = nullptr; }
   } guard{b};
   k_fpcg_init<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, g, x, r, p, st, r32);
   if ((rc = fdm_precondition(b, r, z, pair, act, act_stride))) return rc;
   if (!b->fdm_no_skip) { b->skip_flags = act; b->skip_stride = act_stride; }
+  // p . Ap comes out of the sweep kernel when it produces the final y in one pass (fused faces)
+  const bool fused_dot = !b->fdm_no_fused_dot && sweep_dot_eligible(b);
+  if (fused_dot) {
+    if (!b->d_sweep_dot) HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_sweep_dot, (size_t)b->nblocks * 65 * sizeof(double)));
+    b->sweep_dot_out = b->d_sweep_dot;
+  }
+  const int closure_pts = dispatch_p(b->p, [&](auto Pc) { return SweepTab<decltype(Pc)::value>::BM; }) * (b->max_Nr + 1);
   HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive, 0, 2 * sizeof(int), ctx->stream));
   k_fpcg_update2<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, r, z, Ap, p, st, 1, b->d_nactive);
   const int check_every = 4;
@@ -612,7 +631,8 @@ int fdm_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *stat
     int slot = 0;
     for (int k = 0; k < check_every && it < b->local_maxit; ++k, ++it) {
       if ((rc = apply_async(b, p, Ap))) return rc;
-      k_fpcg_update1<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, Ap, x, r, p, st, tol2, r32);
+      k_fpcg_update1<<<nb, 1024, 0, ctx->stream>>>(b->d_desc, Ap, x, r, p, st, tol2, r32, fused_dot ? b->d_sweep_dot : nullptr,
+                                                   b->sweep_nch, closure_pts);
       if ((rc = fdm_precondition(b, r, z, pair, b->fdm_no_skip ? nullptr : act, act_stride))) return rc;
       slot = (int)(it & 1);
       HSBP_CUDA(ctx, cudaMemsetAsync(b->d_nactive + slot, 0, sizeof(int), ctx->stream));

@@ -7,6 +7,7 @@
 #include "hsbp_internal.h"
 #include "k_generic.cuh"
 #include "k_sweep.cuh"
+#include "k_solve.cuh"
 
 using namespace hsbp;
 
@@ -216,7 +217,7 @@ int hsbp_blocks_destroy(hsbp_blocks *b) {
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_desc); cudaFree(b->d_crr); cudaFree(b->d_css); cudaFree(b->d_crs);
   cudaFree(b->d_crr_s); cudaFree(b->d_css_s); cudaFree(b->d_rtab); cudaFree(b->d_rim);
-  cudaFree(b->d_crs_p);
+  cudaFree(b->d_crs_p); cudaFree(b->d_sweep_dot);
   cudaFree(b->d_tau); cudaFree(b->d_fa); cudaFree(b->d_fb); cudaFree(b->d_t); cudaFree(b->d_w);
   cudaFree(b->d_stage_u); cudaFree(b->d_stage_y);
   for (cudaEvent_t ev : b->pipe_ev) if (ev) cudaEventDestroy(ev);
@@ -342,6 +343,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "fdm_gemm") b->fdm_gemm = (int)value;
   else if (n == "fdm_tc_variant") b->fdm_tc_variant = (int)value;
   else if (n == "fdm_no_skip") b->fdm_no_skip = (int)value;
+  else if (n == "fdm_no_fused_dot") b->fdm_no_fused_dot = (int)value;
   else if (n == "fdm_eig_lib") b->fdm_eig_lib = (int)value;
   else if (n == "sweep_p6_regs") b->sweep_p6_regs = (int)value;
   else if (n == "band_no_stream") b->band_no_stream = (int)value;
@@ -414,7 +416,50 @@ static int apply_async(hsbp_blocks *b, const double *u, double *y, cudaEvent_t *
   });
 }
 
+// the sweep kernel can leave u . M-tilde u per chunk when it produces the final y in one pass (fused faces, deep two-point kernel)
+static bool sweep_dot_eligible(hsbp_blocks *b) {
+  if (b->force_generic || !b->sweep_fold_faces || !b->sweep_deep) return false;
+  if (dispatch_p(b->p, [&](auto Pc) { return sweep_eligible<decltype(Pc)::value>(b) ? 1 : 0; }) != 1) return false;
+  return sweep_points_per_thread(b) == 2;
+}
+
+// out[e] = chunk sums of k_sweep (SweepParams::dot) + u . y on the first closure_pts points of either s-end of the block
+__global__ void __launch_bounds__(256)
+k_block_dot_finish(const BlockDesc *__restrict__ desc, const double *__restrict__ u, const double *__restrict__ y,
+                   const double *__restrict__ part, int nch, int closure_pts, double *__restrict__ out) {
+  __shared__ double scratch[32];
+  const BlockDesc d = desc[blockIdx.x];
+  const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1), o = d.voff;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < 2 * (int64_t)closure_pts; i += blockDim.x) {
+    const int64_t k = i < closure_pts ? i : np - 2 * (int64_t)closure_pts + i;
+    s += u[o + k] * y[o + k];
+  }
+  if (threadIdx.x == 0)
+    for (int c = 0; c < nch; ++c) s += part[(int64_t)blockIdx.x * nch + c];
+  s = cta_sum(s, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 extern "C" {
+
+int hsbp_apply_energy(hsbp_blocks *b, const double *u_dev, double *y_dev, double *energy) {
+  if (!b) return HSBP_ERR_ARG;
+  hsbp_ctx *ctx = b->ctx;
+  if (!energy) HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_apply_energy: null pointer");
+  HSBP_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!sweep_dot_eligible(b)) HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "hsbp_apply_energy: needs the line-marching kernel (uniform blocks of >= 32 points per direction)");
+  if (!b->d_sweep_dot) HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_sweep_dot, (size_t)b->nblocks * 65 * sizeof(double)));
+  b->sweep_dot_out = b->d_sweep_dot;
+  int rc = apply_async(b, u_dev, y_dev);
+  b->sweep_dot_out = nullptr;
+  if (rc) return rc;
+  const int closure_pts = dispatch_p(b->p, [&](auto Pc) { return SweepTab<decltype(Pc)::value>::BM; }) * (b->max_Nr + 1);
+  double *d_out = b->d_sweep_dot + (size_t)b->nblocks * 64;
+  k_block_dot_finish<<<(unsigned)b->nblocks, 256, 0, ctx->stream>>>(b->d_desc, u_dev, y_dev, b->d_sweep_dot, b->sweep_nch, closure_pts, d_out);
+  if ((rc = check_launch(ctx, "k_block_dot_finish"))) return rc;
+  return hsbp_d2h(ctx, energy, d_out, (size_t)b->nblocks * sizeof(double));
+}
 
 int hsbp_apply(hsbp_blocks *b, const double *u_dev, double *y_dev) {
   if (!b) return HSBP_ERR_ARG;

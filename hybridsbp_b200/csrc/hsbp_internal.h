@@ -86,6 +86,10 @@ struct hsbp_blocks {
   double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   float *d_fdm_vr32 = nullptr, *d_fdm_vs32 = nullptr, *d_fdm_dinv32 = nullptr, *d_fdm_a32 = nullptr, *d_fdm_b32 = nullptr;
   float *d_fdm_vrT32 = nullptr, *d_fdm_vsT32 = nullptr, *d_fdm_dinvT32 = nullptr;    // transposes: every tensor-core operand contiguous in k
+  double *d_sweep_dot = nullptr;    // [nblocks][<= 64] chunk sums of p . Ap (FDM-PCG)
+  int fdm_no_fused_dot = 0;         // 1: p . Ap by a separate pass of the update kernel (testing)
+  double *sweep_dot_out = nullptr;  // set around a batched PCG: k_sweep leaves u . M-tilde u per (block, chunk) here (SweepParams::dot)
+  int sweep_nch = 0;                // chunks per block of the last k_sweep launch
   const int *skip_flags = nullptr;  // set around a batched PCG: blocks with skip_flags[e * skip_stride] == 0 are left out of
   int skip_stride = 0;              // hsbp_apply's sweep kernels and the preconditioner (converged blocks)
   int fdm_eig_lib = 0;              // 1: eigen-decompositions of the FDM setup by cuSOLVER syevd (comparison only)

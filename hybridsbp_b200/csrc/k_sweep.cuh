@@ -145,6 +145,10 @@ struct SweepParams {
   // optional: blocks whose flag active[e * active_stride] is 0 are skipped (converged blocks of a batched PCG; y is not written)
   const int *active;
   int active_stride;
+  // optional: dot[e * 2 ncs + chunk] = sum of u * y over the output lines of the chunk that are final when they are written
+  // (all but the first BM lines of either s-end, which collect read-modify-write contributions): the u . M-tilde u of a PCG
+  // step without a second pass over the vectors; summed in a fixed order
+  double *dot;
 };
 
 template <int P> struct SweepCfg {
@@ -231,7 +235,7 @@ template <int T0, int T1, class F> __device__ __forceinline__ void for_lanes(F &
 // NT: upper bound of the CTA size; MINB: CTAs per SM the register allocation is sized for.
 // DEEP: the steady state reads css / crs of older lines from deeper shared-memory rings instead of register
 // windows (SweepCfg::nsb, nsc): 2H+1 lines of u and 2H+1 accumulators remain as per-point register state.
-template <int P, int R, bool DEEP, bool ODD = false>
+template <int P, int R, bool DEEP, bool ODD = false, bool DOT = false>
 __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -269,7 +273,10 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   const int nside = up ? prm.K : Nsp - prm.K;
   const int per = up ? prm.per_up : prm.per_dn;
   const int o0 = cc * per, o1 = min(nside, o0 + per);     // output lines [o0, o1), marching coordinates
-  if (o0 >= o1) return;
+  if (o0 >= o1) {
+    if (DOT && tid == 0) prm.dot[e * nch + c] = 0.0;
+    return;
+  }
   const bool prologue = (o0 == 0);
   const int jstart = prologue ? 0 : o0 - H, jend = o1 - 1 + H;
   const int nlines = jend - jstart + 1;
@@ -362,6 +369,21 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
 
   int j = jstart, n = 0, st = 0;
   uint32_t parity = 0;
+  double dotp = 0.0;                                      // this thread's part of u . y (SweepParams::dot)
+  auto finish = [&]() {                                   // chunk sum of u . y in a fixed order (every thread of the CTA gets here)
+    if constexpr (!DOT) return;
+    double v = dotp;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();                                      // the shared lines are no longer needed
+    if ((tid & 31) == 0) wbuf[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < (nthreads >> 5); ++w) sum += wbuf[w];
+      prm.dot[e * nch + c] = sum;
+    }
+  };
 
   // one marching step: line j arrives, line j-H is completed.  PH: rotation of the register windows
   // (compile time); FAST: steady state, no s-end closure logic.
@@ -598,14 +620,19 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
 #pragma unroll
         for (int q = 0; q < R; ++q)
           if (q < nq) yl[q] += val[q];
-      } else if constexpr (ODD) {
-#pragma unroll
-        for (int q = 0; q < R; ++q)
-          if (q < nq) yl[q] = val[q];
       } else {
 #pragma unroll
-        for (int k = 0; k < R / 2; ++k)
-          *reinterpret_cast<double2 *>(yl + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+        for (int q = 0; q < R; ++q)
+          if (DOT && q < nq) dotp = fma(uw[SL(H)][q], val[q], dotp);
+        if constexpr (ODD) {
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            if (q < nq) yl[q] = val[q];
+        } else {
+#pragma unroll
+          for (int k = 0; k < R / 2; ++k)
+            *reinterpret_cast<double2 *>(yl + 2 * k) = make_double2(val[2 * k], val[2 * k + 1]);
+        }
       }
     }
     ++j; ++n;
@@ -623,7 +650,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   using GenericPH = std::integral_constant<int, W - 1>;    // rotation W-1: slot(k) == k (canonical order)
   const int jfast = prologue ? MCX + H : jstart;           // first step without s-end closure / face logic
   while (j < jfast && j <= jend) step(GenericPH{}, std::false_type{});
-  if (j > jend) return;
+  if (j > jend) { finish(); return; }
 
   constexpr int NAS = DEEP ? 2 * H : 1, NAC = DEEP ? H + 1 : 1;
   constexpr int ELANES = (MCX + R - 1) / R;                // lanes per r-end that patch closure rows
@@ -689,7 +716,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   double *yout = gy + (int64_t)(j - H) * ylstride;         // output line of the next step
 
   // ---- B: rs = Qr^T w and the output line (w buffer awb, accumulators accv, output line yo) --------------------
-  auto outputB = [&](uint32_t awb, const double (&accv)[R], double *yo) {
+  auto outputB = [&](uint32_t awb, const double (&accv)[R], const double (&ucv)[R], double *yo) {
       // ---- B: rs = Qr^T w and the output line ---------------------------------------------------
     double Wv[NV], val[R];
 #pragma unroll
@@ -709,6 +736,12 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
       for (int q = 0; q < R; ++q)
         if ((closm >> q) & 1) val[q] = accv[q];
     }
+    if constexpr (DOT) {
+      dotp = fma(ucv[0], val[0], dotp);
+#pragma unroll
+      for (int q = 1; q < R; ++q)
+        if (!ODD || nq2) dotp = fma(ucv[q], val[q], dotp);
+    }
     if constexpr (ODD) {
       yo[0] = val[0];
       if (nq2) yo[1] = val[1];
@@ -722,7 +755,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
   for (int left = nlines - n; left > 0; --left) {
     mbar_wait_s(abar, parity);
     const bool outp = n >= nout0;                          // line j-H is an output line of this chunk
-    double accout[R];
+    double accout[R], ucen[R];
     if (ownf) {
       // ---- A: line j from shared memory, r-direction work (rotation independent) ---------------
       double U[NV], Bq[NV], cn[R], rr[R], qr[R], wout[R];
@@ -843,6 +876,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
           if constexpr (DEEP) wout[q] *= c2[q];
           else wout[q] *= cw[SL(H)][q];
           accout[q] = acc[SL(0)][q];
+          if constexpr (DOT) ucen[q] = uw[SL(H)][q];
         }
       };
       [&]<int... PHs>(std::integer_sequence<int, PHs...>) {
@@ -879,7 +913,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
         cp_async_arrive_noinc(abar);
       }
     }
-    if (ownf && outp) outputB(aw, accout, yout);
+    if (ownf && outp) outputB(aw, accout, ucen, yout);
     yout += ODD ? ylstr : lstr;
     ++n;
     if (++rw == nwarps) rw = 0;
@@ -896,6 +930,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     aw = c_wsum - aw;
     if (++ph == W) ph = 0;
   }
+  finish();
 }
 
 // register windows: the register allocation is sized through the CTAs per SM (MINB)
@@ -903,9 +938,9 @@ template <int P, int R, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_sweep(const SweepParams prm) { sweep_body<P, R, false>(prm); }
 // deep rings: explicit register cap (shared memory, not registers, bounds the CTAs per SM)
-template <int P, int R, int MAXREG, bool ODD = false>
+template <int P, int R, int MAXREG, bool ODD = false, bool DOT = false>
 __global__ void __maxnreg__(MAXREG)
-k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true, ODD>(prm); }
+k_sweep_deep(const SweepParams prm) { sweep_body<P, R, true, ODD, DOT>(prm); }
 
 // ---- edge preparation ---------------------------------------------------------------------------
 // One CTA per (block, face), launched before k_sweep.  Everything that lives on the rim of a block and
@@ -1231,13 +1266,18 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   constexpr int REGS2 = (P == 6) ? SW_REGS2_P6 : 128;
   constexpr int MINB = (R == 2 ? 65536 / REGS2 : 256) / NT;
   void (*kern)(const SweepParams);
+  const bool dot = b->sweep_dot_out != nullptr;               // u . y per chunk (SweepParams::dot): two-point deep kernels only
+  if (dot && (!DEEP || R != 2)) { ctx->err = "k_sweep: the fused dot product needs the deep-ring two-point kernel"; return HSBP_ERR_STATE; }
   if constexpr (DEEP) {
     if constexpr (P == 6 && R == 2) {    // 7-line windows: 128 registers spill a little, 168 cost a CTA per SM
-      if (odd) kern = k_sweep_deep<P, R, 168, true>;
+      if (odd) kern = dot ? k_sweep_deep<P, R, 168, true, true> : k_sweep_deep<P, R, 168, true>;
+      else if (dot) kern = k_sweep_deep<P, R, 168, false, true>;
       else if (b->sweep_p6_regs == 168) kern = k_sweep_deep<P, R, 168>;
       else kern = k_sweep_deep<P, R, SW_DEEP_REGS2>;
-    } else if (R == 2 && odd) {
-      if constexpr (R == 2) kern = k_sweep_deep<P, 2, SW_DEEP_REGS2, true>;
+    } else if (R == 2 && (odd || dot)) {
+      if constexpr (R == 2)
+        kern = odd ? (dot ? k_sweep_deep<P, 2, SW_DEEP_REGS2, true, true> : k_sweep_deep<P, 2, SW_DEEP_REGS2, true>)
+                   : k_sweep_deep<P, 2, SW_DEEP_REGS2, false, true>;
       else kern = nullptr;
     } else {
       kern = k_sweep_deep<P, R, (R == 2 ? SW_DEEP_REGS2 : (P == 6 ? 255 : SW_DEEP_REGS4))>;
@@ -1276,6 +1316,8 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   prm.fcn = with_faces ? b->d_fa : nullptr; prm.fgm = with_faces ? b->d_fb : nullptr;
   prm.rtab = b->d_rtab;
   prm.active = b->skip_flags; prm.active_stride = b->skip_stride;
+  prm.dot = b->sweep_dot_out;
+  b->sweep_nch = 2 * best;
   prm.Nr = b->max_Nr; prm.Ns = b->max_Ns; prm.ncs = best; prm.K = K; prm.e0 = (int)e0;
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;

@@ -112,6 +112,10 @@ int  hsbp_blocks_get_tau(hsbp_blocks *blocks, double *tau);
 
 /* y = M-tilde u for all blocks (the SpMV `lop[e].M̃ * u`, global_curved.jl:470-492)      */
 int  hsbp_apply(hsbp_blocks *blocks, const double *u_dev, double *y_dev);
+/* y = M-tilde u and energy[e] = u_e . (M-tilde u)_e per block (host array of nblocks doubles) from the same pass: the sweep
+ * kernel leaves the chunk sums, a small kernel adds the closure lines -- the p . A p of a CG step on the reference's
+ * `lop[e].M̃` without a second pass over the vectors.  Line-marching kernel only (HSBP_ERR_UNSUPP otherwise).           */
+int  hsbp_apply_energy(hsbp_blocks *blocks, const double *u_dev, double *y_dev, double *energy);
 /* same through host buffers: H2D of u, apply, D2H of y inside the call                 */
 int  hsbp_apply_host(hsbp_blocks *blocks, const double *u, double *y);
 /* hsbp_apply with CUDA events between its stages.  ms[0] is always the dominant volume kernel:

@@ -182,3 +182,27 @@ def test_compute_tau_rejects_an_indefinite_tensor_anywhere_in_the_block(ctx):
     with pytest.raises(hs.HsbpError):
         blk.compute_tau(1.0)
     blk.close()
+
+
+@pytest.mark.parametrize("p,Nr,Ns,ncs", [(4, 63, 70, 0), (4, 255, 96, 3), (2, 40, 33, 1), (6, 95, 64, 2), (4, 200, 50, 0), (6, 68, 40, 0)])
+def test_apply_energy_from_the_sweep_kernel(ctx, p, Nr, Ns, ncs):
+    """hsbp_apply_energy: u_e . (M-tilde u)_e per block accumulated inside k_sweep (chunk sums, closure lines added by a small
+    kernel) equals the dot product of the vectors; y is the plain apply's y bit for bit"""
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(31 * p + Nr)
+    nb = 3
+    mets = [random_spd_metrics(p, Nr, Ns, rng, scale2=0.05) for _ in range(nb)]
+    bcs = [BCS[(i + 2 * p) % len(BCS)] for i in range(nb)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    blk.set_option("sweep_chunks_per_side", ncs)
+    u = rng.uniform(-1, 1, blk.VNp)
+    du, dy, dy2 = ctx.array(u), ctx.empty(blk.VNp), ctx.empty(blk.VNp)
+    blk.apply(du, dy)
+    assert blk.apply_variant() == 1
+    en = blk.apply_energy(du, dy2)
+    y, y2 = dy.get(), dy2.get()
+    assert np.array_equal(y, y2)
+    for e in range(nb):
+        sl = blk.vol_slice(e)
+        ref = u[sl] @ y[sl]
+        assert abs(en[e] - ref) <= 1e-12 * np.abs(u[sl] * y[sl]).sum(), (e, en[e], ref)

@@ -133,3 +133,24 @@ def test_batched_jacobi_eigensolver_gives_the_library_preconditioner(ctx):
     assert np.all(np.isfinite(z[0]))
     assert np.linalg.norm(z[0] - z[1]) <= 1e-8 * np.linalg.norm(z[1]), np.linalg.norm(z[0] - z[1]) / np.linalg.norm(z[1])
     blk.close()
+
+
+@pytest.mark.parametrize("N", [255, 127])
+def test_p_dot_Ap_from_the_sweep_kernel(ctx, N):
+    """FDM-PCG takes p . M-tilde p from k_sweep (chunk sums + the closure lines summed by the update kernel) instead of a second
+    pass over the vectors (the sum itself is checked in test_apply_gpu.py::test_apply_energy...): same solution"""
+    blk = make_blocks(ctx, 2, 2, N, 255)
+    blk.set_option("fdm_gemm", 3)
+    blk.local_setup(hs.LOCAL_FDM, tol=1e-12, maxit=2000)
+    g = np.random.default_rng(3).uniform(-1, 1, blk.VNp)
+    dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    xs, its = [], []
+    for off in (1, 0):
+        blk.set_option("fdm_no_fused_dot", off)
+        st = blk.local_solve(dg, dx)
+        assert st["failed_blocks"] == 0, st
+        xs.append(dx.get()); its.append(st["iterations_max"])
+    # (the flexible PCG with a TF32 preconditioner is sensitive to the rounding of alpha: the counts differ by a few per cent)
+    assert abs(its[0] - its[1]) <= 0.1 * max(its), its
+    assert np.linalg.norm(xs[0] - xs[1]) <= 1e-8 * np.linalg.norm(xs[0])
+    blk.close()
