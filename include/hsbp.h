@@ -132,7 +132,10 @@ int  hsbp_blocks_force_generic(hsbp_blocks *blocks, int on);
  * shared-memory rings, 0: in registers), "sweep_p6_regs" (128 / 168), "fdm_gemm" (arithmetic of the fast-diagonalisation
  * preconditioner's GEMMs, hand-written kernels: 0 fp64 on the fp64 tensor pipe (mma.sync f64), 3 TF32 on tcgen05 with TMEM
  * accumulators (blocks of 128 / 256 points per direction, fp64 otherwise); -1 cuBLAS TF32, for comparison in tests only;
- * set before hsbp_local_setup),
+ * set before hsbp_local_setup), "fdm_tc_variant" (0: two fused GEMM pairs with TMA operands and a TMEM operand, 1: four
+ * single-GEMM launches; testing), "fdm_eig_lib" (1: eigen-decompositions of the setup by cuSOLVER instead of the batched
+ * Jacobi kernel; comparison in tests only), "fdm_no_skip" (1: converged blocks stay in the kernels of the PCG iteration),
+ * "fdm_no_fused_dot" (1: p . A p by a separate pass instead of inside the sweep kernel),
  * "band_no_stream" (1: plain-load banded solve kernel) */
 int  hsbp_blocks_set_option(hsbp_blocks *blocks, const char *name, int64_t value);
 

@@ -148,6 +148,12 @@ compute_tau!(b::Blocks, tauscale::Real = 2.0) =
 "y = M̃ u for every block (the SpMV lop[e].M̃ * u, global_curved.jl:470-492), device vectors"
 apply!(y::DeviceVector, b::Blocks, u::DeviceVector) =
   check(b.ctx, ccall((:hsbp_apply, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), b.h, u.ptr, y.ptr))
+"y = M̃ u and the per-block energies u_e' * (M̃ u)_e from the same pass (hsbp_apply_energy; line-marching kernel only)"
+function apply_energy!(y::DeviceVector, b::Blocks, u::DeviceVector)
+  en = Vector{Float64}(undef, length(b.Nr))
+  check(b.ctx, ccall((:hsbp_apply_energy, libhsbp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}), b.h, u.ptr, y.ptr, en))
+  en
+end
 "same through host arrays (H2D, kernels, D2H inside the call)"
 function apply(b::Blocks, u::Vector{Float64})
   y = similar(u)
