@@ -224,6 +224,8 @@ def run_ours(args):
     blk.set_option("sweep_deep", args.sweep_deep)
     blk.set_option("sweep_p6_regs", args.sweep_p6_regs)
     blk.set_option("force_generic", 1 if args.generic else 0)
+    if args.sweep_no_pdl:
+        blk.set_option("sweep_no_pdl", 1)
     try:
         blk.set_option("sweep_fold_faces", 0 if args.no_fold else 1)
     except hs.HsbpError:
@@ -465,6 +467,7 @@ def main():
     ap.add_argument("--sweep-p6-regs", type=int, default=168)
     ap.add_argument("--sweep-ncs", type=int, default=0, help="chunks per side of k_sweep (0 = heuristic)")
     ap.add_argument("--generic", action="store_true", help="force the generic two-pass kernels")
+    ap.add_argument("--sweep-no-pdl", action="store_true", help="k_sweep without programmatic dependent launch behind k_edge_prep")
     ap.add_argument("--no-fold", action="store_true", help="face terms by separate gather / scatter kernels")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -343,6 +343,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "fdm_gemm") b->fdm_gemm = (int)value;
   else if (n == "fdm_tc_variant") b->fdm_tc_variant = (int)value;
   else if (n == "fdm_no_skip") b->fdm_no_skip = (int)value;
+  else if (n == "sweep_no_pdl") b->sweep_no_pdl = (int)value;
   else if (n == "fdm_no_fused_dot") b->fdm_no_fused_dot = (int)value;
   else if (n == "fdm_eig_lib") b->fdm_eig_lib = (int)value;
   else if (n == "sweep_p6_regs") b->sweep_p6_regs = (int)value;

@@ -306,6 +306,9 @@ __device__ __forceinline__ void sweep_body(const SweepParams &prm) {
     fence_mbar_init();
   }
   __syncthreads();
+  // programmatic dependent launch: this grid may start while k_edge_prep (which writes the r-end table and the face terms) is
+  // still draining; everything above overlaps with its tail, nothing below may run before it has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   auto issue = [&](int n) {      // marching line jstart + n into its slots  (thread 0 only)
     const int st = n % NST;
     const int64_t g = base + (int64_t)(jstart + n) * lstride;
@@ -966,7 +969,7 @@ __global__ void __launch_bounds__(256, P == 6 ? SW_EDGE_MINB6 : SW_EDGE_MINB)
 k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, const double *__restrict__ css,
             const double *__restrict__ crs, const double *__restrict__ tau, const double *__restrict__ u,
             double *__restrict__ fcn, double *__restrict__ fgm, double *__restrict__ rtab, int with_faces, int e0,
-            const double *__restrict__ rim, const int *__restrict__ active, int active_stride, int upitch) {
+            const double *__restrict__ rim, const int *__restrict__ active, int active_stride, int uNr, int uNs) {
   using S = Sbp<P>;
   using T = SweepTab<P>;
   using C = SweepCfg<P>;
@@ -976,13 +979,19 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
   static_assert(BM <= T::MC, "the closure rows of Qr^T are rows the table replaces");
   extern __shared__ double sm_face[];
   const int e = e0 + (blockIdx.x >> 2), k = blockIdx.x & 3;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // k_sweep's CTAs may take the SMs this grid leaves free
   if (active != nullptr && active[(int64_t)e * active_stride] == 0) return;       // block skipped by the caller (see SweepParams)
-  const BlockDesc d = desc[e];
+  // uniform blocks (the only ones the sweep path serves): sizes and offsets come with the launch, so no address waits for the
+  // descriptor; only the face's boundary-condition code is read from it, and that is needed late
+  BlockDesc d;
+  d.Nr = uNr; d.Ns = uNs;
+  d.voff = (int64_t)e * (uNr + 1) * (uNs + 1);
+  d.foff = (int64_t)e * (2 * (int64_t)(uNr + 1) + 2 * (int64_t)(uNs + 1));
+  const int bck = desc[e].bc[k];
   const FaceGeom fg = face_geom(d, k);
   double *sa = sm_face, *sx = sm_face + fg.nf, *su = sm_face + 2 * fg.nf;      // su[kk][n]: u at the BN end points of line n (r-faces)
   const int Nrp = d.Nr + 1, Nsp = d.Ns + 1;
   const int64_t up = Nrp, uoff = d.voff;                  // lines of u (the caller's vector)
-  (void)upitch;
   constexpr int LF = C::template lf<ODD>(), CLR = C::template clr<ODD>();
   // One face point per thread and trip; every global load of a trip is issued before its first use.
   // Faces longer than the CTA take several trips: the tangential operators need the whole face in shared
@@ -1054,7 +1063,7 @@ k_edge_prep(const BlockDesc *__restrict__ desc, const double *__restrict__ crr, 
             cn = k < 2 ? b[0] : (Hf / fg.hn) * b[0];
             const double g = cn * bsu + fg.sgn * cxf * qt;
             const double tH = tauf;
-            if (d.bc[k] == HSBP_BC_NEUMANN) { alpha = -g / tH; beta = 0.0; }
+            if (bck == HSBP_BC_NEUMANN) { alpha = -g / tH; beta = 0.0; }
             else                            { alpha = -uu[0];  beta = tH * uu[0] - g; }
             sx[n] = cxf * alpha;
             cn *= alpha;
@@ -1322,7 +1331,15 @@ template <int P, int R, int NT, bool DEEP> static int sweep_launch(hsbp_blocks *
   prm.per_up = (K + best - 1) / best;
   prm.per_dn = (Nsp - K + best - 1) / best;
   b->last_sweep_ctas_per_sm = ctas_per_sm;
-  kern<<<(unsigned)(ne * 2 * best), nthreads, sm, ctx->stream>>>(prm);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ne * 2 * best)); cfg.blockDim = dim3((unsigned)nthreads); cfg.dynamicSmemBytes = sm; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = b->sweep_no_pdl ? 0 : 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, prm);
+  }
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) {
     ctx->err = std::string("k_sweep: ") + cudaGetErrorString(e1);
@@ -1359,11 +1376,11 @@ template <int P> static int vol_sweep(hsbp_blocks *b, const double *u, double *y
                                    // caller's vectors (u by 8-byte cp.async, y by 8-byte stores)
     k_edge_prep<P, true><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
-        b->skip_flags, b->skip_stride, 0);
+        b->skip_flags, b->skip_stride, b->max_Nr, b->max_Ns);
   } else {
     k_edge_prep<P><<<(unsigned)(4 * ne), 256, fsm, ctx->stream>>>(
         b->d_desc, b->d_crr, b->d_css, b->d_crs, b->d_tau, u, b->d_fa, b->d_fb, b->d_rtab, with_faces ? 1 : 0, (int)e0, b->d_rim,
-        b->skip_flags, b->skip_stride, 0);
+        b->skip_flags, b->skip_stride, b->max_Nr, b->max_Ns);
   }
   if (ev_between) cudaEventRecord(ev_between, ctx->stream);
   rc = sweep_points_per_thread(b) == 4 ? sweep_launch_nt<P, 4>(b, u, y, with_faces, e0, ne)
