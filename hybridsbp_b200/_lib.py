@@ -93,6 +93,7 @@ def lib():
         "hsbp_trace_create": (cint, [vp, i64, i64p, i64p, i64p, vp, i64p, C.POINTER(vp)]),
         "hsbp_trace_destroy": (cint, [vp]),
         "hsbp_trace_num_lambda": (i64, [vp]),
+        "hsbp_trace_comm_path": (cint, [vp]),
         "hsbp_trace_get_starts": (cint, [vp, i64p]),
         "hsbp_trace_get_D": (cint, [vp, dp]),
         "hsbp_trace_FbarT": (cint, [vp, dp, dp]),

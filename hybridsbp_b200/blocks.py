@@ -241,6 +241,10 @@ class Trace:
     def set_option(self, name, value):
         self.ctx._check(lib().hsbp_trace_set_option(self.h, name.encode(), int(value)))
 
+    def comm_path(self):
+        """0: one rank, 1: NCCL, 2: peer memory (how the last solve exchanged data inside its iteration loop)"""
+        return lib().hsbp_trace_comm_path(self.h)
+
     def last_local_stats(self):
         st = LocalStats()
         self.ctx._check(lib().hsbp_trace_last_local_stats(self.h, C.byref(st)))

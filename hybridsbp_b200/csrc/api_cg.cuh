@@ -11,6 +11,7 @@
 
 #include "k_cg.cuh"
 #include "k_dense.cuh"
+#include "api_p2p.cuh"
 
 namespace {
 
@@ -48,6 +49,7 @@ void precond_free(hsbp_trace *t) {
 }
 
 void trace_free_solver(hsbp_trace *t) {
+  p2p_free(t);
   coarse_free(t);
   cudaFree(t->d_binv); cudaFree(t->d_fx); cudaFree(t->d_f2l); cudaFree(t->d_blk_lf);
   cudaFree(t->d_send); cudaFree(t->d_recv); cudaFree(t->d_facepart); cudaFree(t->d_part1); cudaFree(t->d_red1);
@@ -189,7 +191,8 @@ int dist_rhs(hsbp_trace *t, const double *g, const double *gd, double *bl) {
 
 // the preconditioner stages of one CG iteration (after r is final): first level + partial sums, coarse level,
 // reduction, scalars, and either the new search direction (zonly = 0) or just z (zonly = 1)
-int precond_stages(hsbp_trace *t, int force, int zonly, double *lam, double *r, double *z, double *p, const double *q) {
+int precond_stages(hsbp_trace *t, int force, int zonly, double *lam, double *r, double *z, double *p, const double *q,
+                   bool use_p2p = false) {
   hsbp_ctx *ctx = t->blocks->ctx;
   const unsigned nf = (unsigned)t->nlam_faces;
   const size_t smem = (2 * (size_t)t->max_nl + 256) * sizeof(double);
@@ -206,7 +209,13 @@ int precond_stages(hsbp_trace *t, int force, int zonly, double *lam, double *r, 
                                                                                (int)nf, t->d_red2_in);
     if ((rc = check_launch(ctx, "k_cg_coarse"))) return rc;
   }
-  if (multi && (rc = comm_allreduce(ctx, t->d_red2_in, t->d_red2_out, 3 + (size_t)(t->cmodes > 0 ? t->nGt : 0)))) return rc;
+  if (multi && use_p2p) {                              // partial sums straight into every rank's mailbox (api_p2p.cuh)
+    P2PDev *pp = ((P2PHost *)t->p2p)->d_dev;
+    const int n2 = 3 + (t->cmodes > 0 ? t->nGt : 0);
+    k_p2p_push_b<<<1, 1024, 0, ctx->stream>>>(t->d_state, force & 1, pp, t->d_red2_in, n2);
+    k_p2p_wait_b<<<1, 1024, 0, ctx->stream>>>(t->d_state, force & 1, pp, t->d_red2_out, n2);
+    if ((rc = check_launch(ctx, "k_p2p_push_b / k_p2p_wait_b"))) return rc;
+  } else if (multi && (rc = comm_allreduce(ctx, t->d_red2_in, t->d_red2_out, 3 + (size_t)(t->cmodes > 0 ? t->nGt : 0)))) return rc;
   const int nGt = t->cmodes > 0 ? t->nGt : 0;
   k_cg_scalars<<<(unsigned)std::max(1, (nGt + 7) / 8), 256, 0, ctx->stream>>>(t->d_state, force & 1, nGt, t->ldG, t->d_SG, red2, t->d_cG,
                                                                              t->d_status);
@@ -267,6 +276,14 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
     HSBP_CUDA(ctx, cudaEventCreate((cudaEvent_t *)&t->ev_b));
   }
   HSBP_CUDA(ctx, cudaEventRecord((cudaEvent_t)t->ev_a, ctx->stream));
+  // peer-memory path of the loop's exchanges: set up collectively (every rank reaches this point), NCCL if it is not available
+  if (ctx->world > 1 && t->partitioned && t->p2p_want) {
+    int rcp = p2p_setup(t);
+    if (rcp) return rcp;
+  } else if (t->p2p) {
+    p2p_free(t);
+  }
+  const bool use_p2p = t->p2p != nullptr;
   // one iteration, enqueued: block-face products, q and the local part of p.q, exchange + reduction, the preconditioner stages
   auto enqueue_iteration = [&]() -> int {
     int rc_;
@@ -274,6 +291,13 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
     k_cg_q<<<(unsigned)t->nlam_faces, 128, 0, ctx->stream>>>(t->d_state, 0, 0, t->d_faces, t->d_fx, t->d_D, p, nullptr, t->d_ft, q, t->d_send,
                                                              t->d_part1, t->d_red1);
     if ((rc_ = check_launch(ctx, "k_cg_q"))) return rc_;
+    if (use_p2p) {                                   // cut-face parts and the partial of p.q over NVLink, no NCCL call in the loop
+      P2PDev *pp = ((P2PHost *)t->p2p)->d_dev;
+      k_p2p_push_a<<<1, 1024, 0, ctx->stream>>>(t->d_state, 0, pp, t->d_send, t->d_red1);
+      k_p2p_wait_a<<<1, 1024, 0, ctx->stream>>>(t->d_state, 0, pp, t->d_recv, t->d_red1);
+      if ((rc_ = check_launch(ctx, "k_p2p_push_a / k_p2p_wait_a"))) return rc_;
+      return precond_stages(t, 0, 0, lam, r, z, p, q, true);
+    }
     if (t->partitioned && (rc_ = exchange_vec(t))) return rc_;
     if (ctx->world > 1 && (rc_ = comm_allreduce(ctx, t->d_red1, t->d_red1 + 1, 1))) return rc_;
     return precond_stages(t, 0, 0, lam, r, z, p, q);
@@ -281,7 +305,7 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
   // With condensed blocks an iteration is a fixed sequence of kernels and NCCL calls: a chunk of K iterations is captured once
   // into a CUDA graph and replayed (one launch per chunk instead of 6 + 3 per iteration).
   const bool want_graph = t->d_S != nullptr && t->cg_graph != 0;
-  if (want_graph && (!t->graph_exec || t->graph_lam != lam || t->graph_K != K)) {
+  if (want_graph && (!t->graph_exec || t->graph_lam != lam || t->graph_K != K || t->graph_p2p != use_p2p)) {
     if (t->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)t->graph_exec); t->graph_exec = nullptr; }
     cudaGraph_t g = nullptr;
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -290,7 +314,7 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
       cudaError_t ec = cudaStreamEndCapture(ctx->stream, &g);
       cudaGraphExec_t ge = nullptr;
       if (rcg == HSBP_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
-        t->graph_exec = ge; t->graph_lam = lam; t->graph_K = K;
+        t->graph_exec = ge; t->graph_lam = lam; t->graph_K = K; t->graph_p2p = use_p2p;
       } else {
         t->cg_graph = 0;                      // capture is not possible here (e.g. an NCCL build without graph support): plain launches
         cudaGetLastError();
@@ -328,6 +352,11 @@ int cg_run(hsbp_trace *t, double *lam, double tol, int64_t maxit, hsbp_trace_sta
     HSBP_CUDA(ctx, cudaEventElapsedTime(&ms, (cudaEvent_t)t->ev_a, (cudaEvent_t)t->ev_b));
     st->cg_loop_ms = ms;
   }
+  if (use_p2p) {
+    P2PDev hd;
+    HSBP_CUDA(ctx, cudaMemcpy(&hd, ((P2PHost *)t->p2p)->d_dev, sizeof(hd), cudaMemcpyDeviceToHost));
+    if (hd.error) HSBP_FAIL(ctx, HSBP_ERR_NCCL, "trace CG: a partner's peer-memory flag did not arrive (rank lost or out of step)");
+  }
   HSBP_CUDA(ctx, cudaMemcpy(&h, t->d_state, sizeof(h), cudaMemcpyDeviceToHost));
   st->outer_iterations = h.iter;
   st->converged = h.converged;
@@ -356,8 +385,15 @@ int hsbp_trace_set_option(hsbp_trace *t, const char *name, int64_t value) {
   if (n == "cg_chunk") t->cg_chunk = (int)std::max<int64_t>(1, value);
   else if (n == "cg_graph") t->cg_graph = value ? 1 : 0;
   else if (n == "cg_lookahead") t->cg_lookahead = (int)std::max<int64_t>(0, value);
+  else if (n == "cg_p2p") t->p2p_want = value ? 1 : 0;
   else HSBP_FAIL(ctx, HSBP_ERR_ARG, "hsbp_trace_set_option: unknown option " + n);
   return HSBP_OK;
+}
+
+int hsbp_trace_comm_path(const hsbp_trace *t) {
+  if (!t) return -1;
+  if (t->blocks->ctx->world <= 1) return 0;
+  return t->p2p ? 2 : 1;
 }
 
 int hsbp_trace_last_local_stats(hsbp_trace *t, hsbp_local_stats *stats) {

@@ -27,6 +27,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;   // optional
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   std::string err;
 };
@@ -57,6 +58,7 @@ int nccl_load() {
   HSBP_NCCL_SYM(AllReduce, "ncclAllReduce")
   HSBP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef HSBP_NCCL_SYM
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
   g_nccl.lib = h;
   return 0;
 }

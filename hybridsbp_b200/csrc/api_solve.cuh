@@ -52,6 +52,10 @@ struct hsbp_trace {
   int graph_K = 0;
   void *ev_a = nullptr, *ev_b = nullptr;    // CUDA events around the iteration loop (hsbp_trace_stats::cg_loop_ms)
   uint64_t blocks_generation = 0;       // generation of the blocks' operator the condensed / preconditioner data belong to
+  // peer-memory exchange of the iteration loop (api_p2p.cuh); null: NCCL
+  void *p2p = nullptr;
+  int p2p_want = 1;                     // option "cg_p2p"
+  bool graph_p2p = false;               // the captured graph belongs to this path
 };
 
 namespace {

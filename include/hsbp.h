@@ -260,8 +260,12 @@ int64_t hsbp_trace_coarse_size(const hsbp_trace *trace);      /* coarse dofs: th
 int  hsbp_trace_precond_apply(hsbp_trace *trace, const double *r_dev, double *z_dev);
 /* "cg_chunk" (iterations enqueued between two looks at the device's status word, default 4),
  * "cg_lookahead" (chunks the host runs ahead of the device, default 1), "cg_graph" (1: with condensed blocks a chunk of
- * iterations -- kernels and NCCL calls -- is captured into a CUDA graph once and replayed; 0: plain launches) */
+ * iterations is captured into a CUDA graph once and replayed; 0: plain launches), "cg_p2p" (1, default: the exchanges of the
+ * iteration loop -- cut-face parts, partial sums of the CG scalars -- go straight into the partners' device memory over
+ * NVLink from small kernels of the same graph; 0, or peer mapping not possible: ncclSend / ncclRecv / ncclAllReduce) */
 int  hsbp_trace_set_option(hsbp_trace *trace, const char *name, int64_t value);
+/* which way the last hsbp_trace_solve exchanged data inside its loop: 0 one rank, 1 NCCL, 2 peer memory */
+int  hsbp_trace_comm_path(const hsbp_trace *trace);
 int  hsbp_trace_FbarT(hsbp_trace *trace, const double *u_dev, double *lam_dev);             /* lam = Fbar^T u (this device's blocks) */
 int  hsbp_trace_Fbar_add(hsbp_trace *trace, const double *lam_dev, double alpha, double *y_dev); /* y += a Fbar lam */
 int  hsbp_trace_schur_apply(hsbp_trace *trace, const double *lam_dev, double *out_dev);     /* out = B lam (collective) */

@@ -221,3 +221,6 @@ def test_two_rank_solve_equals_the_single_device_solve(args):
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["ok"], out
     assert out["ranks"][0]["iterations"] == out["ranks"][1]["iterations"]
+    # the loop's exchanges went through peer memory (2) or, where the partner's memory cannot be mapped, NCCL (1); the tool
+    # repeats the solve over NCCL and requires the same solution
+    assert all(r["comm_path"] in (1, 2) and r["iterations_nccl"] == r["iterations"] for r in out["ranks"]), out

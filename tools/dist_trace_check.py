@@ -30,8 +30,15 @@ ctx.comm_init_torch(dist)
 assert ctx.world == world and ctx.rank == rank
 
 pr = dist_trace.StripProblem(ctx, rank, world, nbx, nby, N, p, condense=bool(condense), coarse_modes=modes, local_tol=1e-14)
-st = pr.solve(tol=1e-12, maxit=5000)
+st = pr.solve(tol=1e-12, maxit=5000)             # default: exchanges of the loop through peer memory where it can be mapped
+path = pr.tr.comm_path()
 lam, u = pr.lam.get(), pr.u.get()
+pr.tr.set_option("cg_p2p", 0)                    # the same solve over NCCL: same iteration count, same solution
+st_nccl = pr.solve(tol=1e-12, maxit=5000)
+path_nccl = pr.tr.comm_path()
+lam_nccl = pr.lam.get()
+pr.tr.set_option("cg_p2p", 1)
+st = pr.solve(tol=1e-12, maxit=5000)             # (timed with the mailboxes and the graph in place)
 
 ctx1 = hs.Context(local)                    # the whole mesh on one device, no communicator
 ref = dist_trace.StripProblem(ctx1, 0, 1, nbx * world, nby, N, p, condense=bool(condense), coarse_modes=modes, local_tol=1e-14)
@@ -60,10 +67,14 @@ for f, v in cut_vals.items():
 
 out = dict(rank=rank, world=world, err_lambda=elam, err_u=eu, iterations=st["outer_iterations"], iterations_single=st1["outer_iterations"],
            converged=st["converged"], true_rel_residual=st["true_rel_residual"], issued=st["issued_iterations"],
-           coarse_dofs=st["coarse_dofs"], cut_faces=pr.info["cut_faces"], cut_copies_differ=mismatch, timings=pr.timings)
+           coarse_dofs=st["coarse_dofs"], cut_faces=pr.info["cut_faces"], cut_copies_differ=mismatch, timings=pr.timings,
+           comm_path=path, comm_path_second_solve=path_nccl, iterations_nccl=st_nccl["outer_iterations"],
+           cg_loop_ms=st["cg_loop_ms"], cg_loop_ms_nccl=st_nccl["cg_loop_ms"],
+           nccl_vs_p2p_lambda=float(np.linalg.norm(lam - lam_nccl) / np.linalg.norm(lam)))
 res = [None] * world
 dist.all_gather_object(res, out)
-ok = all(r["err_lambda"] <= 1e-10 and r["err_u"] <= 1e-10 and r["converged"] == 1 and r["cut_copies_differ"] == 0 for r in res)
+ok = all(r["err_lambda"] <= 1e-10 and r["err_u"] <= 1e-10 and r["converged"] == 1 and r["cut_copies_differ"] == 0 and
+         r["nccl_vs_p2p_lambda"] <= 1e-10 and r["comm_path_second_solve"] == 1 for r in res)
 if rank == 0:
     print(json.dumps(dict(ok=ok, ranks=res)))
 pr.close(); ref.close()
