@@ -365,6 +365,7 @@ def run_ours(args):
             if st_t["converged"] != 1 or not st_t["true_rel_residual"] <= 100 * args.trace_tol:
                 raise RuntimeError("trace solve did not converge: %r" % (st_t,))
             info = pr.info
+            comm_path = pr.tr.comm_path()
             out = {"seconds": t_solve, "device_ms": ms_dev, "setup_seconds": t_setup,
                    "setup_breakdown_seconds": {k: round(v, 3) for k, v in tm.items()},
                    "outer_iterations": st_t["outer_iterations"], "issued_iterations": st_t["issued_iterations"],
@@ -380,7 +381,11 @@ def run_ours(args):
                               "%d Legendre modes per face" % info["coarse_modes"] if info["coarse_modes"] else "none"),
                    "lambda_points_per_gpu": info["lambda_points"], "cut_faces_per_gpu": info["cut_faces"],
                    "volume_points_per_gpu": info["volume_points"],
-                   "communication": "inside libhsbp: ncclSend/ncclRecv of cut-face contributions + 2 ncclAllReduce per iteration" if world > 1 else "none (1 GPU)"}
+                   "communication": {0: "none (1 GPU)",
+                                     1: "inside libhsbp: ncclSend/ncclRecv of cut-face contributions + 2 ncclAllReduce per iteration",
+                                     2: "inside libhsbp, no NCCL call in the iteration loop: cut-face contributions and the partial sums of "
+                                        "the CG scalars are written into the partners' device memory over NVLink (cudaIpc-mapped "
+                                        "mailboxes, flags, rank-ordered sums) by kernels of the same CUDA graph"}[comm_path]}
             pr.close()
             return out
 
