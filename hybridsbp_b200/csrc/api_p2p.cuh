@@ -132,16 +132,25 @@ using namespace hsbp;
 struct P2PHost {
   P2PDev *d_dev = nullptr;
   double *mailbox = nullptr;
+  size_t mailbox_bytes = 0;
+  int device = 0;
   std::vector<void *> opened;          // mappings of the partners' mailboxes (cudaIpcCloseMemHandle)
   long long nred2 = 0, nrecv = 0;
 };
 
+// A mailbox that partner processes have mapped must not be freed while they may still have it open, and the ranks do not
+// destroy their traces in step: a released mailbox goes back to this process-wide pool (reused by the next trace that needs
+// one of at most its size on the same device) and is returned to the driver only when the process ends.
+struct MailboxPoolEntry { int device; size_t bytes; double *ptr; };
+std::vector<MailboxPoolEntry> g_mailbox_pool;
+
 void p2p_free(hsbp_trace *t) {
   P2PHost *h = (P2PHost *)t->p2p;
   if (!h) return;
+  if (t->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)t->graph_exec); t->graph_exec = nullptr; }   // it holds the mailbox pointers
   for (void *p : h->opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_dev);
-  cudaFree(h->mailbox);
+  if (h->mailbox) g_mailbox_pool.push_back({h->device, h->mailbox_bytes, h->mailbox});
   delete h;
   t->p2p = nullptr;
 }
@@ -166,8 +175,18 @@ int p2p_setup(hsbp_trace *t) {
   int bad = 0;
   Rec mine;
   memset(&mine, 0, sizeof(mine));
-  if (cudaMalloc((void **)&h->mailbox, mb_doubles * sizeof(double)) != cudaSuccess ||
-      cudaMemset(h->mailbox, 0, mb_doubles * sizeof(double)) != cudaSuccess ||
+  h->device = ctx->device;
+  for (size_t i = 0; i < g_mailbox_pool.size(); ++i)
+    if (g_mailbox_pool[i].device == ctx->device && g_mailbox_pool[i].bytes >= mb_doubles * sizeof(double)) {
+      h->mailbox = g_mailbox_pool[i].ptr; h->mailbox_bytes = g_mailbox_pool[i].bytes;
+      g_mailbox_pool.erase(g_mailbox_pool.begin() + i);
+      break;
+    }
+  if (!h->mailbox) {
+    h->mailbox_bytes = mb_doubles * sizeof(double);
+    if (cudaMalloc((void **)&h->mailbox, h->mailbox_bytes) != cudaSuccess) { h->mailbox = nullptr; bad = 1; cudaGetLastError(); }
+  }
+  if (bad || cudaMemset(h->mailbox, 0, h->mailbox_bytes) != cudaSuccess ||
       cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(mine.handle), h->mailbox) != cudaSuccess) {
     bad = 1;
     cudaGetLastError();
