@@ -174,7 +174,7 @@ def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p, exact=None):
 
 
 def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=None, exact=None, jump_code=None,
-                condense=True):
+                condense=True, coarse_modes=2):
     """One refinement level on the GPU.  Returns dict(eps, tau_eps, lam, u, stats, ...)."""
     verts, EToV, EToF, FToB, dom = mesh
     ne, nf = EToV.shape[1], len(FToB)
@@ -201,6 +201,8 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=No
         # applied inside a CG preconditioned with its exact diagonal blocks
         tr.condense()
         tr.precond_setup(1)
+        if coarse_modes > 0:               # second level: Legendre modes per face (iteration counts independent of the mesh)
+            tr.coarse_setup(coarse_modes)
     FTols = tr.FTolambdastarts
     jump_codes = tuple(sorted(set(int(b) for b in FToB if b >= host.BC_JUMP_INTERFACE))) or (jump_code,)
     FTods = host.bcstarts(FToB, FToE, FToLF, jump_codes, [N] * ne, [N] * ne)
