@@ -240,33 +240,36 @@ constexpr int BS_PB = 16;             // panel width of the streamed solve
 constexpr int BS_THREADS = 512;
 constexpr int BS_WIN = 2048;          // circular window of the right-hand side / solution (doubles); needs kd + 2 BS_PB <= BS_WIN
 
-// inverse of every BS_PB x BS_PB lower-triangular diagonal block of the factor, row-major [i][j]
-__global__ void __launch_bounds__(BS_PB)
+// inverse of every PB x PB lower-triangular diagonal block of the factor, row-major [i][j]
+template <int PB>
+__global__ void __launch_bounds__(PB)
 k_band_invdiag(const BandBlock *__restrict__ bb, const double *__restrict__ AB, double *__restrict__ inv) {
-  __shared__ double D[BS_PB][BS_PB + 1];
+  __shared__ double D[PB][PB + 1];
   const BandBlock b = bb[blockIdx.y];
-  const int k0 = blockIdx.x * BS_PB;
+  const int k0 = blockIdx.x * PB;
   if (k0 >= b.npad) return;
   const double *A = AB + b.off;
   const int c = threadIdx.x;
-  for (int i = 0; i < BS_PB; ++i) D[i][c] = band_get(A, b.ld, b.kd, k0 + i, k0 + c);
+  for (int i = 0; i < PB; ++i) D[i][c] = band_get(A, b.ld, b.kd, k0 + i, k0 + c);
   __syncthreads();
-  double x[BS_PB];                    // column c of the inverse: D x = e_c
+  double x[PB];                    // column c of the inverse: D x = e_c
 #pragma unroll
-  for (int i = 0; i < BS_PB; ++i) {
+  for (int i = 0; i < PB; ++i) {
     double s = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-    for (int j = 0; j < BS_PB; ++j)
+    for (int j = 0; j < PB; ++j)
       if (j < i) s -= D[i][j] * x[j];
     x[i] = (i >= c) ? s / D[i][i] : 0.0;
   }
-  double *out = inv + b.ioff + (int64_t)blockIdx.x * BS_PB * BS_PB;
+  double *out = inv + b.ioff + (int64_t)blockIdx.x * PB * PB;
 #pragma unroll
-  for (int i = 0; i < BS_PB; ++i) out[i * BS_PB + c] = x[i];
+  for (int i = 0; i < PB; ++i) out[i * PB + c] = x[i];
 }
 
-// x_e = (L L^T)^-1 g_e, one CTA per block.  Dynamic shared memory: nst panel stages of BS_PB * ld doubles, nst inverse
-// blocks, the window, 2 * BS_PB doubles, nst mbarriers.
+// x_e = (L L^T)^-1 g_e, one CTA per block.  Dynamic shared memory: nst panel stages of PB * ld doubles, nst inverse
+// blocks, the window, 2 * PB doubles, nst mbarriers.  PB: panel width (16; 8 or 4 when a stage of 16 columns of a wide band
+// would not leave room for two stages, e.g. p = 6 blocks of 137 x 137 points).
+template <int PB>
 __global__ void __launch_bounds__(BS_THREADS, 1)
 k_band_solve_stream(const BandBlock *__restrict__ bb, const double *__restrict__ AB, const double *__restrict__ inv,
                     const double *__restrict__ g, double *__restrict__ x, double *__restrict__ work, int nst, int maxld) {
@@ -276,13 +279,13 @@ k_band_solve_stream(const BandBlock *__restrict__ bb, const double *__restrict__
   const double *Iv = inv + b.ioff;
   double *y = work + b.woff;                                  // forward result (global, npad doubles)
   const int ld = b.ld, kd = b.kd, npad = b.npad, np = b.np, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int npan = npad / BS_PB;
-  double *pan = reinterpret_cast<double *>(band_smem);        // [nst][BS_PB * maxld]
-  double *ivs = pan + (size_t)nst * BS_PB * maxld;            // [nst][BS_PB * BS_PB]
-  double *win = ivs + (size_t)nst * BS_PB * BS_PB;            // [BS_WIN]
-  double *pv = win + BS_WIN;                                  // [2 * BS_PB]: panel solution / column dots
-  uint64_t *full = reinterpret_cast<uint64_t *>(pv + 2 * BS_PB);
-  const uint32_t pan_bytes = (uint32_t)(BS_PB * ld) * 8u, inv_bytes = (uint32_t)(BS_PB * BS_PB) * 8u;
+  const int npan = npad / PB;
+  double *pan = reinterpret_cast<double *>(band_smem);        // [nst][PB * maxld]
+  double *ivs = pan + (size_t)nst * PB * maxld;            // [nst][PB * PB]
+  double *win = ivs + (size_t)nst * PB * PB;            // [BS_WIN]
+  double *pv = win + BS_WIN;                                  // [2 * PB]: panel solution / column dots
+  uint64_t *full = reinterpret_cast<uint64_t *>(pv + 2 * PB);
+  const uint32_t pan_bytes = (uint32_t)(PB * ld) * 8u, inv_bytes = (uint32_t)(PB * PB) * 8u;
   if (tid == 0) {
     for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
@@ -290,45 +293,45 @@ k_band_solve_stream(const BandBlock *__restrict__ bb, const double *__restrict__
   __syncthreads();
   auto issue = [&](int k, int st) {                           // panel k into stage st (thread 0)
     mbar_expect_tx(&full[st], pan_bytes + inv_bytes);
-    bulk_g2s(pan + (size_t)st * BS_PB * maxld, A + (int64_t)k * BS_PB * ld, pan_bytes, &full[st]);
-    bulk_g2s(ivs + (size_t)st * BS_PB * BS_PB, Iv + (int64_t)k * BS_PB * BS_PB, inv_bytes, &full[st]);
+    bulk_g2s(pan + (size_t)st * PB * maxld, A + (int64_t)k * PB * ld, pan_bytes, &full[st]);
+    bulk_g2s(ivs + (size_t)st * PB * PB, Iv + (int64_t)k * PB * PB, inv_bytes, &full[st]);
   };
   // ================= L y = g: panels in increasing order =================
   if (tid == 0) {
     fence_proxy_async();
     for (int k = 0; k < nst && k < npan; ++k) issue(k, k);
   }
-  for (int i = tid; i < BS_PB + kd && i < BS_WIN; i += BS_THREADS) win[i] = (i < np) ? g[b.voff + i] : 0.0;
+  for (int i = tid; i < PB + kd && i < BS_WIN; i += BS_THREADS) win[i] = (i < np) ? g[b.voff + i] : 0.0;
   __syncthreads();
   int st = 0;
   uint32_t parity = 0;
   for (int k = 0; k < npan; ++k) {
-    const int k0 = k * BS_PB;
-    // rows that enter the window for the next panel: k0 + BS_PB + kd .. + BS_PB - 1 (loaded early, stored late)
+    const int k0 = k * PB;
+    // rows that enter the window for the next panel: k0 + PB + kd .. + PB - 1 (loaded early, stored late)
     double gnew = 0.0;
-    const int inew = k0 + BS_PB + kd + (tid - 32);
-    if (wid == 1 && lane < BS_PB && inew < np) gnew = g[b.voff + inew];
+    const int inew = k0 + PB + kd + (tid - 32);
+    if (wid == 1 && lane < PB && inew < np) gnew = g[b.voff + inew];
     mbar_wait(&full[st], parity);
-    const double *P = pan + (size_t)st * BS_PB * maxld;
-    const double *Iq = ivs + (size_t)st * BS_PB * BS_PB;
-    if (wid == 0 && lane < BS_PB) {                           // y_panel = inv(D) r_panel
+    const double *P = pan + (size_t)st * PB * maxld;
+    const double *Iq = ivs + (size_t)st * PB * PB;
+    if (wid == 0 && lane < PB) {                           // y_panel = inv(D) r_panel
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < BS_PB; ++j) s += Iq[lane * BS_PB + j] * win[(k0 + j) & (BS_WIN - 1)];
+      for (int j = 0; j < PB; ++j) s += Iq[lane * PB + j] * win[(k0 + j) & (BS_WIN - 1)];
       pv[lane] = s;
       y[k0 + lane] = s;
     }
     __syncthreads();
-    for (int t = tid; t < kd; t += BS_THREADS) {              // r_i -= sum_j L[i][k0+j] y_j, i = k0 + BS_PB + t
+    for (int t = tid; t < kd; t += BS_THREADS) {              // r_i -= sum_j L[i][k0+j] y_j, i = k0 + PB + t
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < BS_PB; ++j) {
-        const int d = t + BS_PB - j;
+      for (int j = 0; j < PB; ++j) {
+        const int d = t + PB - j;
         if (d <= kd) s += P[j * ld + d] * pv[j];
       }
-      win[(k0 + BS_PB + t) & (BS_WIN - 1)] -= s;
+      win[(k0 + PB + t) & (BS_WIN - 1)] -= s;
     }
-    if (wid == 1 && lane < BS_PB) win[inew & (BS_WIN - 1)] = gnew;
+    if (wid == 1 && lane < PB) win[inew & (BS_WIN - 1)] = gnew;
     __syncthreads();
     if (tid == 0 && k + nst < npan) { fence_proxy_async(); issue(k + nst, st); }
     if (++st == nst) { st = 0; parity ^= 1u; }
@@ -344,28 +347,28 @@ k_band_solve_stream(const BandBlock *__restrict__ bb, const double *__restrict__
   }
   __syncthreads();
   for (int m = 0; m < npan; ++m) {
-    const int k = npan - 1 - m, k0 = k * BS_PB;
+    const int k = npan - 1 - m, k0 = k * PB;
     double yv = 0.0;
-    if (wid == 0 && lane < BS_PB) yv = y[k0 + lane];           // early load
+    if (wid == 0 && lane < PB) yv = y[k0 + lane];           // early load
     mbar_wait(&full[st], parity);
-    const double *P = pan + (size_t)st * BS_PB * maxld;
-    const double *Iq = ivs + (size_t)st * BS_PB * BS_PB;
-    {                                                           // s_j = L[k0+BS_PB.., k0+j] . x[k0+BS_PB..], one warp per column
-      const int j = wid;                                        // BS_THREADS / 32 == BS_PB warps
+    const double *P = pan + (size_t)st * PB * maxld;
+    const double *Iq = ivs + (size_t)st * PB * PB;
+    if (wid < PB) {                                             // s_j = L[k0+PB.., k0+j] . x[k0+PB..], one warp per column
+      const int j = wid;                                        // BS_THREADS / 32 >= PB warps
       double s = 0.0;
-      const int tend = kd - BS_PB + j;                          // d = t + BS_PB - j <= kd
-      for (int t = lane; t <= tend; t += 32) s += P[j * ld + t + BS_PB - j] * win[(k0 + BS_PB + t) & (BS_WIN - 1)];
+      const int tend = kd - PB + j;                          // d = t + PB - j <= kd
+      for (int t = lane; t <= tend; t += 32) s += P[j * ld + t + PB - j] * win[(k0 + PB + t) & (BS_WIN - 1)];
       s = warp_sum(s);
-      if (lane == 0) pv[BS_PB + j] = s;
+      if (lane == 0) pv[PB + j] = s;
     }
     __syncthreads();
-    if (wid == 0 && lane < BS_PB) {                             // x_panel = inv(D)^T (y_panel - s)
-      pv[lane] = yv - pv[BS_PB + lane];
-      __syncwarp((1u << BS_PB) - 1u);
+    if (wid == 0 && lane < PB) {                             // x_panel = inv(D)^T (y_panel - s)
+      pv[lane] = yv - pv[PB + lane];
+      __syncwarp((1u << PB) - 1u);
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < BS_PB; ++j)
-        if (j >= lane) s += Iq[j * BS_PB + lane] * pv[j];
+      for (int j = 0; j < PB; ++j)
+        if (j >= lane) s += Iq[j * PB + lane] * pv[j];
       win[(k0 + lane) & (BS_WIN - 1)] = s;
       if (k0 + lane < np) x[b.voff + k0 + lane] = s;
     }
@@ -410,10 +413,14 @@ template <int P> int band_setup_p(hsbp_blocks *b) {
   HSBP_CUDA(ctx, cudaMalloc((void **)&b->d_band_inv, (size_t)ioff * sizeof(double)));
   // streamed solve: at least two panel stages must fit in shared memory, the window must hold a panel's rows
   {
-    const size_t fixed = (size_t)BS_WIN * 8 + 2 * BS_PB * 8 + 64;
-    const size_t per_stage = (size_t)BS_PB * maxld * 8 + (size_t)BS_PB * BS_PB * 8;
-    int nst = (int)std::min<size_t>(4, (ctx->smem_optin > fixed ? (ctx->smem_optin - fixed) / per_stage : 0));
-    b->band_stream_stages = (nst >= 2 && minkd >= BS_PB && maxkd + 2 * BS_PB <= BS_WIN) ? nst : 0;
+    // widest panel (16, 8, 4 columns) that leaves room for two stages
+    b->band_stream_stages = 0; b->band_pb = BS_PB;
+    for (int pb = BS_PB; pb >= 4 && b->band_stream_stages == 0; pb /= 2) {
+      const size_t fixed = (size_t)BS_WIN * 8 + 2 * pb * 8 + 64 + 2048;
+      const size_t per_stage = (size_t)pb * maxld * 8 + (size_t)pb * pb * 8;
+      const int nst = (int)std::min<size_t>(4, (ctx->smem_optin > fixed ? (ctx->smem_optin - fixed) / per_stage : 0));
+      if (nst >= 2 && minkd >= pb && maxkd + 2 * pb <= BS_WIN) { b->band_stream_stages = nst; b->band_pb = pb; }
+    }
     b->band_maxld = maxld;
     b->band_maxnpad = maxnpad;
   }
@@ -446,7 +453,9 @@ template <int P> int band_setup_p(hsbp_blocks *b) {
       if (nt > 0)
         k_band_update<<<dim3(nt, nt, (unsigned)b->nblocks), CH_THREADS, 0, ctx->stream>>>(dbb, b->d_band, k0);
     }
-    k_band_invdiag<<<dim3((unsigned)(maxnpad / BS_PB), (unsigned)b->nblocks), BS_PB, 0, ctx->stream>>>(dbb, b->d_band, b->d_band_inv);
+    if (b->band_pb == 16) k_band_invdiag<16><<<dim3((unsigned)(maxnpad / 16), (unsigned)b->nblocks), 16, 0, ctx->stream>>>(dbb, b->d_band, b->d_band_inv);
+    else if (b->band_pb == 8) k_band_invdiag<8><<<dim3((unsigned)(maxnpad / 8), (unsigned)b->nblocks), 8, 0, ctx->stream>>>(dbb, b->d_band, b->d_band_inv);
+    else k_band_invdiag<4><<<dim3((unsigned)(maxnpad / 4), (unsigned)b->nblocks), 4, 0, ctx->stream>>>(dbb, b->d_band, b->d_band_inv);
     e1 = cudaGetLastError();
     if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(flag.data(), d_flag, b->nblocks * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
@@ -467,12 +476,17 @@ int band_solve(hsbp_blocks *b, const double *g, double *x, hsbp_local_stats *sta
   hsbp_ctx *ctx = b->ctx;
   if (!b->d_band) HSBP_FAIL(ctx, HSBP_ERR_STATE, "banded Cholesky local solver: not set up");
   if (b->band_stream_stages >= 2 && !b->band_no_stream) {
-    const int nst = b->band_stream_stages;
-    const size_t sm = (size_t)nst * BS_PB * b->band_maxld * 8 + (size_t)nst * BS_PB * BS_PB * 8 + (size_t)BS_WIN * 8 +
-                      2 * BS_PB * 8 + nst * sizeof(uint64_t);
-    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_band_solve_stream, ctx->smem_optin));
-    k_band_solve_stream<<<(unsigned)b->nblocks, BS_THREADS, sm, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band,
-                                                                                b->d_band_inv, g, x, b->d_band_work, nst, b->band_maxld);
+    const int nst = b->band_stream_stages, pb = b->band_pb;
+    const size_t sm = (size_t)nst * pb * b->band_maxld * 8 + (size_t)nst * pb * pb * 8 + (size_t)BS_WIN * 8 +
+                      2 * pb * 8 + nst * sizeof(uint64_t);
+    auto go = [&](auto kern) -> int {
+      HSBP_CUDA(ctx, hsbp_smem_optin(ctx, kern, sm));
+      kern<<<(unsigned)b->nblocks, BS_THREADS, sm, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band, b->d_band_inv, g, x,
+                                                                  b->d_band_work, nst, b->band_maxld);
+      return HSBP_OK;
+    };
+    const int rcl = pb == 16 ? go(k_band_solve_stream<16>) : (pb == 8 ? go(k_band_solve_stream<8>) : go(k_band_solve_stream<4>));
+    if (rcl) return rcl;
   } else {
     k_band_solve<<<(unsigned)b->nblocks, CH_THREADS, 0, ctx->stream>>>((const BandBlock *)b->d_band_desc, b->d_band, g, x,
                                                                       b->d_band_work);

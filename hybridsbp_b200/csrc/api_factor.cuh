@@ -30,8 +30,8 @@ int factor_solve_dev(hsbp_factor *f, const double *g, double *x) {
     const int nst = f->stream_stages;
     const size_t sm = (size_t)nst * BS_PB * f->bb.ld * 8 + (size_t)nst * BS_PB * BS_PB * 8 + (size_t)BS_WIN * 8 + 2 * BS_PB * 8 +
                       nst * sizeof(uint64_t);
-    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_band_solve_stream, ctx->smem_optin));
-    k_band_solve_stream<<<1, BS_THREADS, sm, ctx->stream>>>(f->d_bb, f->d_band, f->d_inv, g, x, f->d_work, nst, f->bb.ld);
+    HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_band_solve_stream<BS_PB>, sm));
+    k_band_solve_stream<BS_PB><<<1, BS_THREADS, sm, ctx->stream>>>(f->d_bb, f->d_band, f->d_inv, g, x, f->d_work, nst, f->bb.ld);
   } else {
     k_band_solve<<<1, CH_THREADS, 0, ctx->stream>>>(f->d_bb, f->d_band, g, x, f->d_work);
   }
@@ -105,7 +105,7 @@ int hsbp_factor_create(hsbp_ctx *ctx, int64_t n, const int64_t *colptr, const in
       const int nt = std::min(ntmax, (q.npad - k0 - CH_NB) / CH_NB);
       if (nt > 0) k_band_update<<<dim3(nt, nt, 1), CH_THREADS, 0, ctx->stream>>>(f->d_bb, f->d_band, k0);
     }
-    k_band_invdiag<<<dim3((unsigned)(q.npad / BS_PB), 1), BS_PB, 0, ctx->stream>>>(f->d_bb, f->d_band, f->d_inv);
+    k_band_invdiag<BS_PB><<<dim3((unsigned)(q.npad / BS_PB), 1), BS_PB, 0, ctx->stream>>>(f->d_bb, f->d_band, f->d_inv);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -82,6 +82,7 @@ struct hsbp_blocks {
   double *d_band_work = nullptr;
   double *d_band_inv = nullptr;             // inverted diagonal blocks of the banded factors (streamed solve)
   int band_stream_stages = 0, band_maxld = 0, band_maxnpad = 0, band_no_stream = 0;
+  int band_pb = 16;                // panel width of the streamed banded solve (16, or 8 / 4 for wide bands)
   double *d_fdm_vr = nullptr, *d_fdm_vs = nullptr;   // generalised eigenvectors of the collapsed 1-D operators (api_fdm.cuh)
   double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   float *d_fdm_vr32 = nullptr, *d_fdm_vs32 = nullptr, *d_fdm_dinv32 = nullptr, *d_fdm_a32 = nullptr, *d_fdm_b32 = nullptr;
