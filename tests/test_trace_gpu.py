@@ -173,6 +173,33 @@ def test_banded_cholesky_local_solver(ctx, p, stream):
         assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, np.linalg.norm(x[sl] - xr) / np.linalg.norm(xr))
 
 
+@pytest.mark.parametrize("p,Nr,Ns", [(6, 110, 20), (6, 215, 19), (4, 180, 17)])
+def test_banded_cholesky_wide_bands_stream_with_narrow_panels(ctx, p, Nr, Ns):
+    """wide bands (long lines, p = 6: half-bandwidth 8 (Nr+1) + 8): sixteen columns per shared-memory stage would leave room for one
+    stage only, the streamed solve then runs on panels of 8 or 4 columns (config 1 / 2 at N = 136, p = 6 took the plain-load kernel
+    before: 22 s of condensation instead of 2.7 s)"""
+    import hybridsbp_b200 as hs
+    rng = np.random.default_rng(900 + Nr)
+    mets = [random_spd_metrics(p, Nr, Ns, rng, scale2=0.2) for _ in range(2)]
+    bcs = [(1, 2, 0, 7), (2, 1, 1, 0)]
+    lops = [orc.locoperator(p, Nr, Ns, m, bc) for m, bc in zip(mets, bcs)]
+    blk = upload_blocks(hs, ctx, p, mets, bcs)
+    g = rng.uniform(-1, 1, blk.VNp)
+    dg, dx = ctx.array(g), ctx.empty(blk.VNp)
+    xs = []
+    for no_stream in (0, 1):
+        blk.set_option("band_no_stream", no_stream)
+        blk.local_setup(hs.LOCAL_BAND)
+        st = blk.local_solve(dg, dx)
+        assert st["failed_blocks"] == 0
+        xs.append(dx.get())
+    for e, lop in enumerate(lops):
+        sl = blk.vol_slice(e)
+        xr = orc.default_factorization(lop.Mt).solve(g[sl])
+        for x in xs:
+            assert np.linalg.norm(x[sl] - xr) <= 1e-10 * np.linalg.norm(xr), (e, np.linalg.norm(x[sl] - xr) / np.linalg.norm(xr))
+
+
 @pytest.mark.parametrize("p,kind,gemm", [(2, "warped", 0), (4, "warped", 0), (6, "warped", 0), (4, "random", 0),
                                          (4, "warped", 1), (4, "warped", 2), (4, "warped", 3)])
 def test_fast_diagonalisation_pcg_local_solver(ctx, p, kind, gemm):
