@@ -13,14 +13,17 @@
 // With the generalised eigen-decompositions  Ar Vr = Hr Vr Lr,  Vr^T Hr Vr = I  (and s likewise)
 //     P^-1 = (Vs (x) Vr) diag(1 / d_ij) (Vs (x) Vr)^T,   d_ij = mr_i + ms_j - c,
 // i.e. for the block's residual as an (Nr+1) x (Ns+1) matrix R:  Z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T  -- four dense
-// GEMMs per block, executed as strided-batched cuBLAS GEMMs (plain library GEMMs; fp64 or, by default, TF32 tensor cores).
+// GEMMs per block, hand-written: two launches of k_fdm_pair (tcgen05 TF32, TMA operands, the intermediate product stays in
+// tensor memory; k_tcgemm.cuh) or k_dgemm_batched (fp64, mma.sync) -- cuBLAS only as a comparison knob for tests.
 //
 //   setup   4 (2 WB + 1) operator applications with coloured probe vectors (all blocks at once); symmetric
-//           eigen-decompositions with cuSOLVER (syevd on H^-1/2 A H^-1/2).  The collapse against the constant carries the
+//           eigen-decompositions of H^-1/2 A H^-1/2 by the batched Jacobi kernel k_jacobi_eig (k_eig.cuh; cuSOLVER syevd as a
+//           comparison knob).  The collapse against the constant carries the
 //           other direction's face penalties as a large shift sigma Hr, which leaves the eigenvectors alone but would
 //           make lr_i + ls_j - c a difference of large numbers; the eigenvalues are therefore Rayleigh quotients of
 //           the operator collapsed against the other direction's lowest mode (a shift of the smallest eigenvalue only).
-//   solve   PCG per block, all blocks at once: M̃ p (k_sweep), update of x / r, z = P^-1 r, update of p.
+//   solve   PCG per block, all blocks at once: M̃ p (k_sweep, which also leaves p . M̃ p), update of x / r, z = P^-1 r, update of p;
+//           blocks that have converged drop out of every kernel.
 #pragma once
 #include <chrono>
 #include <cstdio>

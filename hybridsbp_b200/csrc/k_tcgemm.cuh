@@ -11,8 +11,10 @@
 // reads TMEM with tcgen05.ld (32 lanes x 32 columns per warp and call) and writes row-major fp32 (optionally scaled
 // elementwise -- the "o Dinv" between the GEMM pairs), column-major fp32 or column-major fp64.
 //
-// The preconditioner z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T is four launches of this kernel (api_fdm.cuh); the reference has
-// no counterpart -- it factorises M-tilde (global_curved.jl:698) -- this is the engine of the batched PCG local solver.
+// The preconditioner z = Vr [ (Vr^T R Vs) o Dinv ] Vs^T was four launches of this kernel in the first version; the default is
+// now k_fdm_pair below (two chained GEMMs per launch, TMA operands, TMEM operand), this kernel stays as the comparison variant
+// ("fdm_tc_variant" = 1).  The reference has no counterpart -- it factorises M-tilde (global_curved.jl:698) -- this is the
+// engine of the batched PCG local solver.
 #pragma once
 #include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
