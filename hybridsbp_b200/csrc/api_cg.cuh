@@ -736,13 +736,25 @@ int hsbp_trace_solve(hsbp_trace *t, const double *g_dev, const double *gd_dev, d
   memset(&st, 0, sizeof(st));
   st.coarse_dofs = t->cmodes > 0 ? (int64_t)t->nI + t->nGt : 0;
   const bool collective = ctx->world > 1;
+  // HSBP_TRACE_TIMING=1: phase times of this call on stderr (synchronising; diagnostics only)
+  const bool timing = getenv("HSBP_TRACE_TIMING") != nullptr;
+  auto tnow = [&]() { if (timing) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+  auto tph = tnow();
+  auto tprint = [&](const char *what) {
+    if (!timing) return;
+    auto t1 = tnow();
+    fprintf(stderr, "[trace_solve] %-34s %8.2f ms\n", what, 1e3 * std::chrono::duration<double>(t1 - tph).count());
+    tph = t1;
+  };
   if (n > 0 || collective) {
     if ((rc = dist_rhs(t, g_dev, gd_dev, t->d_r))) return rc;                        // r = b (lambda0 = 0)
+    tprint("right-hand side (local solve)");
     if (n > 0) {
       HSBP_CUDA(ctx, cudaMemcpyAsync(t->d_b, t->d_r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       HSBP_CUDA(ctx, cudaMemsetAsync(lam, 0, n * sizeof(double), ctx->stream));
     }
     if ((rc = cg_run(t, lam, tol, maxit, &st))) return rc;
+    tprint("CG");
     // true residual ||b - B lambda|| / ||b|| with one more application of B (the recurrence can drift when B is applied
     // through inexact local solves)
     if ((rc = dist_schur_apply(t, lam, t->d_q))) return rc;
@@ -760,6 +772,7 @@ int hsbp_trace_solve(hsbp_trace *t, const double *g_dev, const double *gd_dev, d
   } else {
     st.converged = 1;
   }
+  tprint("true residual");
   // u = M^-1 (g - Fbar lambda)
   HSBP_CUDA(ctx, cudaMemcpyAsync(t->d_w, g_dev, (size_t)b->VNp * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   if (n > 0 && (rc = trace_Fbar_add(t, lam, -1.0, t->d_w))) return rc;
@@ -767,6 +780,7 @@ int hsbp_trace_solve(hsbp_trace *t, const double *g_dev, const double *gd_dev, d
   if ((rc = local_solve_impl(b, t->d_w, u_dev, &s))) return rc;
   accumulate(t, s);
   HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  tprint("back-substitution (local solve)");
   st.inner_iterations_sum = t->acc.iterations_sum;
   st.inner_iterations_max = t->acc.iterations_max;
   st.local_solves = t->local_solves;
