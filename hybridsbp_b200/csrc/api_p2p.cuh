@@ -43,13 +43,14 @@ __host__ __device__ inline long long p2p_off_recv(long long nred2) { return 4 * 
 
 __device__ __forceinline__ double p2p_ld(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
 
-// spin until the flags of all ranks have reached epoch e (one thread per rank); gives up after about two seconds
+// spin until the flags of all ranks have reached epoch e (one thread per rank); gives up after about half a minute (a rank that
+// is merely late -- its host was descheduled between two chunks -- must not be mistaken for a lost one)
 __device__ __forceinline__ void p2p_wait_flags(P2PDev *pp, const double *mb, int flag0, unsigned long long e) {
   if ((int)threadIdx.x < pp->world) {
     const volatile unsigned long long *f = reinterpret_cast<const volatile unsigned long long *>(mb) + flag0 + threadIdx.x;
     const long long t0 = clock64();
     while (*f < e) {
-      if (clock64() - t0 > 4000000000ll) { pp->error = 1; break; }
+      if (clock64() - t0 > 60000000000ll) { pp->error = 1; break; }
     }
   }
   __threadfence_system();
