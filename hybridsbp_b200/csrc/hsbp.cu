@@ -344,6 +344,7 @@ int hsbp_blocks_set_option(hsbp_blocks *b, const char *name, int64_t value) {
   else if (n == "fdm_tc_variant") b->fdm_tc_variant = (int)value;
   else if (n == "fdm_no_skip") b->fdm_no_skip = (int)value;
   else if (n == "sweep_no_pdl") b->sweep_no_pdl = (int)value;
+  else if (n == "host_groups") b->host_groups = (int)value;
   else if (n == "fdm_no_fused_dot") b->fdm_no_fused_dot = (int)value;
   else if (n == "fdm_eig_lib") b->fdm_eig_lib = (int)value;
   else if (n == "sweep_p6_regs") b->sweep_p6_regs = (int)value;
@@ -512,7 +513,7 @@ int hsbp_apply_host(hsbp_blocks *b, const double *u, double *y) {
     HSBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HSBP_OK;
   }
-  const int ngroups = (int)std::min<int64_t>(16, b->nblocks / 8);
+  const int ngroups = (int)std::min<int64_t>(b->host_groups > 0 ? b->host_groups : 16, b->nblocks / 8);
   const int64_t per = (b->nblocks + ngroups - 1) / ngroups;
   const int64_t np = (int64_t)(b->max_Nr + 1) * (b->max_Ns + 1);
   if ((int)b->pipe_ev.size() < 2 * ngroups) {

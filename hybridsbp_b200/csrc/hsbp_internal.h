@@ -87,6 +87,7 @@ struct hsbp_blocks {
   double *d_fdm_z = nullptr, *d_fdm_t = nullptr;     // preconditioned residual, GEMM scratch
   float *d_fdm_vr32 = nullptr, *d_fdm_vs32 = nullptr, *d_fdm_dinv32 = nullptr, *d_fdm_a32 = nullptr, *d_fdm_b32 = nullptr;
   float *d_fdm_vrT32 = nullptr, *d_fdm_vsT32 = nullptr, *d_fdm_dinvT32 = nullptr;    // transposes: every tensor-core operand contiguous in k
+  int host_groups = 0;              // groups of blocks hsbp_apply_host pipelines its copies and kernels over (0: 16)
   int sweep_no_pdl = 0;             // 1: k_sweep without programmatic dependent launch behind k_edge_prep (testing / timing)
   double *d_sweep_dot = nullptr;    // [nblocks][<= 64] chunk sums of p . Ap (FDM-PCG)
   int fdm_no_fused_dot = 0;         // 1: p . Ap by a separate pass of the update kernel (testing)
