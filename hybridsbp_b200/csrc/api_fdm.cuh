@@ -386,10 +386,20 @@ template <int P> int fdm_setup_p(hsbp_blocks *b) {
     HSBP_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
     for (int dir = 0; dir < 2; ++dir) {
       const int n = dir == 0 ? Nrp : Nsp;
-      if (eig_smem_bytes(n) + 2048 > (size_t)ctx->smem_optin) { cleanup(); HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "fast-diagonalisation setup: block too large for the batched eigensolver"); }
-      HSBP_CUDA(ctx, hsbp_smem_optin(ctx, k_jacobi_eig, eig_smem_bytes(std::max(Nrp, Nsp))));
-      k_jacobi_eig<<<(unsigned)nb, EIG_THREADS, eig_smem_bytes(n), ctx->stream>>>(n, dir == 0 ? b->d_fdm_vr : b->d_fdm_vs,
-                                                                                 dir == 0 ? d_lr : d_ls, d_t2, 30, 1e-15, d_bad);
+      double *Am = dir == 0 ? b->d_fdm_vr : b->d_fdm_vs, *lm = dir == 0 ? d_lr : d_ls;
+      auto go = [&](auto kern, int cb) -> int {          // widest column block whose 4 cb columns fit in shared memory
+        const size_t sm = eig_smem_bytes(n, cb);
+        HSBP_CUDA(ctx, hsbp_smem_optin(ctx, kern, sm));
+        kern<<<(unsigned)nb, EIG_THREADS, sm, ctx->stream>>>(n, Am, lm, d_t2, 30, 1e-15, d_bad);
+        return HSBP_OK;
+      };
+      const size_t room = (size_t)ctx->smem_optin - 2048;
+      int rce;
+      if (eig_smem_bytes(n, 16) <= room) rce = go(k_jacobi_eig<16>, 16);
+      else if (eig_smem_bytes(n, 8) <= room) rce = go(k_jacobi_eig<8>, 8);
+      else if (eig_smem_bytes(n, 4) <= room) rce = go(k_jacobi_eig<4>, 4);
+      else { cleanup(); HSBP_FAIL(ctx, HSBP_ERR_UNSUPP, "fast-diagonalisation setup: block too large for the batched eigensolver"); }
+      if (rce) { cleanup(); return rce; }
     }
     int bad = 0;
     cudaError_t e2 = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);

@@ -21,9 +21,9 @@
 
 namespace hsbp {
 
-constexpr int EIG_CB = 16;                   // columns per block
+constexpr int EIG_CB = 16;                   // columns per block (8 / 4 for matrices whose 2 x 16 columns of G and V exceed shared memory)
 constexpr int EIG_THREADS = 512;             // 16 warps: one column pair per warp and round-robin step
-inline size_t eig_smem_bytes(int n) { return (size_t)4 * EIG_CB * n * sizeof(double); }
+inline size_t eig_smem_bytes(int n, int cb = EIG_CB) { return (size_t)4 * cb * n * sizeof(double); }
 
 __device__ __forceinline__ double eig_warp_sum(double v) {
 #pragma unroll
@@ -33,11 +33,12 @@ __device__ __forceinline__ double eig_warp_sum(double v) {
 
 // A: [batch][n x n] column-major; in: symmetric matrix, out: eigenvectors as columns, eigenvalues ascending
 // lam: [batch][n]; work: [batch][n x n] scratch; info: incremented once per matrix that did not converge in max_sweeps
+template <int CB>
 __global__ void __launch_bounds__(EIG_THREADS, 1)
 k_jacobi_eig(int n, double *__restrict__ A, double *__restrict__ lam, double *__restrict__ work, int max_sweeps, double tol,
              int *__restrict__ info) {
   extern __shared__ __align__(16) double eig_sm[];
-  constexpr int CB = EIG_CB, M2 = 2 * EIG_CB, RR = 2 * EIG_CB - 1;
+  constexpr int M2 = 2 * CB, RR = 2 * CB - 1;
   double *Gs = eig_sm;                         // [2 CB][n]
   double *Vs = eig_sm + (size_t)M2 * n;        // [2 CB][n]
   __shared__ int s_rot;

@@ -115,10 +115,11 @@ def test_converged_blocks_drop_out_without_changing_the_result(ctx):
     blk.close()
 
 
-def test_batched_jacobi_eigensolver_gives_the_library_preconditioner(ctx):
+@pytest.mark.parametrize("Nr,Ns", [(255, 127), (511, 63)])
+def test_batched_jacobi_eigensolver_gives_the_library_preconditioner(ctx, Nr, Ns):
     """setup with the hand-written batched Jacobi eigensolver (k_eig.cuh) against cuSOLVER syevd (comparison knob): the fp64
-    preconditioner built on either set of eigenvectors is the same operator"""
-    blk = make_blocks(ctx, 2, 2, 255, 127)
+    preconditioner built on either set of eigenvectors is the same operator (512 points per line: column blocks of 8)"""
+    blk = make_blocks(ctx, 2, 2, Nr, Ns)
     rng = np.random.default_rng(77)
     r = rng.uniform(-1, 1, blk.VNp)
     dr, dz = ctx.array(r), ctx.empty(blk.VNp)
