@@ -164,12 +164,29 @@ k_fpcg_update1(const BlockDesc *__restrict__ desc, const double *__restrict__ Ap
   pAp = cta_sum(pAp, scratch);
   const double alpha = s.rz / pAp;
   double rr = 0;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
-    x[o + i] += alpha * p[o + i];
-    const double ri = r[o + i] - alpha * Ap[o + i];
-    r[o + i] = ri;
-    if (r32) r32[o + i] = hsbp::tc::round_tf32((float)ri);
-    rr += ri * ri;
+  if (((o | np) & 1) == 0) {                                     // 16-byte accesses, two independent pairs per trip
+    const double2 *p2 = reinterpret_cast<const double2 *>(p + o), *A2 = reinterpret_cast<const double2 *>(Ap + o);
+    double2 *x2 = reinterpret_cast<double2 *>(x + o), *r2 = reinterpret_cast<double2 *>(r + o);
+    float2 *f2 = r32 ? reinterpret_cast<float2 *>(r32 + o) : nullptr;
+    const int64_t n2 = np >> 1;
+#pragma unroll 2
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 pv = p2[i], av = A2[i];
+      double2 xv = x2[i], rv = r2[i];
+      xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+      rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+      x2[i] = xv; r2[i] = rv;
+      if (f2) f2[i] = make_float2(hsbp::tc::round_tf32((float)rv.x), hsbp::tc::round_tf32((float)rv.y));
+      rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+      x[o + i] += alpha * p[o + i];
+      const double ri = r[o + i] - alpha * Ap[o + i];
+      r[o + i] = ri;
+      if (r32) r32[o + i] = hsbp::tc::round_tf32((float)ri);
+      rr += ri * ri;
+    }
   }
   rr = cta_sum(rr, scratch);
   if (threadIdx.x == 0) {
@@ -197,14 +214,38 @@ k_fpcg_update2(const BlockDesc *__restrict__ desc, const double *__restrict__ r,
     return;
   }
   double rz = 0, zAp = 0;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
-    const double zi = z[o + i];
-    rz += r[o + i] * zi;
-    if (!init) zAp += zi * Ap[o + i];
+  const bool vec2 = ((o | np) & 1) == 0;                         // 16-byte accesses
+  const double2 *z2 = reinterpret_cast<const double2 *>(z + o);
+  const int64_t n2 = np >> 1;
+  if (vec2) {
+    const double2 *r2 = reinterpret_cast<const double2 *>(r + o), *A2 = reinterpret_cast<const double2 *>(Ap + o);
+#pragma unroll 2
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 zv = z2[i], rv = r2[i];
+      rz = fma(rv.x, zv.x, rz); rz = fma(rv.y, zv.y, rz);
+      if (!init) { const double2 av = A2[i]; zAp = fma(zv.x, av.x, zAp); zAp = fma(zv.y, av.y, zAp); }
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+      const double zi = z[o + i];
+      rz += r[o + i] * zi;
+      if (!init) zAp += zi * Ap[o + i];
+    }
   }
   rz = cta_sum(rz, scratch); zAp = cta_sum(zAp, scratch);
   const double beta = init ? 0.0 : -s.alpha * zAp / s.rz;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) p[o + i] = z[o + i] + beta * p[o + i];
+  if (vec2) {
+    double2 *p2 = reinterpret_cast<double2 *>(p + o);
+#pragma unroll 2
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 zv = z2[i];
+      double2 pv = p2[i];
+      pv.x = fma(beta, pv.x, zv.x); pv.y = fma(beta, pv.y, zv.y);
+      p2[i] = pv;
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) p[o + i] = z[o + i] + beta * p[o + i];
+  }
   if (threadIdx.x == 0) {
     s.rz = rz;
     st[blockIdx.x] = s;
