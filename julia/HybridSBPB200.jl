@@ -343,6 +343,9 @@ set_partition!(t::Trace, faces::Vector{<:Integer}, partner::Vector{<:Integer}, g
   check(t.blocks.ctx, ccall((:hsbp_trace_set_partition, libhsbp), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
                             t.h, length(faces), Int64.(faces), Int64.(partner), Int64.(gamma), n_gamma_total))
 
+"how the last trace_solve exchanged data inside its iteration loop: 0 one rank, 1 NCCL, 2 peer memory over NVLink (option \"cg_p2p\")"
+comm_path(t::Trace) = Int(ccall((:hsbp_trace_comm_path, libhsbp), Cint, (Ptr{Cvoid},), t.h))
+
 # ---- SEAS BP1 ODE stage: replaces the body of odefun (seas/BP1/odefun.jl:8-121) ---------------------------
 struct Bp1Params            # layout of hsbp_bp1_params
   Vp::Float64; mu_shear::Float64; sigma_n::Float64; eta::Float64; V0::Float64; tau_z0::Float64
