@@ -135,22 +135,62 @@ k_pcg_update(const BlockDesc *__restrict__ desc, const double *__restrict__ dinv
   if (!s.active) return;
   const int64_t np = (int64_t)(d.Nr + 1) * (d.Ns + 1);
   const int64_t o = d.voff;
+  // blocks whose offset and size are even take 16-byte accesses, two independent pairs per trip (the loops are bandwidth bound)
+  const bool vec2 = ((o | np) & 1) == 0;
+  const int64_t n2 = np >> 1;
+  const double2 *p2c = reinterpret_cast<const double2 *>(p + o), *A2 = reinterpret_cast<const double2 *>(Ap + o);
+  const double2 *d2 = reinterpret_cast<const double2 *>(dinv + o);
   double pAp = 0;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) pAp += p[o + i] * Ap[o + i];
+  if (vec2) {
+#pragma unroll 2
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 pv = p2c[i], av = A2[i];
+      pAp = fma(pv.x, av.x, pAp); pAp = fma(pv.y, av.y, pAp);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) pAp += p[o + i] * Ap[o + i];
+  }
   pAp = cta_sum(pAp, scratch);
   const double alpha = s.rz / pAp;
   double rr = 0, rz = 0;
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
-    x[o + i] += alpha * p[o + i];
-    const double ri = r[o + i] - alpha * Ap[o + i];
-    r[o + i] = ri;
-    rr += ri * ri; rz += ri * ri * dinv[o + i];
+  if (vec2) {
+    double2 *x2 = reinterpret_cast<double2 *>(x + o), *r2 = reinterpret_cast<double2 *>(r + o);
+#pragma unroll 2
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 pv = p2c[i], av = A2[i], dv = d2[i];
+      double2 xv = x2[i], rv = r2[i];
+      xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+      rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+      x2[i] = xv; r2[i] = rv;
+      rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
+      rz = fma(rv.x * rv.x, dv.x, rz); rz = fma(rv.y * rv.y, dv.y, rz);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+      x[o + i] += alpha * p[o + i];
+      const double ri = r[o + i] - alpha * Ap[o + i];
+      r[o + i] = ri;
+      rr += ri * ri; rz += ri * ri * dinv[o + i];
+    }
   }
   rr = cta_sum(rr, scratch); rz = cta_sum(rz, scratch);
   const double beta = rz / s.rz;
   const bool done = !(rr > tol2 * s.g2);
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x)
-    p[o + i] = done ? 0.0 : dinv[o + i] * r[o + i] + beta * p[o + i];
+  if (vec2) {
+    double2 *p2 = reinterpret_cast<double2 *>(p + o);
+    const double2 *r2 = reinterpret_cast<const double2 *>(r + o);
+#pragma unroll 2
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 dv = d2[i], rv = r2[i];
+      double2 pv = p2[i];
+      pv.x = done ? 0.0 : fma(beta, pv.x, dv.x * rv.x);
+      pv.y = done ? 0.0 : fma(beta, pv.y, dv.y * rv.y);
+      p2[i] = pv;
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < np; i += blockDim.x)
+      p[o + i] = done ? 0.0 : dinv[o + i] * r[o + i] + beta * p[o + i];
+  }
   if (threadIdx.x == 0) {
     s.rz = rz; s.rr = rr; s.iters += 1; s.active = done ? 0 : 1;
     st[blockIdx.x] = s;
