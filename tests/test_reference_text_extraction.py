@@ -258,3 +258,35 @@ def test_kernel_closure_code_equals_the_executed_reference_statements(kernel_tab
         wq = w[:BN].copy()
         qt = np.array([getattr(L, "qt_row_%d" % p)(r, ptr(wq)) for r in range(BM)])
         assert np.abs(qt - (Q.T @ w)[:BM]).max() <= 1e-14
+
+
+def test_penalty_constants_equal_the_reference_source_text():
+    """The constants of the penalty parameter tau (global_curved.jl:402-415: layers l, beta, alpha per order) read from the
+    reference's text by executing its assignments, against the oracle's table and against the CUDA source (penalty_consts in
+    k_generic.cuh, Sbp<P>::LPSI in sbp1d.cuh)."""
+    from oracle import hybrid as orc
+    src = open(os.path.join(REF, "global_curved.jl")).read().split("\n")
+    i0 = next(i for i, l in enumerate(src) if re.match(r"\s*if p == 2\s*$", l) and "l = 2" in src[i + 1])
+    ref = {}
+    p = None
+    for l in src[i0:i0 + 16]:
+        m = re.match(r"\s*(?:if|elseif) p == (\d)", l)
+        if m:
+            p = int(m.group(1)); ref[p] = {}
+            continue
+        m = re.match(r"\s*(l|β|α) = (.+)$", l)
+        if m and p is not None:
+            ref[p][m.group(1)] = eval(m.group(2))                 # plain arithmetic: 17 / 48, 13649 / 43200, literals
+    assert set(ref) == {2, 4, 6} and all(set(v) == {"l", "β", "α"} for v in ref.values()), ref
+    for p, v in ref.items():
+        assert orc.PENALTY[p] == (v["l"], v["β"], v["α"])
+    gen = open(os.path.join(ROOT, "hybridsbp_b200", "csrc", "k_generic.cuh")).read()
+    body = gen[gen.index("penalty_consts(int p"):gen.index("template <int P>", gen.index("penalty_consts(int p"))]
+    found = re.findall(r"beta = ([0-9.]+); alpha = ([0-9. /]+);", body)
+    assert len(found) == 3
+    for (b, a), p in zip(found, (2, 4, 6)):
+        assert float(b) == ref[p]["β"] and abs(eval(a) - ref[p]["α"]) == 0.0, (p, b, a)
+    sb = open(os.path.join(ROOT, "hybridsbp_b200", "csrc", "sbp1d.cuh")).read()
+    for p in (2, 4, 6):
+        m = re.search(r"template <> struct Sbp<%d> \{\s*static constexpr int [^;]*LPSI = (\d+);" % p, sb)
+        assert m and int(m.group(1)) == ref[p]["l"], (p, m and m.group(1))
