@@ -290,3 +290,33 @@ def test_penalty_constants_equal_the_reference_source_text():
     for p in (2, 4, 6):
         m = re.search(r"template <> struct Sbp<%d> \{\s*static constexpr int [^;]*LPSI = (\d+);" % p, sb)
         assert m and int(m.group(1)) == ref[p]["l"], (p, m and m.group(1))
+
+
+def test_bp1_parameters_equal_the_reference_source_text():
+    """The physical parameters of the BP1 driver (seas/BP1/BP1.jl:8-26, 54-55, sim_years, tolerances of the solve call :159-161)
+    read from the reference's text, against the literals in the driver (hybridsbp_b200/bp1.py setup, which the oracle's twin shares)."""
+    txt = open(os.path.join(REF, "seas", "BP1", "BP1.jl")).read()
+    ref = {}
+    for name in ("Vp", "ρ", "cs", "σn", "RSamin", "RSamax", "RSb", "RSDc", "RSf0", "RSV0", "RSVinit", "RSH1", "RSH2", "N", "SBPp",
+                 "Lx", "Ly", "sim_years"):
+        m = re.search(r"^\s*%s\s*=\s*([0-9.e+-]+)" % re.escape(name), txt, re.M)
+        assert m, name
+        ref[name] = float(m.group(1))
+    assert ref["N"] == 200 and ref["SBPp"] == 2 and ref["sim_years"] == 1000.0
+    m = re.search(r"atol\s*=\s*([0-9.e+-]+)\s*,\s*rtol\s*=\s*([0-9.e+-]+)", txt)
+    assert m and (float(m.group(1)), float(m.group(2))) == (1e-5, 1e-3)
+    import inspect
+    from hybridsbp_b200 import bp1 as prod            # (the oracle's BP1 twin takes the same setup: one set of literals)
+    for mod in (prod,):
+        srcs = inspect.getsource(mod)
+        lits = {}
+        for py, jl in (("Vp", "Vp"), ("rho", "ρ"), ("cs", "cs"), ("sigma_n", "σn")):
+            m = re.search(r"\b%s = ([0-9.e+-]+)" % py, srcs)
+            assert m, (mod.__name__, py)
+            lits[jl] = float(m.group(1))
+        m = re.search(r"RSamin, RSamax, RSb, RSDc, RSf0, RSV0, RSVinit, RSH1, RSH2 = ([^\n]+)", srcs)
+        assert m, mod.__name__
+        for jl, v in zip(("RSamin", "RSamax", "RSb", "RSDc", "RSf0", "RSV0", "RSVinit", "RSH1", "RSH2"), m.group(1).split(",")):
+            lits[jl] = float(v)
+        for k, v in lits.items():
+            assert v == ref[k], (mod.__name__, k, v, ref[k])
