@@ -320,3 +320,77 @@ def test_bp1_parameters_equal_the_reference_source_text():
             lits[jl] = float(v)
         for k, v in lits.items():
             assert v == ref[k], (mod.__name__, k, v, ref[k])
+
+
+def _julia_function_to_python(lines, name):
+    """Mechanical rewrite of one small Julia function of the reference (scalar arithmetic, if / for / return) into Python source:
+    broadcasting dots dropped, `^` -> `**`, `||` / `&&` -> or / and, `for i = a:b` -> range, blocks closed by `end` -> indentation,
+    the trailing tuple expression -> return."""
+    i0 = next(i for i, l in enumerate(lines) if re.match(r"function %s\(" % name, l))
+    head = lines[i0]
+    i = i0
+    while ")" not in head.split("(", 1)[1] or head.count("(") > head.count(")"):
+        i += 1
+        head += " " + lines[i].strip()
+    args = head[head.index("(") + 1:head.rindex(")")].replace(";", ",")
+    out = ["def %s(%s):" % (name, args)]
+    depth = 1
+    body = []
+    for l in lines[i + 1:]:
+        t = l.strip()
+        if not t:
+            continue
+        if t == "end":
+            depth -= 1
+            if depth == 0:
+                break
+            continue
+        t = t.replace(".*", "*").replace("./", "/").replace(".^", "**").replace("^", "**")
+        t = re.sub(r"\b(exp|asinh|sqrt)\.\(", r"\1(", t)
+        t = t.replace("typeof(x)(NaN)", "float('nan')").replace("||", " or ").replace("&&", " and ")
+        m = re.match(r"for (\w+) = (\w+):(\w+)$", t)
+        ind = "    " * depth
+        if m:
+            body.append(ind + "for %s in range(%s, %s + 1):" % m.groups()); depth += 1
+        elif t.startswith("if "):
+            body.append(ind + t + ":"); depth += 1
+        elif t.startswith("elseif "):
+            body.append("    " * (depth - 1) + "elif " + t[7:] + ":")
+        elif t == "else":
+            body.append("    " * (depth - 1) + "else:")
+        else:
+            body.append(ind + t)
+    if re.match(r"\s*\(.*\)$", body[-1]) and "=" not in body[-1]:
+        body[-1] = "    return " + body[-1].strip()
+    return "\n".join(out + body)
+
+
+def test_rate_and_state_and_newton_equal_the_executed_reference_statements():
+    """rateandstate and newtbndv (global_curved.jl:1029-1075), rewritten mechanically into Python and EXECUTED, against the
+    oracle's restatement: identical floating-point results (same operations in the same order) on random fault states, including
+    the unbracketed case."""
+    import math
+    from oracle import hybrid as orc
+    lines = open(os.path.join(REF, "global_curved.jl")).read().split("\n")
+    # numpy's elementary functions on both sides (libm's differ from them in the last place; Julia has its own again): the test
+    # pins the sequence of operations, not the elementary-function library
+    ns = {"exp": np.exp, "asinh": np.arcsinh, "sqrt": np.sqrt, "abs": abs}
+    exec(_julia_function_to_python(lines, "rateandstate"), ns)
+    exec(_julia_function_to_python(lines, "newtbndv"), ns)
+    rng = np.random.default_rng(42)
+    for _ in range(200):
+        a = rng.uniform(0.01, 0.025); psi = rng.uniform(0.4, 0.9); V0 = 1e-6; sn = 50.0; eta = rng.uniform(2.0, 6.0)
+        tau = rng.uniform(10.0, 40.0); V = 10 ** rng.uniform(-12, 0)
+        g1 = ns["rateandstate"](V, psi, sn, tau, eta, a, V0)
+        g2 = orc.rateandstate(V, psi, sn, tau, eta, a, V0)
+        assert (float(g1[0]), float(g1[1])) == (float(g2[0]), float(g2[1]))
+        fref = lambda v: ns["rateandstate"](v, psi, sn, tau, eta, a, V0)
+        forc = lambda v: orc.rateandstate(v, psi, sn, tau, eta, a, V0)
+        xr = abs(tau / eta)
+        for x0 in (1e-9, V):
+            r1 = ns["newtbndv"](fref, -xr, xr, x0, ftol=1e-12, atolx=1e-12, rtolx=1e-12)
+            r2 = orc.newtbndv(forc, -xr, xr, x0, ftol=1e-12, atolx=1e-12, rtolx=1e-12)
+            assert (float(r1[0]), float(r1[1]), r1[2]) == (float(r2[0]), float(r2[1]), r2[2])
+    r1 = ns["newtbndv"](lambda v: (v * v + 1.0, 2 * v), -1.0, 1.0, 0.3)        # no sign change: the reference's failure tuple
+    r2 = orc.newtbndv(lambda v: (v * v + 1.0, 2 * v), -1.0, 1.0, 0.3)
+    assert math.isnan(r1[0]) and math.isnan(r2[0]) and r1[2] == r2[2] == -500
