@@ -44,7 +44,7 @@ OPS = sorted([
 ], key=len, reverse=True)
 KEYWORDS = {"function", "end", "if", "elseif", "else", "for", "while", "return", "break", "continue", "let", "begin", "const",
             "using", "import", "struct", "try", "catch", "do", "in", "where", "global", "local", "true", "false", "mutable"}
-NUM_RE = re.compile(r"\d+\.\d+(?:[eE][+-]?\d+)?|\d+(?:[eE][+-]?\d+)?")
+NUM_RE = re.compile(r"\d+\.\d+(?:[eE][+-]?\d+)?|\d+\.(?=\s|$|[),;\]])|\d+(?:[eE][+-]?\d+)?")
 
 
 def _id_start(c):
@@ -52,7 +52,7 @@ def _id_start(c):
 
 
 def _id_cont(c):
-    return c.isalnum() or c == "_" or unicodedata.category(c) in ("Mn", "Mc", "No", "Sk") or c in "′" or (
+    return c.isalnum() or c == "_" or unicodedata.category(c) in ("Mn", "Mc", "No") or c in "′" or (
         ord(c) > 127 and unicodedata.category(c) in ("Lo", "Ll", "Lu", "Lm"))
 
 
@@ -179,7 +179,8 @@ class Parser:
         out = []
         self.skip_nl()
         while self.peek().kind != "eof":
-            out.append(self.parse_statement()); self.skip_nl()
+            line = self.peek().line
+            out.append(("ln", line, self.fname, self.parse_statement())); self.skip_nl()
         return ("block", out)
 
     def parse_block(self, terminators=("end",)):
@@ -189,7 +190,8 @@ class Parser:
         self.skip_nl()
         while not (self.peek().kind == "kw" and self.peek().val in terminators):
             if self.peek().kind == "eof": raise SyntaxError("minijulia %s: unexpected end of file in block" % self.fname)
-            out.append(self.parse_statement()); self.skip_nl()
+            line = self.peek().line
+            out.append(("ln", line, self.fname, self.parse_statement())); self.skip_nl()
         self.ctx.pop(); self.tern.pop(); self.index_depth = saved_index
         return ("block", out)
 
@@ -375,7 +377,7 @@ class Parser:
                     if a[0] == "id": pos.append((a[1], None, None, False))
                     elif a[0] == "typed": pos.append((a[1][1], a[2], None, False))
                     else: raise SyntaxError("minijulia: unsupported short-form parameter %r" % (a,))
-                kws = [(k, v, False) for k, v in lhs[3]]
+                kws = [(v[1], None, True) if k == "..." else (k, v, False) for k, v in lhs[3]]
                 return ("func", lhs[1][1], pos, kws, ("block", [rhs]), {})
             return ("assign", lhs, rhs)
         if op == ".=": return ("dotassign", lhs, rhs)
@@ -891,11 +893,23 @@ class Stub:
 
 
 class JFunction:
-    def __init__(self, name):
-        self.name, self.methods = name, []
+    def __init__(self, name, interp=None):
+        self.name, self.methods, self.interp = name, [], interp
+
+    def __call__(self, *args, **kwargs):
+        return self.interp.apply(self, list(args), kwargs)
 
     def __repr__(self):
         return "<julia function %s, %d methods>" % (self.name, len(self.methods))
+
+
+class Closure:
+    """x -> body: parameters, body and the environment it was written in"""
+    def __init__(self, interp, params, body, env):
+        self.interp, self.params, self.body, self.env = interp, params, body, env
+
+    def __call__(self, *args):
+        return self.interp.apply(self, list(args))
 
 
 IDENT = object()
@@ -1074,6 +1088,11 @@ def idx_positions(ix, n):
         return np.nonzero(flat_f(ix))[0], (int(ix.sum()),)
     pos = flat_f(ix).astype(np.int64) - 1
     if pos.size and (pos.min() < 0 or pos.max() >= n): raise JuliaError("BoundsError: index array out of 1:%d" % n)
+    if ix.ndim == 1 and pos.size >= 2:                       # an arithmetic progression (a .+ (1:n)): a slice, so that views alias
+        st = int(pos[1] - pos[0])
+        if st != 0 and np.all(np.diff(pos) == st):
+            hi = int(pos[-1]) + st
+            return slice(int(pos[0]), hi if hi >= 0 else None, st), ix.shape
     return pos, ix.shape
 
 
@@ -1109,6 +1128,8 @@ def jl_getindex(a, idxs, view=False):
         r = a.tocsr()[p0 if s0 is not None else [p0], :].tocsc()[:, p1 if s1 is not None else [p1]]
         if s0 is None or s1 is None: return np.asarray(r.toarray()).reshape(-1)
         return csc(r)
+    if is_number(a) and all(is_number(i) and int(i) == 1 for i in idxs):
+        return a                                           # numbers index like one-element collections
     if not isinstance(a, np.ndarray):
         raise JuliaError("cannot index a %s" % type(a).__name__)
     a = plain(a)
@@ -1493,7 +1514,7 @@ BUILTINS = {
     "min": _minmax(np.min, np.minimum), "max": _minmax(np.max, np.maximum), "sum": _sum,
     "abs": elementwise(np.abs), "sqrt": elementwise(np.sqrt), "exp": elementwise(np.exp), "log": elementwise(np.log),
     "sin": elementwise(np.sin), "cos": elementwise(np.cos), "tan": elementwise(np.tan), "asinh": elementwise(np.arcsinh),
-    "sinh": elementwise(np.sinh), "cosh": elementwise(np.cosh), "tanh": elementwise(np.tanh), "log10": elementwise(np.log10),
+    "sec": elementwise(lambda x: 1.0 / np.cos(x)), "sinh": elementwise(np.sinh), "cosh": elementwise(np.cosh), "tanh": elementwise(np.tanh), "log10": elementwise(np.log10),
     "atan": elementwise(lambda *a: np.arctan2(*a) if len(a) == 2 else np.arctan(*a)), "hypot": elementwise(np.hypot),
     "sign": elementwise(_sign), "isnan": elementwise(np.isnan), "isfinite": elementwise(np.isfinite), "abs2": elementwise(lambda x: x * x),
     "floor": _floor, "div": _div, "range": _range, "transpose": _transpose, "adjoint": jl_adj, "copy": _copy, "push!": _push,
@@ -1555,9 +1576,11 @@ class Interp:
         self.globals = Env()
         self.globals.vars.update(BUILTINS)
         self.globals.vars["include"] = self.include
+        self.globals.vars["open"] = self.open
         self.globals.vars["Iterators"] = NT(["flatten"], [jl_flatten])
         self.globals.vars["PGFPlots"] = Stub()
         self.structs = {}
+        self.include_dirs = []
         self.end_stack = []
         self.views = 0
         self.log = []
@@ -1565,10 +1588,22 @@ class Interp:
     # ---- files
     def include(self, fname):
         import os
-        path = fname if os.path.isabs(fname) else os.path.join(self.basedir, fname)
+        here = self.include_dirs[-1] if self.include_dirs else self.basedir      # relative to the including file
+        path = os.path.normpath(fname if os.path.isabs(fname) else os.path.join(here, fname))
         with open(path) as f:
             ast = parse_source(f.read(), os.path.basename(path))
-        return self.exec_block(ast, self.globals)
+        self.include_dirs.append(os.path.dirname(path))
+        try:
+            return self.exec_block(ast, self.globals)
+        finally:
+            self.include_dirs.pop()
+
+    def open(self, fname):
+        import os
+        d = self.basedir
+        while not os.path.isabs(fname) and not os.path.exists(os.path.join(d, fname)) and d != "/":
+            d = os.path.dirname(d)                        # the drivers are started from the reference's root or their own folder
+        return open(fname if os.path.isabs(fname) else os.path.join(d, fname))
 
     def run(self, src, fname="<string>", env=None):
         return self.exec_block(parse_source(src, fname), env or self.globals)
@@ -1629,7 +1664,7 @@ class Interp:
         _, name, pos, kws, body, typevars = node
         f = env.vars.get(name)
         if not isinstance(f, JFunction):
-            f = JFunction(name); env.vars[name] = f
+            f = JFunction(name, self); env.vars[name] = f
         sig = tuple((p[1], p[3]) for p in pos)
         f.methods = [m for m in f.methods if m["sig"] != sig or m["npos"] != len(pos)]
         f.methods.append({"pos": pos, "kws": kws, "body": body, "env": env, "tv": typevars, "sig": sig, "npos": len(pos)})
@@ -1661,12 +1696,12 @@ class Interp:
                 if s >= bs and s >= 0: best, bs = m, s
             if best is None: raise JuliaError("MethodError: no method of %s for %d arguments" % (f.name, len(args)))
             return self.call_method(f, best, args, kwargs)
-        if isinstance(f, dict) and "lambda" in f:
-            env = Env(f["env"], True)
-            if len(args) != len(f["params"]): raise JuliaError("MethodError: lambda with %d parameters called with %d" % (len(f["params"]), len(args)))
-            for p, a in zip(f["params"], args): env.vars[p] = a
+        if isinstance(f, Closure):
+            env = Env(f.env, True)
+            if len(args) != len(f.params): raise JuliaError("MethodError: lambda with %d parameters called with %d" % (len(f.params), len(args)))
+            for p, a in zip(f.params, args): env.vars[p] = a
             try:
-                return self.ev(f["body"], env)
+                return self.ev(f.body, env)
             except ReturnEx as r:
                 return r.value
         if isinstance(f, TypeSpec):
@@ -1712,6 +1747,19 @@ class Interp:
         k = n[0]
         return getattr(self, "ev_" + k)(n, env)
 
+    def ev_ln(self, n, env):
+        try:
+            return self.ev(n[3], env)
+        except (BreakEx, ContinueEx, ReturnEx):
+            raise
+        except Exception as ex:
+            tr = getattr(ex, "jl_trace", None)
+            if tr is None:
+                tr = ex.jl_trace = []
+                ex.args = (("%s  [at %s:%d]" % (ex.args[0] if ex.args else "", n[2], n[1])),) + tuple(ex.args[1:])
+            tr.append((n[2], n[1]))
+            raise
+
     def ev_nop(self, n, env): return None
     def ev_num(self, n, env): return n[1]
     def ev_regex(self, n, env): return re.compile(n[1])
@@ -1738,7 +1786,7 @@ class Interp:
                     depth, j = 1, i + 2
                     while depth:
                         depth += {"(": 1, ")": -1}.get(s[j], 0); j += 1
-                    out.append(jl_string(self.ev(parse_source(s[i + 2:j - 1])[1][0], env))); i = j
+                    out.append(jl_string(self.ev(parse_source(s[i + 2:j - 1])[1][0][3], env))); i = j
                 else:
                     j = i + 1
                     while j < len(s) and _id_cont(s[j]): j += 1
@@ -1767,7 +1815,7 @@ class Interp:
         return self.define_function(n, env)
 
     def ev_lambda(self, n, env):
-        return {"lambda": True, "params": n[1], "body": n[2], "env": env}
+        return Closure(self, n[1], n[2], env)
 
     def ev_assign(self, n, env):
         val = self.ev(n[2], env)
@@ -1854,6 +1902,7 @@ class Interp:
         if isinstance(it, JRange): return it.arr().tolist()
         if isinstance(it, np.ndarray): return [v.item() if isinstance(v, np.generic) else v for v in flat_f(it)]
         if isinstance(it, dict): return list(it.items())
+        if is_number(it): return [it]                      # numbers iterate over themselves
         return list(it)
 
     def run_for(self, iters, body, env):
@@ -1895,6 +1944,7 @@ class Interp:
     def ev_vect(self, n, env):
         vals = [self.ev(it, env) for it in n[1]]
         if vals and all(is_number(v) for v in vals):
+            if all(isinstance(v, (bool, np.bool_)) for v in vals): return np.array(vals, dtype=np.bool_)
             if all(isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)) for v in vals): return np.array(vals, dtype=np.int64)
             return np.array(vals, dtype=np.float64)
         if not vals: return np.zeros(0)

@@ -1,0 +1,223 @@
+"""The reference executed, not restated: tests/refexec/minijulia.py interprets the reference's own Julia statements (Julia itself is
+not installed in this image), and the oracle -- the restatement every GPU parity test is checked against -- has to reproduce what
+those statements compute.  Covers the 1-D SBP tables and variable-coefficient operators (diagonal_sbp.jl), create_metrics /
+locoperator with curved metrics and every boundary-condition type, the complete square_circle.jl driver (mesh reader, connectivity,
+trace operators, assembleλmatrix, LocalToGLobalRHS!, boundary / jump / source data, trace solve, back substitution, error norms)
+and BP1's setup + odefun.  Also checks that the committed golden vectors are what tools/gen_refexec_golden.py produces.
+
+Runs where /root/reference is mounted (the CPU tier); the golden vectors carry the result to the GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is not mounted on this machine")
+
+from refexec.minijulia import Interp, JuliaError          # noqa: E402
+from oracle import sbp as osbp, hybrid as orc             # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "refexec")
+
+
+def dense(a):
+    return a.toarray() if sp.issparse(a) else np.asarray(a, dtype=float)
+
+
+def relmax(a, b):
+    a, b = dense(a), dense(b)
+    assert a.shape == b.shape
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    it = Interp(REF)
+    it.include("global_curved.jl")
+    return it
+
+
+# ---- the interpreter itself: known answers for the Julia semantics the reference relies on --------------------------------------
+def test_interpreter_semantics():
+    it = Interp(REF)
+    out = it.run("""
+    A = [1 2 3; 4 5 6]                      # rows by ';', columns by blanks
+    v = A[:]                                # column-major
+    B = reshape(1:6, 2, 3)
+    w = [1 -2 3]                            # 'a -b' inside brackets: two elements
+    d = [1 - 2 3]
+    r = 2:2:7
+    x = zeros(4); xv = @view x[2:3]; xv .= 5; xv[1] = 7
+    y = zeros(4); yc = y[2:3]; yc[1] = 7    # a copy: y untouched
+    col = [10, 20]
+    bc = col .* A                           # broadcasting: missing dimensions are trailing
+    k = kron([1 2], [1, 1])
+    s = sparse([1, 1, 2], [1, 1, 2], [1.0, 2.0, 3.0], 2, 2)    # duplicates are summed
+    f(a; scale = 2) = a * scale
+    f(a::AbstractArray; scale = 2) = a .* (10scale)
+    g = (a, b) -> a + 2b
+    t = (first = 1, second = [3.0, 4.0])
+    h = 0
+    for i = 1:3, j = 1:2
+      h += i * j
+    end
+    q = 7 ÷ 2 + div(9, 2) + 2^3
+    (v, B, w, d, collect(r), x, y, bc, k, Matrix(s), f(3), f([1, 2]; scale = 1), g(1, 2), t.second[end], h, q, 4col[2]^2, A', 1 / 2,
+     [x[1:2]; 9], A[end, end], A[2, :], (-1 < 0 < 1), !(1 == 2) && true, length(A), size(A, 2))
+    """)
+    exp = (np.array([1, 4, 2, 5, 3, 6]), np.array([[1, 3, 5], [2, 4, 6]]), np.array([[1, -2, 3]]), np.array([[-1, 3]]), np.array([2, 4, 6]),
+           np.array([0, 7.0, 5, 0]), np.zeros(4), np.array([[10, 20, 30], [80, 100, 120]]), np.array([[1, 2], [1, 2]]),
+           np.array([[3.0, 0], [0, 3.0]]), 6, np.array([10, 20]), 5, 4.0, 18, 15, 1600, np.array([[1, 4], [2, 5], [3, 6]]), 0.5,
+           np.array([0, 7.0, 9]), 6, np.array([4, 5, 6]), True, True, 6, 3)
+    assert len(out) == len(exp)
+    for k, (a, b) in enumerate(zip(out, exp)):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), (k, a, b)
+    with pytest.raises(JuliaError):
+        it.run("zeros(3) + zeros(4)")
+    with pytest.raises(JuliaError):
+        it.run("u = zeros(3); u[4]")
+
+
+# ---- diagonal_sbp.jl ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_sbp_operators_executed(ref, p):
+    N = 23
+    D, HI, H, r = ref.call("diagonal_sbp_D1", p, N)
+    oD, oHI, oH, orr = osbp.diagonal_sbp_D1(p, N)
+    assert relmax(D, oD) < 1e-15 and relmax(H, oH) < 1e-15 and relmax(HI, oHI) < 1e-15 and relmax(r, orr) < 1e-15
+    B = np.random.default_rng(p).uniform(0.5, 2.0, N + 1)
+    out = ref.call("variable_diagonal_sbp_D2", p, N, B)                   # (D, S0, SN, HI, H, M, r)   diagonal_sbp.jl:763
+    oo = osbp.variable_diagonal_sbp_D2(p, N, B)
+    for a, b in zip(out, oo):
+        assert relmax(a, b) < 2e-15
+    out = ref.call("variable_diagonal_sbp_D2", p, N, 1.5)                 # the method for a constant coefficient, :478
+    oo = osbp.variable_diagonal_sbp_D2(p, N, 1.5 * np.ones(N + 1))
+    assert relmax(out[5], oo[5]) < 2e-15
+
+
+# ---- create_metrics / locoperator --------------------------------------------------------------------------------------------------
+def curved_maps():
+    import gen_refexec_golden as gg
+    xf = lambda r, s: (r + 0.1 * np.sin(2 * r) * np.cos(s) + 0.2 * s, 1 + 0.2 * np.cos(2 * r) * np.cos(s), -0.1 * np.sin(2 * r) * np.sin(s) + 0.2)
+    yf = lambda r, s: (s + 0.15 * np.sin(r + s), 0.15 * np.cos(r + s), 1 + 0.15 * np.cos(r + s))
+    return gg.CURVED_MAP, xf, yf
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_locoperator_executed(ref, p):
+    src, xf, yf = curved_maps()
+    ref.run(src)
+    N = 19
+    m = ref.call("create_metrics", p, N, N, ref.globals.lookup("xfun"), ref.globals.lookup("yfun"))
+    om = orc.create_metrics(p, N, N, xf, yf)
+    for k in ("crr", "css", "crs", "J"):
+        assert relmax(m.get(k), getattr(om, k)) < 5e-15
+    for k in ("sJ", "nx", "ny"):
+        for a, b in zip(m.get(k), getattr(om, k)):
+            assert relmax(a, b) < 5e-15
+    for bc in ((1, 1, 1, 1), (0, 2, 7, 1), (2, 2, 0, 0), (7, 0, 2, 8)):
+        lop = ref.call("locoperator", p, N, N, m, bc)
+        ol = orc.locoperator(p, N, N, om, bc)
+        assert relmax(lop.get("M̃"), ol.Mt) < 5e-15
+        assert relmax(lop.get("JH"), ol.JH) < 5e-15
+        for name, mine in (("F", ol.F), ("HfI_FT", ol.HfI_FT), ("HfI_G", ol.HfI_G), ("τ", ol.tau), ("Hf", ol.Hf), ("HfI", ol.HfI)):
+            for a, b in zip(lop.get(name), mine):
+                assert relmax(a, b) < 5e-15, name
+        assert tuple(lop.get("bctype")) == tuple(ol.bctype)
+    with pytest.raises(JuliaError):
+        ref.call("locoperator", p, N, N, m, (1, 3, 1, 1))                 # 'invalid bc', global_curved.jl:484
+    # the reference as written needs Nr == Ns: an unused remainder (global_curved.jl:316) multiplies r-direction matrices with
+    # s-direction coefficients.  The oracle and the CUDA path have no such restriction (they are compared on Nr != Ns elsewhere).
+    with pytest.raises(Exception):
+        ref.call("locoperator", p, N, N + 4, ref.call("create_metrics", p, N, N + 4))
+
+
+def test_penalty_asserts_positive_psi(ref):
+    m = ref.call("create_metrics", 2, 12, 12)
+    bad = np.array(m.get("crr")); bad[5, 5] = -1.0
+    with pytest.raises(JuliaError):
+        ref.call("locoperator", 2, 12, 12, m, (1, 1, 1, 1), crr=bad)     # @assert minimum(ψmin) > 0, :419
+
+
+# ---- the driver of configuration 1 -------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def square_circle_p4():
+    from refexec.drivers import run_square_circle
+    from refexec.oracle_driver import oracle_square_circle_level
+    cap, mesh, _ = run_square_circle(p=4, levels=1, N0=17)
+    return cap[0], mesh, oracle_square_circle_level(4, 17)
+
+
+def test_square_circle_mesh_and_connectivity_executed(square_circle_p4):
+    c, mesh, o = square_circle_p4
+    verts, EToV, EToF, FToB, dom = o["mesh"]                               # the product's reader + the circle fix-up of :27-33
+    for k, a in (("verts", verts), ("EToV", EToV), ("EToF", EToF), ("FToB", FToB), ("EToDomain", dom)):
+        assert np.array_equal(np.asarray(mesh[k], dtype=float), np.asarray(a, dtype=float)), k
+    for k, a in zip(("FToE", "FToLF", "EToO", "EToS"), o["conn"]):
+        assert np.array_equal(np.asarray(mesh[k]).astype(int), np.asarray(a).astype(int)), k
+    assert np.array_equal(c["vstarts"], o["vstarts"]) and np.array_equal(c["FToλstarts"], o["FTol"]) and np.array_equal(c["FToδstarts"], o["FTod"])
+
+
+def test_square_circle_operators_executed(square_circle_p4):
+    c, mesh, o = square_circle_p4
+    assert relmax(c["FbarT"], o["FbarT"]) < 1e-14
+    assert relmax(c["D"], o["D"]) < 1e-14
+    assert relmax(c["B"], o["B"]) < 1e-13                                  # assembleλmatrix: 56 x 4 x 18 local solves
+    for e in (1, 9, 30, 56):                                               # straight, curved (circle) and boundary blocks
+        assert relmax(c["lop"][e]["M̃"], o["lops"][e - 1].Mt) < 1e-14
+        for lf in range(4):
+            assert relmax(c["lop"][e]["F"][lf], o["lops"][e - 1].F[lf]) < 1e-14
+
+
+def test_square_circle_solution_executed(square_circle_p4):
+    c, mesh, o = square_circle_p4
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+    assert rel(o["delta"], c["δ"]) < 1e-14 and rel(o["g"], c["g"]) < 1e-13 and rel(o["gd"], c["gδ"]) < 1e-13
+    assert rel(o["bl"], c["bλ"]) < 1e-12
+    assert rel(o["lam"], c["λ"]) < 1e-11 and rel(o["u"], c["u"]) < 1e-11
+    assert abs(o["eps"] - c["ϵ"][0]) < 1e-6 * c["ϵ"][0] and abs(o["teps"] - c["τϵ"][0]) < 1e-6 * c["τϵ"][0]
+
+
+# ---- BP1 ---------------------------------------------------------------------------------------------------------------------------
+def test_bp1_setup_and_odefun_executed():
+    import gen_refexec_golden as gg
+    from refexec.drivers import run_bp1_setup
+    from hybridsbp_b200 import bp1
+    from oracle.bp1 import OdeFun
+    N = 40
+    it, sol, yf = run_bp1_setup(N)
+    prob, opts = sol.get("prob"), sol.get("options")
+    su = bp1.setup(N=N)                                                    # the product's host-side setup
+    assert np.allclose(np.array(prob.get("u0")), su.psi_delta0, rtol=1e-14, atol=0)
+    assert np.allclose(yf, su.yf, rtol=1e-14, atol=1e-14)
+    assert np.allclose(np.array(prob.get("p").get("RSa")), su.RSa, rtol=1e-15)
+    assert opts["atol"] == 1e-5 and opts["rtol"] == 1e-3 and opts["dt"] == 31556926 and tuple(prob.get("tspan")) == (0, 1000.0 * 31556926)
+    o = OdeFun(su.p, su.N, su.metrics, su.LFtoB, su.RSa, su.params)
+    for t, y in gg.bp1_states(np.array(prob.get("u0")), N):
+        d = np.zeros(2 * (N + 1))
+        prob.get("f")(d, y.copy(), prob.get("p"), t)
+        do, rejected = o(t, y)
+        assert not rejected and not prob.get("p").get("reject_step")[0]
+        assert np.max(np.abs(d - do)) <= 1e-13 * np.max(np.abs(do))
+    y = np.array(prob.get("u0")); y[3] = np.nan                            # a failed node: reject_step is set, no exception
+    prob.get("f")(np.zeros(2 * (N + 1)), y, prob.get("p"), 0.0)
+    assert prob.get("p").get("reject_step")[0] and o(0.0, y)[1]
+
+
+# ---- the committed golden vectors are what the generator writes ----------------------------------------------------------------------
+def test_golden_vectors_are_reproducible(tmp_path, square_circle_p4, monkeypatch):
+    import gen_refexec_golden as gg
+    monkeypatch.setattr(gg, "OUT", str(tmp_path))
+    gg.gen_locoperator(4); gg.gen_bp1(40)
+    for name in ("locoperator_p4.npz", "bp1_odefun_N40.npz"):
+        a, b = np.load(os.path.join(GOLD, name)), np.load(os.path.join(str(tmp_path), name))
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (name, k)
+    g = np.load(os.path.join(GOLD, "square_circle_p4.npz"))
+    c = square_circle_p4[0]
+    assert np.array_equal(g["lam"], c["λ"]) and np.array_equal(g["u"], c["u"]) and np.array_equal(g["gdelta"], c["gδ"])
