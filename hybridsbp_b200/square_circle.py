@@ -119,8 +119,9 @@ def geometry(mesh, p, N, maps=None):
     return out
 
 
-def jump_data(mesh, conn, mets, FTods, N, exact=None):
-    """delta on the jump faces: exact value on the plus side minus the minus side (:321-330)."""
+def jump_data(mesh, conn, mets, FTods, N, exact=None, slip=None):
+    """delta on the jump faces: exact value on the plus side minus the minus side (:321-330), or a given slip(x, y) evaluated at
+    the minus side's face points."""
     verts, EToV, EToF, FToB, dom = mesh
     FToE, FToLF, EToO, EToS = conn
     exact = exact or ExactSolution
@@ -130,7 +131,7 @@ def jump_data(mesh, conn, mets, FTods, N, exact=None):
             e1, e2 = FToE[:, f] - 1
             lf1 = FToLF[0, f] - 1
             xf, yf = mets[e1].facecoord[0][lf1], mets[e1].facecoord[1][lf1]
-            delta[FTods[f] - 1:FTods[f + 1] - 1] = exact.v(xf, yf, dom[e2]) - exact.v(xf, yf, dom[e1])
+            delta[FTods[f] - 1:FTods[f + 1] - 1] = slip(xf, yf) if slip else exact.v(xf, yf, dom[e2]) - exact.v(xf, yf, dom[e1])
     return delta
 
 
@@ -174,7 +175,7 @@ def face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p, exact=None):
 
 
 def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=None, exact=None, jump_code=None,
-                condense=True, coarse_modes=2):
+                condense=True, coarse_modes=2, slip=None):
     """One refinement level on the GPU.  Returns dict(eps, tau_eps, lam, u, stats, ...)."""
     verts, EToV, EToF, FToB, dom = mesh
     ne, nf = EToV.shape[1], len(FToB)
@@ -208,7 +209,7 @@ def solve_level(ctx, mesh, p, N, local_mode=None, tol=1e-12, maxit=5000, maps=No
     FTods = host.bcstarts(FToB, FToE, FToLF, jump_codes, [N] * ne, [N] * ne)
     tau = blk.get_tau()
     taus = [[tau[blk.face_slice(e, lf + 1)] for lf in range(4)] for e in range(ne)]
-    delta = jump_data(mesh, conn, mets, FTods, N, exact)
+    delta = jump_data(mesh, conn, mets, FTods, N, exact, slip)
     v, gd = face_data(mesh, conn, mets, taus, FTols, FTods, delta, N, p, exact)
     Hw = host.norm_weights(p, N)
     JH = [(m.J * Hw[:, None] * Hw[None, :]).reshape(-1, order="F") for m in mets]      # global_curved.jl:491

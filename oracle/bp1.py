@@ -3,9 +3,12 @@
 of CHOLMOD), computetraction_mod, rateandstate + newtbndv per fault node, sequentially and with the reference's
 early returns on failure.
 
-Parity status: unpinned by golden data (the reference stores no BP1 output and its integrator dependency is
-unpinned); pinned by construction identities (tests/test_oracle_bp1.py): at t = 0 with psi = psi0, delta = 0 the
-slip rate equals the initial rate 1e-9 that tau_z0 and theta are built from (BP1.jl:104-113).
+Parity status: the right-hand side is pinned by executing the reference's own statements -- BP1.jl's setup and odefun.jl
+interpreted by tests/refexec/minijulia.py give the same d(psi, delta)/dt as OdeFun to 1e-13 at three states, and the same
+rejection on a NaN state (tests/test_reference_executed.py; golden copy tests/golden/refexec/bp1_odefun_N40.npz).  The
+integrator is NOT pinned that way: OrdinaryDiffEq is an unvendored, unpinned dependency, Tsit5 below is restated from the
+published tableau (order conditions in tests/test_oracle_bp1.py).  Also pinned by construction: at t = 0 with psi = psi0,
+delta = 0 the slip rate equals the initial rate 1e-9 that tau_z0 and theta are built from (BP1.jl:104-113).
 """
 import numpy as np
 

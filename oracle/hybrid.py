@@ -24,9 +24,19 @@ Third-party arithmetic the reference delegates to (SuiteSparse CHOLMOD via the
 (`splu`) on the same SPD matrices; any correct direct solver agrees to
 O(cond * eps).
 
-Parity status: "parity unpinned" by golden vectors (the reference has none and
-cannot be run here); pinned instead by the reference's identities, see
-tests/test_oracle_*.py.
+Parity status: the reference ships no golden vectors and Julia is not installed
+here, so the reference's own source text is EXECUTED instead: an interpreter
+for the Julia subset these files use (tests/refexec/minijulia.py) runs
+create_metrics, locoperator, read_inp_2d, connectivityarrays, the trace
+operators, assembleλmatrix and the whole square_circle.jl driver statement by
+statement, and every function of this module has to reproduce those outputs
+(tests/test_reference_executed.py: operators to 1e-14, lambda and u of the
+driver to 1e-11).  The outputs are committed as golden vectors
+(tests/golden/refexec/, generator tools/gen_refexec_golden.py) for the tests
+that run without the reference tree.  Also pinned by the reference's
+identities, see tests/test_oracle_*.py.  What stays unpinned: CHOLMOD's
+arithmetic (replaced as described above) and anything the interpreter's own
+numpy / scipy runtime would get wrong in the same way as this module.
 
 Conventions kept from the reference: entity ids stored in arrays (EToV, EToF,
 FToE, FToLF, EToS) are 1-based; offsets vstarts / FTolambdastarts are 1-based

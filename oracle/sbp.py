@@ -10,8 +10,13 @@ Coefficient data come from oracle/sbp_tables.json (made by
 oracle/gen_sbp_tables.py from the reference's published tables).
 
 Parity status: the reference ships no golden vectors and its host language is
-not available in the build container, so this restatement is pinned by the
-reference's own identities instead (tests/test_oracle_sbp.py): SBP property
+not available in the build container.  Pinned (1) by executing the reference's
+own statements: tests/refexec/minijulia.py interprets diagonal_sbp.jl as it
+lies under /root/reference, and diagonal_sbp_D1 / variable_diagonal_sbp_D2 here
+return the same matrices to 2e-15 (tests/test_reference_executed.py; a second,
+regex-based execution of the coefficient statements is in
+tests/test_reference_text_extraction.py); (2) by the reference's own
+identities (tests/test_oracle_sbp.py): SBP property
 Q + Q^T = diag(-1, 0, ..., 0, 1), accuracy conditions on polynomials, symmetry
 and zero row sums of M, mirror symmetry of the two closures, the PSD remainder
 of check_residual.jl:8-17 and the constant-coefficient limit.

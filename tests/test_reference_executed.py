@@ -182,6 +182,29 @@ def test_square_circle_solution_executed(square_circle_p4):
     assert abs(o["eps"] - c["ϵ"][0]) < 1e-6 * c["ϵ"][0] and abs(o["teps"] - c["τϵ"][0]) < 1e-6 * c["τϵ"][0]
 
 
+# ---- configuration 2: the reference's functions on the flower mesh (reversed faces) --------------------------------------------------
+def test_flower_mesh_reversed_faces_executed():
+    """gloλoperator's flipped branch (`FToλstarts[f+1] .- Ie`, `rot180(τ)`, global_curved.jl:546-549), in_jump's three branches and
+    the reversed g-delta views, with slip data on the jump faces: tests/refexec/flower_driver.jl drives the reference's functions"""
+    from refexec.drivers import run_flower
+    from refexec.oracle_driver import oracle_square_circle_level
+    from hybridsbp_b200 import flower
+    c = run_flower(4, 17)
+    o = oracle_square_circle_level(4, 17, mesh=flower.load_mesh(), maps=flower.block_maps, exact=flower.Smooth,
+                                   slip=lambda x, y: 0.3 * np.sin(x) * np.cos(2 * y))
+    assert int((~np.asarray(c["EToO"]).astype(bool)).sum()) == 27 and int((np.asarray(c["FToB"]) == 7).sum()) == 18
+    for k, a in zip(("verts", "EToV", "EToF", "FToB"), o["mesh"]):
+        assert np.array_equal(np.asarray(c[k], dtype=float), np.asarray(a, dtype=float)), k
+    for k, a in zip(("FToE", "FToLF", "EToO", "EToS"), o["conn"]):
+        assert np.array_equal(np.asarray(c[k]).astype(int), np.asarray(a).astype(int)), k
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+    assert relmax(c["FbarT"], o["FbarT"]) < 1e-14 and relmax(c["D"], o["D"]) < 1e-14 and relmax(c["B"], o["B"]) < 1e-13
+    assert rel(o["delta"], c["δ"]) < 1e-14 and rel(o["g"], c["g"]) < 1e-13 and rel(o["gd"], c["gδ"]) < 1e-13 and rel(o["bl"], c["bλ"]) < 1e-12
+    assert rel(o["lam"], c["λ"]) < 1e-11 and rel(o["u"], c["u"]) < 1e-11 and rel(o["tauf"], c["τf"]) < 1e-11
+    g = np.load(os.path.join(GOLD, "flower_p4.npz"))
+    assert np.array_equal(g["lam"], c["λ"]) and np.array_equal(g["u"], c["u"]) and np.array_equal(g["traction"], c["τf"])
+
+
 # ---- BP1 ---------------------------------------------------------------------------------------------------------------------------
 def test_bp1_setup_and_odefun_executed():
     import gen_refexec_golden as gg
@@ -206,6 +229,24 @@ def test_bp1_setup_and_odefun_executed():
     y = np.array(prob.get("u0")); y[3] = np.nan                            # a failed node: reject_step is set, no exception
     prob.get("f")(np.zeros(2 * (N + 1)), y, prob.get("p"), 0.0)
     assert prob.get("p").get("reject_step")[0] and o(0.0, y)[1]
+
+
+def test_bp1_odefun_at_the_reference_resolution_executed():
+    """N = 200, p = 2 (BP1.jl:28-32 as written): the reference's odefun at the five stored states of tests/golden/bp1/states_N200.npz
+    -- initial, interseismic, the middle of the first earthquake (max V = 0.7 m/s), post-seismic -- against the stored outputs the
+    GPU tests use (they were generated by the oracle)"""
+    from refexec.drivers import run_bp1_setup
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bp1", "states_N200.npz"))
+    it, sol, yf = run_bp1_setup(200)
+    prob = sol.get("prob")
+    for k in range(len(g["t"])):
+        d = np.zeros(402)
+        prob.get("f")(d, g["y"][k].copy(), prob.get("p"), float(g["t"][k]))
+        ref = g["dpsiV"][k]
+        assert not prob.get("p").get("reject_step")[0]
+        assert np.max(np.abs(d[201:] - ref[201:])) <= 1e-12 * np.max(np.abs(ref[201:]))
+        assert np.max(np.abs(d[:201] - ref[:201])) <= 1e-12 * np.max(np.abs(ref[:201]))
+    assert np.max(np.abs(g["dpsiV"][3][201:])) > 0.5                        # the coseismic state is among them
 
 
 # ---- the committed golden vectors are what the generator writes ----------------------------------------------------------------------

@@ -52,6 +52,19 @@ def test_oracle_square_circle_vs_reference_output(p):
     assert abs(o["eps"] - g["eps"]) < 1e-6 * g["eps"] and abs(o["teps"] - g["teps"]) < 1e-6 * g["teps"]
 
 
+def test_oracle_flower_vs_reference_output():
+    from tests.refexec.oracle_driver import oracle_square_circle_level
+    from hybridsbp_b200 import flower
+    g = np.load(os.path.join(GOLD, "flower_p4.npz"))
+    o = oracle_square_circle_level(4, int(g["N"]), mesh=flower.load_mesh(), maps=flower.block_maps, exact=flower.Smooth,
+                                   slip=lambda x, y: 0.3 * np.sin(x) * np.cos(2 * y))
+    assert np.array_equal(np.asarray(o["conn"][2]).astype(int), g["EToO"]) and np.array_equal(o["conn"][3], g["EToS"])
+    assert np.array_equal(o["FTol"], g["FTolstarts"]) and np.array_equal(o["FTod"], g["FTodstarts"])
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(o["delta"], g["delta"]) < 1e-14 and rel(o["gd"], g["gdelta"]) < 1e-13 and rel(o["bl"], g["blambda"]) < 1e-12
+    assert rel(o["lam"], g["lam"]) < 1e-11 and rel(o["u"], g["u"]) < 1e-11 and rel(o["tauf"], g["traction"]) < 1e-11
+
+
 def test_oracle_bp1_odefun_vs_reference_output():
     from hybridsbp_b200 import bp1
     from oracle.bp1 import OdeFun

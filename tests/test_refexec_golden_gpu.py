@@ -61,6 +61,19 @@ def test_square_circle_level1_vs_reference_output(ctx, p):
     assert rel(r["u"], g["u"]) <= 1e-10, r["stats"]
 
 
+def test_flower_reversed_faces_vs_reference_output(ctx):
+    """67 blocks, 27 faces seen in reversed orientation from their plus side, given slip on the 18 jump faces"""
+    from hybridsbp_b200 import flower
+    g = np.load(os.path.join(GOLD, "flower_p4.npz"))
+    r = flower.solve_level(ctx, flower.load_mesh(), 4, int(g["N"]), tol=1e-13, slip=lambda x, y: 0.3 * np.sin(x) * np.cos(2 * y))
+    assert r["stats"]["converged"] == 1, r["stats"]
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert np.array_equal(r["FTols"], g["FTolstarts"]) and np.array_equal(r["FTods"], g["FTodstarts"])
+    assert rel(r["delta"], g["delta"]) <= 1e-13 and rel(r["gd"], g["gdelta"]) <= 1e-12 and rel(r["g_full"][::37], g["g_sample"]) <= 1e-12
+    assert rel(r["lam"], g["lam"]) <= 1e-10, r["stats"]
+    assert rel(r["u"], g["u"]) <= 1e-10, r["stats"]
+
+
 def test_bp1_rhs_vs_reference_output(ctx):
     from hybridsbp_b200 import bp1, LOCAL_BAND
     g = np.load(os.path.join(GOLD, "bp1_odefun_N40.npz"))

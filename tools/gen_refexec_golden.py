@@ -11,6 +11,8 @@ Files
                              square_circle.jl's second level): coefficients, three boundary-condition sets, tau, y = M~ u, F_k' u,
                              traction operator HfI_FT_k u for a stored u
   square_circle_p{4,6}.npz   square_circle.jl:1-431 at its first level (56 blocks, N = 17): delta, g-delta, b-lambda, lambda, u, errors
+  flower_p4.npz              the reference's functions on meshes/flower_v2.inp (27 reversed faces, given slip on the 18 jump faces)
+                             through tests/refexec/flower_driver.jl: delta, g-delta, b-lambda, lambda, u, fault traction
   bp1_odefun_N40.npz         seas/BP1/BP1.jl:1-158 (setup) + odefun.jl:8-121 at three states: y, t -> d(psi, delta)/dt
 """
 import os
@@ -21,7 +23,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from refexec.minijulia import Interp                                  # noqa: E402
-from refexec.drivers import run_square_circle, run_bp1_setup, REF     # noqa: E402
+from refexec.drivers import run_square_circle, run_bp1_setup, run_flower, REF     # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "refexec")
 CURVED_MAP = """
@@ -69,6 +71,14 @@ def gen_square_circle(p):
     print("square_circle p=%d written: eps = %.6e, traction eps = %.6e" % (p, c["ϵ"][0], c["τϵ"][0]))
 
 
+def gen_flower(p=4):
+    c = run_flower(p, 17)
+    np.savez_compressed(os.path.join(OUT, "flower_p%d.npz" % p), p=p, N=17, delta=c["δ"], gdelta=c["gδ"], blambda=c["bλ"], lam=c["λ"], u=c["u"],
+                        g_sample=c["g"][::37], traction=c["τf"], FTolstarts=c["FToλstarts"], FTodstarts=c["FToδstarts"],
+                        EToO=np.asarray(c["EToO"]).astype(np.int64), EToS=c["EToS"], FToB=c["FToB"])
+    print("flower p=%d written" % p)
+
+
 def bp1_states(y0, N):
     rng = np.random.default_rng(3)
     out = []
@@ -100,4 +110,5 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     for p in (2, 4, 6): gen_locoperator(p)
     gen_bp1(40)
+    gen_flower(4)
     for p in (4, 6): gen_square_circle(p)
