@@ -641,6 +641,8 @@ class Parser:
                 return ("view", e)
             if v == "views":
                 return ("viewsblock", self.parse_expr())
+            if v == "show":
+                return ("show", self.parse_expr())
             raise SyntaxError("minijulia %s:%d: macro @%s in an expression" % (self.fname, tok.line, v))
         if k == "id": return ("id", v)
         if k == "kw":
@@ -1506,6 +1508,33 @@ def _isempty(a):
     return jl_length(a) == 0
 
 
+class _Rng:
+    gen = np.random.default_rng(777)
+
+
+def _rand(*d):
+    if d and isinstance(d[0], JType): d = d[1:]
+    return np.asfortranarray(_Rng.gen.uniform(0.0, 1.0, _dims(d))) if d else float(_Rng.gen.uniform())
+
+
+def _eigen(A):
+    A = np.asarray(jl_matrix(A), dtype=float)
+    if np.allclose(A, A.T, rtol=0, atol=1e-14 * max(1.0, np.abs(A).max())):
+        w, V = np.linalg.eigh((A + A.T) / 2)
+    else:
+        w, V = np.linalg.eig(A)
+    return NT(["values", "vectors"], [w, V])
+
+
+def _extrema(a):
+    a = np.asarray(to_arr(a))
+    return (a.min().item(), a.max().item())
+
+
+def _enumerate(x):
+    return [(i + 1, v) for i, v in enumerate(Interp.iterate(None, x))]
+
+
 BUILTINS = {
     "size": jl_size, "length": jl_length, "zeros": jl_zeros, "ones": lambda *a: jl_zeros(*a, fill=1), "fill": jl_fill,
     "fill!": _fill_inplace, "sparse": jl_sparse, "spzeros": lambda m, n: csc((int(m), int(n))), "findnz": jl_findnz, "kron": jl_kron,
@@ -1519,7 +1548,9 @@ BUILTINS = {
     "sign": elementwise(_sign), "isnan": elementwise(np.isnan), "isfinite": elementwise(np.isfinite), "abs2": elementwise(lambda x: x * x),
     "floor": _floor, "div": _div, "range": _range, "transpose": _transpose, "adjoint": jl_adj, "copy": _copy, "push!": _push,
     "haskey": _haskey, "error": jl_error, "string": jl_string, "println": lambda *a: None, "print": lambda *a: None,
-    "isapprox": jl_isapprox, "norm": _norm, "rand": lambda *d: np.random.default_rng(7).uniform(0.5, 1.5, _dims(d)) if d else 0.37,
+    "isapprox": jl_isapprox, "norm": _norm, "rand": _rand, "eigen": _eigen, "eigvals": lambda A: _eigen(A).get("values"), "extrema": _extrema, "enumerate": _enumerate,
+    "mod": lambda a, b: a % b, "real": elementwise(np.real), "imag": elementwise(np.imag), "exp10": elementwise(lambda x: 10.0 ** x),
+    "ceil": elementwise(np.ceil), "Random": Stub(),
     "view": jl_view, "ntuple": _ntuple, "typeof": jl_typeof, "nnz": lambda A: int(csc(A).nnz), "rot180": _rot180,
     "cholesky": lambda A: Factor(A), "lu": lambda A: Factor(A), "Symmetric": lambda A: A, "mul!": _mul_inplace, "blockdiag": _blockdiag,
     "occursin": _occursin, "split": jl_split, "parse": jl_parse, "readlines": _readlines, "open": lambda fn: open(fn),
@@ -1584,6 +1615,7 @@ class Interp:
         self.end_stack = []
         self.views = 0
         self.log = []
+        _Rng.gen = np.random.default_rng(777)
 
     # ---- files
     def include(self, fname):
@@ -1771,7 +1803,12 @@ class Interp:
     def ev_typed(self, n, env): return self.ev(n[1], env)
     def ev_break(self, n, env): raise BreakEx()
     def ev_continue(self, n, env): raise ContinueEx()
-    def ev_show(self, n, env): return None
+    def ev_show(self, n, env):
+        try:
+            self.log.append(self.ev(n[1], env))
+        except JuliaError:
+            pass
+        return None
     def ev_pyhook(self, n, env): return n[1](env)
 
     def ev_str(self, n, env):
@@ -1827,7 +1864,13 @@ class Interp:
         lhs = n[1]
         val = self.ev(n[2], env)
         if lhs[0] == "index":
-            self.assign(lhs, val, env)
+            a = self.ev(lhs[1], env)
+            if isinstance(a, (tuple, list, NT, dict)):                      # element of a container: broadcast into that array
+                tgt = jl_getindex(a, self.eval_indices(a, lhs[2], env))
+                _, v = align(tgt, to_arr(val))
+                tgt[...] = v
+            else:
+                self.assign(lhs, val, env)
         else:
             a = self.ev(lhs, env)
             v = to_arr(val)
@@ -1899,6 +1942,7 @@ class Interp:
         return None
 
     def iterate(self, it):
+        if isinstance(it, NT): return list(it._values)
         if isinstance(it, JRange): return it.arr().tolist()
         if isinstance(it, np.ndarray): return [v.item() if isinstance(v, np.generic) else v for v in flat_f(it)]
         if isinstance(it, dict): return list(it.items())

@@ -143,6 +143,39 @@ def test_penalty_asserts_positive_psi(ref):
         ref.call("locoperator", 2, 12, 12, m, (1, 1, 1, 1), crr=bad)     # @assert minimum(ψmin) > 0, :419
 
 
+# ---- mesh reader and connectivity on every mesh the reference ships ------------------------------------------------------------------
+@pytest.mark.parametrize("mesh", ["meshes/square_circle.inp", "meshes/flower_v2.inp", "seas/BP1/meshes/1_1_block.inp", "seas/BP1/meshes/BP1_v1.inp"])
+def test_read_inp_2d_and_connectivity_executed(ref, mesh):
+    """read_inp_2d (global_curved.jl:802-946) and connectivityarrays (:82-132) as the reference runs them, against the product's
+    host-side reader (hybridsbp_b200/host.py) and the oracle's, on the repository's copies of the same files"""
+    from hybridsbp_b200 import host
+    path = os.path.join(REF, mesh)
+    mine = os.path.join(ROOT, "meshes", os.path.basename(mesh))
+    assert open(path).read() == open(mine).read()
+    # square_circle.inp / 1_1_block.inp carry side sets 4 and 5, which the reader's assertion (:937) only accepts after the drivers'
+    # bc_map (square_circle.jl:11-12, BP1.jl:36-37); the other two meshes are read with the default map
+    bc_map = np.array([1, 1, 2, 2, 7]) if ("square" in mesh or "1_1" in mesh) else None
+    if bc_map is None:
+        out, hv, ov = ref.call("read_inp_2d", path), host.read_inp_2d(mine), orc.read_inp_2d(mine)
+    else:
+        out, hv, ov = ref.call("read_inp_2d", path, bc_map=bc_map), host.read_inp_2d(mine, list(bc_map)), orc.read_inp_2d(mine, list(bc_map))
+        if "square" in mesh:
+            with pytest.raises(JuliaError):
+                ref.call("read_inp_2d", path)
+    for a, b, c in zip(out, hv, ov):
+        assert np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+        assert np.array_equal(np.asarray(a, dtype=float), np.asarray(c, dtype=float))
+    conn = ref.call("connectivityarrays", out[1], out[2])
+    for a, b, c in zip(conn, host.connectivityarrays(hv[1], hv[2]), orc.connectivityarrays(ov[1], ov[2])):
+        assert np.array_equal(np.asarray(a).astype(int), np.asarray(b).astype(int))
+        assert np.array_equal(np.asarray(a).astype(int), np.asarray(c).astype(int))
+    Nr = np.full(out[1].shape[1], 9); Ns = np.full(out[1].shape[1], 11)
+    for codes in (7, (7, 8), 1):
+        a = ref.call("bcstarts", out[3], conn[0], conn[1], codes, Nr, Ns)  # :714-728
+        b = host.bcstarts(hv[3], conn[0], conn[1], codes if isinstance(codes, tuple) else (codes,), list(Nr), list(Ns))
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
 # ---- the driver of configuration 1 -------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def square_circle_p4():
@@ -247,6 +280,25 @@ def test_bp1_odefun_at_the_reference_resolution_executed():
         assert np.max(np.abs(d[201:] - ref[201:])) <= 1e-12 * np.max(np.abs(ref[201:]))
         assert np.max(np.abs(d[:201] - ref[:201])) <= 1e-12 * np.max(np.abs(ref[:201]))
     assert np.max(np.abs(g["dpsiV"][3][201:])) > 0.5                        # the coseismic state is among them
+
+
+# ---- the reference's own check scripts, as written -----------------------------------------------------------------------------------
+def test_reference_check_scripts_executed():
+    """check_residual.jl, global_op_eigenvalues.jl and local_op_eigenvalues.jl run through the interpreter (random samples reduced
+    from 1000 to 2, plotting statements dropped): their assertions hold and the quantities they plot have the advertised signs"""
+    from refexec.drivers import run_check_script
+    _, log = run_check_script("check_residual.jl")
+    assert len(log) == 6                                                   # extrema of Re, Im of eig(A - D1' H diag(b) D1) for p = 2, 4, 6
+    for re_ext, im_ext in zip(log[0::2], log[1::2]):
+        assert re_ext[0] > -1e-12 and re_ext[1] > 1 and im_ext == (0.0, 0.0)
+    names = ("min_eig_noSchur", "min_eig_Schur_M", "min_eig_Schur_D")
+    cap, _ = run_check_script("global_op_eigenvalues.jl", 2, names)       # contains @assert B ≈ D - F̄ᵀ A11⁻¹ F̄  (:84)
+    for k in names:
+        assert np.asarray(cap[0][k]).shape == (3, 2) and np.asarray(cap[0][k]).min() > 0
+    cap, _ = run_check_script("local_op_eigenvalues.jl", 2, ("min_eig", "max_eig"))
+    assert np.asarray(cap[0]["min_eig"]).shape == (3, 2, 2) and np.asarray(cap[0]["min_eig"]).min() > 0      # SPD for Dirichlet and Neumann faces
+    sweep = np.asarray(cap[1]["min_eig"])                                  # tau scale 1e-2 ... 1e2: indefinite when the penalty is too small
+    assert sweep[:, 0].max() < 0 and sweep[:, -1].min() > 0
 
 
 # ---- the committed golden vectors are what the generator writes ----------------------------------------------------------------------
