@@ -299,6 +299,9 @@ def test_reference_check_scripts_executed():
     assert np.asarray(cap[0]["min_eig"]).shape == (3, 2, 2) and np.asarray(cap[0]["min_eig"]).min() > 0      # SPD for Dirichlet and Neumann faces
     sweep = np.asarray(cap[1]["min_eig"])                                  # tau scale 1e-2 ... 1e2: indefinite when the penalty is too small
     assert sweep[:, 0].max() < 0 and sweep[:, -1].min() > 0
+    it = Interp(os.path.join(REF, "seas", "BP1"))                          # single_block.jl: u = 1 is reproduced on the stretched block
+    it.include("single_block.jl")
+    assert it.log[0] == (1, 4) and np.max(np.abs(np.asarray(it.log[-1]) - 1)) < 1e-9
 
 
 # ---- the committed golden vectors are what the generator writes ----------------------------------------------------------------------
