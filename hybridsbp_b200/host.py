@@ -169,11 +169,37 @@ def connectivityarrays(EToV, EToF):
 # ------------------------------------------------------------------------------------------
 # transfinite blend
 # ------------------------------------------------------------------------------------------
+def d1_matrix(p, N):
+    """Dense first-derivative SBP operator on [-1, 1] with N + 1 points (diagonal_sbp.jl:67-157)."""
+    from ._sbp_d1 import D1_TABLES
+    if p not in D1_TABLES:
+        raise ValueError("Operators for order %d are not implemented" % p)
+    d, bd = np.array(D1_TABLES[p]["d"]), np.array(D1_TABLES[p]["bd"])
+    bm, bn = bd.shape
+    Np = N + 1
+    if Np < 2 * bm or Np < bn:
+        raise ValueError("Grid not big enough to support the operator")
+    D = np.zeros((Np, Np))
+    D[:bm, :bn] = bd                                     # :144-146
+    D[Np - bm:, Np - bn:] = -bd[::-1, ::-1]              # :147-149
+    h = p // 2
+    for i in range(bm, Np - bm):                         # :139-142
+        D[i, i - h:i + h + 1] = d
+    return D / (2.0 / N)
+
+
 def transfinite_blend(*args):
     """Three call forms, as in the reference:
-      transfinite_blend(a1, a2, a3, a4, a1s, a2s, a3r, a4r, r, s)   edge curves + derivatives
-      transfinite_blend(v1, v2, v3, v4, r, s)                       straight block from corner values
+      transfinite_blend(a1, a2, a3, a4, a1s, a2s, a3r, a4r, r, s)   edge curves + derivatives        (global_curved.jl:19-51)
+      transfinite_blend(a1, a2, a3, a4, r, s, p)                    edge derivatives by the SBP operator of order p (:53-64)
+      transfinite_blend(v1, v2, v3, v4, r, s)                       straight block from corner values  (:66-78)
     Returns (x, x_r, x_s)."""
+    if len(args) == 7:
+        a1, a2, a3, a4, r, s, p = args
+        Nrp, Nsp = r.shape
+        Dr, Ds = d1_matrix(p, Nrp - 1), d1_matrix(p, Nsp - 1)
+        return transfinite_blend(a1, a2, a3, a4, lambda t: a1(t) @ Ds.T, lambda t: a2(t) @ Ds.T,
+                                 lambda t: Dr @ a3(r), lambda t: Dr @ a4(r), r, s)          # as written: a3r, a4r differentiate a(r)
     if len(args) == 6:
         v1, v2, v3, v4, r, s = args
         lin = lambda a, b: (lambda t: a * (1 - t) / 2 + b * (1 + t) / 2)

@@ -3,7 +3,7 @@
 CPU restatement (numpy / scipy.sparse) of the reference's block-local operator
 construction and hybridized (trace) global assembly, function by function:
 
-  transfinite_blend       global_curved.jl:19-78
+  transfinite_blend (+ _sbp, _corners: the three methods)   global_curved.jl:19-78
   connectivityarrays      global_curved.jl:82-132
   create_metrics          global_curved.jl:136-209
   locoperator             global_curved.jl:211-506
@@ -75,6 +75,19 @@ def transfinite_blend(a1, a2, a3, a4, a1s, a2s, a3r, a4r, r, s):
     xs = ((1 + r) * a2s(s) / 2 + (1 - r) * a1s(s) / 2 + a4(r) / 2 - a3(r) / 2 -
           (+(1 + r) * a2(1.0) + (1 - r) * a1(1.0) - (1 + r) * a2(-1.0) - (1 - r) * a1(-1.0)) / 4)
     return x, xr, xs
+
+
+def transfinite_blend_sbp(a1, a2, a3, a4, r, s, p):
+    """Edge derivatives by the order-p SBP first derivative, global_curved.jl:53-64 (as written: the closures for the r-derivatives
+    ignore their argument and differentiate a3(r), a4(r))."""
+    Nrp, Nsp = r.shape
+    Dr = diagonal_sbp_D1(p, Nrp - 1)[0]
+    Ds = diagonal_sbp_D1(p, Nsp - 1)[0]
+    a2s = lambda t: (Ds @ a2(t).T).T                 # a2(s) * Ds'
+    a1s = lambda t: (Ds @ a1(t).T).T
+    a4r = lambda t: Dr @ a4(r)
+    a3r = lambda t: Dr @ a3(r)
+    return transfinite_blend(a1, a2, a3, a4, a1s, a2s, a3r, a4r, r, s)
 
 
 def transfinite_blend_corners(v1, v2, v3, v4, r, s):

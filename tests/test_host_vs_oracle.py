@@ -83,3 +83,20 @@ def test_blend_and_metrics_agree_on_every_block(name):
             for c in range(2):
                 assert np.max(np.abs(mh.facecoord[c][k] - mo.facecoord[c][k])) <= 1e-13 * max(1.0, np.max(np.abs(mo.facecoord[c][k])))
     assert worst <= 2e-13, worst          # different order of the same additions (BP1_v1 spans 400 km)
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_host_d1_matrix_and_generated_table(p):
+    """the host mirror's first-derivative operator (table generated by tools/gen_host_d1.py) against the oracle's"""
+    import importlib.util
+    import os
+    from oracle import sbp as osbp
+    for N in (3 * p + 1, 40):
+        assert np.max(np.abs(host.d1_matrix(p, N) - osbp.diagonal_sbp_D1(p, N)[0].toarray())) < 1e-14
+    if p > 2:
+        with pytest.raises(ValueError):
+            host.d1_matrix(p, p)                                           # grid too small for the closure (diagonal_sbp.jl:129-131)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_host_d1", os.path.join(root, "tools", "gen_host_d1.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    assert mod.render() == open(os.path.join(root, "hybridsbp_b200", "_sbp_d1.py")).read()

@@ -136,6 +136,34 @@ def test_locoperator_executed(ref, p):
         ref.call("locoperator", p, N, N + 4, ref.call("create_metrics", p, N, N + 4))
 
 
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_transfinite_blend_three_methods_executed(ref, p):
+    """global_curved.jl:19-78: analytic edge derivatives, SBP-differentiated edges (:53-64), corner values (:66-78) -- the reference's
+    methods against the oracle's and the product's host-side mirror (whose D1 table is generated, hybridsbp_b200/_sbp_d1.py)"""
+    from hybridsbp_b200 import host
+    ref.run("""
+    b1(t) = -1 .+ 0.1 .* (1 .- t .^ 2)
+    b2(t) =  1 .+ 0.05 .* (1 .- t .^ 2)
+    b3(t) = t .+ 0.0 .* t
+    b4(t) = t .+ 0.0 .* t
+    """)
+    b1, b2 = (lambda t: -1 + 0.1 * (1 - t ** 2)), (lambda t: 1 + 0.05 * (1 - t ** 2))
+    b3 = b4 = lambda t: t + 0.0 * t
+    N = 17
+    r = np.asfortranarray(np.repeat(np.linspace(-1, 1, N + 1)[:, None], N + 1, axis=1)); s = np.asfortranarray(r.T)
+    assert np.max(np.abs(host.d1_matrix(p, N) - dense(ref.call("diagonal_sbp_D1", p, N)[0]))) < 1e-14
+    out = ref.call("transfinite_blend", *[ref.globals.lookup(k) for k in ("b1", "b2", "b3", "b4")], r, s, p)
+    for a, b, c in zip(out, orc.transfinite_blend_sbp(b1, b2, b3, b4, r, s, p), host.transfinite_blend(b1, b2, b3, b4, r, s, p)):
+        assert np.max(np.abs(np.asarray(a) - b)) < 1e-14 and np.max(np.abs(np.asarray(a) - c)) < 1e-14
+    out = ref.call("transfinite_blend", 0.1, 1.3, -0.2, 1.1, r, s)
+    for a, b, c in zip(out, orc.transfinite_blend_corners(0.1, 1.3, -0.2, 1.1, r, s), host.transfinite_blend(0.1, 1.3, -0.2, 1.1, r, s)):
+        assert np.max(np.abs(np.asarray(a) - b)) < 1e-14 and np.max(np.abs(np.asarray(a) - c)) < 1e-14
+    with pytest.raises(JuliaError):                                         # edges that do not meet at the corners, :25
+        ref.call("transfinite_blend", ref.globals.lookup("b2"), ref.globals.lookup("b2"), ref.globals.lookup("b3"), ref.globals.lookup("b4"), r, s, p)
+    with pytest.raises(AssertionError):
+        host.transfinite_blend(b2, b2, b3, b4, r, s, p)
+
+
 def test_penalty_asserts_positive_psi(ref):
     m = ref.call("create_metrics", 2, 12, 12)
     bad = np.array(m.get("crr")); bad[5, 5] = -1.0
