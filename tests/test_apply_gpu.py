@@ -67,6 +67,28 @@ def test_apply_warped_mesh(ctx, p, N):
 
 
 @pytest.mark.parametrize("p", [2, 4, 6])
+def test_apply_against_extended_precision(ctx, p):
+    """the CUDA result and the oracle's fp64 SpMV both against an 80-bit (numpy.longdouble) evaluation of
+    M~ u on small blocks (marching-kernel and generic-kernel sizes), in the normwise measure of the parity bar"""
+    import hybridsbp_b200 as hs
+    assert np.finfo(np.longdouble).nmant >= 63
+    rng = np.random.default_rng(4242 + p)
+    for N, generic in ((3 * p + 2, True), (34, False)):
+        m = random_spd_metrics(p, N, N, rng)
+        bc = (1, 2, 0, 7)
+        lop = orc.locoperator(p, N, N, m, bc)
+        blk = upload_blocks(hs, ctx, p, [m], [bc])
+        blk.force_generic(generic)
+        u = rng.uniform(-1, 1, blk.VNp)
+        y = blk.apply_host(u)
+        yld = lop.Mt.toarray().astype(np.longdouble) @ u.astype(np.longdouble)
+        scale = np.max(abs(lop.Mt) @ np.abs(u))
+        assert float(np.max(np.abs(y - yld))) / scale < TOL
+        assert float(np.max(np.abs(lop.Mt @ u - yld))) / scale < 1e-14
+        blk.close()
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
 def test_face_operators(ctx, p):
     """F_k^T u, F_k v and the traction operator against the oracle's sparse F_k / HfI_FT_k."""
     import hybridsbp_b200 as hs
