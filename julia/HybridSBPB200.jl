@@ -1,7 +1,8 @@
 # HybridSBPB200.jl -- thin `ccall` layer over libhsbp.so (include/hsbp.h) plus the drop-in type for the
 # reference's `factorization` plugin.
 #
-# NOT EXECUTED IN THE BUILD CONTAINER: Julia is not installed there.  This file mirrors, call for call,
+# NOT EXECUTED IN THE BUILD CONTAINER: Julia is not installed there (tests/test_binding_signatures_cpu.py checks every ccall's
+# symbol, return type and argument types, and the struct layouts, against include/hsbp.h).  This file mirrors, call for call,
 # hybridsbp_b200/_lib.py + blocks.py (the ctypes twin that the tests run); keep the two in sync.
 #
 # Usage inside the reference (square_circle.jl:297-299, seas/BP1/BP1.jl:78):
