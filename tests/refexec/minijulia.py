@@ -961,8 +961,6 @@ def jl_add(a, b, sign=1):
         r = (csc(a) + csc(b)) if sign > 0 else (csc(a) - csc(b))
         return csc(r)
     if isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.shape != b.shape:
-        if a.size == b.size and {a.ndim, b.ndim} == {1, 2}:
-            raise JuliaError("dimension mismatch in +/-: %s vs %s" % (a.shape, b.shape))
         raise JuliaError("dimension mismatch in +/-: %s vs %s" % (a.shape, b.shape))
     return a + b if sign > 0 else a - b
 
@@ -982,7 +980,7 @@ def jl_mul(a, b):
         if a.ndim == 1: raise JuliaError("vector * sparse matrix")
         return np.asarray(a @ b)
     if isinstance(a, RowVec) and b.ndim == 1:
-        return (plain(a).reshape(-1) @ b).item() if True else None
+        return (plain(a).reshape(-1) @ b).item()
     if a.ndim == 1 and b.ndim == 2:
         if b.shape[0] != 1: raise JuliaError("vector * matrix with more than one row")
         return plain(a).reshape(-1, 1) @ plain(b)
@@ -1856,7 +1854,6 @@ class Interp:
 
     def ev_assign(self, n, env):
         val = self.ev(n[2], env)
-        if n[1][0] == "id" and isinstance(val, RowVec) is False and isinstance(val, np.ndarray) and False: val = val
         self.assign(n[1], val, env)
         return val
 
