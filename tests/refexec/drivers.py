@@ -96,7 +96,7 @@ def run_bp1_setup(N=200):
 def run_flower(p=4, N0=17):
     """tests/refexec/flower_driver.jl (ours, in the style of square_circle.jl) on top of the reference's global_curved.jl"""
     it = Interp(REF)
-    it.globals.vars["SBPp"], it.globals.vars["N0"] = p, N0
+    it.globals.vars["order"], it.globals.vars["npts"] = p, N0
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "flower_driver.jl")) as f:
         out = it.run(f.read(), "flower_driver.jl")
     return to_python(out)

@@ -1,103 +1,93 @@
-# Configuration 2 (meshes/flower_v2.inp: 67 blocks, interfaces with reversed orientation) driven through the REFERENCE's functions.
-# The reference ships the mesh without a driver; this one is written for the tests, in the style of square_circle.jl, and is run
-# by tests/refexec/minijulia.py with global_curved.jl included from /root/reference.  Unlike square_circle.jl the slip on the
-# jump faces is a given function (not the jump of an exact solution), so that every branch of `in_jump` carries data.
+# Configuration 2 (meshes/flower_v2.inp: 67 blocks, interfaces seen in reversed orientation from their plus side) solved with the
+# REFERENCE's functions -- read_inp_2d, connectivityarrays, transfinite_blend (corner form), create_metrics, locoperator,
+# LocalGlobalOperators, bcstarts, assembleλmatrix, locbcarray!, locsourcearray!, LocalToGLobalRHS!, computetraction -- which
+# tests/refexec/minijulia.py takes from global_curved.jl under /root/reference.  The reference ships this mesh without a driver;
+# this file is the test suite's own (inputs: the globals `order` and `npts`).  The slip on the jump faces is a prescribed
+# function of position rather than the jump of a manufactured solution, so that all three orientation branches of the jump data
+# carry non-zero values.
 include("global_curved.jl")
 
 let
-  (verts, EToV, EToF, FToB, EToDomain) = read_inp_2d("meshes/flower_v2.inp")
-  (nelems, nfaces) = (size(EToV, 2), size(FToB, 1))
-  (FToE, FToLF, EToO, EToS) = connectivityarrays(EToV, EToF)
-  Nr = fill(N0, nelems)
-  Ns = fill(N0, nelems)
+  mesh = read_inp_2d("meshes/flower_v2.inp")
+  corners, blockcorner, blockface, facebc = mesh[1], mesh[2], mesh[3], mesh[4]
+  nblocks = size(blockcorner, 2)
+  nsides = length(facebc)
+  conn = connectivityarrays(blockcorner, blockface)
+  faceblock, facelocal, sameway, side = conn[1], conn[2], conn[3], conn[4]
+  sizes = fill(npts, nblocks)
 
-  vex(x, y, e) = sin.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2) .+ 0.1 .* x .* y
-  vex_x(x, y, e) = 0.9 .* cos.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2) .+ 0.1 .* y
-  vex_y(x, y, e) = -0.7 .* sin.(0.9 .* x .+ 0.3) .* sin.(0.7 .* y .- 0.2) .+ 0.1 .* x
-  laplace(x, y, e) = -(0.9^2 + 0.7^2) .* sin.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2)
+  # manufactured field (continuous across every interface) and the prescribed slip
+  field(x, y) = sin.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2) .+ 0.1 .* x .* y
+  field_x(x, y) = 0.9 .* cos.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2) .+ 0.1 .* y
+  field_y(x, y) = -0.7 .* sin.(0.9 .* x .+ 0.3) .* sin.(0.7 .* y .- 0.2) .+ 0.1 .* x
+  minus_laplacian(x, y) = (0.9^2 + 0.7^2) .* sin.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2)
   slip(x, y) = 0.3 .* sin.(x) .* cos.(2 .* y)
 
-  OPTYPE = typeof(locoperator(2, 16, 16))
-  lop = Dict{Int64, OPTYPE}()
-  for e = 1:nelems
-    (x1, x2, x3, x4) = verts[1, EToV[:, e]]
-    (y1, y2, y3, y4) = verts[2, EToV[:, e]]
-    xt(r, s) = transfinite_blend(x1, x2, x3, x4, r, s)
-    yt(r, s) = transfinite_blend(y1, y2, y3, y4, r, s)
-    metrics = create_metrics(SBPp, Nr[e], Ns[e], xt, yt)
-    lop[e] = locoperator(SBPp, Nr[e], Ns[e], metrics, FToB[EToF[:, e]])
+  # one straight-sided block per element: corner blend -> metrics -> local operator
+  ops = Dict{Int64, Any}()
+  for b = 1:nblocks
+    cx = corners[1, blockcorner[:, b]]
+    cy = corners[2, blockcorner[:, b]]
+    mapx = (r, s) -> transfinite_blend(cx[1], cx[2], cx[3], cx[4], r, s)
+    mapy = (r, s) -> transfinite_blend(cy[1], cy[2], cy[3], cy[4], r, s)
+    ops[b] = locoperator(order, npts, npts, create_metrics(order, npts, npts, mapx, mapy), facebc[blockface[:, b]])
   end
 
-  (M, FbarT, D, vstarts, FToλstarts) = LocalGlobalOperators(lop, Nr, Ns, FToB, FToE, FToLF, EToO, EToS, (x) -> cholesky(Symmetric(x)))
-  locfactors = M.F
-  FToδstarts = bcstarts(FToB, FToE, FToLF, BC_JUMP_INTERFACE, Nr, Ns)
-  VNp = vstarts[nelems+1]-1
-  λNp = FToλstarts[nfaces+1]-1
-  δNp = FToδstarts[nfaces+1]-1
-  B = assembleλmatrix(FToλstarts, vstarts, EToF, FToB, locfactors, D, FbarT)
-  BF = cholesky(Symmetric(B))
+  glob = LocalGlobalOperators(ops, sizes, sizes, facebc, faceblock, facelocal, sameway, side, A -> cholesky(Symmetric(A)))
+  solvers, traceT, diagD, vstart, tstart = glob[1].F, glob[2], glob[3], glob[4], glob[5]
+  jstart = bcstarts(facebc, faceblock, facelocal, BC_JUMP_INTERFACE, sizes, sizes)
+  schur = assembleλmatrix(tstart, vstart, blockface, facebc, solvers, diagD, traceT)
+  schur_solver = cholesky(Symmetric(schur))
 
-  (bλ, λ, gδ) = (zeros(λNp), zeros(λNp), zeros(λNp))
-  (u, g) = (zeros(VNp), zeros(VNp))
-  δ = zeros(δNp)
-  for f = 1:nfaces
-    if FToB[f] == BC_JUMP_INTERFACE
-      e1 = FToE[1, f]
-      lf1 = FToLF[1, f]
-      (xf, yf) = lop[e1].facecoord
-      δ[FToδstarts[f]:(FToδstarts[f+1]-1)] = slip(xf[lf1], yf[lf1])
-    end
+  nvol = vstart[end] - 1
+  ntrace = tstart[end] - 1
+  jumps = zeros(jstart[end] - 1)
+  for f = 1:nsides
+    facebc[f] == BC_JUMP_INTERFACE || continue
+    b, lf = faceblock[1, f], facelocal[1, f]
+    jumps[jstart[f]:(jstart[f+1]-1)] = slip(ops[b].facecoord[1][lf], ops[b].facecoord[2][lf])
   end
 
-  bc_Dirichlet = (lf, x, y, e, δ) -> vex(x, y, e)
-  bc_Neumann   = (lf, x, y, nx, ny, e, δ) -> (nx .* vex_x(x, y, e) + ny .* vex_y(x, y, e))
-  in_jump      = (lf, x, y, e, δ) -> begin
-    f = EToF[lf, e]
-    if EToS[lf, e] == 1
-      return -δ[FToδstarts[f]:(FToδstarts[f+1]-1)]
-    elseif EToO[lf, e]
-      return  δ[FToδstarts[f]:(FToδstarts[f+1]-1)]
-    else
-      return  δ[(FToδstarts[f+1]-1):-1:FToδstarts[f]]
-    end
+  # the face's slice of a trace-sized / jump-sized vector, in the order block b sees it on its local face lf
+  seen_from(vec, starts, b, lf; aliased = false) = begin
+    f = blockface[lf, b]
+    rng = sameway[lf, b] ? (starts[f]:(starts[f+1]-1)) : ((starts[f+1]-1):-1:starts[f])
+    aliased ? view(vec, rng) : vec[rng]
+  end
+  dirichlet = (lf, x, y, b) -> field(x, y)
+  neumann = (lf, x, y, nx, ny, b) -> nx .* field_x(x, y) + ny .* field_y(x, y)
+  half_of_this = (lf, x, y, b) -> (side[lf, b] == 1 ? -1 : 1) .* seen_from(jumps, jstart, b, lf)
+
+  vol_rhs = zeros(nvol)
+  trace_rhs = zeros(ntrace)
+  for b = 1:nblocks
+    mine = view(vol_rhs, vstart[b]:(vstart[b+1]-1))
+    trace_parts = ntuple(lf -> seen_from(trace_rhs, tstart, b, lf; aliased = true), 4)
+    locbcarray!(mine, trace_parts, ops[b], facebc[blockface[:, b]], dirichlet, neumann, half_of_this, (b))
+    locsourcearray!(mine, (x, y) -> minus_laplacian(x, y), ops[b])
   end
 
-  for e = 1:nelems
-    gδe = ntuple(4) do lf
-      f = EToF[lf, e]
-      if EToO[lf, e]
-        return @view gδ[FToλstarts[f]:(FToλstarts[f+1]-1)]
-      else
-        return @view gδ[(FToλstarts[f+1]-1):-1:FToλstarts[f]]
-      end
-    end
-    locbcarray!((@view g[vstarts[e]:vstarts[e+1]-1]), gδe, lop[e], FToB[EToF[:,e]], bc_Dirichlet, bc_Neumann, in_jump, (e, δ))
-    source = (x, y, e) -> (-laplace(x, y, e))
-    locsourcearray!((@view g[vstarts[e]:vstarts[e+1]-1]), source, lop[e], e)
+  reduced = zeros(ntrace)
+  work = zeros(nvol)
+  LocalToGLobalRHS!(reduced, vol_rhs, trace_rhs, work, solvers, traceT, vstart)
+  trace = schur_solver \ reduced
+  coupled = vol_rhs - traceT' * trace
+  solution = zeros(nvol)
+  for b = 1:nblocks
+    rows = vstart[b]:(vstart[b+1]-1)
+    solution[rows] = solvers[b] \ coupled[rows]
   end
 
-  LocalToGLobalRHS!(bλ, g, gδ, u, locfactors, FbarT, vstarts)
-  λ[:] = BF \ bλ
-  u[:] = -FbarT' * λ
-  u[:] .= g .+ u
-  for e = 1:nelems
-    @views u[vstarts[e]:(vstarts[e+1]-1)] = locfactors[e] \ u[vstarts[e]:(vstarts[e+1]-1)]
+  fault_traction = zeros(length(jumps))
+  for f = 1:nsides
+    facebc[f] == BC_JUMP_INTERFACE || continue
+    b, lf = faceblock[1, f], facelocal[1, f]
+    rows = vstart[b]:(vstart[b+1]-1)
+    fault_traction[jstart[f]:(jstart[f+1]-1)] = computetraction(ops[b], lf, solution[rows], trace[tstart[f]:(tstart[f+1]-1)],
+                                                                 jumps[jstart[f]:(jstart[f+1]-1)])
   end
 
-  # traction on the minus side of every jump face (computetraction, global_curved.jl:638-644)
-  τf = zeros(δNp)
-  for f = 1:nfaces
-    if FToB[f] == BC_JUMP_INTERFACE
-      e1 = FToE[1, f]
-      lf1 = FToLF[1, f]
-      λrng = FToλstarts[f]:(FToλstarts[f+1]-1)
-      δrng = FToδstarts[f]:(FToδstarts[f+1]-1)
-      urng = vstarts[e1]:(vstarts[e1+1]-1)
-      τf[δrng] = computetraction(lop[e1], lf1, u[urng], λ[λrng], δ[δrng])
-    end
-  end
-
-  (verts = verts, EToV = EToV, EToF = EToF, FToB = FToB, FToE = FToE, FToLF = FToLF, EToO = EToO, EToS = EToS,
-   vstarts = vstarts, FToλstarts = FToλstarts, FToδstarts = FToδstarts, FbarT = FbarT, D = D, B = B,
-   δ = δ, g = g, gδ = gδ, bλ = bλ, λ = λ, u = u, τf = τf)
+  (verts = corners, EToV = blockcorner, EToF = blockface, FToB = facebc, FToE = faceblock, FToLF = facelocal, EToO = sameway, EToS = side,
+   vstarts = vstart, FToλstarts = tstart, FToδstarts = jstart, FbarT = traceT, D = diagD, B = schur,
+   δ = jumps, g = vol_rhs, gδ = trace_rhs, bλ = reduced, λ = trace, u = solution, τf = fault_traction)
 end

@@ -456,7 +456,11 @@ class Parser:
             if self.ctx[-1] == "bracket" and tok.sp and not tok.sp_after and tok.val in ("+", "-"):
                 return lhs                                   # `[a -b]`: a new element, not a difference
             self.next(); self.skip_nl_after_operator()
-            rhs = sub()
+            nxt = self.peek()
+            if node and nxt.kind == "kw" and nxt.val in ("break", "continue", "return"):
+                rhs = self.parse_statement()                 # cond || continue
+            else:
+                rhs = sub()
             lhs = (node, lhs, rhs) if node else ("bin", tok.val, lhs, rhs)
 
     def parse_or(self):
