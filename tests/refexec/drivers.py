@@ -116,8 +116,8 @@ def run_check_script(name, num_samp=2, capture=()):
     def fn(n):
         if n[0] == "assign" and n[1] == ("id", "num_samp"): return ("assign", n[1], ("num", num_samp))
         if n[0] in ("assign", "call", "for", "show") and contains_id(n, PLOTTING): return None
-        if n[0] == "call" and n[1] == ("id", "range") and any(k == "length" for k, _ in n[3]):      # tau sweep of local_op_eigenvalues.jl
-            return ("call", n[1], n[2], [(k, ("num", 4) if k == "length" and v == ("num", 100) else v) for k, v in n[3]], n[4])
+        if n[0] == "call" and n[1] == ("id", "range") and any(k[0] == "length" for k in n[3]):      # tau sweep of local_op_eigenvalues.jl
+            return ("call", n[1], n[2], [(k, ("num", 4) if k == "length" and v == ("num", 100) else v, a) for k, v, a in n[3]], n[4])
         if n[0] == "let":
             hook = lambda env: captured.append({k: to_python(env.vars[k]) for k in capture if k in env.vars})
             return ("let", ("block", n[1][1] + [("pyhook", hook)]))

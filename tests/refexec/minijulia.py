@@ -214,7 +214,8 @@ class Parser:
                 while self.peek(False).kind != "nl": self.next(False)
                 return ("nop",)
             if v == "const": self.next(); return self.parse_statement()
-            if v in ("global", "local"): self.next(); return self.parse_statement()
+            if v == "global": self.next(); return ("global", self.parse_statement())
+            if v == "local": self.next(); return self.parse_statement()
             if v in ("struct", "mutable"): return self.parse_struct()
         if tok.kind == "macro":
             return self.parse_macro_statement()
@@ -377,7 +378,8 @@ class Parser:
                     if a[0] == "id": pos.append((a[1], None, None, False))
                     elif a[0] == "typed": pos.append((a[1][1], a[2], None, False))
                     else: raise SyntaxError("minijulia: unsupported short-form parameter %r" % (a,))
-                kws = [(v[1], None, True) if k == "..." else (k, v, False) for k, v in lhs[3]]
+                pos += [(k, None, v, False) for k, v, after in lhs[3] if not after]          # f(a, b = 2a) = ...: positional default
+                kws = [(v[1], None, True) if k == "..." else (k, v, False) for k, v, after in lhs[3] if after]
                 return ("func", lhs[1][1], pos, kws, ("block", [rhs]), {})
             return ("assign", lhs, rhs)
         if op == ".=": return ("dotassign", lhs, rhs)
@@ -616,9 +618,9 @@ class Parser:
                 self.next(); e = ("splat", e)
             if self.is_kw("for"):                                   # generator argument
                 e = self.parse_generator(e)
-            if e[0] == "assign" and e[1][0] == "id": kwargs.append((e[1][1], e[2]))
-            elif in_kw and e[0] == "id": kwargs.append((e[1], e))
-            elif in_kw and e[0] == "splat": kwargs.append(("...", e[1]))
+            if e[0] == "assign" and e[1][0] == "id": kwargs.append((e[1][1], e[2], in_kw))
+            elif in_kw and e[0] == "id": kwargs.append((e[1], e, True))
+            elif in_kw and e[0] == "splat": kwargs.append(("...", e[1], True))
             else: args.append(e)
             if self.is_op(","): self.next()
         self.expect_op(")")
@@ -656,8 +658,12 @@ class Parser:
             if v == "begin":
                 body = self.parse_block(); self.expect_kw("end"); return body
             if v == "let":
-                while self.peek(False).kind != "nl": self.next(False)
-                body = self.parse_block(); self.expect_kw("end"); return ("let", body)
+                binds = []
+                while self.peek(False).kind != "nl":                  # let a = 1, b = 2
+                    binds.append(self.parse_expr())
+                    if self.is_op(",", self.peek(False)): self.next(False)
+                body = self.parse_block(); self.expect_kw("end")
+                return ("let", ("block", binds + body[1]))
             if v == "if": return self.parse_if()
             if v == "try":
                 body = self.parse_block(("catch", "end"))
@@ -1270,6 +1276,7 @@ def jl_reshape(a, *dims):
 
 def jl_length(a):
     if isinstance(a, (np.ndarray,)): return int(a.size)
+    if isinstance(a, NT): return len(a._values)
     if sp.issparse(a): return int(a.shape[0] * a.shape[1])
     return len(a)
 
@@ -1801,7 +1808,18 @@ class Interp:
     def ev_colon(self, n, env): return COLON
     def ev_paren(self, n, env): return self.ev(n[1], env)
     def ev_block(self, n, env): return self.exec_block(n, env)
-    def ev_let(self, n, env): return self.exec_block(n[1], Env(env))
+    def ev_let(self, n, env):
+        e = Env(env)
+        for st in n[1][1]:                                   # bindings on the `let` line are new locals even if the name exists outside
+            inner = st[3] if st[0] == "ln" else st
+            if inner[0] == "assign" and inner[1][0] == "id" and st[0] != "ln": e.vars[inner[1][1]] = self.ev(inner[2], env)
+        return self.exec_block(("block", [st for st in n[1][1] if st[0] == "ln" or st[0] != "assign"]), e)
+
+    def ev_global(self, n, env):
+        st = n[1]
+        if st[0] == "assign" and st[1][0] == "id":
+            val = self.ev(st[2], env); self.globals.vars[st[1][1]] = val; return val
+        return self.ev(st, env)
     def ev_typed(self, n, env): return self.ev(n[1], env)
     def ev_break(self, n, env): raise BreakEx()
     def ev_continue(self, n, env): raise ContinueEx()
@@ -1992,7 +2010,7 @@ class Interp:
             if all(isinstance(v, (bool, np.bool_)) for v in vals): return np.array(vals, dtype=np.bool_)
             if all(isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)) for v in vals): return np.array(vals, dtype=np.int64)
             return np.array(vals, dtype=np.float64)
-        if not vals: return np.zeros(0)
+        if not vals: return []                                   # Any[]: grows by push!
         if len(vals) == 1 and isinstance(vals[0], JRange): return [vals[0]]
         return list(vals)
 
@@ -2103,7 +2121,7 @@ class Interp:
             if a[0] == "splat": args.extend(self.iterate(self.ev(a[1], env)))
             else: args.append(self.ev(a, env))
         kwargs = {}
-        for kname, kv in kwn:
+        for kname, kv, _ in kwn:
             if kname == "...": kwargs.update(self.ev(kv, env))
             else: kwargs[kname] = self.ev(kv, env)
         if dotted:

@@ -82,6 +82,86 @@ def test_interpreter_semantics():
         it.run("u = zeros(3); u[4]")
 
 
+def test_interpreter_semantics_scoping_dispatch_and_linear_algebra():
+    """more known answers: mesh-grid krons, findnz order, operator precedence, empty / reversed ranges, `end` in indices, linear
+    indexing, interpolation, do-blocks, named tuples, short circuits, closures (one binding per loop iteration, captured locals),
+    let / global, default arguments, dispatch on Number / AbstractArray, aliasing vs rebinding vs in-place broadcast, comparisons,
+    integer and float division, adjoints and solves"""
+    it = Interp(REF)
+    out = it.run(r'''
+    r = range(-1, stop=1, length=5)
+    R = ones(1, 3) ⊗ r                 # R[i, j] = r[i]
+    S = r[1:3]' ⊗ ones(5)              # S[i, j] = r[j]
+    A = sparse([2, 1, 2], [1, 2, 2], [5.0, 6.0, 7.0], 2, 2)
+    (I1, J1, V1) = findnz(A)            # column-major order
+    (I2, J2, V2) = findnz(sparse(transpose(A)))
+    v = [1.0, 2.0, 3.0]
+    quad = v' * sparse([1, 2, 3], [1, 2, 3], [2.0, 2.0, 2.0]) * v
+    pw = (-2^2, 2.0^-1, -v[2]^2, 2^3^2)
+    emp = (length(1:0), length(3:-1:1), collect(5:-2:1))
+    idx = 2 .+ (1:3)
+    m = reshape(collect(1:12), 3, 4)
+    ends = (m[end, 1], m[1, end], m[end], m[end-1, end-1], v[end:-1:1])
+    lin = m[[2, 5, 12]]
+    sub = m[2:3, [1, 4]]
+    name = "blk"
+    str = "x$(1 + 2)_$name"
+    tup = ntuple(4) do k
+      k^2
+    end
+    nt = (a = 1, b = "two", c = [3.0])
+    (a1, b1) = (nt.a, nt.c[1])
+    tern = 3 > 2 ? (1:3)[2] : -1
+    hits = 0
+    sc = (false && (hits += 1; true), true || (hits += 1; true), hits)
+    acc = []
+    for (i, w) in enumerate([10, 20])
+      push!(acc, i * w)
+    end
+    fs = [() -> k for k = 1:3]
+    caps = [f() for f in fs]
+    function counter()
+      n = 0
+      bump() = (n += 1)
+      bump(); bump()
+      n
+    end
+    let q = 5
+      global from_let = q + 1
+    end
+    g(a, b = 2a) = a + b
+    kind(x::Number) = "number"
+    kind(x::AbstractArray) = "array"
+    kind(x) = "other"
+    kinds = (kind(1.5), kind([1]), kind(1:3), kind(sin), kind("s"))
+    w = [1.0, 2.0, 3.0]; alias = w; alias[1] = 9.0
+    w2 = w; w2 += [1.0, 1.0, 1.0]
+    z = zeros(3); z .= w .* 2
+    eqs = ([1, 2] == [1, 2], [1, 2] == [2, 1], [1, 2][end:-1:1] == [2, 1], [1.0, 2.0] ≈ [1.0, 2.0 + 1e-12], 7 ∈ (1, 7), 3 ∈ 1:2)
+    dv = (7 / 2, div(7, 2), 7 ÷ 2, 7 % 3, 2 * 3 / 4)
+    un = -[1, 2] .+ 1
+    cmpc = 1 < 2 <= 2 != 3
+    A2 = [1 2; 3 4]
+    tr = (A2', A2 * [1, 1], [1, 1]' * A2, A2 .* [10, 20], A2 * A2, A2 \ [5.0, 11.0])
+    (R[:, 2], S[4, :], I1, J1, V1, I2, J2, V2, quad, pw, emp, collect(idx), ends, lin, sub, str, tup, (a1, b1), tern, sc, acc, caps, counter(),
+     from_let, g(1), g(1, 1), kinds, w, w2, z, eqs, dv, un, cmpc, tr)
+    ''')
+    r5 = np.array([-1, -0.5, 0, 0.5, 1])
+    exp = (r5, r5[:3], [2, 1, 2], [1, 2, 2], [5.0, 6, 7], [2, 1, 2], [1, 2, 2], [6.0, 5, 7], 28.0, (-4, 0.5, -4.0, 512), (0, 3, [5, 3, 1]), [3, 4, 5],
+           (3, 10, 12, 8, [3.0, 2, 1]), [2, 5, 12], [[2, 11], [3, 12]], "x3_blk", (1, 4, 9, 16), (1, 3.0), 2, (False, True, 0), [10, 40], [1, 2, 3], 2,
+           6, 3, 2, ("number", "array", "array", "other", "other"), [9.0, 2, 3], [10.0, 3, 4], [18.0, 4, 6], (True, False, True, True, True, False),
+           (3.5, 3, 3, 1, 1.5), [0, -1], True, ([[1, 3], [2, 4]], [3, 7], [[4, 6]], [[10, 20], [60, 80]], [[7, 10], [15, 22]], [1.0, 2.0]))
+
+    def same(a, b):
+        if isinstance(b, tuple):
+            return isinstance(a, tuple) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(b, str): return a == b
+        return np.array_equal(np.asarray(a), np.asarray(b))
+    assert len(out) == len(exp)
+    for k, (a, b) in enumerate(zip(out, exp)):
+        assert same(a, b), (k, a, b)
+
+
 # ---- diagonal_sbp.jl ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("p", [2, 4, 6])
 def test_sbp_operators_executed(ref, p):
