@@ -208,6 +208,11 @@ def test_locoperator_executed(ref, p):
             for a, b in zip(lop.get(name), mine):
                 assert relmax(a, b) < 5e-15, name
         assert tuple(lop.get("bctype")) == tuple(ol.bctype)
+    lop = ref.call("locoperator", p, N, N, m, (1, 2, 0, 7), **{"τscale": 1})   # keyword of :214 (local_op_eigenvalues.jl uses 1)
+    ol = orc.locoperator(p, N, N, om, (1, 2, 0, 7), tauscale=1.0)
+    assert relmax(lop.get("M̃"), ol.Mt) < 5e-15
+    for a, b in zip(lop.get("τ"), ol.tau):
+        assert relmax(a, b) < 5e-15
     with pytest.raises(JuliaError):
         ref.call("locoperator", p, N, N, m, (1, 3, 1, 1))                 # 'invalid bc', global_curved.jl:484
     # the reference as written needs Nr == Ns: an unused remainder (global_curved.jl:316) multiplies r-direction matrices with
