@@ -179,6 +179,17 @@ def test_sbp_operators_executed(ref, p):
     assert relmax(out[5], oo[5]) < 2e-15
 
 
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_constant_and_variable_second_derivative_agree_executed(ref, p):
+    """the reference's own 'affine mesh test' (global_curved.jl:274-277, commented out there): with b = 1 the variable-coefficient
+    stiffness is SN - S0 - H D2 of diagonal_sbp_D2 (diagonal_sbp.jl:203-465), two independently typed sets of tables"""
+    N = 25
+    D2, S0, SN, HI, H, r = ref.call("diagonal_sbp_D2", p, N)
+    Dv, S0v, SNv, HIv, Hv, Mv, rv = ref.call("variable_diagonal_sbp_D2", p, N, np.ones(N + 1))
+    assert relmax(Mv, SN - S0 - H @ D2) < 1e-14 and relmax(Dv, D2) < 1e-14 and relmax(S0v, S0) == 0 and relmax(SNv, SN) == 0
+    assert relmax(osbp.variable_diagonal_sbp_D2(p, N, np.ones(N + 1))[5], SN - S0 - H @ D2) < 1e-14
+
+
 # ---- create_metrics / locoperator --------------------------------------------------------------------------------------------------
 def curved_maps():
     import gen_refexec_golden as gg
