@@ -52,6 +52,17 @@ def test_oracle_square_circle_vs_reference_output(p):
     assert abs(o["eps"] - g["eps"]) < 1e-6 * g["eps"] and abs(o["teps"] - g["teps"]) < 1e-6 * g["teps"]
 
 
+def test_oracle_square_circle_level3_vs_reference_output():
+    from tests.refexec.oracle_driver import oracle_square_circle_level
+    g = np.load(os.path.join(GOLD, "square_circle_p4_N68.npz"))
+    o = oracle_square_circle_level(4, int(g["N"]))
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert np.array_equal(o["FTol"], g["FTolstarts"]) and np.array_equal(o["FTod"], g["FTodstarts"])
+    assert rel(o["delta"], g["delta"]) < 1e-14 and rel(o["gd"], g["gdelta"]) < 1e-13
+    assert rel(o["lam"], g["lam"]) < 1e-11 and rel(o["u"][::31], g["u_sample"]) < 1e-11
+    assert abs(o["eps"] - g["eps"][2]) < 1e-4 * g["eps"][2] and abs(o["teps"] - g["teps"][2]) < 1e-6 * g["teps"][2]
+
+
 def test_oracle_flower_vs_reference_output():
     from tests.refexec.oracle_driver import oracle_square_circle_level
     from hybridsbp_b200 import flower

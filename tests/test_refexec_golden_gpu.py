@@ -61,6 +61,21 @@ def test_square_circle_level1_vs_reference_output(ctx, p):
     assert rel(r["u"], g["u"]) <= 1e-10, r["stats"]
 
 
+def test_square_circle_level3_vs_reference_output(ctx):
+    """third level of square_circle.jl (N = 68: 69 points per line, banded block factors, condensed trace system with the two-level
+    preconditioner) against the executed reference's direct sparse solves"""
+    from hybridsbp_b200 import square_circle as sc
+    g = np.load(os.path.join(GOLD, "square_circle_p4_N68.npz"))
+    r = sc.solve_level(ctx, sc.load_mesh(sc.default_mesh_path()), 4, int(g["N"]), tol=1e-13)
+    assert r["stats"]["converged"] == 1, r["stats"]
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert np.array_equal(r["FTols"], g["FTolstarts"]) and np.array_equal(r["FTods"], g["FTodstarts"])
+    assert rel(r["delta"], g["delta"]) <= 1e-13 and rel(r["gd"], g["gdelta"]) <= 1e-12
+    assert rel(r["lam"], g["lam"]) <= 1e-10, (rel(r["lam"], g["lam"]), r["stats"])
+    assert rel(r["u"][::31], g["u_sample"]) <= 1e-10 and abs(np.linalg.norm(r["u"]) - float(g["u_norm"])) <= 1e-10 * float(g["u_norm"])
+    assert abs(r["eps"] - g["eps"][2]) <= 1e-2 * g["eps"][2] and abs(r["tau_eps"] - g["teps"][2]) <= 1e-3 * g["teps"][2]
+
+
 def test_flower_reversed_faces_vs_reference_output(ctx):
     """67 blocks, 27 faces seen in reversed orientation from their plus side, given slip on the 18 jump faces"""
     from hybridsbp_b200 import flower

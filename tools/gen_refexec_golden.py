@@ -11,6 +11,7 @@ Files
                              square_circle.jl's second level): coefficients, three boundary-condition sets, tau, y = M~ u, F_k' u,
                              traction operator HfI_FT_k u for a stored u
   square_circle_p{4,6}.npz   square_circle.jl:1-431 at its first level (56 blocks, N = 17): delta, g-delta, b-lambda, lambda, u, errors
+  square_circle_p4_N68.npz   the same driver run for three levels; third level (N = 68): lambda, g-delta, delta, every 31st entry of u
   flower_p4.npz              the reference's functions on meshes/flower_v2.inp (27 reversed faces, given slip on the 18 jump faces)
                              through tests/refexec/flower_driver.jl: delta, g-delta, b-lambda, lambda, u, fault traction
   bp1_odefun_N40.npz         seas/BP1/BP1.jl:1-158 (setup) + odefun.jl:8-121 at three states: y, t -> d(psi, delta)/dt
@@ -71,6 +72,17 @@ def gen_square_circle(p):
     print("square_circle p=%d written: eps = %.6e, traction eps = %.6e" % (p, c["ϵ"][0], c["τϵ"][0]))
 
 
+def gen_square_circle_level3(p=4):
+    """third refinement level (N = 68, 69 points per line: the banded local solver and the odd line lengths of k_sweep on the GPU side);
+    u is stored as every 31st entry plus its norm to keep the file small"""
+    cap, mesh, _ = run_square_circle(p=p, levels=3, N0=17, keep=("λ", "u", "gδ", "δ", "ϵ", "τϵ", "FToλstarts", "FToδstarts", "vstarts"))
+    c = cap[2]
+    np.savez_compressed(os.path.join(OUT, "square_circle_p%d_N68.npz" % p), p=p, N=68, delta=c["δ"], gdelta=c["gδ"], lam=c["λ"],
+                        u_sample=c["u"][::31], u_norm=np.linalg.norm(c["u"]), eps=cap[2]["ϵ"], teps=cap[2]["τϵ"],
+                        FTolstarts=c["FToλstarts"], FTodstarts=c["FToδstarts"])
+    print("square_circle p=%d, three levels: eps = %s" % (p, ["%.9e" % v for v in cap[2]["ϵ"]]))
+
+
 def gen_flower(p=4):
     c = run_flower(p, 17)
     np.savez_compressed(os.path.join(OUT, "flower_p%d.npz" % p), p=p, N=17, delta=c["δ"], gdelta=c["gδ"], blambda=c["bλ"], lam=c["λ"], u=c["u"],
@@ -112,3 +124,4 @@ if __name__ == "__main__":
     gen_bp1(40)
     gen_flower(4)
     for p in (4, 6): gen_square_circle(p)
+    gen_square_circle_level3(4)
