@@ -175,3 +175,43 @@ def test_struct_layouts_agree():
         assert pyf == cf, cname
         assert jname in js, jname
         assert js[jname] == cf, jname
+
+
+def check_julia_blocks(src):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from refexec.minijulia import lex
+    src = re.sub(r'"""(.*?)"""', lambda m: '"' + m.group(1).replace('"', "'").replace("\n", " ") + '"', src, flags=re.S)   # doc strings
+    src = re.sub(r"(\d)_(\d)", r"\1\2", src)                                                                        # 100_000
+    toks = lex(src)
+    openers = {"function", "if", "for", "while", "let", "begin", "try", "do", "struct"}
+    depth, sq, par, curly, stack = 0, 0, 0, 0, []
+    prev = None
+    for t in toks:
+        if t.kind == "op":
+            sq += {"[": 1, "]": -1}.get(t.val, 0); par += {"(": 1, ")": -1}.get(t.val, 0); curly += {"{": 1, "}": -1}.get(t.val, 0)
+            assert sq >= 0 and par >= 0 and curly >= 0, "unbalanced bracket at line %d" % t.line
+        if t.kind == "id" and t.val == "module":
+            depth += 1; stack.append(("module", t.line))
+        if t.kind == "kw":
+            if t.val in openers and sq == 0:
+                if t.val == "struct" and prev is not None and prev.kind == "kw" and prev.val == "mutable": pass
+                depth += 1; stack.append((t.val, t.line))
+            elif t.val == "end" and sq == 0:
+                depth -= 1
+                assert depth >= 0, "`end` without an opener at line %d" % t.line
+                stack.pop()
+        if t.kind != "nl": prev = t
+    assert (depth, sq, par, curly) == (0, 0, 0, 0), "unclosed blocks: %r" % (stack[-3:],)
+
+
+def test_julia_twin_block_structure_balances():
+    """lexical sanity of the Julia file: every block opener (module, struct, function, if, for, while, let, begin, try, do) has its
+    `end` (an `end` inside square brackets is an index), brackets balance, no token the lexer cannot read"""
+    src = open(os.path.join(ROOT, "julia", "HybridSBPB200.jl")).read()
+    check_julia_blocks(src)
+    k = src.rindex("\nend")
+    with pytest.raises(AssertionError):
+        check_julia_blocks(src[:k] + src[k + 4:])                       # the checker notices a missing `end` ...
+    with pytest.raises(AssertionError):
+        check_julia_blocks(src.replace("function close(c::Context)", "function close(c::Context", 1))    # ... and an open parenthesis
