@@ -52,6 +52,8 @@ def test_oracle_square_circle_vs_reference_output(p):
     assert abs(o["eps"] - g["eps"]) < 1e-6 * g["eps"] and abs(o["teps"] - g["teps"]) < 1e-6 * g["teps"]
 
 
+@pytest.mark.skipif(not os.environ.get("HSBP_SLOW_TESTS"), reason="one minute of sparse factorisations; set HSBP_SLOW_TESTS=1 "
+                    "(measured: lambda 1.4e-13, u 1.2e-13, profiles/r02c_reference_executed_convergence.txt)")
 def test_oracle_square_circle_level3_vs_reference_output():
     from tests.refexec.oracle_driver import oracle_square_circle_level
     g = np.load(os.path.join(GOLD, "square_circle_p4_N68.npz"))
