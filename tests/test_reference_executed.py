@@ -339,6 +339,17 @@ def test_square_circle_solution_executed(square_circle_p4):
     assert abs(o["eps"] - c["ϵ"][0]) < 1e-6 * c["ϵ"][0] and abs(o["teps"] - c["τϵ"][0]) < 1e-6 * c["τϵ"][0]
 
 
+def test_square_circle_order_2_executed():
+    """the same driver at SBP order 2 (BP1's order): lambda, u and the error norms of the oracle against the executed reference"""
+    from refexec.drivers import run_square_circle
+    from refexec.oracle_driver import oracle_square_circle_level
+    cap, _, _ = run_square_circle(p=2, levels=1, N0=17, keep=("λ", "u", "gδ", "ϵ", "τϵ"))
+    c, o = cap[0], oracle_square_circle_level(2, 17)
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+    assert rel(o["gd"], c["gδ"]) < 1e-13 and rel(o["lam"], c["λ"]) < 1e-11 and rel(o["u"], c["u"]) < 1e-11
+    assert abs(o["eps"] - c["ϵ"][0]) < 1e-7 * c["ϵ"][0] and abs(o["teps"] - c["τϵ"][0]) < 1e-7 * c["τϵ"][0]
+
+
 # ---- configuration 2: the reference's functions on the flower mesh (reversed faces) --------------------------------------------------
 def test_flower_mesh_reversed_faces_executed():
     """gloλoperator's flipped branch (`FToλstarts[f+1] .- Ie`, `rot180(τ)`, global_curved.jl:546-549), in_jump's three branches and
