@@ -23,11 +23,12 @@ def oracle_square_circle_level(p, N, mesh=None, maps=None, exact=None, slip=None
         lops.append(orc.locoperator(p, N, N, om, FToB[EToF[:, e] - 1]))
     Ns = [N] * ne
     M, FbarT, D, vstarts, FTol = orc.LocalGlobalOperators(lops, Ns, Ns, FToB, FToE, FToLF, EToO, EToS)
-    FTod = orc.bcstarts(FToB, FToE, FToLF, orc.BC_JUMP_INTERFACE, Ns, Ns)
+    jump_codes = tuple(sorted(set(int(b) for b in FToB if b >= orc.BC_JUMP_INTERFACE))) or (orc.BC_JUMP_INTERFACE,)
+    FTod = orc.bcstarts(FToB, FToE, FToLF, jump_codes, Ns, Ns)
     E = exact or sc.ExactSolution
     delta = np.zeros(FTod[-1] - 1)
     for f in range(len(FToB)):                                                    # square_circle.jl:321-330
-        if FToB[f] == orc.BC_JUMP_INTERFACE:
+        if FToB[f] >= orc.BC_JUMP_INTERFACE:
             e1, e2 = FToE[:, f] - 1
             lf1 = FToLF[0, f] - 1
             xf, yf = lops[e1].facecoord[0][lf1], lops[e1].facecoord[1][lf1]
@@ -68,7 +69,7 @@ def oracle_square_circle_level(p, N, mesh=None, maps=None, exact=None, slip=None
     teps = 0.0                                                                    # :402-420
     tauf = np.zeros(FTod[-1] - 1)
     for f in range(len(FToB)):
-        if FToB[f] == orc.BC_JUMP_INTERFACE:
+        if FToB[f] >= orc.BC_JUMP_INTERFACE:
             e1 = FToE[0, f] - 1; lf1 = FToLF[0, f] - 1
             xf, yf = lops[e1].facecoord[0][lf1], lops[e1].facecoord[1][lf1]
             nx, ny = lops[e1].nx[lf1], lops[e1].ny[lf1]

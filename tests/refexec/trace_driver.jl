@@ -1,14 +1,15 @@
-# Configuration 2 (meshes/flower_v2.inp: 67 blocks, interfaces seen in reversed orientation from their plus side) solved with the
+# A mesh of straight-sided blocks -- configuration 2, meshes/flower_v2.inp (67 blocks, interfaces seen in reversed orientation from
+# their plus side), or seas/BP1/meshes/BP1_v1.inp (194 blocks, two kinds of jump interfaces: side sets 7 and 8) -- solved with the
 # REFERENCE's functions -- read_inp_2d, connectivityarrays, transfinite_blend (corner form), create_metrics, locoperator,
 # LocalGlobalOperators, bcstarts, assembleλmatrix, locbcarray!, locsourcearray!, LocalToGLobalRHS!, computetraction -- which
-# tests/refexec/minijulia.py takes from global_curved.jl under /root/reference.  The reference ships this mesh without a driver;
-# this file is the test suite's own (inputs: the globals `order` and `npts`).  The slip on the jump faces is a prescribed
+# tests/refexec/minijulia.py takes from global_curved.jl under /root/reference.  The reference ships these meshes without drivers;
+# this file is the test suite's own (inputs: the globals `meshfile`, `jumpcodes`, `slipshift`, `order` and `npts`).  The slip on the jump faces is a prescribed
 # function of position rather than the jump of a manufactured solution, so that all three orientation branches of the jump data
 # carry non-zero values.
 include("global_curved.jl")
 
 let
-  mesh = read_inp_2d("meshes/flower_v2.inp")
+  mesh = read_inp_2d(meshfile)
   corners, blockcorner, blockface, facebc = mesh[1], mesh[2], mesh[3], mesh[4]
   nblocks = size(blockcorner, 2)
   nsides = length(facebc)
@@ -21,7 +22,7 @@ let
   field_x(x, y) = 0.9 .* cos.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2) .+ 0.1 .* y
   field_y(x, y) = -0.7 .* sin.(0.9 .* x .+ 0.3) .* sin.(0.7 .* y .- 0.2) .+ 0.1 .* x
   minus_laplacian(x, y) = (0.9^2 + 0.7^2) .* sin.(0.9 .* x .+ 0.3) .* cos.(0.7 .* y .- 0.2)
-  slip(x, y) = 0.3 .* sin.(x) .* cos.(2 .* y)
+  slip(x, y) = 0.3 .* sin.(x .+ slipshift) .* cos.(2 .* y)      # slipshift = 0 on the flower mesh; the BP1 fault lies on x = 0
 
   # one straight-sided block per element: corner blend -> metrics -> local operator
   ops = Dict{Int64, Any}()
@@ -35,7 +36,7 @@ let
 
   glob = LocalGlobalOperators(ops, sizes, sizes, facebc, faceblock, facelocal, sameway, side, A -> cholesky(Symmetric(A)))
   solvers, traceT, diagD, vstart, tstart = glob[1].F, glob[2], glob[3], glob[4], glob[5]
-  jstart = bcstarts(facebc, faceblock, facelocal, BC_JUMP_INTERFACE, sizes, sizes)
+  jstart = bcstarts(facebc, faceblock, facelocal, jumpcodes, sizes, sizes)
   schur = assembleλmatrix(tstart, vstart, blockface, facebc, solvers, diagD, traceT)
   schur_solver = cholesky(Symmetric(schur))
 
@@ -43,7 +44,7 @@ let
   ntrace = tstart[end] - 1
   jumps = zeros(jstart[end] - 1)
   for f = 1:nsides
-    facebc[f] == BC_JUMP_INTERFACE || continue
+    facebc[f] >= BC_JUMP_INTERFACE || continue
     b, lf = faceblock[1, f], facelocal[1, f]
     jumps[jstart[f]:(jstart[f+1]-1)] = slip(ops[b].facecoord[1][lf], ops[b].facecoord[2][lf])
   end
@@ -80,7 +81,7 @@ let
 
   fault_traction = zeros(length(jumps))
   for f = 1:nsides
-    facebc[f] == BC_JUMP_INTERFACE || continue
+    facebc[f] >= BC_JUMP_INTERFACE || continue
     b, lf = faceblock[1, f], facelocal[1, f]
     rows = vstart[b]:(vstart[b+1]-1)
     fault_traction[jstart[f]:(jstart[f+1]-1)] = computetraction(ops[b], lf, solution[rows], trace[tstart[f]:(tstart[f+1]-1)],

@@ -353,7 +353,7 @@ def test_square_circle_order_2_executed():
 # ---- configuration 2: the reference's functions on the flower mesh (reversed faces) --------------------------------------------------
 def test_flower_mesh_reversed_faces_executed():
     """gloλoperator's flipped branch (`FToλstarts[f+1] .- Ie`, `rot180(τ)`, global_curved.jl:546-549), in_jump's three branches and
-    the reversed g-delta views, with slip data on the jump faces: tests/refexec/flower_driver.jl drives the reference's functions"""
+    the reversed g-delta views, with slip data on the jump faces: tests/refexec/trace_driver.jl drives the reference's functions"""
     from refexec.drivers import run_flower
     from refexec.oracle_driver import oracle_square_circle_level
     from hybridsbp_b200 import flower
@@ -371,6 +371,25 @@ def test_flower_mesh_reversed_faces_executed():
     assert rel(o["lam"], c["λ"]) < 1e-11 and rel(o["u"], c["u"]) < 1e-11 and rel(o["tauf"], c["τf"]) < 1e-11
     g = np.load(os.path.join(GOLD, "flower_p4.npz"))
     assert np.array_equal(g["lam"], c["λ"]) and np.array_equal(g["u"], c["u"]) and np.array_equal(g["traction"], c["τf"])
+
+
+def test_multiblock_bp1_mesh_two_jump_codes_executed():
+    """seas/BP1/meshes/BP1_v1.inp (194 blocks, 104 reversed faces, jump interfaces of two kinds: side sets 7 and 8 -- every
+    `>= BC_JUMP_INTERFACE` branch of locoperator, locbcarray!, assembleλmatrix, bcstarts with a tuple of codes): the reference's
+    functions driven by tests/refexec/trace_driver.jl against the oracle's, slip on both kinds of interfaces (p = 2, 7 points per line)"""
+    from refexec.drivers import run_trace_driver
+    from refexec.oracle_driver import oracle_square_circle_level
+    from hybridsbp_b200 import flower, host
+    c = run_trace_driver("seas/BP1/meshes/BP1_v1.inp", 2, 6, (7, 8), 0.4)
+    o = oracle_square_circle_level(2, 6, mesh=host.read_inp_2d(os.path.join(ROOT, "meshes", "BP1_v1.inp")), maps=flower.block_maps,
+                                   exact=flower.Smooth, slip=lambda x, y: 0.3 * np.sin(x + 0.4) * np.cos(2 * y))
+    FToB = np.asarray(c["FToB"])
+    assert {int(k): int((FToB == k).sum()) for k in np.unique(FToB)} == {0: 346, 1: 10, 2: 30, 7: 13, 8: 9}
+    assert int((~np.asarray(c["EToO"]).astype(bool)).sum()) == 104
+    assert np.array_equal(o["FTol"], c["FToλstarts"]) and np.array_equal(o["FTod"], c["FToδstarts"])
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+    assert np.linalg.norm(c["δ"]) > 1 and rel(o["delta"], c["δ"]) < 1e-12 and rel(o["g"], c["g"]) < 1e-13 and rel(o["gd"], c["gδ"]) < 1e-12
+    assert rel(o["bl"], c["bλ"]) < 1e-12 and rel(o["lam"], c["λ"]) < 1e-11 and rel(o["u"], c["u"]) < 1e-11 and rel(o["tauf"], c["τf"]) < 1e-10
 
 
 # ---- BP1 ---------------------------------------------------------------------------------------------------------------------------

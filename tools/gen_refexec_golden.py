@@ -13,7 +13,7 @@ Files
   square_circle_p{4,6}.npz   square_circle.jl:1-431 at its first level (56 blocks, N = 17): delta, g-delta, b-lambda, lambda, u, errors
   square_circle_p4_N68.npz   the same driver run for three levels; third level (N = 68): lambda, g-delta, delta, every 31st entry of u
   flower_p4.npz              the reference's functions on meshes/flower_v2.inp (27 reversed faces, given slip on the 18 jump faces)
-                             through tests/refexec/flower_driver.jl: delta, g-delta, b-lambda, lambda, u, fault traction
+                             through tests/refexec/trace_driver.jl: delta, g-delta, b-lambda, lambda, u, fault traction
   bp1_odefun_N40.npz         seas/BP1/BP1.jl:1-158 (setup) + odefun.jl:8-121 at three states: y, t -> d(psi, delta)/dt
 """
 import os
