@@ -105,3 +105,27 @@ def run_trace_driver(meshfile, p=4, N0=17, jumpcodes=7, slipshift=0.0):
 
 def run_flower(p=4, N0=17):
     return run_trace_driver("meshes/flower_v2.inp", p, N0, 7)
+
+
+PLOTTING = ("Plot", "BrailleCanvas", "annotate!", "lineplot!", "display", "PGFPlots", "pgf_axis", "plt", "plt_max", "plt_min")
+
+
+def run_check_script(name, num_samp=2, capture=()):
+    """one of the reference's own check scripts (local_op_eigenvalues.jl, global_op_eigenvalues.jl, check_residual.jl) as written, with
+    the number of random samples reduced and the plotting statements dropped; returns (captured variables per `let` block, @show log)"""
+    it = Interp(REF)
+    with open(os.path.join(REF, name)) as f:
+        ast = parse_source(f.read(), name)
+    captured = []
+
+    def fn(n):
+        if n[0] == "assign" and n[1] == ("id", "num_samp"): return ("assign", n[1], ("num", num_samp))
+        if n[0] in ("assign", "call", "for", "show") and contains_id(n, PLOTTING): return None
+        if n[0] == "call" and n[1] == ("id", "range") and any(k[0] == "length" for k in n[3]):      # tau sweep of local_op_eigenvalues.jl
+            return ("call", n[1], n[2], [(k, ("num", 4) if k == "length" and v == ("num", 100) else v, a) for k, v, a in n[3]], n[4])
+        if n[0] == "let":
+            hook = lambda env: captured.append({k: to_python(env.vars[k]) for k in capture if k in env.vars})
+            return ("let", ("block", n[1][1] + [("pyhook", hook)]))
+        return n
+    it.exec_block(rewrite(ast, fn), it.globals)
+    return captured, it.log
